@@ -1,0 +1,614 @@
+// K1+K2+K3: hash partition of a columnar table on sm_100a.
+//
+// Replaces the grouping/repartition step of the reference's map path:
+//   fugue/execution/native_execution_engine.py:166-168  (safe_groupby_apply)
+//   fugue_dask/_utils.py:44-59, 124-130, 146-169        (hash_repartition)
+//
+// Design (HBM-bound byte movement; no tensor-core work exists on this path):
+//   * the row range is cut into `nchunks` contiguous chunks, one per resident CTA
+//     (2 CTAs per SM x 148 SMs), each chunk a whole number of TILE-row tiles;
+//   * pass 1 (fb_hist_kernel)   : per-chunk histogram of partition ids (reads the
+//     key column(s) only: 8 B/row for the benchmark schema);
+//   * scan  (fb_scan_*_kernel)  : exclusive prefix per partition over chunks, then
+//     over partitions -> part_offsets[num+1] and chunk bases;
+//   * pass 2 (fb_scatter_kernel): every CTA walks its chunk tile by tile; inside a
+//     tile rows are ranked stably per partition with warp match/ballot counters in
+//     shared memory, each column tile is loaded coalesced, permuted through shared
+//     memory into partition order and written out as contiguous runs
+//     (1 run per partition present in the tile), so global writes are coalesced.
+//     Running per-partition output cursors live in shared memory for the whole
+//     chunk, so no per-tile table is ever materialised in HBM.
+//   Algorithmic traffic 128 B/row (read 64 + write 64) for the 8x8-byte schema;
+//   the implementation adds the 8 B/row key re-read of pass 1.
+#include "fb_common.cuh"
+
+namespace {
+
+constexpr int kBlock = 512;             // threads per CTA
+constexpr int kItems = 8;               // rows per thread per tile
+constexpr int kTile = kBlock * kItems;  // 4096 rows per tile
+constexpr int kWarps = kBlock / 32;
+constexpr int kCtasPerSm = 2;
+
+struct FbCols {
+  const void* src[FB_MAX_COLS];
+  void* dst[FB_MAX_COLS];
+  int32_t width[FB_MAX_COLS];
+  int32_t ncols;
+};
+
+struct ChunkGeom {
+  int64_t nrows;
+  int64_t tiles_per_chunk;
+  int32_t nchunks;
+};
+
+inline ChunkGeom make_geom(int dev, int64_t nrows) {
+  ChunkGeom g;
+  g.nrows = nrows;
+  int64_t ntiles = (nrows + kTile - 1) / kTile;
+  if (ntiles < 1) ntiles = 1;
+  int64_t max_chunks = (int64_t)fb_sm_count(dev) * kCtasPerSm;
+  g.tiles_per_chunk = (ntiles + max_chunks - 1) / max_chunks;
+  g.nchunks = (int32_t)((ntiles + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
+  return g;
+}
+
+template <bool kSingleU64>
+__device__ __forceinline__ uint32_t compute_pid(const FbKeys& keys, const FbDiv& dv, int64_t row) {
+  uint64_t h;
+  if (kSingleU64) {
+    h = fb_hash_single_u64(__ldg((const unsigned long long*)keys.ptr[0] + row));
+  } else {
+    h = fb_row_hash(keys, row);
+  }
+  return fb_fastmod(h, dv);
+}
+
+// ---------------------------------------------------------------------------
+// K1 alone: materialise partition ids (tests, repartition planning)
+// ---------------------------------------------------------------------------
+template <bool kSingleU64>
+__global__ void fb_pid_kernel(FbKeys keys, FbDiv dv, int64_t nrows, uint32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nrows; i += stride) out[i] = compute_pid<kSingleU64>(keys, dv, i);
+}
+
+// ---------------------------------------------------------------------------
+// pass 1: per-chunk histogram. hist layout: [chunk][num]
+// ---------------------------------------------------------------------------
+template <bool kSingleU64>
+__global__ void __launch_bounds__(kBlock)
+fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t s_hist[];
+  for (uint32_t b = threadIdx.x; b < num; b += kBlock) s_hist[b] = 0;
+  __syncthreads();
+  const int64_t row0 = (int64_t)blockIdx.x * g.tiles_per_chunk * kTile;
+  int64_t row1 = row0 + g.tiles_per_chunk * kTile;
+  if (row1 > g.nrows) row1 = g.nrows;
+  const unsigned lane = threadIdx.x & 31;
+  // kItems independent key loads in flight per thread
+  for (int64_t base = row0; base < row1; base += kTile) {
+    uint32_t pid[kItems];
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+      int64_t row = base + (int64_t)r * kBlock + threadIdx.x;
+      pid[r] = row < row1 ? compute_pid<kSingleU64>(keys, dv, row) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+      // warp-aggregated shared-memory increment: one atomic per distinct pid per warp
+      unsigned peers = __match_any_sync(0xFFFFFFFFu, pid[r]);
+      if (pid[r] != 0xFFFFFFFFu && (peers & fb_lanemask_lt()) == 0)
+        atomicAdd(&s_hist[pid[r]], (uint32_t)__popc(peers));
+    }
+    (void)lane;
+  }
+  __syncthreads();
+  uint32_t* out = hist + (size_t)blockIdx.x * num;
+  for (uint32_t b = threadIdx.x; b < num; b += kBlock) out[b] = s_hist[b];
+}
+
+// ---------------------------------------------------------------------------
+// scan A: one CTA per partition id: exclusive prefix over chunks (in place),
+// total -> totals[b].  nchunks <= 2 * SM count (<= 1024 handled generally).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fb_scan_chunks_kernel(uint32_t* __restrict__ hist, uint32_t num, int32_t nchunks,
+                      int64_t* __restrict__ totals) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_carry;
+  const uint32_t b = blockIdx.x;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int32_t c0 = 0; c0 < nchunks; c0 += 256) {
+    int32_t c = c0 + threadIdx.x;
+    uint32_t v = c < nchunks ? hist[(size_t)c * num + b] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (unsigned w = 0; w < warp; ++w) wbase += s_warp[w];
+    uint32_t carry = s_carry;
+    if (c < nchunks) hist[(size_t)c * num + b] = carry + wbase + x - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = carry + wbase + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[b] = (int64_t)s_carry;
+}
+
+// scan B: single CTA: exclusive prefix over partitions (int64), in place on
+// offsets[0..num]; input totals in offsets[0..num-1].
+__global__ void __launch_bounds__(1024)
+fb_scan_parts_kernel(int64_t* __restrict__ offsets, uint32_t num) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < num; b0 += 1024) {
+    uint32_t b = b0 + threadIdx.x;
+    int64_t v = b < num ? offsets[b] : 0;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int64_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int64_t wbase = 0;
+    for (unsigned w = 0; w < warp; ++w) wbase += s_warp[w];
+    int64_t carry = s_carry;
+    if (b < num) offsets[b] = carry + wbase + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + wbase + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[num] = s_carry;
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: scatter.  Shared memory layout (dynamic):
+//   buf[2][kTile * 8]          column staging, double buffered      64 KB
+//   cursor[nb]     int64       running output position per partition
+//   delta[nb]      int64       cursor[b] - bin_start[b] for the current tile
+//   bin_start[nb]  uint32      exclusive prefix of the tile histogram
+//   warp_cnt[kWarps][nb] u32   per-warp per-partition counters / prefixes
+//   pid_sorted[kTile] uint16   partition id of every slot of the permuted tile
+// nb = num + 1 (one sentinel bin that collects the rows past the end of the chunk)
+// ---------------------------------------------------------------------------
+__host__ __device__ inline size_t scatter_smem_bytes(uint32_t num) {
+  size_t nb = (size_t)num + 1;
+  size_t nb_pad = (nb + 1) & ~(size_t)1;
+  return 2 * (size_t)kTile * 8 + nb_pad * 8 * 2 + nb_pad * 4 + (size_t)kWarps * nb_pad * 4 +
+         (size_t)kTile * 2 + 64;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_col_tile(const void* __restrict__ src, int64_t warp_row0,
+                                              int64_t row_end, unsigned lane, T (&v)[kItems]) {
+  const T* p = (const T*)src;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    int64_t row = warp_row0 + r * 32 + lane;
+    if (row < row_end) v[r] = __ldg(p + row);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void permute_col_tile(T* __restrict__ buf, const uint32_t (&pos)[kItems],
+                                                 const T (&v)[kItems]) {
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) buf[pos[r]] = v[r];
+}
+
+template <typename T>
+__device__ __forceinline__ void write_col_tile(void* __restrict__ dst, const T* __restrict__ buf,
+                                               const uint16_t* __restrict__ pid_sorted,
+                                               const int64_t* __restrict__ delta, int tile_rows) {
+  T* out = (T*)dst;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    int j = k * kBlock + threadIdx.x;
+    if (j < tile_rows) out[delta[pid_sorted[j]] + j] = buf[j];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void move_columns_of_width(const FbCols& cols, int width, uint8_t* buf0,
+                                                      uint8_t* buf1, const uint32_t (&pos)[kItems],
+                                                      const uint16_t* pid_sorted, const int64_t* delta,
+                                                      int64_t warp_row0, int64_t row_end, unsigned lane,
+                                                      int tile_rows, int& phase) {
+  T v[kItems];
+  int c = 0;
+  // find first column of this width
+  while (c < cols.ncols && cols.width[c] != width) ++c;
+  if (c >= cols.ncols) return;
+  load_col_tile<T>(cols.src[c], warp_row0, row_end, lane, v);
+  while (c < cols.ncols) {
+    T* buf = (T*)((phase & 1) ? buf1 : buf0);
+    permute_col_tile<T>(buf, pos, v);
+    int nxt = c + 1;
+    while (nxt < cols.ncols && cols.width[nxt] != width) ++nxt;
+    if (nxt < cols.ncols) load_col_tile<T>(cols.src[nxt], warp_row0, row_end, lane, v);  // prefetch
+    __syncthreads();
+    write_col_tile<T>(cols.dst[c], buf, pid_sorted, delta, tile_rows);
+    ++phase;
+    c = nxt;
+  }
+}
+
+template <bool kSingleU64>
+__global__ void __launch_bounds__(kBlock, kCtasPerSm)
+fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g,
+                  const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets,
+                  FbCols cols) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t nb = num + 1;
+  const uint32_t nb_pad = (nb + 1) & ~1u;
+  uint8_t* buf0 = smem;
+  uint8_t* buf1 = smem + (size_t)kTile * 8;
+  int64_t* cursor = (int64_t*)(smem + 2 * (size_t)kTile * 8);
+  int64_t* delta = cursor + nb_pad;
+  uint32_t* bin_start = (uint32_t*)(delta + nb_pad);
+  uint32_t* warp_cnt = bin_start + nb_pad;
+  uint16_t* pid_sorted = (uint16_t*)(warp_cnt + (size_t)kWarps * nb_pad);
+  __shared__ uint32_t s_scan_warp[kWarps];
+
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t chunk_row0 = (int64_t)blockIdx.x * g.tiles_per_chunk * kTile;
+  int64_t chunk_row1 = chunk_row0 + g.tiles_per_chunk * kTile;
+  if (chunk_row1 > g.nrows) chunk_row1 = g.nrows;
+
+  for (uint32_t b = threadIdx.x; b < nb; b += kBlock)
+    cursor[b] = b < num ? part_offsets[b] + (int64_t)chunk_base[(size_t)blockIdx.x * num + b] : 0;
+  // (visibility of cursor[] is covered by the barriers inside the tile loop)
+
+  int phase = 0;
+  uint32_t* my_cnt = warp_cnt + (size_t)warp * nb_pad;
+
+  for (int64_t tile_row0 = chunk_row0; tile_row0 < chunk_row1; tile_row0 += kTile) {
+    const int tile_rows = (int)((chunk_row1 - tile_row0) < kTile ? (chunk_row1 - tile_row0) : kTile);
+    const int64_t warp_row0 = tile_row0 + (int64_t)warp * (32 * kItems);
+
+    // -- 1. partition ids of my rows (warp-striped: row = warp_row0 + r*32 + lane)
+    uint32_t pid[kItems];
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+      int64_t row = warp_row0 + r * 32 + lane;
+      pid[r] = row < chunk_row1 ? compute_pid<kSingleU64>(keys, dv, row) : num;
+    }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * nb_pad; i += kBlock) warp_cnt[i] = 0;
+    __syncthreads();
+
+    // -- 2. stable rank inside (warp, partition): match-any peers + warp-private counters
+    uint32_t pos[kItems];
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+      unsigned peers = __match_any_sync(0xFFFFFFFFu, pid[r]);
+      unsigned before = __popc(peers & fb_lanemask_lt());
+      int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if ((int)lane == leader) {
+        old = my_cnt[pid[r]];
+        my_cnt[pid[r]] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xFFFFFFFFu, old, leader);
+      pos[r] = old + before;
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // -- 3. per partition: exclusive prefix over warps; tile histogram -> bin_start
+    for (uint32_t b = threadIdx.x; b < nb; b += kBlock) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        uint32_t t = warp_cnt[(size_t)w * nb_pad + b];
+        warp_cnt[(size_t)w * nb_pad + b] = run;
+        run += t;
+      }
+      bin_start[b] = run;
+    }
+    __syncthreads();
+    // block-wide exclusive scan of bin_start[0..nb): thread t owns bins [t*per, (t+1)*per)
+    {
+      const uint32_t per = (nb + kBlock - 1) / kBlock;
+      uint32_t b0 = threadIdx.x * per;
+      uint32_t sum = 0;
+      for (uint32_t i = 0; i < per; ++i)
+        if (b0 + i < nb) sum += bin_start[b0 + i];
+      uint32_t x = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (unsigned)o) x += y;
+      }
+      if (lane == 31) s_scan_warp[warp] = x;
+      __syncthreads();
+      uint32_t wbase = 0;
+      for (unsigned w = 0; w < warp; ++w) wbase += s_scan_warp[w];
+      uint32_t run = wbase + x - sum;
+      for (uint32_t i = 0; i < per; ++i) {
+        if (b0 + i < nb) {
+          uint32_t t = bin_start[b0 + i];
+          bin_start[b0 + i] = run;
+          // delta = where slot j of the permuted tile lands in the output: cursor - bin_start + j
+          delta[b0 + i] = cursor[b0 + i] - (int64_t)run;
+          cursor[b0 + i] += t;
+          run += t;
+        }
+      }
+    }
+    __syncthreads();
+
+    // -- 4. final slot of every row inside the permuted tile
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+      pos[r] += bin_start[pid[r]] + my_cnt[pid[r]];
+      pid_sorted[pos[r]] = (uint16_t)pid[r];
+    }
+    // (pid_sorted visibility: first barrier inside the column loop)
+
+    // -- 5. move the columns: coalesced load -> permute in smem -> run-coalesced store
+    move_columns_of_width<uint64_t>(cols, 8, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
+                                    lane, tile_rows, phase);
+    move_columns_of_width<uint32_t>(cols, 4, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
+                                    lane, tile_rows, phase);
+    move_columns_of_width<uint16_t>(cols, 2, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
+                                    lane, tile_rows, phase);
+    move_columns_of_width<uint8_t>(cols, 1, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
+                                   lane, tile_rows, phase);
+    __syncthreads();  // all reads of delta/pid_sorted/bufs done before the next tile rewrites them
+  }
+}
+
+// ---------------------------------------------------------------------------
+// validity bitmap <-> byte mask
+// ---------------------------------------------------------------------------
+__global__ void fb_bits_to_bytes_kernel(const uint8_t* __restrict__ bits, int64_t bit_offset,
+                                        int64_t nrows, uint8_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nrows; i += stride) {
+    int64_t j = i + bit_offset;
+    out[i] = (bits[j >> 3] >> (j & 7)) & 1;
+  }
+}
+
+__global__ void fb_bytes_to_bits_kernel(const uint8_t* __restrict__ bytes, int64_t nrows,
+                                        uint8_t* __restrict__ out, unsigned long long* null_count) {
+  // one thread per output byte
+  int64_t nbytes = (nrows + 7) >> 3;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long nulls = 0;
+  for (; i < nbytes; i += stride) {
+    uint8_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int64_t r = i * 8 + k;
+      if (r < nrows) {
+        if (bytes[r]) v |= (uint8_t)(1u << k);
+        else ++nulls;
+      }
+    }
+    out[i] = v;
+  }
+  if (null_count != nullptr && nulls) atomicAdd(null_count, nulls);
+}
+
+bool single_u64_key(int nkeys, const int32_t* widths, const uint8_t* const* valid) {
+  return nkeys == 1 && widths[0] == 8 && (valid == nullptr || valid[0] == nullptr);
+}
+
+int fill_keys(FbKeys& k, int nkeys, const void* const* ptrs, const int32_t* widths,
+              const uint8_t* const* valid) {
+  FB_CHECK(nkeys >= 1 && nkeys <= FB_MAX_KEYS, "nkeys=%d out of range [1,%d]", nkeys, FB_MAX_KEYS);
+  memset(&k, 0, sizeof(k));
+  k.nkeys = nkeys;
+  for (int i = 0; i < nkeys; ++i) {
+    FB_CHECK(widths[i] == 1 || widths[i] == 2 || widths[i] == 4 || widths[i] == 8,
+             "key %d has unsupported width %d", i, widths[i]);
+    FB_CHECK(ptrs[i] != nullptr, "key %d pointer is NULL", i);
+    k.ptr[i] = ptrs[i];
+    k.width[i] = widths[i];
+    k.valid[i] = valid ? valid[i] : nullptr;
+  }
+  return 0;
+}
+
+struct PlanLayout {
+  size_t hist_bytes;     // uint32 [nchunks][num]
+  size_t total_bytes;
+};
+
+PlanLayout plan_layout(const ChunkGeom& g, uint32_t num) {
+  PlanLayout l;
+  l.hist_bytes = (((size_t)g.nchunks * num * sizeof(uint32_t)) + 255) & ~(size_t)255;
+  l.total_bytes = l.hist_bytes + 256;
+  return l;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t fb_partition_scratch_bytes(int dev, int64_t nrows, uint32_t num_partitions) {
+  if (nrows < 0 || num_partitions == 0) return 0;
+  ChunkGeom g = make_geom(dev, nrows);
+  return plan_layout(g, num_partitions).total_bytes;
+}
+
+int fb_partition_ids(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                     const int32_t* key_widths, const uint8_t* const* key_valid,
+                     uint32_t num_partitions, uint32_t* out_pids) {
+  FB_CHECK(nrows >= 0, "nrows < 0");
+  FB_CHECK(num_partitions >= 1, "num_partitions must be >= 1");
+  if (nrows == 0) return 0;
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  FbDiv dv = fb_make_div(num_partitions);
+  int64_t blocks = (nrows + 255) / 256;
+  int64_t maxb = (int64_t)fb_sm_count(dev) * 16;
+  if (blocks > maxb) blocks = maxb;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (single_u64_key(nkeys, key_widths, key_valid))
+    fb_pid_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(k, dv, nrows, out_pids);
+  else
+    fb_pid_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(k, dv, nrows, out_pids);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                      const int32_t* key_widths, const uint8_t* const* key_valid,
+                      uint32_t num_partitions, void* scratch, size_t scratch_bytes,
+                      int64_t* out_part_offsets) {
+  FB_CHECK(nrows >= 0, "nrows < 0");
+  FB_CHECK(nrows < ((int64_t)1 << 32), "nrows=%lld exceeds the 2^32-1 rows one call handles",
+           (long long)nrows);
+  FB_CHECK(num_partitions >= 1 && num_partitions <= FB_MAX_PARTITIONS,
+           "num_partitions=%u out of range [1,%d]", num_partitions, FB_MAX_PARTITIONS);
+  FB_CHECK(out_part_offsets != nullptr, "out_part_offsets is NULL");
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nrows == 0) {
+    FB_CUDA(cudaMemsetAsync(out_part_offsets, 0, sizeof(int64_t) * ((size_t)num_partitions + 1), st));
+    return 0;
+  }
+  ChunkGeom g = make_geom(dev, nrows);
+  PlanLayout l = plan_layout(g, num_partitions);
+  FB_CHECK(scratch != nullptr && scratch_bytes >= l.total_bytes,
+           "scratch too small: need %zu bytes, got %zu", l.total_bytes, scratch_bytes);
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  FbDiv dv = fb_make_div(num_partitions);
+  uint32_t* hist = (uint32_t*)scratch;
+  size_t smem = (size_t)num_partitions * sizeof(uint32_t);
+  if (single_u64_key(nkeys, key_widths, key_valid))
+    fb_hist_kernel<true><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g, hist);
+  else
+    fb_hist_kernel<false><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g, hist);
+  FB_CUDA(cudaGetLastError());
+  fb_scan_chunks_kernel<<<num_partitions, 256, 0, st>>>(hist, num_partitions, g.nchunks, out_part_offsets);
+  FB_CUDA(cudaGetLastError());
+  fb_scan_parts_kernel<<<1, 1024, 0, st>>>(out_part_offsets, num_partitions);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                       const int32_t* key_widths, const uint8_t* const* key_valid,
+                       uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
+                       const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
+                       const int32_t* col_widths, void* const* out_col_ptrs) {
+  FB_CHECK(nrows >= 0 && nrows < ((int64_t)1 << 32), "nrows out of range");
+  FB_CHECK(num_partitions >= 1 && num_partitions <= FB_MAX_PARTITIONS,
+           "num_partitions=%u out of range [1,%d]", num_partitions, FB_MAX_PARTITIONS);
+  FB_CHECK(ncols >= 0, "ncols < 0");
+  if (nrows == 0 || ncols == 0) return 0;
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  ChunkGeom g = make_geom(dev, nrows);
+  PlanLayout l = plan_layout(g, num_partitions);
+  FB_CHECK(scratch != nullptr && scratch_bytes >= l.total_bytes, "scratch too small");
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  FbDiv dv = fb_make_div(num_partitions);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool single = single_u64_key(nkeys, key_widths, key_valid);
+  size_t smem = scatter_smem_bytes(num_partitions);
+  static thread_local int smem_set[2] = {0, 0};
+  // opt in to > 48 KB of dynamic shared memory (per function, per device context)
+  FB_CUDA(cudaFuncSetAttribute(fb_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)scatter_smem_bytes(FB_MAX_PARTITIONS)));
+  FB_CUDA(cudaFuncSetAttribute(fb_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)scatter_smem_bytes(FB_MAX_PARTITIONS)));
+  (void)smem_set;
+  for (int c0 = 0; c0 < ncols; c0 += FB_MAX_COLS) {
+    FbCols cols;
+    memset(&cols, 0, sizeof(cols));
+    cols.ncols = ncols - c0 < FB_MAX_COLS ? ncols - c0 : FB_MAX_COLS;
+    for (int c = 0; c < cols.ncols; ++c) {
+      int w = col_widths[c0 + c];
+      FB_CHECK(w == 1 || w == 2 || w == 4 || w == 8, "column %d has unsupported width %d", c0 + c, w);
+      FB_CHECK(col_ptrs[c0 + c] != nullptr && out_col_ptrs[c0 + c] != nullptr,
+               "column %d pointer is NULL", c0 + c);
+      cols.src[c] = col_ptrs[c0 + c];
+      cols.dst[c] = out_col_ptrs[c0 + c];
+      cols.width[c] = w;
+    }
+    if (single)
+      fb_scatter_kernel<true><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g,
+                                                               (const uint32_t*)scratch, part_offsets, cols);
+    else
+      fb_scatter_kernel<false><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g,
+                                                                (const uint32_t*)scratch, part_offsets, cols);
+    FB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int fb_partition_cols(int dev, void* stream, int64_t nrows, int ncols, const void* const* col_ptrs,
+                      const int32_t* col_widths, const int32_t* key_col_idx, int nkeys,
+                      const uint8_t* const* key_valid, uint32_t num_partitions,
+                      void* const* out_col_ptrs, int64_t* out_part_offsets, void* scratch,
+                      size_t scratch_bytes) {
+  FB_CHECK(nkeys >= 1 && nkeys <= FB_MAX_KEYS, "nkeys=%d out of range [1,%d]", nkeys, FB_MAX_KEYS);
+  const void* kp[FB_MAX_KEYS];
+  int32_t kw[FB_MAX_KEYS];
+  for (int i = 0; i < nkeys; ++i) {
+    FB_CHECK(key_col_idx[i] >= 0 && key_col_idx[i] < ncols, "key column index %d out of range", key_col_idx[i]);
+    kp[i] = col_ptrs[key_col_idx[i]];
+    kw[i] = col_widths[key_col_idx[i]];
+  }
+  if (int rc = fb_partition_plan(dev, stream, nrows, nkeys, kp, kw, key_valid, num_partitions, scratch,
+                                 scratch_bytes, out_part_offsets))
+    return rc;
+  return fb_partition_apply(dev, stream, nrows, nkeys, kp, kw, key_valid, num_partitions, scratch,
+                            scratch_bytes, out_part_offsets, ncols, col_ptrs, col_widths, out_col_ptrs);
+}
+
+int fb_bits_to_bytes(int dev, void* stream, const uint8_t* bits, int64_t bit_offset, int64_t nrows,
+                     uint8_t* out_bytes) {
+  if (nrows <= 0) return 0;
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  int64_t blocks = (nrows + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fb_bits_to_bytes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, bit_offset, nrows, out_bytes);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fb_bytes_to_bits(int dev, void* stream, const uint8_t* bytes, int64_t nrows, uint8_t* out_bits,
+                     int64_t* out_null_count) {
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_null_count) FB_CUDA(cudaMemsetAsync(out_null_count, 0, sizeof(int64_t), st));
+  if (nrows <= 0) return 0;
+  int64_t nbytes = (nrows + 7) / 8;
+  int64_t blocks = (nbytes + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fb_bytes_to_bits_kernel<<<(unsigned)blocks, 256, 0, st>>>(bytes, nrows, out_bits,
+                                                           (unsigned long long*)out_null_count);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

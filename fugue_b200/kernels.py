@@ -1,0 +1,158 @@
+"""Thin tensor-level wrappers over the C ABI.
+
+torch is used here only as the owner of device memory and streams; every
+operation is a call into ``libfugue_b200.so``.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MAX_PARTITIONS = 1024
+MAX_KEYS = 8
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_cols(cols: Sequence[torch.Tensor]) -> Tuple[torch.device, int]:
+    assert len(cols) > 0, "no columns"
+    dev = cols[0].device
+    n = cols[0].shape[0]
+    for c in cols:
+        if not c.is_cuda:
+            raise _lib.FugueB200KernelError("fugue_b200 kernels need CUDA tensors (no CPU path)")
+        if c.device != dev or c.dim() != 1 or c.shape[0] != n or not c.is_contiguous():
+            raise ValueError("columns must be 1-d contiguous tensors of equal length on one device")
+        if c.element_size() not in (1, 2, 4, 8):
+            raise ValueError(f"unsupported column width {c.element_size()}")
+    return dev, n
+
+
+def _valid_ptrs(valid: Optional[Sequence[Optional[torch.Tensor]]], nkeys: int):
+    if valid is None or all(v is None for v in valid):
+        return None
+    assert len(valid) == nkeys
+    for v in valid:
+        if v is not None:
+            assert v.dtype == torch.uint8 and v.is_contiguous() and v.is_cuda
+    return _lib.ptr_array([0 if v is None else v.data_ptr() for v in valid])
+
+
+def partition_ids(keys: Sequence[torch.Tensor], num: int,
+                  valid: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """K1: ``hash_pandas_object(df[keys], index=False) % num`` per row (int32 tensor)."""
+    lib = _lib.load()
+    dev, n = _check_cols(keys)
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    vp = _valid_ptrs(valid, len(keys))
+    _lib.check(lib.fb_partition_ids(
+        dev.index, _stream_ptr(dev), n, len(keys),
+        _lib.ptr_array([k.data_ptr() for k in keys]),
+        _lib.i32_array([k.element_size() for k in keys]),
+        vp, num, out.data_ptr()))
+    return out
+
+
+def partition_scratch_bytes(device: torch.device, nrows: int, num: int) -> int:
+    return int(_lib.load().fb_partition_scratch_bytes(device.index, nrows, num))
+
+
+class PartitionPlan:
+    """Result of pass 1 (histogram + scan): partition offsets and the chunk bases
+    needed by pass 2.  Holds references to the key columns it was built from."""
+
+    def __init__(self, keys, valid, num, scratch, offsets):
+        self.keys = list(keys)
+        self.valid = None if valid is None else list(valid)
+        self.num = num
+        self.scratch = scratch
+        self.offsets = offsets  # int64 [num + 1] on device
+        self.nrows = self.keys[0].shape[0]
+
+
+def partition_plan(keys: Sequence[torch.Tensor], num: int,
+                   valid: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                   scratch: Optional[torch.Tensor] = None,
+                   offsets: Optional[torch.Tensor] = None) -> PartitionPlan:
+    lib = _lib.load()
+    dev, n = _check_cols(keys)
+    need = partition_scratch_bytes(dev, n, num)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    if offsets is None:
+        offsets = torch.empty(num + 1, dtype=torch.int64, device=dev)
+    vp = _valid_ptrs(valid, len(keys))
+    _lib.check(lib.fb_partition_plan(
+        dev.index, _stream_ptr(dev), n, len(keys),
+        _lib.ptr_array([k.data_ptr() for k in keys]),
+        _lib.i32_array([k.element_size() for k in keys]),
+        vp, num, scratch.data_ptr(), scratch.numel(), offsets.data_ptr()))
+    return PartitionPlan(keys, valid, num, scratch, offsets)
+
+
+def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
+                    out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    lib = _lib.load()
+    dev, n = _check_cols(list(cols) + plan.keys)
+    if out is None:
+        out = [torch.empty_like(c) for c in cols]
+    else:
+        _check_cols(list(out) + plan.keys)
+    vp = _valid_ptrs(plan.valid, len(plan.keys))
+    _lib.check(lib.fb_partition_apply(
+        dev.index, _stream_ptr(dev), n, len(plan.keys),
+        _lib.ptr_array([k.data_ptr() for k in plan.keys]),
+        _lib.i32_array([k.element_size() for k in plan.keys]),
+        vp, plan.num, plan.scratch.data_ptr(), plan.scratch.numel(), plan.offsets.data_ptr(),
+        len(cols), _lib.ptr_array([c.data_ptr() for c in cols]),
+        _lib.i32_array([c.element_size() for c in cols]),
+        _lib.ptr_array([o.data_ptr() for o in out])))
+    return list(out)
+
+
+def partition_columns(cols: Sequence[torch.Tensor], key_idx: Sequence[int], num: int,
+                      key_valid: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                      out: Optional[Sequence[torch.Tensor]] = None,
+                      scratch: Optional[torch.Tensor] = None,
+                      offsets: Optional[torch.Tensor] = None
+                      ) -> Tuple[List[torch.Tensor], torch.Tensor]:
+    """K1+K2+K3 through ``fb_partition_cols``: stable hash partition of ``cols``."""
+    lib = _lib.load()
+    dev, n = _check_cols(cols)
+    need = partition_scratch_bytes(dev, n, num)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    if offsets is None:
+        offsets = torch.empty(num + 1, dtype=torch.int64, device=dev)
+    if out is None:
+        out = [torch.empty_like(c) for c in cols]
+    vp = _valid_ptrs(key_valid, len(key_idx))
+    _lib.check(lib.fb_partition_cols(
+        dev.index, _stream_ptr(dev), n, len(cols),
+        _lib.ptr_array([c.data_ptr() for c in cols]),
+        _lib.i32_array([c.element_size() for c in cols]),
+        _lib.i32_array(list(key_idx)), len(key_idx), vp, num,
+        _lib.ptr_array([o.data_ptr() for o in out]), offsets.data_ptr(),
+        scratch.data_ptr(), scratch.numel()))
+    return list(out), offsets
+
+
+def bits_to_bytes(bits: torch.Tensor, bit_offset: int, nrows: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(nrows, dtype=torch.uint8, device=bits.device)
+    _lib.check(lib.fb_bits_to_bytes(bits.device.index, _stream_ptr(bits.device), bits.data_ptr(),
+                                    bit_offset, nrows, out.data_ptr()))
+    return out
+
+
+def bytes_to_bits(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    n = mask.shape[0]
+    out = torch.empty((n + 7) // 8, dtype=torch.uint8, device=mask.device)
+    nulls = torch.zeros(1, dtype=torch.int64, device=mask.device)
+    _lib.check(lib.fb_bytes_to_bits(mask.device.index, _stream_ptr(mask.device), mask.data_ptr(), n,
+                                    out.data_ptr(), nulls.data_ptr()))
+    return out, nulls

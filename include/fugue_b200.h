@@ -1,0 +1,111 @@
+/* fugue_b200 - C ABI of the B200-native hot path of a Fugue ExecutionEngine.
+ *
+ * The reference (fugue-project/fugue v0.9.4) is pure Python and has no FFI of
+ * its own; its drop-in boundary is a set of Python ABCs
+ * (fugue/execution/execution_engine.py: MapEngine :277-335, SQLEngine :183-274,
+ * ExecutionEngine :338-1241).  This header is the C boundary that sits directly
+ * below the Python classes in fugue_b200/ that implement those ABCs; every entry
+ * point cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message of the
+ *     last error of the calling thread is returned by fb_last_error().
+ *   - `dev` is a CUDA device ordinal, `stream` a cudaStream_t (NULL = default
+ *     stream).  Calls are asynchronous with respect to the host unless stated.
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - a table is a set of equal-length, fixed-width columns (Arrow primitive
+ *     layout: one contiguous little-endian buffer per column, width 1/2/4/8
+ *     bytes).  NULLs are carried as a byte-per-row mask column (1 = valid);
+ *     fb_bits_to_bytes / fb_bytes_to_bits convert from/to Arrow validity bitmaps.
+ *   - no global mutable state; scratch memory is supplied by the caller
+ *     (fb_*_scratch_bytes says how much) so nothing is allocated in a timed region.
+ */
+#ifndef FUGUE_B200_H
+#define FUGUE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+#define FB_MAX_KEYS 8        /* key columns of a PartitionSpec / join / group-by */
+#define FB_MAX_COLS 64       /* payload columns moved by one partition call */
+#define FB_MAX_PARTITIONS 1024 /* physical partitions handled by one radix pass */
+
+int fb_abi_version(void);
+const char* fb_last_error(void);
+
+/* Device discovery: number of SMs and bytes of HBM of device `dev`. */
+int fb_device_info(int dev, int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * K1  key tuple -> physical partition id
+ * Replaces: fugue_dask/_utils.py:146-169 (_add_hash_index)
+ *             pd.util.hash_pandas_object(df[cols], index=False).mod(num)
+ *           (same expression in fugue_ray/_utils/dataframe.py:115-118).
+ * Bit-exact with pandas for fixed-width key columns; a NULL key cell hashes as
+ * the float64 NaN bit pattern (see oracle/hash_partition.py).
+ * key_valid[k] may be NULL (column has no NULLs) and key_valid itself may be NULL.
+ * --------------------------------------------------------------------------- */
+int fb_partition_ids(int dev, void* stream, int64_t nrows, int nkeys,
+                     const void* const* key_ptrs, const int32_t* key_widths,
+                     const uint8_t* const* key_valid, uint32_t num_partitions,
+                     uint32_t* out_pids);
+
+/* Host-side evaluation of the device's division-free `hash % num` (for tests). */
+uint32_t fb_debug_fastmod_host(uint64_t hash, uint32_t num_partitions);
+
+/* ---------------------------------------------------------------------------
+ * K1+K2+K3  hash partition of a columnar table  (the map_dataframe hot path)
+ * Replaces: PandasMapEngine.map_dataframe's grouping step
+ *             fugue/execution/native_execution_engine.py:166-168
+ *           and the distributed engines' physical repartition
+ *             fugue_dask/execution_engine.py:160-181, 263-303  (hash_repartition)
+ *             fugue_dask/_utils.py:44-59, 124-130
+ * Output: every column reordered so that rows of physical partition p occupy
+ * [part_offsets[p], part_offsets[p+1]); input order is kept inside a partition
+ * (stable), so results are deterministic.
+ *
+ * fb_partition_plan  : pass 1 (histogram) + scan; fills part_offsets (device,
+ *                      num_partitions+1 int64) and the plan held in `scratch`.
+ * fb_partition_apply : pass 2 (scatter) for any subset of columns, using the
+ *                      plan; may be called several times (e.g. column by column
+ *                      while later columns are still arriving over PCIe).
+ * fb_partition_cols  : plan + apply in one call.
+ * --------------------------------------------------------------------------- */
+size_t fb_partition_scratch_bytes(int dev, int64_t nrows, uint32_t num_partitions);
+
+int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys,
+                      const void* const* key_ptrs, const int32_t* key_widths,
+                      const uint8_t* const* key_valid, uint32_t num_partitions,
+                      void* scratch, size_t scratch_bytes, int64_t* out_part_offsets);
+
+int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys,
+                       const void* const* key_ptrs, const int32_t* key_widths,
+                       const uint8_t* const* key_valid, uint32_t num_partitions,
+                       const void* scratch, size_t scratch_bytes,
+                       const int64_t* part_offsets, int ncols,
+                       const void* const* col_ptrs, const int32_t* col_widths,
+                       void* const* out_col_ptrs);
+
+int fb_partition_cols(int dev, void* stream, int64_t nrows, int ncols,
+                      const void* const* col_ptrs, const int32_t* col_widths,
+                      const int32_t* key_col_idx, int nkeys,
+                      const uint8_t* const* key_valid, uint32_t num_partitions,
+                      void* const* out_col_ptrs, int64_t* out_part_offsets,
+                      void* scratch, size_t scratch_bytes);
+
+/* Arrow validity bitmap (LSB first) <-> byte mask. `bit_offset` is the Arrow
+ * array offset. */
+int fb_bits_to_bytes(int dev, void* stream, const uint8_t* bits, int64_t bit_offset,
+                     int64_t nrows, uint8_t* out_bytes);
+int fb_bytes_to_bits(int dev, void* stream, const uint8_t* bytes, int64_t nrows,
+                     uint8_t* out_bits, int64_t* out_null_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUGUE_B200_H */
