@@ -20,6 +20,8 @@
 //     chunk, so no per-tile table is ever materialised in HBM.
 //   Algorithmic traffic 128 B/row (read 64 + write 64) for the 8x8-byte schema;
 //   the implementation adds the 8 B/row key re-read of pass 1.
+#include <mutex>
+
 #include "fb_common.cuh"
 
 namespace {
@@ -76,38 +78,62 @@ __global__ void fb_pid_kernel(FbKeys keys, FbDiv dv, int64_t nrows, uint32_t* __
 }
 
 // ---------------------------------------------------------------------------
-// pass 1: per-chunk histogram. hist layout: [chunk][num]
+// Warp-level "which lanes hold my value": kBits ballots instead of the hardware
+// MATCH instruction (MATCH.ANY runs on the ADU pipe at ~70 cycles per warp
+// instruction on sm_100 - measured with ncu, profiles/r1_v1_* - and caps the
+// whole kernel; ballots issue at full rate).  `m` starts as the mask of lanes
+// that take part.
 // ---------------------------------------------------------------------------
-template <bool kSingleU64>
+template <int kBits>
+__device__ __forceinline__ unsigned match_lanes(uint32_t v, unsigned m) {
+#pragma unroll
+  for (int b = 0; b < kBits; ++b) {
+    const bool bit = (v >> b) & 1u;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------------------
+// pass 1: per-chunk histogram. hist layout: [chunk][num]
+// shared: cnt[kWarps][num] warp-private counters (no atomics)
+// ---------------------------------------------------------------------------
+template <bool kSingleU64, int kBits>
 __global__ void __launch_bounds__(kBlock)
 fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist) {
-  extern __shared__ uint32_t s_hist[];
-  for (uint32_t b = threadIdx.x; b < num; b += kBlock) s_hist[b] = 0;
+  extern __shared__ uint32_t s_cnt[];
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * num; i += kBlock) s_cnt[i] = 0;
   __syncthreads();
   const int64_t row0 = (int64_t)blockIdx.x * g.tiles_per_chunk * kTile;
   int64_t row1 = row0 + g.tiles_per_chunk * kTile;
   if (row1 > g.nrows) row1 = g.nrows;
-  const unsigned lane = threadIdx.x & 31;
-  // kItems independent key loads in flight per thread
+  const unsigned lt = fb_lanemask_lt();
+  uint32_t* my = s_cnt + (size_t)(threadIdx.x >> 5) * num;
   for (int64_t base = row0; base < row1; base += kTile) {
     uint32_t pid[kItems];
+    const bool full = base + kTile <= row1;
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
       int64_t row = base + (int64_t)r * kBlock + threadIdx.x;
-      pid[r] = row < row1 ? compute_pid<kSingleU64>(keys, dv, row) : 0xFFFFFFFFu;
+      pid[r] = (full || row < row1) ? compute_pid<kSingleU64>(keys, dv, row) : 0xFFFFFFFFu;
     }
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
-      // warp-aggregated shared-memory increment: one atomic per distinct pid per warp
-      unsigned peers = __match_any_sync(0xFFFFFFFFu, pid[r]);
-      if (pid[r] != 0xFFFFFFFFu && (peers & fb_lanemask_lt()) == 0)
-        atomicAdd(&s_hist[pid[r]], (uint32_t)__popc(peers));
+      const bool ok = pid[r] != 0xFFFFFFFFu;
+      unsigned m = match_lanes<kBits>(pid[r], __ballot_sync(0xFFFFFFFFu, ok));
+      if (ok && (m & lt) == 0) my[pid[r]] += (uint32_t)__popc(m);
+      __syncwarp();
     }
-    (void)lane;
   }
   __syncthreads();
   uint32_t* out = hist + (size_t)blockIdx.x * num;
-  for (uint32_t b = threadIdx.x; b < num; b += kBlock) out[b] = s_hist[b];
+  for (uint32_t b = threadIdx.x; b < num; b += kBlock) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s_cnt[(size_t)w * num + b];
+    out[b] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -177,199 +203,228 @@ fb_scan_parts_kernel(int64_t* __restrict__ offsets, uint32_t num) {
 }
 
 // ---------------------------------------------------------------------------
-// pass 2: scatter.  Shared memory layout (dynamic):
-//   buf[2][kTile * 8]          column staging, double buffered      64 KB
-//   cursor[nb]     int64       running output position per partition
-//   delta[nb]      int64       cursor[b] - bin_start[b] for the current tile
-//   bin_start[nb]  uint32      exclusive prefix of the tile histogram
-//   warp_cnt[kWarps][nb] u32   per-warp per-partition counters / prefixes
-//   pid_sorted[kTile] uint16   partition id of every slot of the permuted tile
-// nb = num + 1 (one sentinel bin that collects the rows past the end of the chunk)
+// pass 2: scatter.  Dynamic shared memory, addressed from one extern array so
+// that every access compiles to LDS/STS with offsets computed once per tile:
+//   [0, 2*T*8)                buf[2][T] uint64   column staging, double buffered
+//   then uint32 regions (nbp = padded number of bins; bins = num + 1 sentinel that
+//   collects the slots past the end of a partial tile):
+//     delta[nbp]              (cursor - bin_start) of the current tile, mod 2^32
+//     cursor[nbp]             running output row of every partition for this chunk
+//     bin_start[nbp]          exclusive prefix of the tile histogram
+//     cnt[kWarps][nbp]        warp-private counters -> exclusive prefix over warps
+//     scanw[32]               warp totals of the block scan
+//   then pid_sorted[T] uint16 partition id of every slot of the permuted tile
 // ---------------------------------------------------------------------------
+__host__ __device__ inline uint32_t nb_padded(uint32_t num) { return (num + 1 + 3) & ~3u; }
+
 __host__ __device__ inline size_t scatter_smem_bytes(uint32_t num) {
-  size_t nb = (size_t)num + 1;
-  size_t nb_pad = (nb + 1) & ~(size_t)1;
-  return 2 * (size_t)kTile * 8 + nb_pad * 8 * 2 + nb_pad * 4 + (size_t)kWarps * nb_pad * 4 +
-         (size_t)kTile * 2 + 64;
+  size_t nbp = nb_padded(num);
+  return 2 * (size_t)kTile * 8 + (3 + (size_t)kWarps) * nbp * 4 + 32 * 4 + (size_t)kTile * 2;
 }
 
-template <typename T>
-__device__ __forceinline__ void load_col_tile(const void* __restrict__ src, int64_t warp_row0,
-                                              int64_t row_end, unsigned lane, T (&v)[kItems]) {
-  const T* p = (const T*)src;
+constexpr int kMaxPer = (FB_MAX_PARTITIONS + 1 + kBlock - 1) / kBlock;  // bins per thread in the scan
+
+struct TileCtx {  // all pointers are into shared memory
+  uint64_t* buf;
+  uint32_t* delta;
+  uint32_t* cursor;
+  uint32_t* bin_start;
+  uint32_t* cnt;
+  uint32_t* scanw;
+  uint16_t* pid_sorted;
+  uint32_t nbp;
+};
+
+template <typename T, bool kFull>
+__device__ __forceinline__ void load_col(const void* __restrict__ src, int64_t warp_row0, int warp_rows,
+                                         unsigned lane, T (&v)[kItems]) {
+  const T* __restrict__ p = (const T*)src + warp_row0 + lane;
 #pragma unroll
-  for (int r = 0; r < kItems; ++r) {
-    int64_t row = warp_row0 + r * 32 + lane;
-    if (row < row_end) v[r] = __ldg(p + row);
-  }
+  for (int r = 0; r < kItems; ++r)
+    if (kFull || r * 32 + (int)lane < warp_rows) v[r] = __ldg(p + r * 32);
 }
 
-template <typename T>
-__device__ __forceinline__ void permute_col_tile(T* __restrict__ buf, const uint32_t (&pos)[kItems],
-                                                 const T (&v)[kItems]) {
-#pragma unroll
-  for (int r = 0; r < kItems; ++r) buf[pos[r]] = v[r];
-}
-
-template <typename T>
-__device__ __forceinline__ void write_col_tile(void* __restrict__ dst, const T* __restrict__ buf,
-                                               const uint16_t* __restrict__ pid_sorted,
-                                               const int64_t* __restrict__ delta, int tile_rows) {
-  T* out = (T*)dst;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    int j = k * kBlock + threadIdx.x;
-    if (j < tile_rows) out[delta[pid_sorted[j]] + j] = buf[j];
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void move_columns_of_width(const FbCols& cols, int width, uint8_t* buf0,
-                                                      uint8_t* buf1, const uint32_t (&pos)[kItems],
-                                                      const uint16_t* pid_sorted, const int64_t* delta,
-                                                      int64_t warp_row0, int64_t row_end, unsigned lane,
-                                                      int tile_rows, int& phase) {
-  T v[kItems];
+// Moves every column of width sizeof(T): coalesced load -> permute through shared memory ->
+// run-coalesced store.  One barrier per column (double buffered staging).
+template <typename T, bool kFull>
+__device__ __forceinline__ void move_columns(const FbCols& cols, const TileCtx& cx,
+                                             const uint32_t (&pos)[kItems], const uint32_t (&dst)[kItems],
+                                             int64_t warp_row0, int warp_rows, int tile_rows,
+                                             unsigned lane, int& phase) {
   int c = 0;
-  // find first column of this width
-  while (c < cols.ncols && cols.width[c] != width) ++c;
+  while (c < cols.ncols && cols.width[c] != (int)sizeof(T)) ++c;
   if (c >= cols.ncols) return;
-  load_col_tile<T>(cols.src[c], warp_row0, row_end, lane, v);
+  T v[kItems];
+  load_col<T, kFull>(cols.src[c], warp_row0, warp_rows, lane, v);
   while (c < cols.ncols) {
-    T* buf = (T*)((phase & 1) ? buf1 : buf0);
-    permute_col_tile<T>(buf, pos, v);
+    T* __restrict__ buf = (T*)(cx.buf + (size_t)(phase & 1) * kTile);
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) buf[pos[r]] = v[r];
     int nxt = c + 1;
-    while (nxt < cols.ncols && cols.width[nxt] != width) ++nxt;
-    if (nxt < cols.ncols) load_col_tile<T>(cols.src[nxt], warp_row0, row_end, lane, v);  // prefetch
+    while (nxt < cols.ncols && cols.width[nxt] != (int)sizeof(T)) ++nxt;
+    if (nxt < cols.ncols) load_col<T, kFull>(cols.src[nxt], warp_row0, warp_rows, lane, v);  // prefetch
     __syncthreads();
-    write_col_tile<T>(cols.dst[c], buf, pid_sorted, delta, tile_rows);
+    T* __restrict__ out = (T*)cols.dst[c];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      const int j = k * kBlock + (int)threadIdx.x;
+      if (kFull || j < tile_rows) out[dst[k]] = buf[j];
+    }
     ++phase;
     c = nxt;
   }
 }
 
-template <bool kSingleU64>
+template <bool kSingleU64, int kBits, bool kFull, bool kAll8>
+__device__ __forceinline__ void scatter_tile(const FbKeys& keys, const FbDiv& dv, const uint32_t num,
+                                             const FbCols& cols, const TileCtx& cx,
+                                             const int64_t tile_row0, const int tile_rows, int& phase) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = fb_lanemask_lt();
+  const uint32_t nb = num + 1;
+  const uint32_t nbp = cx.nbp;
+  uint32_t* __restrict__ my_cnt = cx.cnt + warp * nbp;
+  const int64_t warp_row0 = tile_row0 + (int64_t)warp * (32 * kItems);
+  const int warp_rows = tile_rows - (int)warp * (32 * kItems);  // rows of this warp's stripe that exist
+
+  // -- 1. partition ids of my rows (warp-striped: row = warp_row0 + r*32 + lane)
+  uint32_t pid[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const bool ok = kFull || (r * 32 + (int)lane) < warp_rows;
+    pid[r] = ok ? compute_pid<kSingleU64>(keys, dv, warp_row0 + r * 32 + lane) : num;
+  }
+
+  // -- 2. stable rank inside (warp, partition): ballot match + warp-private counters
+  //       (counters are zero here: cleared before the tile loop and at the end of every tile)
+  uint32_t pos[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const unsigned m = match_lanes<kBits + (kFull ? 0 : 1)>(pid[r], 0xFFFFFFFFu);
+    const unsigned before = __popc(m & lt);
+    uint32_t old = 0;
+    if (before == 0) {
+      old = my_cnt[pid[r]];
+      my_cnt[pid[r]] = old + __popc(m);
+    }
+    __syncwarp();
+    old = __shfl_sync(0xFFFFFFFFu, old, __ffs(m) - 1);
+    pos[r] = old + before;
+  }
+  __syncthreads();
+
+  // -- 3. per partition: exclusive prefix over warps, then block-wide exclusive scan of the
+  //       tile histogram.  Thread t owns bins [t*per, t*per + per).
+  {
+    const uint32_t per = (nb + kBlock - 1) / kBlock;
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t tot[kMaxPer];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      tot[i] = 0;
+      if ((uint32_t)i < per && b0 + i < nb) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const uint32_t t = cx.cnt[w * nbp + b0 + i];
+          cx.cnt[w * nbp + b0 + i] = run;
+          run += t;
+        }
+        tot[i] = run;
+        sum += run;
+      }
+    }
+    uint32_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) cx.scanw[warp] = x;
+    __syncthreads();
+    uint32_t run = x - sum;
+    {
+      const uint32_t wt = lane < kWarps ? cx.scanw[lane] : 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t v = __shfl_sync(0xFFFFFFFFu, wt, w);
+        if ((unsigned)w < warp) run += v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      if ((uint32_t)i < per && b0 + i < nb) {
+        const uint32_t cur = cx.cursor[b0 + i];
+        cx.bin_start[b0 + i] = run;
+        cx.delta[b0 + i] = cur - run;  // slot j of the permuted tile lands at output row delta + j
+        cx.cursor[b0 + i] = cur + tot[i];
+        run += tot[i];
+      }
+    }
+  }
+  __syncthreads();
+
+  // -- 4. final slot of every row inside the permuted tile; publish the slot -> pid map
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    pos[r] += cx.bin_start[pid[r]] + my_cnt[pid[r]];
+    cx.pid_sorted[pos[r]] = (uint16_t)pid[r];
+  }
+  __syncthreads();
+  // output row of the slots this thread writes (same for every column)
+  uint32_t dst[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int j = k * kBlock + (int)threadIdx.x;
+    dst[k] = cx.delta[cx.pid_sorted[j]] + (uint32_t)j;
+  }
+  // counters are dead from here on: clear them for the next tile (visibility is covered by the
+  // barriers of the column loop / the trailing barrier)
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * nbp; i += kBlock) cx.cnt[i] = 0;
+
+  // -- 5. move the columns
+  move_columns<uint64_t, kFull>(cols, cx, pos, dst, warp_row0, warp_rows, tile_rows, lane, phase);
+  if (!kAll8) {
+    move_columns<uint32_t, kFull>(cols, cx, pos, dst, warp_row0, warp_rows, tile_rows, lane, phase);
+    move_columns<uint16_t, kFull>(cols, cx, pos, dst, warp_row0, warp_rows, tile_rows, lane, phase);
+    move_columns<uint8_t, kFull>(cols, cx, pos, dst, warp_row0, warp_rows, tile_rows, lane, phase);
+  }
+  __syncthreads();  // staging buffers, delta, pid_sorted are rewritten by the next tile
+}
+
+template <bool kSingleU64, int kBits, bool kAll8>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm)
 fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g,
                   const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets,
                   FbCols cols) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const uint32_t nb = num + 1;
-  const uint32_t nb_pad = (nb + 1) & ~1u;
-  uint8_t* buf0 = smem;
-  uint8_t* buf1 = smem + (size_t)kTile * 8;
-  int64_t* cursor = (int64_t*)(smem + 2 * (size_t)kTile * 8);
-  int64_t* delta = cursor + nb_pad;
-  uint32_t* bin_start = (uint32_t*)(delta + nb_pad);
-  uint32_t* warp_cnt = bin_start + nb_pad;
-  uint16_t* pid_sorted = (uint16_t*)(warp_cnt + (size_t)kWarps * nb_pad);
-  __shared__ uint32_t s_scan_warp[kWarps];
+  extern __shared__ __align__(16) uint64_t smem64[];
+  TileCtx cx;
+  cx.nbp = nb_padded(num);
+  cx.buf = smem64;
+  cx.delta = (uint32_t*)(smem64 + 2 * kTile);
+  cx.cursor = cx.delta + cx.nbp;
+  cx.bin_start = cx.cursor + cx.nbp;
+  cx.cnt = cx.bin_start + cx.nbp;
+  cx.scanw = cx.cnt + kWarps * cx.nbp;
+  cx.pid_sorted = (uint16_t*)(cx.scanw + 32);
 
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t chunk_row0 = (int64_t)blockIdx.x * g.tiles_per_chunk * kTile;
   int64_t chunk_row1 = chunk_row0 + g.tiles_per_chunk * kTile;
   if (chunk_row1 > g.nrows) chunk_row1 = g.nrows;
 
-  for (uint32_t b = threadIdx.x; b < nb; b += kBlock)
-    cursor[b] = b < num ? part_offsets[b] + (int64_t)chunk_base[(size_t)blockIdx.x * num + b] : 0;
-  // (visibility of cursor[] is covered by the barriers inside the tile loop)
+  for (uint32_t b = threadIdx.x; b < cx.nbp; b += kBlock)
+    cx.cursor[b] = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)blockIdx.x * num + b] : 0u;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * cx.nbp; i += kBlock) cx.cnt[i] = 0;
+  __syncthreads();
 
   int phase = 0;
-  uint32_t* my_cnt = warp_cnt + (size_t)warp * nb_pad;
-
   for (int64_t tile_row0 = chunk_row0; tile_row0 < chunk_row1; tile_row0 += kTile) {
-    const int tile_rows = (int)((chunk_row1 - tile_row0) < kTile ? (chunk_row1 - tile_row0) : kTile);
-    const int64_t warp_row0 = tile_row0 + (int64_t)warp * (32 * kItems);
-
-    // -- 1. partition ids of my rows (warp-striped: row = warp_row0 + r*32 + lane)
-    uint32_t pid[kItems];
-#pragma unroll
-    for (int r = 0; r < kItems; ++r) {
-      int64_t row = warp_row0 + r * 32 + lane;
-      pid[r] = row < chunk_row1 ? compute_pid<kSingleU64>(keys, dv, row) : num;
-    }
-    for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * nb_pad; i += kBlock) warp_cnt[i] = 0;
-    __syncthreads();
-
-    // -- 2. stable rank inside (warp, partition): match-any peers + warp-private counters
-    uint32_t pos[kItems];
-#pragma unroll
-    for (int r = 0; r < kItems; ++r) {
-      unsigned peers = __match_any_sync(0xFFFFFFFFu, pid[r]);
-      unsigned before = __popc(peers & fb_lanemask_lt());
-      int leader = __ffs(peers) - 1;
-      uint32_t old = 0;
-      if ((int)lane == leader) {
-        old = my_cnt[pid[r]];
-        my_cnt[pid[r]] = old + __popc(peers);
-      }
-      old = __shfl_sync(0xFFFFFFFFu, old, leader);
-      pos[r] = old + before;
-      __syncwarp();
-    }
-    __syncthreads();
-
-    // -- 3. per partition: exclusive prefix over warps; tile histogram -> bin_start
-    for (uint32_t b = threadIdx.x; b < nb; b += kBlock) {
-      uint32_t run = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        uint32_t t = warp_cnt[(size_t)w * nb_pad + b];
-        warp_cnt[(size_t)w * nb_pad + b] = run;
-        run += t;
-      }
-      bin_start[b] = run;
-    }
-    __syncthreads();
-    // block-wide exclusive scan of bin_start[0..nb): thread t owns bins [t*per, (t+1)*per)
-    {
-      const uint32_t per = (nb + kBlock - 1) / kBlock;
-      uint32_t b0 = threadIdx.x * per;
-      uint32_t sum = 0;
-      for (uint32_t i = 0; i < per; ++i)
-        if (b0 + i < nb) sum += bin_start[b0 + i];
-      uint32_t x = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= (unsigned)o) x += y;
-      }
-      if (lane == 31) s_scan_warp[warp] = x;
-      __syncthreads();
-      uint32_t wbase = 0;
-      for (unsigned w = 0; w < warp; ++w) wbase += s_scan_warp[w];
-      uint32_t run = wbase + x - sum;
-      for (uint32_t i = 0; i < per; ++i) {
-        if (b0 + i < nb) {
-          uint32_t t = bin_start[b0 + i];
-          bin_start[b0 + i] = run;
-          // delta = where slot j of the permuted tile lands in the output: cursor - bin_start + j
-          delta[b0 + i] = cursor[b0 + i] - (int64_t)run;
-          cursor[b0 + i] += t;
-          run += t;
-        }
-      }
-    }
-    __syncthreads();
-
-    // -- 4. final slot of every row inside the permuted tile
-#pragma unroll
-    for (int r = 0; r < kItems; ++r) {
-      pos[r] += bin_start[pid[r]] + my_cnt[pid[r]];
-      pid_sorted[pos[r]] = (uint16_t)pid[r];
-    }
-    // (pid_sorted visibility: first barrier inside the column loop)
-
-    // -- 5. move the columns: coalesced load -> permute in smem -> run-coalesced store
-    move_columns_of_width<uint64_t>(cols, 8, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
-                                    lane, tile_rows, phase);
-    move_columns_of_width<uint32_t>(cols, 4, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
-                                    lane, tile_rows, phase);
-    move_columns_of_width<uint16_t>(cols, 2, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
-                                    lane, tile_rows, phase);
-    move_columns_of_width<uint8_t>(cols, 1, buf0, buf1, pos, pid_sorted, delta, warp_row0, chunk_row1,
-                                   lane, tile_rows, phase);
-    __syncthreads();  // all reads of delta/pid_sorted/bufs done before the next tile rewrites them
+    const int64_t left = chunk_row1 - tile_row0;
+    if (left >= kTile)
+      scatter_tile<kSingleU64, kBits, true, kAll8>(keys, dv, num, cols, cx, tile_row0, kTile, phase);
+    else
+      scatter_tile<kSingleU64, kBits, false, kAll8>(keys, dv, num, cols, cx, tile_row0, (int)left, phase);
   }
 }
 
@@ -406,6 +461,48 @@ __global__ void fb_bytes_to_bits_kernel(const uint8_t* __restrict__ bytes, int64
     out[i] = v;
   }
   if (null_count != nullptr && nulls) atomicAdd(null_count, nulls);
+}
+
+inline int bits_for(uint32_t num) { return num <= 16 ? 4 : (num <= 256 ? 8 : 10); }
+
+#define FB_DISPATCH_SB(single, bits, LAUNCH)                 \
+  do {                                                       \
+    if (single) {                                            \
+      if (bits == 4) LAUNCH(true, 4);                        \
+      else if (bits == 8) LAUNCH(true, 8);                   \
+      else LAUNCH(true, 10);                                 \
+    } else {                                                 \
+      if (bits == 4) LAUNCH(false, 4);                       \
+      else if (bits == 8) LAUNCH(false, 8);                  \
+      else LAUNCH(false, 10);                                \
+    }                                                        \
+  } while (0)
+
+template <typename K>
+cudaError_t optin(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// opt in to > 48 KB of dynamic shared memory, once per device
+cudaError_t ensure_smem_optin(int dev) {
+  static std::mutex mu;
+  static uint64_t done = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && (done >> dev) & 1) return cudaSuccess;
+  const size_t sc = scatter_smem_bytes(FB_MAX_PARTITIONS);
+  const size_t hs = (size_t)kWarps * FB_MAX_PARTITIONS * sizeof(uint32_t);
+  cudaError_t e = cudaSuccess;
+#define FB_OPTIN(S, B)                                                   \
+  do {                                                                   \
+    if (e == cudaSuccess) e = optin(fb_scatter_kernel<S, B, true>, sc);  \
+    if (e == cudaSuccess) e = optin(fb_scatter_kernel<S, B, false>, sc); \
+    if (e == cudaSuccess) e = optin(fb_hist_kernel<S, B>, hs);           \
+  } while (0)
+  FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
+  FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
+#undef FB_OPTIN
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done |= (1ull << dev);
+  return e;
 }
 
 bool single_u64_key(int nkeys, const int32_t* widths, const uint8_t* const* valid) {
@@ -498,11 +595,14 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   FbDiv dv = fb_make_div(num_partitions);
   uint32_t* hist = (uint32_t*)scratch;
-  size_t smem = (size_t)num_partitions * sizeof(uint32_t);
-  if (single_u64_key(nkeys, key_widths, key_valid))
-    fb_hist_kernel<true><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g, hist);
-  else
-    fb_hist_kernel<false><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g, hist);
+  size_t smem = (size_t)kWarps * num_partitions * sizeof(uint32_t);
+  FB_CUDA(ensure_smem_optin(dev));
+  const bool single = single_u64_key(nkeys, key_widths, key_valid);
+  const int bits = bits_for(num_partitions);
+#define FB_LAUNCH_HIST(S, B) \
+  fb_hist_kernel<S, B><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g, hist)
+  FB_DISPATCH_SB(single, bits, FB_LAUNCH_HIST);
+#undef FB_LAUNCH_HIST
   FB_CUDA(cudaGetLastError());
   fb_scan_chunks_kernel<<<num_partitions, 256, 0, st>>>(hist, num_partitions, g.nchunks, out_part_offsets);
   FB_CUDA(cudaGetLastError());
@@ -532,13 +632,8 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
   cudaStream_t st = (cudaStream_t)stream;
   const bool single = single_u64_key(nkeys, key_widths, key_valid);
   size_t smem = scatter_smem_bytes(num_partitions);
-  static thread_local int smem_set[2] = {0, 0};
-  // opt in to > 48 KB of dynamic shared memory (per function, per device context)
-  FB_CUDA(cudaFuncSetAttribute(fb_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)scatter_smem_bytes(FB_MAX_PARTITIONS)));
-  FB_CUDA(cudaFuncSetAttribute(fb_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)scatter_smem_bytes(FB_MAX_PARTITIONS)));
-  (void)smem_set;
+  FB_CUDA(ensure_smem_optin(dev));
+  const int bits = bits_for(num_partitions);
   for (int c0 = 0; c0 < ncols; c0 += FB_MAX_COLS) {
     FbCols cols;
     memset(&cols, 0, sizeof(cols));
@@ -552,12 +647,19 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
       cols.dst[c] = out_col_ptrs[c0 + c];
       cols.width[c] = w;
     }
-    if (single)
-      fb_scatter_kernel<true><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g,
-                                                               (const uint32_t*)scratch, part_offsets, cols);
-    else
-      fb_scatter_kernel<false><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g,
-                                                                (const uint32_t*)scratch, part_offsets, cols);
+    bool all8 = true;
+    for (int c = 0; c < cols.ncols; ++c) all8 = all8 && cols.width[c] == 8;
+#define FB_LAUNCH_SCATTER(S, B)                                                                   \
+  do {                                                                                            \
+    if (all8)                                                                                     \
+      fb_scatter_kernel<S, B, true><<<g.nchunks, kBlock, smem, st>>>(                             \
+          k, dv, num_partitions, g, (const uint32_t*)scratch, part_offsets, cols);                \
+    else                                                                                          \
+      fb_scatter_kernel<S, B, false><<<g.nchunks, kBlock, smem, st>>>(                            \
+          k, dv, num_partitions, g, (const uint32_t*)scratch, part_offsets, cols);                \
+  } while (0)
+    FB_DISPATCH_SB(single, bits, FB_LAUNCH_SCATTER);
+#undef FB_LAUNCH_SCATTER
     FB_CUDA(cudaGetLastError());
   }
   return 0;
