@@ -5,21 +5,28 @@
 //   fugue_dask/_utils.py:44-59, 124-130, 146-169        (hash_repartition)
 //
 // Design (HBM-bound byte movement; no tensor-core work exists on this path):
-//   * the row range is cut into `nchunks` contiguous chunks, one per resident CTA
-//     (2 CTAs per SM x 148 SMs), each chunk a whole number of TILE-row tiles;
+//   * the row range is cut into contiguous chunks of whole TILE-row tiles (at most
+//     2 x #SM of them) plus one tail chunk holding the final partial tile;
 //   * pass 1 (fb_hist_kernel)   : per-chunk histogram of partition ids (reads the
 //     key column(s) only: 8 B/row for the benchmark schema);
 //   * scan  (fb_scan_*_kernel)  : exclusive prefix per partition over chunks, then
 //     over partitions -> part_offsets[num+1] and chunk bases;
-//   * pass 2 (fb_scatter_kernel): every CTA walks its chunk tile by tile; inside a
-//     tile rows are ranked stably per partition with warp match/ballot counters in
-//     shared memory, each column tile is loaded coalesced, permuted through shared
-//     memory into partition order and written out as contiguous runs
-//     (1 run per partition present in the tile), so global writes are coalesced.
-//     Running per-partition output cursors live in shared memory for the whole
-//     chunk, so no per-tile table is ever materialised in HBM.
+//   * pass 2, fast path (fb_scatter_tma_kernel; single 8-byte key, 8-byte columns):
+//     one persistent CTA per SM = 1 producer warp + 16 consumer warps.  The producer
+//     streams (tile, column) units into a ring of 32 KB shared-memory stages with
+//     TMA bulk copies (cp.async.bulk + mbarrier complete_tx), running several units
+//     ahead of the consumers, across tile and chunk boundaries.  Consumers hash the
+//     staged key tile, rank rows stably per partition (ballot match + warp-private
+//     counters), build the slot -> source-row map of the partition-ordered tile and
+//     then, per column, gather straight from the staged tile and store contiguous
+//     runs (one run per partition present in the tile) to global memory.  Running
+//     per-partition output cursors live in shared memory for the whole chunk.
+//   * pass 2, generic path (fb_scatter_kernel; any widths/keys, partial tiles):
+//     register-staged loads, permutation through double-buffered shared memory.
 //   Algorithmic traffic 128 B/row (read 64 + write 64) for the 8x8-byte schema;
 //   the implementation adds the 8 B/row key re-read of pass 1.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "fb_common.cuh"
@@ -41,19 +48,33 @@ struct FbCols {
 
 struct ChunkGeom {
   int64_t nrows;
-  int64_t tiles_per_chunk;
-  int32_t nchunks;
+  int64_t full_rows;        // rows covered by whole tiles
+  int64_t tiles_per_chunk;  // whole tiles per full chunk
+  int32_t nchunks_full;     // chunks made of whole tiles
+  int32_t nchunks;          // + 1 if there is a partial tail tile
 };
 
 inline ChunkGeom make_geom(int dev, int64_t nrows) {
   ChunkGeom g;
   g.nrows = nrows;
-  int64_t ntiles = (nrows + kTile - 1) / kTile;
-  if (ntiles < 1) ntiles = 1;
-  int64_t max_chunks = (int64_t)fb_sm_count(dev) * kCtasPerSm;
-  g.tiles_per_chunk = (ntiles + max_chunks - 1) / max_chunks;
-  g.nchunks = (int32_t)((ntiles + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
+  const int64_t ntiles_full = nrows / kTile;
+  g.full_rows = ntiles_full * kTile;
+  const int64_t max_chunks = (int64_t)fb_sm_count(dev) * kCtasPerSm;
+  g.tiles_per_chunk = ntiles_full > 0 ? (ntiles_full + max_chunks - 1) / max_chunks : 1;
+  g.nchunks_full = (int32_t)((ntiles_full + g.tiles_per_chunk - 1) / g.tiles_per_chunk);
+  g.nchunks = g.nchunks_full + (g.full_rows < nrows ? 1 : 0);
   return g;
+}
+
+__host__ __device__ __forceinline__ void chunk_range(const ChunkGeom& g, int c, int64_t& r0, int64_t& r1) {
+  if (c < g.nchunks_full) {
+    r0 = (int64_t)c * g.tiles_per_chunk * kTile;
+    r1 = r0 + g.tiles_per_chunk * kTile;
+    if (r1 > g.full_rows) r1 = g.full_rows;
+  } else {
+    r0 = g.full_rows;
+    r1 = g.nrows;
+  }
 }
 
 template <bool kSingleU64>
@@ -105,9 +126,8 @@ fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __res
   extern __shared__ uint32_t s_cnt[];
   for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * num; i += kBlock) s_cnt[i] = 0;
   __syncthreads();
-  const int64_t row0 = (int64_t)blockIdx.x * g.tiles_per_chunk * kTile;
-  int64_t row1 = row0 + g.tiles_per_chunk * kTile;
-  if (row1 > g.nrows) row1 = g.nrows;
+  int64_t row0, row1;
+  chunk_range(g, (int)blockIdx.x, row0, row1);
   const unsigned lt = fb_lanemask_lt();
   uint32_t* my = s_cnt + (size_t)(threadIdx.x >> 5) * num;
   for (int64_t base = row0; base < row1; base += kTile) {
@@ -395,10 +415,10 @@ __device__ __forceinline__ void scatter_tile(const FbKeys& keys, const FbDiv& dv
 
 template <bool kSingleU64, int kBits, bool kAll8>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm)
-fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g,
+fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, int chunk0,
                   const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets,
                   FbCols cols) {
-  extern __shared__ __align__(16) uint64_t smem64[];
+  extern __shared__ __align__(128) uint64_t smem64[];
   TileCtx cx;
   cx.nbp = nb_padded(num);
   cx.buf = smem64;
@@ -409,12 +429,12 @@ fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g,
   cx.scanw = cx.cnt + kWarps * cx.nbp;
   cx.pid_sorted = (uint16_t*)(cx.scanw + 32);
 
-  const int64_t chunk_row0 = (int64_t)blockIdx.x * g.tiles_per_chunk * kTile;
-  int64_t chunk_row1 = chunk_row0 + g.tiles_per_chunk * kTile;
-  if (chunk_row1 > g.nrows) chunk_row1 = g.nrows;
+  const int chunk = chunk0 + (int)blockIdx.x;
+  int64_t chunk_row0, chunk_row1;
+  chunk_range(g, chunk, chunk_row0, chunk_row1);
 
   for (uint32_t b = threadIdx.x; b < cx.nbp; b += kBlock)
-    cx.cursor[b] = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)blockIdx.x * num + b] : 0u;
+    cx.cursor[b] = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)chunk * num + b] : 0u;
   for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * cx.nbp; i += kBlock) cx.cnt[i] = 0;
   __syncthreads();
 
@@ -425,6 +445,249 @@ fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g,
       scatter_tile<kSingleU64, kBits, true, kAll8>(keys, dv, num, cols, cx, tile_row0, kTile, phase);
     else
       scatter_tile<kSingleU64, kBits, false, kAll8>(keys, dv, num, cols, cx, tile_row0, (int)left, phase);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2, fast path: TMA-pipelined scatter (see the design note at the top).
+// Shared memory (dynamic, one CTA per SM):
+//   ring[S][kTile] uint64        S x 32 KB stages filled by cp.async.bulk
+//   full[S], empty[S] mbarriers
+//   delta[nbp] cursor[nbp] bin_start[nbp] uint32
+//   scanw[32] uint32
+//   cnt[kWarps][nbp] uint16      warp-private counters -> exclusive prefix over warps
+//   slotinfo[kTile] uint32       (pid << 16 | source row) for every slot of the permuted tile
+// ---------------------------------------------------------------------------
+constexpr int kTmaThreads = kBlock + 32;   // 16 consumer warps + 1 producer warp
+constexpr int kMaxUnits = FB_MAX_COLS + 1;
+constexpr uint32_t kStageBytes = (uint32_t)kTile * 8;
+
+struct TmaUnits {
+  const uint64_t* src[kMaxUnits];  // unit 0 is the key column
+  uint64_t* dst[kMaxUnits];        // nullptr: hash-only unit (key is not a payload column)
+  int32_t nunits;
+};
+
+__host__ __device__ inline size_t tma_book_bytes(uint32_t num) {
+  size_t nbp = nb_padded(num);
+  return 2 * 8 * 16 /*barriers, up to 16 stages*/ + 3 * nbp * 4 + 32 * 4 + (size_t)kWarps * nbp * 2 +
+         (size_t)kTile * 4;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FB_DONE;\n"
+      "bra FB_WAIT;\n"
+      "FB_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA engine; SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory"); }
+
+template <int kBits>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+fb_scatter_tma_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages,
+                      const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
+  extern __shared__ __align__(128) uint64_t smem64[];
+  const uint32_t nbp = nb_padded(num);
+  const uint32_t nb = num + 1;
+  uint64_t* ring = smem64;
+  uint64_t* bars = ring + (size_t)nstages * kTile;      // full[0..16), empty[0..16)
+  uint32_t* delta = (uint32_t*)(bars + 32);
+  uint32_t* cursor = delta + nbp;
+  uint32_t* bin_start = cursor + nbp;
+  uint32_t* scanw = bin_start + nbp;
+  uint16_t* cnt = (uint16_t*)(scanw + 32);
+  uint32_t* slotinfo = (uint32_t*)(cnt + (size_t)kWarps * nbp);
+
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 16);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kWarps) {
+    // ===================== producer: one elected lane drives the TMA engine =====================
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      const uint32_t ring_s = smem_u32(ring);
+      uint32_t s = 0, ph = 0;
+      for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
+        int64_t r0, r1;
+        chunk_range(g, chunk, r0, r1);
+        for (int64_t t0 = r0; t0 < r1; t0 += kTile) {
+          for (int u = 0; u < units.nunits; ++u) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(bar_full + 8 * s, kStageBytes);
+            tma_load_1d(ring_s + s * kStageBytes, units.src[u] + t0, kStageBytes, bar_full + 8 * s, pol);
+            if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================ consumers (16 warps) ================================
+  const unsigned lt = fb_lanemask_lt();
+  uint16_t* __restrict__ my_cnt = cnt + (size_t)warp * nbp;
+  for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
+  uint32_t s = 0, ph = 0;
+
+  for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
+    int64_t r0, r1;
+    chunk_range(g, chunk, r0, r1);
+    consumer_sync();  // previous chunk's readers of cursor[] are done
+    for (uint32_t b = threadIdx.x; b < nbp; b += kBlock)
+      cursor[b] = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)chunk * num + b] : 0u;
+    // (visibility: barrier A below)
+
+    for (int64_t t0 = r0; t0 < r1; t0 += kTile) {
+      // ---- unit 0: the key tile -> partition ids (warp-striped rows: warp*256 + r*32 + lane)
+      mbar_wait(bar_full + 8 * s, ph);
+      const uint64_t* __restrict__ kst = ring + (size_t)s * kTile;
+      uint32_t pid[kItems];
+#pragma unroll
+      for (int r = 0; r < kItems; ++r)
+        pid[r] = fb_fastmod(fb_hash_single_u64(kst[warp * (32 * kItems) + r * 32 + lane]), dv);
+
+      // ---- stable rank inside (warp, partition)
+      uint32_t pos[kItems];
+#pragma unroll
+      for (int r = 0; r < kItems; ++r) {
+        const unsigned m = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
+        const unsigned before = __popc(m & lt);
+        uint32_t old = 0;
+        if (before == 0) {
+          old = my_cnt[pid[r]];
+          my_cnt[pid[r]] = (uint16_t)(old + __popc(m));
+        }
+        __syncwarp();
+        old = __shfl_sync(0xFFFFFFFFu, old, __ffs(m) - 1);
+        pos[r] = old + before;
+      }
+      consumer_sync();  // A
+
+      // ---- exclusive prefix over warps per partition, block scan of the tile histogram
+      {
+        const uint32_t per = (nb + kBlock - 1) / kBlock;
+        const uint32_t b0 = threadIdx.x * per;
+        uint32_t tot[kMaxPer];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          tot[i] = 0;
+          if ((uint32_t)i < per && b0 + i < nb) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+              const uint32_t t = cnt[w * nbp + b0 + i];
+              cnt[w * nbp + b0 + i] = (uint16_t)run;
+              run += t;
+            }
+            tot[i] = run;
+            sum += run;
+          }
+        }
+        uint32_t x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+          if (lane >= (unsigned)o) x += y;
+        }
+        if (lane == 31) scanw[warp] = x;
+        consumer_sync();  // B
+        uint32_t run = x - sum;
+        {
+          const uint32_t wt = lane < kWarps ? scanw[lane] : 0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, wt, w);
+            if ((unsigned)w < warp) run += v;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          if ((uint32_t)i < per && b0 + i < nb) {
+            const uint32_t cur = cursor[b0 + i];
+            bin_start[b0 + i] = run;
+            delta[b0 + i] = cur - run;  // slot j of the permuted tile lands at output row delta + j
+            cursor[b0 + i] = cur + tot[i];
+            run += tot[i];
+          }
+        }
+      }
+      consumer_sync();  // C
+
+      // ---- slot of every row in the permuted tile; publish slot -> (pid, source row)
+#pragma unroll
+      for (int r = 0; r < kItems; ++r) {
+        const uint32_t slot = pos[r] + bin_start[pid[r]] + my_cnt[pid[r]];
+        slotinfo[slot] = (pid[r] << 16) | (warp * (32 * kItems) + r * 32 + lane);
+      }
+      __syncwarp();
+      for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;  // my row is private again: clear it
+      consumer_sync();  // D
+      uint32_t src[kItems], dst[kItems];
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        const uint32_t j = k * kBlock + threadIdx.x;
+        const uint32_t info = slotinfo[j];
+        src[k] = info & 0xFFFFu;
+        dst[k] = delta[info >> 16] + j;
+      }
+
+      // ---- per column: gather from the staged tile, store partition-contiguous runs
+      for (int u = 0; u < units.nunits; ++u) {
+        if (u > 0) mbar_wait(bar_full + 8 * s, ph);
+        const uint64_t* __restrict__ st = ring + (size_t)s * kTile;
+        uint64_t* __restrict__ out = units.dst[u];
+        if (out != nullptr) {
+          uint64_t v[kItems];
+#pragma unroll
+          for (int k = 0; k < kItems; ++k) v[k] = st[src[k]];
+#pragma unroll
+          for (int k = 0; k < kItems; ++k) out[dst[k]] = v[k];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done with the stage
+        if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+      }
+    }
   }
 }
 
@@ -498,6 +761,13 @@ cudaError_t ensure_smem_optin(int dev) {
     if (e == cudaSuccess) e = optin(fb_scatter_kernel<S, B, false>, sc); \
     if (e == cudaSuccess) e = optin(fb_hist_kernel<S, B>, hs);           \
   } while (0)
+  {
+    int smem_max = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) e = optin(fb_scatter_tma_kernel<4>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_tma_kernel<8>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_tma_kernel<10>, (size_t)smem_max);
+  }
   FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
   FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
 #undef FB_OPTIN
@@ -649,17 +919,61 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
     }
     bool all8 = true;
     for (int c = 0; c < cols.ncols; ++c) all8 = all8 && cols.width[c] == 8;
-#define FB_LAUNCH_SCATTER(S, B)                                                                   \
-  do {                                                                                            \
-    if (all8)                                                                                     \
-      fb_scatter_kernel<S, B, true><<<g.nchunks, kBlock, smem, st>>>(                             \
-          k, dv, num_partitions, g, (const uint32_t*)scratch, part_offsets, cols);                \
-    else                                                                                          \
-      fb_scatter_kernel<S, B, false><<<g.nchunks, kBlock, smem, st>>>(                            \
-          k, dv, num_partitions, g, (const uint32_t*)scratch, part_offsets, cols);                \
+    // ---- fast path: TMA-pipelined kernel over the whole-tile chunks
+    bool tma = single && all8 && g.nchunks_full > 0 && ((uintptr_t)k.ptr[0] % 16 == 0) &&
+               getenv("FB_DISABLE_TMA") == nullptr;
+    for (int c = 0; c < cols.ncols && tma; ++c) tma = ((uintptr_t)cols.src[c] % 16 == 0);
+    int first_generic_chunk = 0;
+    if (tma) {
+      TmaUnits units;
+      memset(&units, 0, sizeof(units));
+      units.src[0] = (const uint64_t*)k.ptr[0];
+      units.dst[0] = nullptr;
+      units.nunits = 1;
+      for (int c = 0; c < cols.ncols; ++c) {
+        if (cols.src[c] == k.ptr[0] && units.dst[0] == nullptr) {
+          units.dst[0] = (uint64_t*)cols.dst[c];  // the key column is a payload column too
+        } else {
+          units.src[units.nunits] = (const uint64_t*)cols.src[c];
+          units.dst[units.nunits] = (uint64_t*)cols.dst[c];
+          ++units.nunits;
+        }
+      }
+      int smem_max = 0;
+      FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      const size_t book = tma_book_bytes(num_partitions);
+      int nstages = (int)(((size_t)smem_max - book) / kStageBytes);
+      if (nstages > 16) nstages = 16;
+      FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
+      const size_t tsmem = (size_t)nstages * kStageBytes + book;
+      int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
+      if (bits == 4)
+        fb_scatter_tma_kernel<4><<<grid, kTmaThreads, tsmem, st>>>(units, dv, num_partitions, g, nstages,
+                                                                   (const uint32_t*)scratch, part_offsets);
+      else if (bits == 8)
+        fb_scatter_tma_kernel<8><<<grid, kTmaThreads, tsmem, st>>>(units, dv, num_partitions, g, nstages,
+                                                                   (const uint32_t*)scratch, part_offsets);
+      else
+        fb_scatter_tma_kernel<10><<<grid, kTmaThreads, tsmem, st>>>(units, dv, num_partitions, g, nstages,
+                                                                    (const uint32_t*)scratch, part_offsets);
+      FB_CUDA(cudaGetLastError());
+      first_generic_chunk = g.nchunks_full;
+    }
+    // ---- generic path: everything (no TMA) or just the partial tail tile
+    const int ngen = g.nchunks - first_generic_chunk;
+    if (ngen > 0) {
+#define FB_LAUNCH_SCATTER(S, B)                                                                     \
+  do {                                                                                              \
+    if (all8)                                                                                       \
+      fb_scatter_kernel<S, B, true><<<ngen, kBlock, smem, st>>>(                                    \
+          k, dv, num_partitions, g, first_generic_chunk, (const uint32_t*)scratch, part_offsets, cols); \
+    else                                                                                            \
+      fb_scatter_kernel<S, B, false><<<ngen, kBlock, smem, st>>>(                                   \
+          k, dv, num_partitions, g, first_generic_chunk, (const uint32_t*)scratch, part_offsets, cols); \
   } while (0)
-    FB_DISPATCH_SB(single, bits, FB_LAUNCH_SCATTER);
+      FB_DISPATCH_SB(single, bits, FB_LAUNCH_SCATTER);
 #undef FB_LAUNCH_SCATTER
+    }
     FB_CUDA(cudaGetLastError());
   }
   return 0;
