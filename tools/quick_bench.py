@@ -10,6 +10,27 @@ def main():
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(0)
     key = torch.randint(0, 1 << 16, (n,), dtype=torch.int64, device=dev, generator=g)
+    pattern = os.environ.get("FB_PATTERN", "")
+    if pattern:
+        # aligned-run experiment: every tile holds exactly `rep` consecutive... rows per partition
+        reps = [int(x) for x in pattern.split(",")]
+        rep = reps[0]
+        cand = torch.arange(0, 1 << 16, dtype=torch.int64, device=dev)
+        pid = K.partition_ids([cand], num).long()
+        first = torch.full((num,), -1, dtype=torch.int64, device=dev)
+        # pick one key per partition id
+        order = torch.argsort(pid, stable=True)
+        sp = pid[order]
+        starts = torch.searchsorted(sp, torch.arange(num, device=dev))
+        keys_per_pid = cand[order][starts]
+        if len(reps) == 1:
+            pat = keys_per_pid.repeat_interleave(rep)          # rep rows of pid 0, rep rows of pid 1, ...
+        else:  # first half of the partitions gets reps[0] rows per tile, second half reps[1]
+            cnt = torch.tensor([reps[0]] * (num // 2) + [reps[1]] * (num - num // 2), device=dev)
+            pat = keys_per_pid.repeat_interleave(cnt)
+        perm = torch.randperm(pat.numel(), device=dev, generator=g) if os.environ.get("FB_SHUFFLE") else None
+        if perm is not None: pat = pat[perm]
+        key = pat.repeat((n + pat.numel() - 1) // pat.numel())[:n].contiguous()
     cols = [key] + [torch.randint(-(2**62), 2**62, (n,), dtype=torch.int64, device=dev, generator=g) for _ in range(3)] \
         + [torch.randn(n, dtype=torch.float64, device=dev, generator=g) for _ in range(4)]
     out = [torch.empty_like(c) for c in cols]
