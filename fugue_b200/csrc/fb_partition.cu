@@ -449,18 +449,34 @@ fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, int chunk0,
 }
 
 // ---------------------------------------------------------------------------
-// pass 2, fast path: TMA-pipelined scatter (see the design note at the top).
-// Shared memory (dynamic, one CTA per SM):
-//   ring[S][kTile] uint64        S x 32 KB stages filled by cp.async.bulk
-//   full[S], empty[S] mbarriers
-//   delta[nbp] cursor[nbp] bin_start[nbp] uint32
-//   scanw[32] uint32
-//   cnt[kWarps][nbp] uint16      warp-private counters -> exclusive prefix over warps
-//   slotinfo[kTile] uint32       (pid << 16 | source row) for every slot of the permuted tile
+// pass 2, fast path: TMA-pipelined scatter with software write-combining.
+//
+// Measured on B200 (profiles/r1_notes.md): a partition-ordered tile written as
+// 8-byte-aligned runs costs 4.8 ms / 100 M rows because run heads/tails are partial
+// 32-byte sectors (L2 fills them from DRAM and writes them back twice); the same
+// traffic with sector-aligned runs costs 3.2 ms, with linear stores 2.2 ms.  So every
+// partition keeps its last (< G) rows per column in a shared-memory carry buffer and
+// only whole G-row groups (G * 8 B = one or more full sectors) are stored; the
+// carried rows are prepended to the partition's rows of the next tile.  Partial
+// stores happen only at chunk heads/tails (2 per partition per column per chunk).
+//
+// Shared memory (dynamic, one CTA per SM), T = kTile, E = num * (G - 1):
+//   ring[S][T] uint64          S x 32 KB stages filled by cp.async.bulk (TMA)
+//   carry[ncols + 1][E] uint64 carried rows per column (+1 spare: new carry is written
+//                              to the spare buffer, buffers rotate every column step)
+//   slotinfo[T + E] uint32     output slot -> (partition << 16 | source descriptor)
+//   carryinfo[E] uint16        new carry entry -> source descriptor
+//   per-partition uint32 arrays: wpos, kcnt, binfo, bin_start, wstart, wdelta
+//   cnt[kWarps][nbp] uint16, scanw[64] uint32, mbarriers
+// Source descriptor: [0, T) row of the staged tile; [T, T + E) old carry entry;
+// 0xFFFF nothing (phantom row at a chunk head / unused carry entry).
 // ---------------------------------------------------------------------------
 constexpr int kTmaThreads = kBlock + 32;   // 16 consumer warps + 1 producer warp
 constexpr int kMaxUnits = FB_MAX_COLS + 1;
 constexpr uint32_t kStageBytes = (uint32_t)kTile * 8;
+constexpr int kSwcMaxCols = 8;             // payload columns per launch (carry buffers in smem)
+constexpr uint32_t kSwcMaxNum = 256;
+constexpr int kSwcG = 4;                   // rows per write-combining group (4 x 8 B = one 32 B sector)
 
 struct TmaUnits {
   const uint64_t* src[kMaxUnits];  // unit 0 is the key column
@@ -468,10 +484,17 @@ struct TmaUnits {
   int32_t nunits;
 };
 
-__host__ __device__ inline size_t tma_book_bytes(uint32_t num) {
-  size_t nbp = nb_padded(num);
-  return 2 * 8 * 16 /*barriers, up to 16 stages*/ + 3 * nbp * 4 + 32 * 4 + (size_t)kWarps * nbp * 2 +
-         (size_t)kTile * 4;
+template <int G>
+__host__ __device__ inline size_t swc_book_bytes(uint32_t num, int ncols) {
+  const size_t nbp = nb_padded(num);
+  const size_t E = (size_t)num * (G - 1);
+  size_t b = 2 * 8 * 16;                       // mbarriers (up to 16 stages)
+  b += (size_t)(ncols + 1) * E * 8;            // carry buffers
+  b += ((size_t)kTile + E) * 4;                // slotinfo
+  b += 6 * nbp * 4 + 64 * 4;                   // per-partition arrays + scanw
+  b += (size_t)kWarps * nbp * 2;               // cnt
+  b += ((E * 2 + 15) / 16) * 16;               // carryinfo
+  return b;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -482,9 +505,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Relaxed arrive: releasing a ring stage must not wait for this warp's outstanding global
-// stores (a release-arrive drains them: ~1 us per column, measured).  Ordering of the stage
-// reads is by issue order: the arrive is issued after the STGs that consume the LDS results.
+// Relaxed arrive: releasing a ring stage does not have to order this warp's global stores.
+// The stage reads are ordered by issue: the arrive is issued after the instructions that
+// consume the LDS results.
 __device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
   asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -515,21 +538,30 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, 
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory"); }
 
-template <int kBits>
+template <int kBits, int G>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-fb_scatter_tma_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int dbg,
+fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols,
                       const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
+  constexpr uint32_t T = kTile;
+  constexpr uint32_t GM = G - 1;
+  constexpr int kSlotRounds = (kTile + (int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
+  constexpr int kEntryRounds = ((int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
   extern __shared__ __align__(128) uint64_t smem64[];
   const uint32_t nbp = nb_padded(num);
-  const uint32_t nb = num + 1;
+  const uint32_t E = num * GM;
   uint64_t* ring = smem64;
-  uint64_t* bars = ring + (size_t)nstages * kTile;      // full[0..16), empty[0..16)
-  uint32_t* delta = (uint32_t*)(bars + 32);
-  uint32_t* cursor = delta + nbp;
-  uint32_t* bin_start = cursor + nbp;
-  uint32_t* scanw = bin_start + nbp;
-  uint16_t* cnt = (uint16_t*)(scanw + 32);
-  uint32_t* slotinfo = (uint32_t*)(cnt + (size_t)kWarps * nbp);
+  uint64_t* bars = ring + (size_t)nstages * T;  // full[0..16), empty[0..16)
+  uint64_t* carry = bars + 32;                  // (ncols + 1) buffers of E entries
+  uint32_t* slotinfo = (uint32_t*)(carry + (size_t)(ncols + 1) * E);
+  uint32_t* wpos = slotinfo + T + E;            // output row of the first pending row of a partition
+  uint32_t* kcnt = wpos + nbp;                  // pending rows | phantom rows << 8
+  uint32_t* binfo = kcnt + nbp;                 // this tile: kold | phold << 4 | w << 8
+  uint32_t* bin_start = binfo + nbp;            // exclusive prefix of the tile histogram
+  uint32_t* wstart = bin_start + nbp;           // exclusive prefix of rows written this tile
+  uint32_t* wdelta = wstart + nbp;              // wpos - wstart: slot j lands at output row wdelta + j
+  uint32_t* scanw = wdelta + nbp;               // [0,16) tile hist totals, [16,32) written totals, [32] W
+  uint16_t* cnt = (uint16_t*)(scanw + 64);
+  uint16_t* carryinfo = cnt + (size_t)kWarps * nbp;
 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 16);
@@ -552,7 +584,7 @@ fb_scatter_tma_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
       for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
         int64_t r0, r1;
         chunk_range(g, chunk, r0, r1);
-        for (int64_t t0 = r0; t0 < r1; t0 += kTile) {
+        for (int64_t t0 = r0; t0 < r1; t0 += T) {
           for (int u = 0; u < units.nunits; ++u) {
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(bar_full + 8 * s, kStageBytes);
@@ -570,19 +602,24 @@ fb_scatter_tma_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
   uint16_t* __restrict__ my_cnt = cnt + (size_t)warp * nbp;
   for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
   uint32_t s = 0, ph = 0;
+  const int nbuf = ncols + 1;
+  int rot = 0;  // carry buffer of payload column c is (c + rot) mod nbuf; (rot - 1) mod nbuf is spare
 
   for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
     int64_t r0, r1;
     chunk_range(g, chunk, r0, r1);
-    consumer_sync();  // previous chunk's readers of cursor[] are done
-    for (uint32_t b = threadIdx.x; b < nbp; b += kBlock)
-      cursor[b] = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)chunk * num + b] : 0u;
+    consumer_sync();  // previous chunk's flush is complete
+    for (uint32_t b = threadIdx.x; b < nbp; b += kBlock) {
+      const uint32_t p0 = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)chunk * num + b] : 0u;
+      wpos[b] = p0 & ~GM;
+      kcnt[b] = (p0 & GM) | ((p0 & GM) << 8);  // rows before p0 in its group are phantoms
+    }
     // (visibility: barrier A below)
 
-    for (int64_t t0 = r0; t0 < r1; t0 += kTile) {
+    for (int64_t t0 = r0; t0 < r1; t0 += T) {
       // ---- unit 0: the key tile -> partition ids (warp-striped rows: warp*256 + r*32 + lane)
       mbar_wait(bar_full + 8 * s, ph);
-      const uint64_t* __restrict__ kst = ring + (size_t)s * kTile;
+      const uint64_t* __restrict__ kst = ring + (size_t)s * T;
       uint32_t pid[kItems];
 #pragma unroll
       for (int r = 0; r < kItems; ++r)
@@ -605,98 +642,178 @@ fb_scatter_tma_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
       }
       consumer_sync();  // A
 
-      // ---- exclusive prefix over warps per partition, block scan of the tile histogram
+      // ---- per partition (thread b < num): tile count, rows to write, new pending state;
+      //      block scans of (count, written)
       {
-        const uint32_t per = (nb + kBlock - 1) / kBlock;
-        const uint32_t b0 = threadIdx.x * per;
-        uint32_t tot[kMaxPer];
-        uint32_t sum = 0;
+        const uint32_t b = threadIdx.x;
+        uint32_t n = 0, w = 0, kold = 0, phold = 0;
+        if (b < num) {
 #pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-          tot[i] = 0;
-          if ((uint32_t)i < per && b0 + i < nb) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-              const uint32_t t = cnt[w * nbp + b0 + i];
-              cnt[w * nbp + b0 + i] = (uint16_t)run;
-              run += t;
-            }
-            tot[i] = run;
-            sum += run;
+          for (int wi = 0; wi < kWarps; ++wi) {
+            const uint32_t t = cnt[wi * nbp + b];
+            cnt[wi * nbp + b] = (uint16_t)n;
+            n += t;
           }
+          const uint32_t kc = kcnt[b];
+          kold = kc & 0xFFu;
+          phold = kc >> 8;
+          const uint32_t wp = wpos[b];
+          const uint32_t end = wp + kold + n;
+          const uint32_t aend = end & ~GM;
+          uint32_t knew = kold + n;
+          if (aend > wp) {
+            w = aend - wp;
+            knew = end - aend;
+            wpos[b] = aend;
+            kcnt[b] = knew;  // phantoms are consumed by the first write
+          } else {
+            kcnt[b] = knew | (phold << 8);
+          }
+          binfo[b] = kold | (phold << 4) | (w << 8);
         }
-        uint32_t x = sum;
+        // two inclusive warp scans
+        uint32_t xn = n, xw = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-          if (lane >= (unsigned)o) x += y;
+          const uint32_t yn = __shfl_up_sync(0xFFFFFFFFu, xn, o);
+          const uint32_t yw = __shfl_up_sync(0xFFFFFFFFu, xw, o);
+          if (lane >= (unsigned)o) { xn += yn; xw += yw; }
         }
-        if (lane == 31) scanw[warp] = x;
+        if (lane == 31) { scanw[warp] = xn; scanw[16 + warp] = xw; }
         consumer_sync();  // B
-        uint32_t run = x - sum;
+        uint32_t bn = xn - n, bw = xw - w;
         {
-          const uint32_t wt = lane < kWarps ? scanw[lane] : 0;
+          const uint32_t tn = lane < kWarps ? scanw[lane] : 0;
+          const uint32_t tw = lane < kWarps ? scanw[16 + lane] : 0;
 #pragma unroll
-          for (int w = 0; w < kWarps; ++w) {
-            const uint32_t v = __shfl_sync(0xFFFFFFFFu, wt, w);
-            if ((unsigned)w < warp) run += v;
+          for (int wi = 0; wi < kWarps; ++wi) {
+            const uint32_t vn = __shfl_sync(0xFFFFFFFFu, tn, wi);
+            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, tw, wi);
+            if ((unsigned)wi < warp) { bn += vn; bw += vw; }
           }
         }
-#pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-          if ((uint32_t)i < per && b0 + i < nb) {
-            const uint32_t cur = cursor[b0 + i];
-            bin_start[b0 + i] = run;
-            delta[b0 + i] = cur - run;  // slot j of the permuted tile lands at output row delta + j
-            cursor[b0 + i] = cur + tot[i];
-            run += tot[i];
-          }
+        if (b < num) {
+          bin_start[b] = bn;
+          wstart[b] = bw;
+          // the rows written this tile start at the old wpos = (new wpos) - w  when w > 0
+          wdelta[b] = (w ? wpos[b] - w : wpos[b]) - bw;
         }
+        if (threadIdx.x == kBlock - 1) scanw[32] = bw + w;  // W: slots to store this tile
       }
       consumer_sync();  // C
 
-      // ---- slot of every row in the permuted tile; publish slot -> (pid, source row)
+      // ---- every new row and every old carry entry finds its place: an output slot of this
+      //      tile or an entry of the new carry
 #pragma unroll
       for (int r = 0; r < kItems; ++r) {
-        const uint32_t slot = pos[r] + bin_start[pid[r]] + my_cnt[pid[r]];
-        slotinfo[slot] = (pid[r] << 16) | (warp * (32 * kItems) + r * 32 + lane);
+        const uint32_t b = pid[r];
+        const uint32_t bi = binfo[b];
+        const uint32_t i = (bi & 0xFu) + pos[r] + my_cnt[b];  // index in the partition's pending list
+        const uint32_t w = bi >> 8;
+        const uint32_t row = warp * (32 * kItems) + r * 32 + lane;
+        if (i < w) slotinfo[wstart[b] + i] = (b << 16) | row;
+        else carryinfo[b * GM + (i - w)] = (uint16_t)row;
+      }
+#pragma unroll
+      for (int q = 0; q < kEntryRounds; ++q) {
+        const uint32_t e = q * kBlock + threadIdx.x;
+        if (e < E) {
+          const uint32_t b = e / GM, i = e - b * GM;
+          const uint32_t bi = binfo[b];
+          const uint32_t kold = bi & 0xFu, phold = (bi >> 4) & 0xFu, w = bi >> 8;
+          const uint32_t n = (b + 1 < num ? bin_start[b + 1] : T) - bin_start[b];
+          const uint32_t desc = i < phold ? 0xFFFFu : T + e;
+          if (i < kold) {  // an old carry entry
+            if (i < w) slotinfo[wstart[b] + i] = (b << 16) | desc;
+            else carryinfo[e] = (uint16_t)desc;  // w == 0: stays pending at the same index
+          }
+          // new carry entries nobody else writes: beyond the pending list
+          const uint32_t li = w + i;  // list index that lands in new carry entry i
+          if (li >= kold + n) carryinfo[e] = 0xFFFFu;
+        }
       }
       __syncwarp();
-      for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;  // my row is private again: clear it
+      for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;  // my counter row is private again
       consumer_sync();  // D
-      uint32_t src[kItems], dst[kItems];
+
+      const uint32_t W = scanw[32];
+      uint32_t srcd[kSlotRounds], dst[kSlotRounds];
 #pragma unroll
-      for (int k = 0; k < kItems; ++k) {
+      for (int k = 0; k < kSlotRounds; ++k) {
         const uint32_t j = k * kBlock + threadIdx.x;
-        const uint32_t info = slotinfo[j];
-        src[k] = info & 0xFFFFu;
-        dst[k] = delta[info >> 16] + j;
-        if (dbg & 2) dst[k] = (uint32_t)t0 + j;  // experiment: linear (fully coalesced) stores
+        srcd[k] = 0xFFFFu;
+        dst[k] = 0;
+        if (j < W) {
+          const uint32_t info = slotinfo[j];
+          srcd[k] = info & 0xFFFFu;
+          dst[k] = wdelta[info >> 16] + j;
+        }
+      }
+      uint32_t csrc[kEntryRounds];
+#pragma unroll
+      for (int q = 0; q < kEntryRounds; ++q) {
+        const uint32_t e = q * kBlock + threadIdx.x;
+        csrc[q] = e < E ? (uint32_t)carryinfo[e] : 0xFFFFu;
       }
 
-      // ---- per column: gather from the staged tile, store partition-contiguous runs
+      // ---- per column: gather from the staged tile / old carry, store whole sector groups,
+      //      save the new carry
+      int c = 0;  // payload column index (for the carry buffers)
       for (int u = 0; u < units.nunits; ++u) {
         if (u > 0) mbar_wait(bar_full + 8 * s, ph);
-        const uint64_t* __restrict__ st = ring + (size_t)s * kTile;
         uint64_t* __restrict__ out = units.dst[u];
         if (out != nullptr) {
-          uint64_t v[kItems];
+          const uint64_t* __restrict__ st = ring + (size_t)s * T;
+          int bo = c + rot; if (bo >= nbuf) bo -= nbuf;
+          int bn = c + rot - 1; if (bn < 0) bn += nbuf; if (bn >= nbuf) bn -= nbuf;
+          const uint64_t* __restrict__ oldc = carry + (size_t)bo * E;
+          uint64_t* __restrict__ newc = carry + (size_t)bn * E;
+          uint64_t v[kSlotRounds], cv[kEntryRounds];
 #pragma unroll
-          for (int k = 0; k < kItems; ++k) v[k] = st[src[k]];
-          if (dbg & 1) {  // experiment: no stores
-            uint64_t acc = 0;
+          for (int k = 0; k < kSlotRounds; ++k)
+            if (srcd[k] != 0xFFFFu) v[k] = srcd[k] < T ? st[srcd[k]] : oldc[srcd[k] - T];
 #pragma unroll
-            for (int k = 0; k < kItems; ++k) acc ^= v[k];
-            if (acc == 0x123456789ULL) out[0] = acc;
-          } else {
+          for (int q = 0; q < kEntryRounds; ++q)
+            if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : oldc[csrc[q] - T];
 #pragma unroll
-            for (int k = 0; k < kItems; ++k) out[dst[k]] = v[k];
+          for (int k = 0; k < kSlotRounds; ++k)
+            if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
+          consumer_sync();  // every warp has read this column's old carry (= the next spare)
+#pragma unroll
+          for (int q = 0; q < kEntryRounds; ++q) {
+            const uint32_t e = q * kBlock + threadIdx.x;
+            if (csrc[q] != 0xFFFFu) newc[e] = cv[q];
           }
+          // this column now lives in buffer (c + rot - 1); its old buffer is the next column's spare
+          ++c;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(bar_empty + 8 * s);  // this warp is done with the stage
         if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+      }
+      // after the tile: column c's data is in buffer (c + rot - 1) mod nbuf
+      rot = rot == 0 ? nbuf - 1 : rot - 1;
+    }
+
+    // ---- chunk end: flush the pending rows (partial sector groups)
+    consumer_sync();
+    {
+      int c = 0;
+      for (int u = 0; u < units.nunits; ++u) {
+        uint64_t* __restrict__ out = units.dst[u];
+        if (out == nullptr) continue;
+        int bo = c + rot; if (bo >= nbuf) bo -= nbuf;
+        const uint64_t* __restrict__ oldc = carry + (size_t)bo * E;
+#pragma unroll
+        for (int q = 0; q < kEntryRounds; ++q) {
+          const uint32_t e = q * kBlock + threadIdx.x;
+          if (e < E) {
+            const uint32_t b = e / GM, i = e - b * GM;
+            const uint32_t kc = kcnt[b];
+            if (i < (kc & 0xFFu) && i >= (kc >> 8)) out[wpos[b] + i] = oldc[e];
+          }
+        }
+        ++c;
       }
     }
   }
@@ -775,9 +892,8 @@ cudaError_t ensure_smem_optin(int dev) {
   {
     int smem_max = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e == cudaSuccess) e = optin(fb_scatter_tma_kernel<4>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_tma_kernel<8>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_tma_kernel<10>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcG>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcG>, (size_t)smem_max);
   }
   FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
   FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
@@ -912,81 +1028,93 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
   FbDiv dv = fb_make_div(num_partitions);
   cudaStream_t st = (cudaStream_t)stream;
   const bool single = single_u64_key(nkeys, key_widths, key_valid);
-  size_t smem = scatter_smem_bytes(num_partitions);
+  const size_t smem = scatter_smem_bytes(num_partitions);
   FB_CUDA(ensure_smem_optin(dev));
   const int bits = bits_for(num_partitions);
-  for (int c0 = 0; c0 < ncols; c0 += FB_MAX_COLS) {
-    FbCols cols;
-    memset(&cols, 0, sizeof(cols));
-    cols.ncols = ncols - c0 < FB_MAX_COLS ? ncols - c0 : FB_MAX_COLS;
-    for (int c = 0; c < cols.ncols; ++c) {
-      int w = col_widths[c0 + c];
-      FB_CHECK(w == 1 || w == 2 || w == 4 || w == 8, "column %d has unsupported width %d", c0 + c, w);
-      FB_CHECK(col_ptrs[c0 + c] != nullptr && out_col_ptrs[c0 + c] != nullptr,
-               "column %d pointer is NULL", c0 + c);
-      cols.src[c] = col_ptrs[c0 + c];
-      cols.dst[c] = out_col_ptrs[c0 + c];
-      cols.width[c] = w;
+
+  for (int c = 0; c < ncols; ++c) {
+    const int w = col_widths[c];
+    FB_CHECK(w == 1 || w == 2 || w == 4 || w == 8, "column %d has unsupported width %d", c, w);
+    FB_CHECK(col_ptrs[c] != nullptr && out_col_ptrs[c] != nullptr, "column %d pointer is NULL", c);
+  }
+
+  // generic kernel over chunks [chunk0, chunk0 + nch) for the columns listed in idx[0..n)
+  auto launch_generic = [&](const int* idx, int n, int chunk0, int nch) -> int {
+    for (int c0 = 0; c0 < n && nch > 0; c0 += FB_MAX_COLS) {
+      FbCols cols;
+      memset(&cols, 0, sizeof(cols));
+      cols.ncols = n - c0 < FB_MAX_COLS ? n - c0 : FB_MAX_COLS;
+      bool all8 = true;
+      for (int c = 0; c < cols.ncols; ++c) {
+        cols.src[c] = col_ptrs[idx[c0 + c]];
+        cols.dst[c] = out_col_ptrs[idx[c0 + c]];
+        cols.width[c] = col_widths[idx[c0 + c]];
+        all8 = all8 && cols.width[c] == 8;
+      }
+#define FB_LAUNCH_SCATTER(S, B)                                                                        \
+  do {                                                                                                 \
+    if (all8)                                                                                          \
+      fb_scatter_kernel<S, B, true><<<nch, kBlock, smem, st>>>(k, dv, num_partitions, g, chunk0,       \
+                                                               (const uint32_t*)scratch, part_offsets, cols); \
+    else                                                                                               \
+      fb_scatter_kernel<S, B, false><<<nch, kBlock, smem, st>>>(k, dv, num_partitions, g, chunk0,      \
+                                                                (const uint32_t*)scratch, part_offsets, cols); \
+  } while (0)
+      FB_DISPATCH_SB(single, bits, FB_LAUNCH_SCATTER);
+#undef FB_LAUNCH_SCATTER
+      FB_CUDA(cudaGetLastError());
     }
-    bool all8 = true;
-    for (int c = 0; c < cols.ncols; ++c) all8 = all8 && cols.width[c] == 8;
-    // ---- fast path: TMA-pipelined kernel over the whole-tile chunks
-    bool tma = single && all8 && g.nchunks_full > 0 && ((uintptr_t)k.ptr[0] % 16 == 0) &&
-               getenv("FB_DISABLE_TMA") == nullptr;
-    for (int c = 0; c < cols.ncols && tma; ++c) tma = ((uintptr_t)cols.src[c] % 16 == 0);
-    int first_generic_chunk = 0;
-    if (tma) {
+    return 0;
+  };
+
+  // ---- split the columns: fast path (TMA + write combining) vs generic
+  const bool fast_ok = single && num_partitions <= kSwcMaxNum && g.nchunks_full > 0 &&
+                       ((uintptr_t)k.ptr[0] % 16 == 0) && getenv("FB_DISABLE_TMA") == nullptr;
+  int* fast_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
+  int* gen_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
+  int nfast = 0, ngen = 0;
+  for (int c = 0; c < ncols; ++c) {
+    if (fast_ok && col_widths[c] == 8 && (uintptr_t)col_ptrs[c] % 16 == 0) fast_idx[nfast++] = c;
+    else gen_idx[ngen++] = c;
+  }
+  if (int rc = launch_generic(gen_idx, ngen, 0, g.nchunks)) return rc;
+
+  if (nfast > 0) {
+    int smem_max = 0;
+    FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
+    for (int c0 = 0; c0 < nfast; c0 += kSwcMaxCols) {
+      const int nb = nfast - c0 < kSwcMaxCols ? nfast - c0 : kSwcMaxCols;
       TmaUnits units;
       memset(&units, 0, sizeof(units));
       units.src[0] = (const uint64_t*)k.ptr[0];
       units.dst[0] = nullptr;
       units.nunits = 1;
-      for (int c = 0; c < cols.ncols; ++c) {
-        if (cols.src[c] == k.ptr[0] && units.dst[0] == nullptr) {
-          units.dst[0] = (uint64_t*)cols.dst[c];  // the key column is a payload column too
+      for (int c = 0; c < nb; ++c) {
+        const int ci = fast_idx[c0 + c];
+        if (col_ptrs[ci] == k.ptr[0] && units.dst[0] == nullptr) {
+          units.dst[0] = (uint64_t*)out_col_ptrs[ci];  // the key column is a payload column too
         } else {
-          units.src[units.nunits] = (const uint64_t*)cols.src[c];
-          units.dst[units.nunits] = (uint64_t*)cols.dst[c];
+          units.src[units.nunits] = (const uint64_t*)col_ptrs[ci];
+          units.dst[units.nunits] = (uint64_t*)out_col_ptrs[ci];
           ++units.nunits;
         }
       }
-      int smem_max = 0;
-      FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-      const size_t book = tma_book_bytes(num_partitions);
+      const size_t book = swc_book_bytes<kSwcG>(num_partitions, nb);
       int nstages = (int)(((size_t)smem_max - book) / kStageBytes);
       if (nstages > 16) nstages = 16;
       FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
       const size_t tsmem = (size_t)nstages * kStageBytes + book;
-      const int dbg = getenv("FB_DEBUG_SCATTER") ? atoi(getenv("FB_DEBUG_SCATTER")) : 0;
-      int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
       if (bits == 4)
-        fb_scatter_tma_kernel<4><<<grid, kTmaThreads, tsmem, st>>>(units, dv, num_partitions, g, nstages, dbg,
-                                                                   (const uint32_t*)scratch, part_offsets);
-      else if (bits == 8)
-        fb_scatter_tma_kernel<8><<<grid, kTmaThreads, tsmem, st>>>(units, dv, num_partitions, g, nstages, dbg,
-                                                                   (const uint32_t*)scratch, part_offsets);
+        fb_scatter_swc_kernel<4, kSwcG><<<grid, kTmaThreads, tsmem, st>>>(
+            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
       else
-        fb_scatter_tma_kernel<10><<<grid, kTmaThreads, tsmem, st>>>(units, dv, num_partitions, g, nstages, dbg,
-                                                                    (const uint32_t*)scratch, part_offsets);
+        fb_scatter_swc_kernel<8, kSwcG><<<grid, kTmaThreads, tsmem, st>>>(
+            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
       FB_CUDA(cudaGetLastError());
-      first_generic_chunk = g.nchunks_full;
     }
-    // ---- generic path: everything (no TMA) or just the partial tail tile
-    const int ngen = g.nchunks - first_generic_chunk;
-    if (ngen > 0) {
-#define FB_LAUNCH_SCATTER(S, B)                                                                     \
-  do {                                                                                              \
-    if (all8)                                                                                       \
-      fb_scatter_kernel<S, B, true><<<ngen, kBlock, smem, st>>>(                                    \
-          k, dv, num_partitions, g, first_generic_chunk, (const uint32_t*)scratch, part_offsets, cols); \
-    else                                                                                            \
-      fb_scatter_kernel<S, B, false><<<ngen, kBlock, smem, st>>>(                                   \
-          k, dv, num_partitions, g, first_generic_chunk, (const uint32_t*)scratch, part_offsets, cols); \
-  } while (0)
-      FB_DISPATCH_SB(single, bits, FB_LAUNCH_SCATTER);
-#undef FB_LAUNCH_SCATTER
-    }
-    FB_CUDA(cudaGetLastError());
+    // the partial tail tile of the fast columns
+    if (int rc = launch_generic(fast_idx, nfast, g.nchunks_full, g.nchunks - g.nchunks_full)) return rc;
   }
   return 0;
 }
