@@ -1,0 +1,258 @@
+"""Functional API with the reference's names: ``transform``, ``engine_context``,
+``make_execution_engine``, ``as_fugue_engine_df``, ``repartition`` ...
+
+Mirrors
+  * ``fa.transform``            fugue/workflow/api.py:34-184
+  * ``fa.engine_context``       fugue/execution/api.py:21-50
+  * ``make_execution_engine``   fugue/execution/factory.py:237-339
+  * function -> transformer     fugue/extensions/transformer/convert.py:328-385, 576-594
+                                fugue/dataframe/function_wrapper.py:49-148
+The reference builds a two-task DAG (adagio) around one ``map_dataframe`` call; that
+driver-side plumbing is O(1) and is collapsed into a direct call here.
+"""
+import contextvars
+import inspect
+import re
+from contextlib import contextmanager
+from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, get_type_hints
+
+import pandas as pd
+import pyarrow as pa
+
+from .dataframe import (ArrayDataFrame, ArrowDataFrame, B200DataFrame, DataFrame, LocalDataFrame,
+                        PandasDataFrame, as_fugue_df)
+from .execution_engine import B200ExecutionEngine, assert_or_throw
+from .partition import PartitionCursor, PartitionSpec
+from .schema import Schema
+from .table import B200Table
+
+_CONTEXT_ENGINE: "contextvars.ContextVar[Optional[B200ExecutionEngine]]" = contextvars.ContextVar(
+    "fugue_b200_engine", default=None)
+_GLOBAL_ENGINE: List[Optional[B200ExecutionEngine]] = [None]
+_ENGINE_FACTORIES: Dict[str, Callable[..., B200ExecutionEngine]] = {}
+
+
+def register_execution_engine(name: str, func: Callable[..., B200ExecutionEngine],
+                              on_dup: str = "overwrite") -> None:
+    """fugue/execution/factory.py:18-88 (name registration only)."""
+    if name in _ENGINE_FACTORIES and on_dup == "ignore":
+        return
+    if name in _ENGINE_FACTORIES and on_dup == "throw":
+        raise KeyError(f"{name} is already registered")
+    _ENGINE_FACTORIES[name] = func
+
+
+register_execution_engine("b200", lambda conf, **kw: B200ExecutionEngine(conf, **kw))
+
+
+def make_execution_engine(engine: Any = None, conf: Any = None, infer_by: Optional[List[Any]] = None,
+                          **kwargs: Any) -> B200ExecutionEngine:
+    """None -> context engine -> global engine -> a new "b200" engine."""
+    if isinstance(engine, B200ExecutionEngine):
+        if conf:
+            engine.conf.update(dict(conf))
+        return engine
+    if engine is None:
+        cur = _CONTEXT_ENGINE.get() or _GLOBAL_ENGINE[0]
+        if cur is not None:
+            return cur
+        engine = "b200"
+    if isinstance(engine, str):
+        assert_or_throw(engine in _ENGINE_FACTORIES, lambda: ValueError(
+            f"{engine!r} is not a registered execution engine (this package provides 'b200')"))
+        return _ENGINE_FACTORIES[engine](conf, **kwargs)
+    raise TypeError(f"{engine} can't be converted to an execution engine")
+
+
+@contextmanager
+def engine_context(engine: Any = None, engine_conf: Any = None, infer_by: Any = None
+                   ) -> Iterator[B200ExecutionEngine]:
+    e = make_execution_engine(engine, engine_conf, infer_by=infer_by)
+    token = _CONTEXT_ENGINE.set(e)
+    try:
+        yield e
+    finally:
+        _CONTEXT_ENGINE.reset(token)
+
+
+def set_global_engine(engine: Any, engine_conf: Any = None) -> B200ExecutionEngine:
+    e = make_execution_engine(engine, engine_conf)
+    _GLOBAL_ENGINE[0] = e
+    return e
+
+
+def clear_global_engine() -> None:
+    _GLOBAL_ENGINE[0] = None
+
+
+def get_context_engine() -> B200ExecutionEngine:
+    return make_execution_engine(None)
+
+
+def as_fugue_engine_df(engine: B200ExecutionEngine, df: Any, schema: Any = None) -> DataFrame:
+    """fugue/execution/api.py:124-142."""
+    return engine.to_df(df, schema)
+
+
+def repartition(df: Any, partition: Any, engine: Any = None, engine_conf: Any = None,
+                as_fugue: bool = False) -> Any:
+    e = make_execution_engine(engine, engine_conf)
+    res = e.repartition(e.to_df(df), PartitionSpec(partition))
+    return res if as_fugue or isinstance(df, DataFrame) else res.native
+
+
+# ----------------------------------------------------------------------------------------
+# function wrapper: decides how the user function sees a partition
+# ----------------------------------------------------------------------------------------
+class _FuncAsTransformer:
+    """What ``_to_transformer(using, schema)`` builds in the reference
+    (extensions/transformer/convert.py:328-385): validates the signature, resolves the output
+    schema and adapts LocalDataFrame <-> the annotated types."""
+
+    def __init__(self, func: Callable, schema: Any, params: Optional[Dict[str, Any]]):
+        assert_or_throw(callable(func), lambda: TypeError(f"{func} is not callable"))
+        self._func = func
+        self._params = dict(params or {})
+        sig = inspect.signature(func)
+        try:
+            hints = get_type_hints(func)
+        except Exception:
+            hints = {}
+        names = list(sig.parameters)
+        assert_or_throw(len(names) >= 1, lambda: TypeError("transformer needs a dataframe parameter"))
+        self._df_param = names[0]
+        self._in_kind = self._kind(hints.get(names[0], sig.parameters[names[0]].annotation))
+        self._out_kind = self._kind(hints.get("return", sig.return_annotation))
+        assert_or_throw(self._in_kind is not None, lambda: TypeError(
+            f"first parameter of {func.__name__} must be annotated with B200Table, pd.DataFrame, "
+            "pa.Table, List[List[Any]], Iterable[List[Any]], List[Dict[str, Any]] or a Fugue DataFrame"))
+        self._wants_cursor = [n for n in names[1:] if hints.get(n, None) is PartitionCursor]
+        self._schema_expr = schema if schema is not None else self._schema_from_comment(func)
+        assert_or_throw(self._schema_expr is not None, lambda: ValueError(
+            "schema is required (argument or a '# schema:' comment above the function)"))
+
+    @staticmethod
+    def _schema_from_comment(func: Callable) -> Optional[str]:
+        # fugue/_utils/interfaceless.py:9-73 (parse_comment_annotation)
+        try:
+            src = inspect.getsource(func)
+        except Exception:
+            return None
+        for line in src.splitlines():
+            m = re.match(r"^\s*#\s*schema\s*:\s*(.+)$", line)
+            if m:
+                return m.group(1).strip()
+            if line.strip().startswith("def "):
+                break
+        return None
+
+    @staticmethod
+    def _kind(tp: Any) -> Optional[str]:
+        if tp is inspect.Parameter.empty or tp is None:
+            return None
+        if tp is B200Table:
+            return "b200"
+        if tp is pd.DataFrame:
+            return "pandas"
+        if tp is pa.Table:
+            return "pyarrow"
+        if inspect.isclass(tp) and issubclass(tp, DataFrame):
+            return "fugue"
+        s = str(tp)
+        if "Dict" in s or "dict" in s:
+            return "dicts"
+        if "List" in s or "list" in s or "Iterable" in s:
+            return "array"
+        return None
+
+    def get_format_hint(self) -> Optional[str]:
+        return {"b200": "b200", "pandas": "pandas", "pyarrow": "pyarrow"}.get(self._in_kind)
+
+    def get_output_schema(self, df: DataFrame) -> Schema:
+        if isinstance(self._schema_expr, Schema):
+            return self._schema_expr
+        return df.schema.transform(self._schema_expr)
+
+    def _to_input(self, df: DataFrame) -> Any:
+        k = self._in_kind
+        if k == "b200":
+            assert_or_throw(isinstance(df, B200DataFrame), lambda: TypeError(
+                "a B200Table-typed function can only run on the b200 engine"))
+            return df.native
+        if k == "pandas":
+            return df.as_pandas()
+        if k == "pyarrow":
+            return df.as_arrow()
+        if k == "array":
+            return df.as_array(type_safe=True)
+        if k == "dicts":
+            return df.as_dicts()
+        return df
+
+    def _to_output(self, out: Any, schema: Schema) -> DataFrame:
+        if isinstance(out, B200Table):
+            return B200DataFrame(out)  # map_dataframe asserts the schema (native_execution_engine.py:149-153)
+        if isinstance(out, DataFrame):
+            return out
+        if isinstance(out, (pd.DataFrame, pa.Table)):
+            return ArrowDataFrame(out, schema)
+        if out is None:
+            return ArrowDataFrame(None, schema)
+        out = list(out)
+        if out and isinstance(out[0], dict):
+            out = [[r.get(n) for n in schema.names] for r in out]
+        return ArrayDataFrame(out, schema)
+
+    def make_runner(self, output_schema: Schema, ignore_errors: List[type]
+                    ) -> Callable[[PartitionCursor, DataFrame], DataFrame]:
+        def run(cursor: PartitionCursor, df: DataFrame) -> DataFrame:
+            kw = dict(self._params)
+            for n in self._wants_cursor:
+                kw[n] = cursor
+            try:
+                return self._to_output(self._func(self._to_input(df), **kw), output_schema)
+            except tuple(ignore_errors) if ignore_errors else ():  # processors.py:330-338
+                return ArrowDataFrame(None, output_schema)
+
+        return run
+
+
+def transform(
+    df: Any,
+    using: Any,
+    schema: Any = None,
+    params: Any = None,
+    partition: Any = None,
+    callback: Any = None,
+    ignore_errors: Optional[List[Any]] = None,
+    persist: bool = False,
+    as_local: bool = False,
+    save_path: Optional[str] = None,
+    checkpoint: bool = False,
+    engine: Any = None,
+    engine_conf: Any = None,
+    as_fugue: bool = False,
+) -> Any:
+    """``fa.transform`` (fugue/workflow/api.py:34-184) on the B200 engine.
+
+    ``using`` may be typed on ``B200Table`` (runs once per device table, vectorised over the
+    logical partitions - the GPU hot path), or on pandas / arrow / lists (called once per
+    logical partition on the host after the device partitioned the table).
+    """
+    assert_or_throw(callback is None, NotImplementedError("callback (RPC) is out of scope"))
+    assert_or_throw(save_path is None and not checkpoint,
+                    NotImplementedError("save_path / checkpoint are out of scope"))
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    tf = _FuncAsTransformer(using, schema, params)
+    spec = PartitionSpec(partition)
+    edf = e.to_df(df)
+    out_schema = tf.get_output_schema(edf)
+    runner = tf.make_runner(out_schema, list(ignore_errors or []))
+    res: DataFrame = e.map_engine.map_dataframe(edf, runner, out_schema, spec,
+                                                map_func_format_hint=tf.get_format_hint())
+    if persist:
+        res = e.persist(res)
+    res = e.convert_yield_dataframe(res, as_local)
+    if as_fugue or isinstance(df, DataFrame):
+        return res
+    return res.as_pandas() if res.is_local else res.native

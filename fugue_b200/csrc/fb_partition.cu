@@ -120,22 +120,26 @@ __device__ __forceinline__ unsigned match_lanes(uint32_t v, unsigned m) {
 // pass 1: per-chunk histogram. hist layout: [chunk][num]
 // shared: cnt[kWarps][num] warp-private counters (no atomics)
 // ---------------------------------------------------------------------------
+constexpr int kHistBlock = 1024;  // 2 CTAs/SM -> full occupancy (32 registers/thread)
+constexpr int kHistWarps = kHistBlock / 32;
+constexpr int kHistRows = kHistBlock * kItems;
+
 template <bool kSingleU64, int kBits>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kHistBlock, 2)
 fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist) {
   extern __shared__ uint32_t s_cnt[];
-  for (uint32_t i = threadIdx.x; i < (uint32_t)kWarps * num; i += kBlock) s_cnt[i] = 0;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kHistWarps * num; i += kHistBlock) s_cnt[i] = 0;
   __syncthreads();
   int64_t row0, row1;
   chunk_range(g, (int)blockIdx.x, row0, row1);
   const unsigned lt = fb_lanemask_lt();
   uint32_t* my = s_cnt + (size_t)(threadIdx.x >> 5) * num;
-  for (int64_t base = row0; base < row1; base += kTile) {
+  for (int64_t base = row0; base < row1; base += kHistRows) {
     uint32_t pid[kItems];
-    const bool full = base + kTile <= row1;
+    const bool full = base + kHistRows <= row1;
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
-      int64_t row = base + (int64_t)r * kBlock + threadIdx.x;
+      int64_t row = base + (int64_t)r * kHistBlock + threadIdx.x;
       pid[r] = (full || row < row1) ? compute_pid<kSingleU64>(keys, dv, row) : 0xFFFFFFFFu;
     }
 #pragma unroll
@@ -148,10 +152,10 @@ fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __res
   }
   __syncthreads();
   uint32_t* out = hist + (size_t)blockIdx.x * num;
-  for (uint32_t b = threadIdx.x; b < num; b += kBlock) {
+  for (uint32_t b = threadIdx.x; b < num; b += kHistBlock) {
     uint32_t t = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += s_cnt[(size_t)w * num + b];
+#pragma unroll 8
+    for (int w = 0; w < kHistWarps; ++w) t += s_cnt[(size_t)w * num + b];
     out[b] = t;
   }
 }
@@ -881,7 +885,7 @@ cudaError_t ensure_smem_optin(int dev) {
   std::lock_guard<std::mutex> lock(mu);
   if (dev >= 0 && dev < 64 && (done >> dev) & 1) return cudaSuccess;
   const size_t sc = scatter_smem_bytes(FB_MAX_PARTITIONS);
-  const size_t hs = (size_t)kWarps * FB_MAX_PARTITIONS * sizeof(uint32_t);
+  const size_t hs = (size_t)kHistWarps * FB_MAX_PARTITIONS * sizeof(uint32_t);
   cudaError_t e = cudaSuccess;
 #define FB_OPTIN(S, B)                                                   \
   do {                                                                   \
@@ -992,12 +996,12 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   FbDiv dv = fb_make_div(num_partitions);
   uint32_t* hist = (uint32_t*)scratch;
-  size_t smem = (size_t)kWarps * num_partitions * sizeof(uint32_t);
+  size_t smem = (size_t)kHistWarps * num_partitions * sizeof(uint32_t);
   FB_CUDA(ensure_smem_optin(dev));
   const bool single = single_u64_key(nkeys, key_widths, key_valid);
   const int bits = bits_for(num_partitions);
 #define FB_LAUNCH_HIST(S, B) \
-  fb_hist_kernel<S, B><<<g.nchunks, kBlock, smem, st>>>(k, dv, num_partitions, g, hist)
+  fb_hist_kernel<S, B><<<g.nchunks, kHistBlock, smem, st>>>(k, dv, num_partitions, g, hist)
   FB_DISPATCH_SB(single, bits, FB_LAUNCH_HIST);
 #undef FB_LAUNCH_HIST
   FB_CUDA(cudaGetLastError());

@@ -1,0 +1,362 @@
+"""Host-side DataFrame types mirroring the reference's interface.
+
+* ``DataFrame`` / ``LocalDataFrame``    fugue/dataframe/dataframe.py:29-299
+* ``ArrowDataFrame`` / ``PandasDataFrame`` / ``ArrayDataFrame``
+                                       fugue/dataframe/{arrow,pandas,array}_dataframe.py
+  (all three are thin constructors over one pyarrow-backed local frame here)
+* ``B200DataFrame``                    the engine's own frame: a ``B200Table`` in HBM,
+  ``is_local == False`` so ``transform()`` hands back the device table
+  (fugue/workflow/api.py:184) and ``as_local()`` is the explicit D2H.
+* ``df_eq``                            fugue/dataframe/utils.py:24-94 (_df_eq)
+"""
+from typing import Any, Dict, Iterable, List, Optional
+
+import pandas as pd
+import pyarrow as pa
+
+from .schema import Schema
+
+
+class FugueDataFrameOperationError(Exception):
+    pass
+
+
+class FugueDatasetEmptyError(Exception):
+    pass
+
+
+class DataFrame:
+    def __init__(self, schema: Any = None):
+        self._schema = schema if isinstance(schema, Schema) else Schema(schema)
+        self._metadata: Optional[Dict[str, Any]] = None
+
+    # ---- Dataset (fugue/dataset/dataset.py:14-110) -------------------------------------
+    @property
+    def metadata(self) -> Dict[str, Any]:
+        if self._metadata is None:
+            self._metadata = {}
+        return self._metadata
+
+    @property
+    def has_metadata(self) -> bool:
+        return self._metadata is not None and len(self._metadata) > 0
+
+    def reset_metadata(self, metadata: Any) -> None:
+        self._metadata = dict(metadata) if metadata is not None else None
+
+    @property
+    def schema(self) -> Schema:
+        return self._schema
+
+    @property
+    def columns(self) -> List[str]:
+        return self._schema.names
+
+    # ---- abstract ---------------------------------------------------------------------
+    @property
+    def native(self) -> Any:  # pragma: no cover
+        raise NotImplementedError
+
+    @property
+    def is_local(self) -> bool:  # pragma: no cover
+        raise NotImplementedError
+
+    @property
+    def is_bounded(self) -> bool:
+        return True
+
+    @property
+    def num_partitions(self) -> int:
+        return 1
+
+    @property
+    def empty(self) -> bool:
+        return self.count() == 0
+
+    def count(self) -> int:  # pragma: no cover
+        raise NotImplementedError
+
+    def as_arrow(self, type_safe: bool = False) -> pa.Table:  # pragma: no cover
+        raise NotImplementedError
+
+    # ---- derived ----------------------------------------------------------------------
+    def as_local(self) -> "LocalDataFrame":
+        return self.as_local_bounded()
+
+    def as_local_bounded(self) -> "LocalDataFrame":
+        res = ArrowDataFrame(self.as_arrow(), self.schema)
+        if self.has_metadata:
+            res.reset_metadata(self.metadata)
+        return res
+
+    def as_pandas(self) -> pd.DataFrame:
+        return self.as_arrow().to_pandas()
+
+    def as_array(self, columns: Optional[List[str]] = None, type_safe: bool = False) -> List[List[Any]]:
+        t = self.as_arrow()
+        if columns is not None:
+            t = t.select(columns)
+        cols = [c.to_pylist() for c in t.columns]
+        return [list(r) for r in zip(*cols)] if cols else []
+
+    def as_array_iterable(self, columns: Optional[List[str]] = None, type_safe: bool = False) -> Iterable[List[Any]]:
+        return iter(self.as_array(columns, type_safe))
+
+    def as_dicts(self, columns: Optional[List[str]] = None) -> List[Dict[str, Any]]:
+        names = columns or self.columns
+        return [dict(zip(names, r)) for r in self.as_array(columns)]
+
+    def peek_array(self) -> List[Any]:
+        if self.empty:
+            raise FugueDatasetEmptyError("dataframe is empty")
+        return self.head(1).as_array()[0]
+
+    def peek_dict(self) -> Dict[str, Any]:
+        return dict(zip(self.columns, self.peek_array()))
+
+    def head(self, n: int, columns: Optional[List[str]] = None) -> "LocalDataFrame":
+        t = self.as_arrow().slice(0, n)
+        if columns is not None:
+            t = t.select(columns)
+        return ArrowDataFrame(t)
+
+    def __getitem__(self, columns: List[Any]) -> "DataFrame":
+        for c in columns:
+            if c not in self._schema:
+                raise FugueDataFrameOperationError(f"{c} not in {self._schema}")
+        if len(columns) == 0:
+            raise FugueDataFrameOperationError("must select at least one column")
+        return self._select_cols(columns)
+
+    def drop(self, columns: List[str]) -> "DataFrame":
+        for c in columns:
+            if c not in self._schema:
+                raise FugueDataFrameOperationError(f"{c} not in {self._schema}")
+        if len(columns) >= len(self._schema):
+            raise FugueDataFrameOperationError("can't drop all columns")
+        return self._select_cols([c for c in self.columns if c not in set(columns)])
+
+    def _select_cols(self, columns: List[Any]) -> "DataFrame":  # pragma: no cover
+        raise NotImplementedError
+
+    def rename(self, columns: Dict[str, str]) -> "DataFrame":  # pragma: no cover
+        raise NotImplementedError
+
+    def __copy__(self) -> "DataFrame":
+        return self
+
+    def __deepcopy__(self, memo: Any) -> "DataFrame":
+        return self
+
+
+class LocalDataFrame(DataFrame):
+    @property
+    def is_local(self) -> bool:
+        return True
+
+    def as_local_bounded(self) -> "LocalDataFrame":
+        return self
+
+
+def _rows_to_arrow(rows: Any, schema: Schema) -> pa.Table:
+    rows = list(rows) if rows is not None else []
+    ncol = len(schema)
+    cols: List[List[Any]] = [[] for _ in range(ncol)]
+    for r in rows:
+        r = list(r)
+        assert len(r) == ncol, f"row {r} doesn't match schema {schema}"
+        for i in range(ncol):
+            cols[i].append(r[i])
+    arrays = []
+    for vals, tp in zip(cols, schema.types):
+        if pa.types.is_timestamp(tp) or pa.types.is_date(tp):
+            vals = [pd.Timestamp(v).to_pydatetime() if isinstance(v, str) else v for v in vals]
+            if pa.types.is_date(tp):
+                vals = [v.date() if hasattr(v, "date") and callable(v.date) and v is not None else v for v in vals]
+        if pa.types.is_floating(tp) or pa.types.is_integer(tp):
+            vals = [None if (isinstance(v, float) and v != v) else v for v in vals]
+        arrays.append(pa.array(vals, type=tp))
+    return pa.Table.from_arrays(arrays, schema=schema.pa_schema)
+
+
+class ArrowDataFrame(LocalDataFrame):
+    """pyarrow-backed local bounded frame (fugue/dataframe/arrow_dataframe.py:45-200)."""
+
+    def __init__(self, df: Any = None, schema: Any = None):
+        if df is None:
+            sch = Schema(schema)
+            self._native = _rows_to_arrow([], sch)
+        elif isinstance(df, pa.Table):
+            if schema is not None:
+                sch = Schema(schema)
+                if Schema(df.schema) != sch:
+                    df = df.select(sch.names).cast(sch.pa_schema) if set(sch.names) <= set(df.schema.names) \
+                        else df.rename_columns(sch.names).cast(sch.pa_schema)
+            else:
+                sch = Schema(df.schema)
+            self._native = df
+        elif isinstance(df, pd.DataFrame):
+            if schema is None:
+                t = pa.Table.from_pandas(df, preserve_index=False)
+                sch = Schema(t.schema)
+            else:
+                sch = Schema(schema)
+                t = pa.Table.from_pandas(df[sch.names], schema=sch.pa_schema, preserve_index=False, safe=False)
+            self._native = t
+        elif isinstance(df, DataFrame):
+            t = df.as_arrow()
+            sch = Schema(schema) if schema is not None else df.schema
+            self._native = t if Schema(t.schema) == sch else t.cast(sch.pa_schema)
+        elif isinstance(df, (list, tuple)) or hasattr(df, "__iter__"):
+            if schema is None:
+                raise FugueDataFrameOperationError("schema is required to build a dataframe from rows")
+            sch = Schema(schema)
+            self._native = _rows_to_arrow(df, sch)
+        else:
+            raise ValueError(f"{type(df)} is not supported")
+        super().__init__(sch)
+
+    @property
+    def native(self) -> pa.Table:
+        return self._native
+
+    def count(self) -> int:
+        return self._native.num_rows
+
+    def as_arrow(self, type_safe: bool = False) -> pa.Table:
+        return self._native
+
+    def _select_cols(self, columns: List[Any]) -> "DataFrame":
+        return ArrowDataFrame(self._native.select(columns))
+
+    def rename(self, columns: Dict[str, str]) -> "DataFrame":
+        try:
+            sch = self.schema.rename(columns)
+        except Exception as e:
+            raise FugueDataFrameOperationError(str(e)) from e
+        return ArrowDataFrame(self._native.rename_columns(sch.names))
+
+
+class PandasDataFrame(ArrowDataFrame):
+    """Constructor-compatible with fugue/dataframe/pandas_dataframe.py:38-95."""
+
+    def __init__(self, df: Any = None, schema: Any = None, pandas_df_wrapper: bool = False):
+        super().__init__(df, schema)
+
+
+class ArrayDataFrame(ArrowDataFrame):
+    """Constructor-compatible with fugue/dataframe/array_dataframe.py (rows + schema)."""
+
+    def __init__(self, df: Any = None, schema: Any = None):
+        super().__init__([] if df is None else df, schema)
+
+
+class B200DataFrame(DataFrame):
+    """A ``B200Table`` in HBM behind the reference's DataFrame interface."""
+
+    def __init__(self, table: Any, schema: Any = None):
+        from .table import B200Table
+
+        if isinstance(table, B200DataFrame):
+            table = table.native
+        if not isinstance(table, B200Table):
+            raise ValueError(f"B200DataFrame wraps a B200Table, got {type(table)}")
+        if schema is not None and Schema(schema) != table.schema:
+            sch = Schema(schema)
+            if sch.names != table.schema.names:
+                if len(sch) != len(table.schema):
+                    raise FugueDataFrameOperationError(f"{sch} doesn't match {table.schema}")
+                table = table.rename(dict(zip(table.schema.names, sch.names)))
+            if sch != table.schema:
+                raise FugueDataFrameOperationError(
+                    f"device table of {table.schema} can't be viewed as {sch}; cast on the host first")
+        self._table = table
+        super().__init__(table.schema)
+
+    @property
+    def native(self) -> Any:
+        return self._table
+
+    def native_as_df(self) -> Any:
+        return self._table
+
+    @property
+    def is_local(self) -> bool:
+        return False
+
+    @property
+    def num_partitions(self) -> int:
+        return self._table.num_partitions
+
+    def count(self) -> int:
+        return self._table.num_rows
+
+    @property
+    def empty(self) -> bool:
+        return self._table.num_rows == 0
+
+    def as_arrow(self, type_safe: bool = False) -> pa.Table:
+        return self._table.to_arrow()
+
+    def peek_array(self) -> List[Any]:
+        if self.empty:
+            raise FugueDatasetEmptyError("dataframe is empty")
+        return ArrowDataFrame(self._table.slice(0, 1).to_arrow()).as_array()[0]
+
+    def head(self, n: int, columns: Optional[List[str]] = None) -> LocalDataFrame:
+        t = self._table.slice(0, min(n, self._table.num_rows))
+        if columns is not None:
+            t = t.select(columns)
+        return ArrowDataFrame(t.to_arrow())
+
+    def _select_cols(self, columns: List[Any]) -> DataFrame:
+        return B200DataFrame(self._table.select(columns))
+
+    def rename(self, columns: Dict[str, str]) -> DataFrame:
+        try:
+            return B200DataFrame(self._table.rename(columns))
+        except Exception as e:
+            raise FugueDataFrameOperationError(str(e)) from e
+
+
+def as_fugue_df(df: Any, schema: Any = None) -> DataFrame:
+    """fugue/dataframe/api.py ``as_fugue_df`` for the types this package knows."""
+    from .table import B200Table
+
+    if isinstance(df, DataFrame):
+        return df
+    if isinstance(df, B200Table):
+        return B200DataFrame(df, schema)
+    if isinstance(df, (pa.Table, pd.DataFrame)):
+        return ArrowDataFrame(df, schema)
+    if isinstance(df, (list, tuple)) or hasattr(df, "__iter__"):
+        return ArrayDataFrame(df, schema)
+    raise ValueError(f"{type(df)} can't be converted to a Fugue DataFrame")
+
+
+def df_eq(df: Any, data: Any, schema: Any = None, digits: int = 8, check_order: bool = False,
+          check_schema: bool = True, check_content: bool = True, throw: bool = False) -> bool:
+    """Order-insensitive multiset equality with abs tol 10**-digits
+    (fugue/dataframe/utils.py:24-94)."""
+    df1 = as_fugue_df(df).as_local_bounded()
+    df2 = as_fugue_df(data, schema).as_local_bounded()
+    try:
+        assert df1.count() == df2.count(), f"count mismatch {df1.count()}, {df2.count()}"
+        assert not check_schema or df1.schema == df2.schema, \
+            f"schema mismatch {df1.schema}, {df2.schema}"
+        if not check_content:
+            return True
+        d1, d2 = df1.as_pandas(), df2.as_pandas()
+        d2.columns = d1.columns
+        if not check_order:
+            d1 = d1.sort_values(list(d1.columns))
+            d2 = d2.sort_values(list(d2.columns))
+        d1 = d1.reset_index(drop=True)
+        d2 = d2.reset_index(drop=True)
+        pd.testing.assert_frame_equal(d1, d2, rtol=0, atol=10 ** (-digits), check_dtype=False,
+                                      check_exact=False)
+        return True
+    except AssertionError:
+        if throw:
+            raise
+        return False

@@ -1,0 +1,288 @@
+"""``B200ExecutionEngine`` / ``B200MapEngine``: the drop-in boundary of the hot path.
+
+Mirrors the reference ABCs (names, argument meaning, error behaviour):
+  * ``MapEngine.map_dataframe``      fugue/execution/execution_engine.py:283-315
+      native implementation          fugue/execution/native_execution_engine.py:81-169
+  * ``ExecutionEngine``              fugue/execution/execution_engine.py:338-1241
+      to_df :93-114, repartition :488-502, persist :513-537, broadcast :504-511,
+      join :539-561, aggregate :889-939, convert_yield_dataframe :941-960
+The arithmetic runs in ``libfugue_b200.so`` through ``fugue_b200.kernels``; there is
+no CPU implementation of the partition/join/aggregate steps in this package.
+"""
+import logging
+from typing import Any, Callable, Dict, List, Optional
+
+import pandas as pd
+import pyarrow as pa
+import torch
+
+from . import kernels as K
+from .dataframe import (ArrowDataFrame, B200DataFrame, DataFrame, LocalDataFrame, PandasDataFrame,
+                        as_fugue_df)
+from .partition import KEYWORD_PARALLELISM, KEYWORD_ROWCOUNT, PartitionCursor, PartitionSpec
+from .schema import Schema
+from .table import B200Table
+
+FUGUE_B200_CONF_DEVICE = "fugue.b200.device"
+FUGUE_B200_CONF_DEFAULT_PARTITIONS = "fugue.b200.default.partitions"
+FUGUE_B200_DEFAULT_PARTITIONS = 256
+
+
+def assert_or_throw(cond: bool, exc: Any) -> None:
+    if not cond:
+        e = exc() if callable(exc) and not isinstance(exc, type) else exc
+        if isinstance(e, str):
+            raise AssertionError(e)
+        raise e
+
+
+class _ScratchPool:
+    """Reusable scratch / offsets buffers so no device allocation happens in steady state."""
+
+    def __init__(self) -> None:
+        self._scratch: Dict[Any, torch.Tensor] = {}
+
+    def scratch(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        cur = self._scratch.get(device)
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self._scratch[device] = cur
+        return cur
+
+
+class B200MapEngine:
+    """fugue/execution/execution_engine.py:277-335 (MapEngine facet)."""
+
+    def __init__(self, execution_engine: "B200ExecutionEngine"):
+        assert_or_throw(isinstance(execution_engine, B200ExecutionEngine),
+                        lambda: TypeError(f"{self} expects a B200ExecutionEngine"))
+        self._execution_engine = execution_engine
+
+    @property
+    def execution_engine(self) -> "B200ExecutionEngine":
+        return self._execution_engine
+
+    @property
+    def execution_engine_constraint(self):
+        return B200ExecutionEngine
+
+    @property
+    def is_distributed(self) -> bool:
+        return self._execution_engine.is_distributed
+
+    @property
+    def log(self) -> logging.Logger:
+        return self._execution_engine.log
+
+    @property
+    def conf(self) -> Dict[str, Any]:
+        return self._execution_engine.conf
+
+    def to_df(self, df: Any, schema: Any = None) -> DataFrame:
+        return self._execution_engine.to_df(df, schema)
+
+    def map_dataframe(
+        self,
+        df: DataFrame,
+        map_func: Callable[[PartitionCursor, LocalDataFrame], LocalDataFrame],
+        output_schema: Any,
+        partition_spec: PartitionSpec,
+        on_init: Optional[Callable[[int, DataFrame], Any]] = None,
+        map_func_format_hint: Optional[str] = None,
+    ) -> DataFrame:
+        engine = self._execution_engine
+        output_schema = Schema(output_schema)
+        is_coarse = partition_spec.algo == "coarse"
+        presort = partition_spec.get_sorts(df.schema, with_partition_keys=is_coarse)
+        cursor = partition_spec.get_cursor(df.schema, 0)
+        edf = engine.to_df(df)
+        if on_init is not None:
+            on_init(0, edf)
+        keyed = len(partition_spec.partition_by) > 0 and not is_coarse
+        if keyed:
+            edf = engine.repartition(edf, partition_spec)  # K1+K2+K3 on the device
+        if map_func_format_hint == "b200":
+            # device-vectorised map: the function is typed on B200Table and is called once per
+            # device table, the physical partitions delimited by table.offsets
+            assert_or_throw(len(presort) == 0, NotImplementedError(
+                "presort with a B200Table-typed function needs the segmented device sort"))
+            cursor.set(lambda: edf.peek_array(), 0, 0)
+            out = map_func(cursor, edf)
+            res = engine.to_df(out)
+            assert_or_throw(res.schema == output_schema,
+                            lambda: f"map output {res.schema} mismatches given {output_schema}")
+            return res
+        return self._map_on_host(edf, map_func, output_schema, partition_spec, cursor, presort, keyed)
+
+    # Python callbacks typed on pandas/arrow/lists run per logical partition on the host, exactly
+    # as native_execution_engine.py:104-169 does; the device did the physical partitioning.
+    def _map_on_host(self, edf: B200DataFrame, map_func: Any, output_schema: Schema,
+                     spec: PartitionSpec, cursor: PartitionCursor, presort: Any, keyed: bool) -> DataFrame:
+        engine = self._execution_engine
+        presort_keys = list(presort.keys())
+        presort_asc = list(presort.values())
+        pdf = edf.as_pandas()
+        outs: List[pd.DataFrame] = []
+
+        def run(sub: pd.DataFrame, partition_no: int) -> None:
+            if presort_keys:
+                sub = sub.sort_values(presort_keys, ascending=presort_asc)
+            sub = sub.reset_index(drop=True)
+            input_df = PandasDataFrame(sub, edf.schema)
+            cursor.set(lambda: input_df.peek_array(), partition_no, 0)
+            out = map_func(cursor, input_df)
+            outs.append(as_fugue_df(out).as_pandas())
+
+        if not keyed:
+            if len(spec.partition_by) == 0 and spec.num_partitions != "0":
+                import numpy as np
+
+                n = spec.get_num_partitions(**{KEYWORD_ROWCOUNT: lambda: len(pdf),
+                                               KEYWORD_PARALLELISM: lambda: 1})
+                if presort_keys:
+                    pdf = pdf.sort_values(presort_keys, ascending=presort_asc).reset_index(drop=True)
+                    presort_keys = []
+                for p, sub in enumerate(np.array_split(pdf, n)):
+                    if len(sub) > 0:
+                        run(sub, p)
+            else:
+                run(pdf, 0)
+        elif len(pdf) > 0:
+            offsets = edf.native.offsets.cpu().tolist()
+            no = 0
+            for p in range(len(offsets) - 1):
+                if offsets[p + 1] == offsets[p]:
+                    continue
+                part = pdf.iloc[offsets[p]:offsets[p + 1]]
+                for _, sub in part.groupby(spec.partition_by, dropna=False, sort=True):
+                    no += 1
+                    run(sub, no)
+        if not outs:
+            return engine.to_df(ArrowDataFrame(None, output_schema))
+        res = pd.concat(outs, ignore_index=True)
+        return engine.to_df(PandasDataFrame(res, output_schema))
+
+
+class B200ExecutionEngine:
+    """The engine object ``fa.engine_context`` / ``fa.transform(engine=...)`` see."""
+
+    def __init__(self, conf: Any = None, **kwargs: Any):
+        self._conf: Dict[str, Any] = dict(conf or {})
+        self._conf.update(kwargs)
+        self._log = logging.getLogger("fugue_b200")
+        if not torch.cuda.is_available():
+            from ._lib import FugueB200KernelError
+
+            raise FugueB200KernelError(
+                "B200ExecutionEngine needs a CUDA device: this engine has no CPU fallback")
+        from . import _lib
+
+        _lib.load()  # fail loudly here if the CUDA library is missing
+        self._device = torch.device("cuda", int(self._conf.get(FUGUE_B200_CONF_DEVICE,
+                                                               torch.cuda.current_device())))
+        self._map_engine = B200MapEngine(self)
+        self._pool = _ScratchPool()
+
+    def __repr__(self) -> str:
+        return f"B200ExecutionEngine({self._device})"
+
+    # ---- facets / properties ----------------------------------------------------------
+    @property
+    def conf(self) -> Dict[str, Any]:
+        return self._conf
+
+    @property
+    def log(self) -> logging.Logger:
+        return self._log
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @property
+    def is_distributed(self) -> bool:
+        return False
+
+    @property
+    def map_engine(self) -> B200MapEngine:
+        return self._map_engine
+
+    def create_default_map_engine(self) -> B200MapEngine:
+        return B200MapEngine(self)
+
+    def get_current_parallelism(self) -> int:
+        return 1
+
+    def stop(self) -> None:
+        self._pool = _ScratchPool()
+
+    # ---- ingest -----------------------------------------------------------------------
+    def to_df(self, df: Any, schema: Any = None) -> B200DataFrame:
+        """Any dataframe-like -> engine dataframe; returns the input itself if it already is one
+        (execution_engine.py:107-112)."""
+        if isinstance(df, B200DataFrame):
+            assert_or_throw(schema is None or Schema(schema) == df.schema,
+                            lambda: ValueError(f"schema {schema} doesn't match {df.schema}"))
+            return df
+        if isinstance(df, B200Table):
+            return B200DataFrame(df, schema)
+        if isinstance(df, DataFrame):
+            res = B200DataFrame(B200Table.from_arrow(df.as_arrow(), self._device,
+                                                     Schema(schema) if schema is not None else df.schema))
+            if df.has_metadata:
+                res.reset_metadata(df.metadata)
+            return res
+        local = as_fugue_df(df, schema)
+        return B200DataFrame(B200Table.from_arrow(local.as_arrow(), self._device, local.schema))
+
+    def persist(self, df: Any, lazy: bool = False, **kwargs: Any) -> B200DataFrame:
+        return self.to_df(df)  # already materialised in HBM
+
+    def broadcast(self, df: Any) -> B200DataFrame:
+        return self.to_df(df)
+
+    def convert_yield_dataframe(self, df: DataFrame, as_local: bool) -> DataFrame:
+        return df.as_local() if as_local else df
+
+    # ---- repartition (K1+K2+K3) ---------------------------------------------------------
+    def _num_partitions(self, spec: PartitionSpec, nrows: int) -> int:
+        n = spec.get_num_partitions(**{KEYWORD_ROWCOUNT: lambda: nrows,
+                                       KEYWORD_PARALLELISM: lambda: self.get_current_parallelism()})
+        if n <= 0:
+            n = int(self._conf.get(FUGUE_B200_CONF_DEFAULT_PARTITIONS, FUGUE_B200_DEFAULT_PARTITIONS))
+        return n
+
+    def repartition(self, df: Any, partition_spec: PartitionSpec) -> B200DataFrame:
+        """Physical repartition.  With keys every algo co-locates equal keys by hashing them
+        (``hash_pandas_object(df[keys]) % num``, fugue_dask/_utils.py:146-169); without keys the
+        single-device table already is one physical partition."""
+        edf = self.to_df(df)
+        keys = partition_spec.partition_by
+        if len(keys) == 0:
+            return edf
+        t: B200Table = edf.native
+        for k in keys:
+            assert_or_throw(k in t.schema, lambda: KeyError(f"{k} not in {t.schema}"))
+        num = self._num_partitions(partition_spec, t.num_rows)
+        assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
+            f"num_partitions={num}: one radix pass handles up to {K.MAX_PARTITIONS} partitions"))
+        if t.offsets is not None and t.partition_keys == keys and t.num_partitions == num:
+            return edf  # already partitioned this way
+        kidx = [t.schema.index_of_key(k) for k in keys]
+        kvalid = [t.valid[i] for i in kidx]
+        # validity masks travel as extra 1-byte columns
+        cols = list(t.columns)
+        vpos: Dict[int, int] = {}
+        for i, v in enumerate(t.valid):
+            if v is not None:
+                vpos[i] = len(cols)
+                cols.append(v)
+        scratch = self._pool.scratch(t.device, K.partition_scratch_bytes(t.device, t.num_rows, num))
+        out, offsets = K.partition_columns(cols, kidx, num, kvalid, scratch=scratch)
+        ncol = len(t.columns)
+        valid = [out[vpos[i]] if i in vpos else None for i in range(ncol)]
+        res = B200Table(t.schema, out[:ncol], valid, t.dictionaries, offsets, list(keys))
+        rdf = B200DataFrame(res)
+        if edf.has_metadata:
+            rdf.reset_metadata(edf.metadata)
+        return rdf

@@ -1,0 +1,195 @@
+"""The B200 engine behind the reference's interface: cases follow
+fugue_test/execution_suite.py (test_map :208-256, test_map_with_special_values :258-314) and
+fugue_test/builtin_suite.py (test_transform_by :516-545), README.md:31-67 (config 1)."""
+from typing import Any, Dict, List
+
+import numpy as np
+import pandas as pd
+import pyarrow as pa
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from fugue_b200 import api as fa
+from fugue_b200.dataframe import ArrayDataFrame, B200DataFrame, PandasDataFrame, df_eq
+from fugue_b200.execution_engine import B200ExecutionEngine
+from fugue_b200.partition import PartitionSpec
+from fugue_b200.table import B200Table
+from oracle import native_engine as ora
+
+
+@pytest.fixture(scope="module")
+def engine():
+    return fa.make_execution_engine("b200")
+
+
+def select_top(cursor, data):
+    return ArrayDataFrame([cursor.row], cursor.row_schema)
+
+
+def test_to_df_roundtrip(engine):
+    o = ArrayDataFrame([[1.1, 2, "x", True], [None, None, None, None], [3.3, 4, "y", False]],
+                       "a:double,b:int,c:str,d:bool")
+    a = fa.as_fugue_engine_df(engine, o)
+    assert isinstance(a, B200DataFrame) and not a.is_local and a.count() == 3
+    assert engine.to_df(a) is a
+    df_eq(a, o, throw=True)
+    assert a.peek_array() == [1.1, 2, "x", True]
+    df_eq(a[["c", "a"]], [["x", 1.1], [None, None], ["y", 3.3]], "c:str,a:double", throw=True)
+    df_eq(a.rename({"a": "aa"}), o.as_array(), "aa:double,b:int,c:str,d:bool", throw=True)
+    e = fa.as_fugue_engine_df(engine, [], "a:int,b:str")
+    assert e.empty and e.count() == 0
+    df_eq(e, [], "a:int,b:str", throw=True)
+    p = engine.to_df(pd.DataFrame({"x": np.arange(5), "y": np.arange(5) * 0.5}))
+    assert p.schema == "x:long,y:double" and p.as_array()[4] == [4, 2.0]
+
+
+def test_map(engine):
+    def noop(cursor, data):
+        return data
+
+    def on_init(partition_no, data):
+        assert partition_no >= 0
+        data.peek_array()
+
+    e = engine
+    o = ArrayDataFrame([[1, 2], [None, 2], [None, 1], [3, 4], [None, 4]], "a:double,b:int")
+    a = fa.as_fugue_engine_df(e, o)
+    c = e.map_engine.map_dataframe(a, noop, a.schema, PartitionSpec())
+    df_eq(c, o, throw=True)
+    c = e.map_engine.map_dataframe(a, noop, a.schema, PartitionSpec(by=["a"], presort="b"))
+    df_eq(c, o, throw=True)
+    c = e.map_engine.map_dataframe(a, select_top, a.schema, PartitionSpec(by=["a"], presort="b"))
+    df_eq(c, [[None, 1], [1, 2], [3, 4]], "a:double,b:int", throw=True)
+    c = e.map_engine.map_dataframe(a, select_top, a.schema,
+                                   PartitionSpec(partition_by=["a"], presort="b DESC"))
+    df_eq(c, [[None, 4], [1, 2], [3, 4]], "a:double,b:int", throw=True)
+    c = e.map_engine.map_dataframe(a, select_top, a.schema,
+                                   PartitionSpec(partition_by=["a"], presort="b DESC", num_partitions=3),
+                                   on_init=on_init)
+    df_eq(c, [[None, 4], [1, 2], [3, 4]], "a:double,b:int", throw=True)
+
+
+def test_map_with_special_values(engine):
+    e = engine
+    o = ArrayDataFrame([[1, None, 1], [1, None, 0], [None, None, 2]], "a:double,b:double,c:int")
+    c = e.map_engine.map_dataframe(o, select_top, o.schema, PartitionSpec(by=["a", "b"], presort="c"))
+    df_eq(c, [[1, None, 0], [None, None, 2]], "a:double,b:double,c:int", throw=True)
+    from datetime import datetime
+
+    dt = datetime(2024, 5, 6, 7, 8, 9)
+    o = ArrayDataFrame([[dt, 2, 1], [None, 2, None], [None, 1, None], [dt, 5, 1], [None, 4, None]],
+                       "a:datetime,b:int,c:double")
+    c = e.map_engine.map_dataframe(o, select_top, o.schema,
+                                   PartitionSpec(by=["a", "c"], presort="b DESC"))
+    df_eq(c, [[None, 4, None], [dt, 5, 1]], "a:datetime,b:int,c:double", throw=True)
+
+
+def test_map_schema_mismatch_raises(engine):
+    def bad(t: B200Table) -> B200Table:
+        return t.select(["a"])
+
+    with pytest.raises(AssertionError):
+        fa.transform(ArrayDataFrame([[1, 2]], "a:long,b:long"), bad, schema="*", engine=engine)
+
+
+def test_transform_readme_example(engine):
+    # BASELINE config 1 / README.md:31-67: plumbing check on the engine
+    input_df = pd.DataFrame({"id": [0, 1, 2], "value": ["A", "B", "C"]})
+    map_dict = {"A": "Apple", "B": "Banana", "C": "Carrot"}
+
+    def map_letter_to_food(df: pd.DataFrame, mapping: Dict[str, str]) -> pd.DataFrame:
+        df["value"] = df["value"].map(mapping)
+        return df
+
+    res = fa.transform(input_df, map_letter_to_food, schema="*", params=dict(mapping=map_dict),
+                       engine=engine, as_local=True)
+    assert isinstance(res, pd.DataFrame)
+    assert res.sort_values("id").values.tolist() == [[0, "Apple"], [1, "Banana"], [2, "Carrot"]]
+
+
+def test_transform_by_keys_host_callbacks(engine):
+    # builtin_suite.py:516-545: per logical partition callbacks, counts per key
+    def count_rows(df: List[List[Any]]) -> List[List[Any]]:
+        return [[df[0][0], len(df)]]
+
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 37, 1000)
+    pdf = pd.DataFrame({"k": keys, "v": rng.standard_normal(1000)})
+    res = fa.transform(pdf, count_rows, schema="k:long,ct:long", partition=dict(by=["k"], num=16),
+                       engine=engine, as_local=True)
+    exp = pdf.groupby("k").size().reset_index(name="ct")
+    assert sorted(res.values.tolist()) == sorted(exp.values.tolist())
+
+    # same thing typed on pandas with presort: first row per key after sorting by v descending
+    def top(df: pd.DataFrame) -> pd.DataFrame:
+        return df.head(1)
+
+    res = fa.transform(pdf, top, schema="*", partition=dict(by=["k"], presort="v desc"), engine=engine,
+                       as_local=True)
+    exp = ora.map_dataframe(pdf, lambda c, d: d.head(1), ["k", "v"], ["k"], {"v": False})
+    assert df_eq(PandasDataFrame(res, "k:long,v:double"), exp.values.tolist(), "k:long,v:double", throw=True)
+
+
+def test_transform_identity_device_function_matches_native_oracle(engine):
+    """The hot path: hash PartitionSpec + identity map typed on the device table."""
+    def identity(t: B200Table) -> B200Table:
+        return t
+
+    rng = np.random.default_rng(1)
+    n = 200_000
+    pdf = pd.DataFrame({"key": rng.integers(0, 1 << 16, n), "i1": rng.integers(-2**62, 2**62, n),
+                        "v0": rng.standard_normal(n), "v1": rng.standard_normal(n)})
+    spec = PartitionSpec(by="key", algo="hash", num=256)
+    dev = fa.transform(pdf, identity, schema="*", partition=spec, engine=engine)
+    assert isinstance(dev, B200Table) and dev.num_partitions == 256 and dev.partition_keys == ["key"]
+    got = dev.to_pandas()
+    # reference semantics (NativeExecutionEngine restated): same multiset of rows
+    exp = ora.map_dataframe(pdf.iloc[:20000], lambda c, d: d, list(pdf.columns), ["key"])
+    assert len(exp) == 20000
+    s_got = got.sort_values(list(got.columns)).reset_index(drop=True)
+    s_all = pdf.sort_values(list(pdf.columns)).reset_index(drop=True)
+    pd.testing.assert_frame_equal(s_got, s_all, check_exact=True)
+    # physical layout: rows of partition p are exactly the rows whose key hashes to p, input order kept
+    pid = pd.util.hash_pandas_object(pdf[["key"]], index=False).mod(256).to_numpy()
+    order = np.argsort(pid, kind="stable")
+    pd.testing.assert_frame_equal(got, pdf.iloc[order].reset_index(drop=True), check_exact=True)
+    off = dev.offsets.cpu().numpy()
+    assert np.array_equal(np.diff(off), np.bincount(pid, minlength=256))
+
+
+def test_transform_device_function_elementwise(engine):
+    def scale(t: B200Table, factor: float) -> B200Table:
+        cols = list(t.columns)
+        cols[t.schema.index_of_key("v")] = t.column("v") * factor
+        return t.with_columns(t.schema, cols, t.valid)
+
+    pdf = pd.DataFrame({"k": [1, 2, 1, 3], "v": [1.0, 2.0, 3.0, 4.0]})
+    res = fa.transform(pdf, scale, schema="*", params=dict(factor=2.0), partition=dict(by="k", num=4),
+                       engine=engine, as_local=True)
+    assert sorted(res.values.tolist()) == [[1, 2.0], [1, 6.0], [2, 4.0], [3, 8.0]]
+
+
+def test_repartition_is_idempotent_and_keeps_nulls(engine):
+    o = ArrayDataFrame([[1, "a"], [None, "b"], [2, None], [None, "d"], [1, "e"]], "k:long,s:str")
+    spec = PartitionSpec(by=["k"], num=8)
+    r1 = engine.repartition(o, spec)
+    r2 = engine.repartition(r1, spec)
+    assert r2 is r1
+    df_eq(r1, o, throw=True)
+    t = r1.native
+    off = t.offsets.cpu().tolist()
+    keys = t.to_pandas()["k"]
+    # all NULL keys are in one physical partition
+    parts = [set(np.where(keys.isna().to_numpy())[0])]
+    nullpos = sorted(parts[0])
+    assert len({next(p for p in range(8) if off[p] <= i < off[p + 1]) for i in nullpos}) == 1
+
+
+def test_engine_context_and_missing_gpu_path():
+    with fa.engine_context("b200") as e:
+        assert fa.get_context_engine() is e
+        assert isinstance(e, B200ExecutionEngine) and e.get_current_parallelism() == 1
+    with pytest.raises(ValueError):
+        fa.make_execution_engine("spark")
