@@ -132,32 +132,47 @@ class B200Table:
         valids: List[Optional[torch.Tensor]] = []
         dicts: Dict[str, pa.Array] = {}
         for name, tp in zip(sch.names, sch.types):
-            arr = table.column(name)
-            arr = arr.combine_chunks() if isinstance(arr, pa.ChunkedArray) else arr
-            if isinstance(arr, pa.ChunkedArray):  # zero chunks
-                arr = pa.array([], type=arr.type)
-            if arr.type != tp and not pa.types.is_dictionary(arr.type):
-                arr = arr.cast(tp)
-            if pa.types.is_string(tp) or pa.types.is_large_string(tp):
-                enc = arr if pa.types.is_dictionary(arr.type) else arr.dictionary_encode()
-                dicts[name] = enc.dictionary
-                arr = enc.indices.cast(pa.int32())
-            elif pa.types.is_boolean(tp):
-                arr = pc.cast(arr, pa.uint8())
-            n = len(arr)
+            col = table.column(name)
+            chunks = list(col.chunks) if isinstance(col, pa.ChunkedArray) else [col]
+            is_str = pa.types.is_string(tp) or pa.types.is_large_string(tp)
+            if is_str or len(chunks) == 0:
+                # dictionary encoding needs one dictionary: combine on the host (ingest, not hot path)
+                arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) and len(chunks) > 0 \
+                    else (chunks[0] if chunks else pa.array([], type=tp))
+                if isinstance(arr, pa.ChunkedArray):
+                    arr = pa.array([], type=tp)
+                chunks = [arr]
+            prepared = []
+            for arr in chunks:  # no host-side concatenation: every chunk is copied to its slice
+                if arr.type != tp and not pa.types.is_dictionary(arr.type):
+                    arr = arr.cast(tp)
+                if is_str:
+                    enc = arr if pa.types.is_dictionary(arr.type) else arr.dictionary_encode()
+                    dicts[name] = enc.dictionary
+                    arr = enc.indices.cast(pa.int32())
+                elif pa.types.is_boolean(tp):
+                    arr = pc.cast(arr, pa.uint8())
+                prepared.append(arr)
+            n = sum(len(a) for a in prepared)
             st = _np_storage(tp)
-            bufs = arr.buffers()
-            if n == 0:
-                host = np.empty(0, dtype=st)
-            else:
-                host = np.frombuffer(bufs[1], dtype=st, count=n + arr.offset)[arr.offset:]
-            cols.append(_from_readonly(host).to(device, non_blocking=True))
-            if arr.null_count > 0 and bufs[0] is not None:
-                bits = np.frombuffer(bufs[0], dtype=np.uint8)
-                dbits = _from_readonly(bits).to(device, non_blocking=True)
-                valids.append(K.bits_to_bytes(dbits, arr.offset, n))
-            else:
-                valids.append(None)
+            dcol = torch.empty(n, dtype=_storage_dtype(tp), device=device)
+            has_nulls = any(a.null_count > 0 for a in prepared)
+            dvalid = torch.ones(n, dtype=torch.uint8, device=device) if has_nulls else None
+            pos = 0
+            for arr in prepared:
+                m = len(arr)
+                if m == 0:
+                    continue
+                bufs = arr.buffers()
+                host = np.frombuffer(bufs[1], dtype=st, count=m + arr.offset)[arr.offset:]
+                dcol[pos:pos + m].copy_(_from_readonly(host), non_blocking=True)
+                if arr.null_count > 0 and bufs[0] is not None:
+                    bits = np.frombuffer(bufs[0], dtype=np.uint8)
+                    dbits = _from_readonly(bits).to(device, non_blocking=True)
+                    dvalid[pos:pos + m].copy_(K.bits_to_bytes(dbits, arr.offset, m))
+                pos += m
+            cols.append(dcol)
+            valids.append(dvalid)
         return B200Table(sch, cols, valids, dicts)
 
     def to_arrow(self) -> pa.Table:
