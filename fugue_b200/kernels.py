@@ -156,3 +156,21 @@ def bytes_to_bits(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     _lib.check(lib.fb_bytes_to_bits(mask.device.index, _stream_ptr(mask.device), mask.data_ptr(), n,
                                     out.data_ptr(), nulls.data_ptr()))
     return out, nulls
+
+
+def copy_segments(src_cols: Sequence[torch.Tensor], dst_cols: Sequence[torch.Tensor],
+                  src_off: torch.Tensor, dst_off: torch.Tensor, seg_len: torch.Tensor) -> None:
+    """For every column: dst[dst_off[s]:+len[s]] = src[src_off[s]:+len[s]] (all tables on device)."""
+    lib = _lib.load()
+    dev = src_cols[0].device
+    nseg = int(seg_len.shape[0])
+    if nseg == 0 or len(src_cols) == 0:
+        return
+    ptr_src = torch.tensor([c.data_ptr() for c in src_cols], dtype=torch.int64, device=dev)
+    ptr_dst = torch.tensor([c.data_ptr() for c in dst_cols], dtype=torch.int64, device=dev)
+    widths = torch.tensor([c.element_size() for c in src_cols], dtype=torch.int32, device=dev)
+    for t in (src_off, dst_off, seg_len):
+        assert t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
+    _lib.check(lib.fb_copy_segments(dev.index, _stream_ptr(dev), len(src_cols), ptr_src.data_ptr(),
+                                    ptr_dst.data_ptr(), widths.data_ptr(), nseg, src_off.data_ptr(),
+                                    dst_off.data_ptr(), seg_len.data_ptr()))

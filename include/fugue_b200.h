@@ -105,6 +105,17 @@ int fb_bits_to_bytes(int dev, void* stream, const uint8_t* bits, int64_t bit_off
 int fb_bytes_to_bits(int dev, void* stream, const uint8_t* bytes, int64_t nrows,
                      uint8_t* out_bits, int64_t* out_null_count);
 
+/* ---------------------------------------------------------------------------
+ * Segment copy (multi-GPU exchange epilogue): for every column,
+ * out[dst_off[s] .. +len[s]) = in[src_off[s] .. +len[s]).  ALL pointer arguments
+ * (pointer tables, widths, offset tables) are DEVICE memory.  No reference
+ * counterpart: the reference delegates shuffles to Dask/Spark/Ray
+ * (fugue_dask/_utils.py:124-130).
+ * --------------------------------------------------------------------------- */
+int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_cols,
+                     void* const* d_dst_cols, const int32_t* d_widths, int nseg,
+                     const int64_t* d_src_off, const int64_t* d_dst_off, const int64_t* d_len);
+
 #ifdef __cplusplus
 }
 #endif

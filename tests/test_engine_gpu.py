@@ -193,3 +193,18 @@ def test_engine_context_and_missing_gpu_path():
         assert isinstance(e, B200ExecutionEngine) and e.get_current_parallelism() == 1
     with pytest.raises(ValueError):
         fa.make_execution_engine("spark")
+
+
+def test_multi_gpu_repartition_if_two_gpus_visible():
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "dist_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
