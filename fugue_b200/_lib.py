@@ -44,6 +44,10 @@ SIGNATURES = {
                                     C.c_int, _vpp, C.c_uint32, _vpp, _vp, _vp, C.c_size_t]),
     "fb_bits_to_bytes": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "fb_bytes_to_bits": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp, _vp]),
+    "fb_groupby_table_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "fb_groupby_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int, _vpp, _vpp, _i32p, C.c_int64,
+                                 _vp, _vp]),
+    "fb_groupby_extract": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _i32p, _vp, _vp, _vp, _vp, _vp]),
     "fb_copy_segments": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
 }
 

@@ -256,3 +256,23 @@ def transform(
     if as_fugue or isinstance(df, DataFrame):
         return res
     return res.as_pandas() if res.is_local else res.native
+
+
+def aggregate(df: Any, partition_by: Any = None, engine: Any = None, engine_conf: Any = None,
+              as_fugue: bool = False, as_local: bool = False, **agg_kwcols: Any) -> Any:
+    """``fa.aggregate`` (fugue/execution/api.py:1175-1232):
+    ``aggregate(df, "key", s=f.sum(col("v0")), c=f.count(all_cols()))``."""
+    from .column import AggFuncExpr
+
+    assert_or_throw(len(agg_kwcols) > 0, ValueError("at least one aggregation is required"))
+    cols = []
+    for k, v in agg_kwcols.items():
+        assert_or_throw(isinstance(v, AggFuncExpr), lambda: ValueError(f"{k}={v!r} is not an aggregation"))
+        cols.append(v.alias(k))
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    spec = None if partition_by is None else PartitionSpec(by=partition_by)
+    res: DataFrame = e.aggregate(e.to_df(df), spec, cols)
+    res = e.convert_yield_dataframe(res, as_local)
+    if as_fugue or isinstance(df, DataFrame):
+        return res
+    return res.as_pandas() if res.is_local else res.native

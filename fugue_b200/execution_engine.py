@@ -286,3 +286,118 @@ class B200ExecutionEngine:
         if edf.has_metadata:
             rdf.reset_metadata(edf.metadata)
         return rdf
+
+    # ---- aggregate (K6) -----------------------------------------------------------------
+    def aggregate(self, df: Any, partition_spec: Optional[PartitionSpec], agg_cols: List[Any]) -> B200DataFrame:
+        """``ExecutionEngine.aggregate`` (execution_engine.py:889-939): ``partition_spec.partition_by``
+        are the GROUP BY keys, ``agg_cols`` aggregation expressions with names
+        (fugue_b200.column.functions).  Runs the sm_100a hash group-by kernel."""
+        import pyarrow as pa
+
+        from .column import AggFuncExpr
+
+        assert_or_throw(len(agg_cols) > 0, ValueError("agg_cols can't be empty"))
+        for a in agg_cols:
+            assert_or_throw(isinstance(a, AggFuncExpr), lambda: ValueError(f"{a} is not an aggregation"))
+            assert_or_throw(a.output_name != "", lambda: ValueError(f"{a} must have an alias"))
+        edf = self.to_df(df)
+        t: B200Table = edf.native
+        keys = [] if partition_spec is None else list(partition_spec.partition_by)
+        n = t.num_rows
+        dev = t.device
+        # ---- the 8-byte group key
+        assert_or_throw(len(keys) <= 1, NotImplementedError(
+            "group-by on more than one key column: pack the keys into one 8-byte column first"))
+        if len(keys) == 1:
+            ki = t.schema.index_of_key(keys[0])
+            kcol, kvalid, ktype = t.columns[ki], t.valid[ki], t.schema.types[ki]
+            if kcol.dtype == torch.float64:
+                kcol = torch.where(kcol == 0, torch.zeros_like(kcol), kcol)  # -0.0 groups with 0.0
+                key64 = kcol.view(torch.int64)
+            elif kcol.dtype == torch.float32:
+                kcol = torch.where(kcol == 0, torch.zeros_like(kcol), kcol)
+                key64 = kcol.view(torch.int32).to(torch.int64)
+            else:
+                key64 = kcol if kcol.dtype == torch.int64 else kcol.to(torch.int64)
+        else:
+            key64, kvalid, ktype = torch.zeros(n, dtype=torch.int64, device=dev), None, None
+        # ---- aggregates
+        vals: List[Any] = []
+        vvalid: List[Any] = []
+        ops: List[int] = []
+        plan: List[Any] = []  # (name, kind, slots..., out_type)
+
+        def add(v: Any, m: Any, op: int) -> int:
+            vals.append(v)
+            vvalid.append(m)
+            ops.append(op)
+            return len(ops) - 1
+
+        for a in agg_cols:
+            fn, arg = a.func, a.arg.name
+            if fn == "COUNT":
+                if arg == "*":
+                    plan.append((a.output_name, "plain", add(None, None, K.AGG_COUNT), pa.int64(), None))
+                else:
+                    ci = t.schema.index_of_key(arg)
+                    plan.append((a.output_name, "plain", add(None, t.valid[ci], K.AGG_COUNT), pa.int64(), None))
+                continue
+            ci = t.schema.index_of_key(arg)
+            c, m, tp = t.columns[ci], t.valid[ci], t.schema.types[ci]
+            assert_or_throw(arg not in t.dictionaries, NotImplementedError(f"{fn} on a string column"))
+            is_f = pa.types.is_floating(tp)
+            c8 = c if c.element_size() == 8 else c.to(torch.float64 if is_f else torch.int64)
+            nn = add(None, m, K.AGG_COUNT) if m is not None else None  # non-null count -> result validity
+            if fn == "SUM":
+                plan.append((a.output_name, "plain", add(c8, m, K.AGG_SUM_F64 if is_f else K.AGG_SUM_I64),
+                             pa.float64() if is_f else pa.int64(), nn))
+            elif fn in ("MIN", "MAX"):
+                op = {("MIN", True): K.AGG_MIN_F64, ("MAX", True): K.AGG_MAX_F64,
+                      ("MIN", False): K.AGG_MIN_I64, ("MAX", False): K.AGG_MAX_I64}[(fn, is_f)]
+                plan.append((a.output_name, "plain", add(c8, m, op), tp, nn))
+            elif fn == "AVG":
+                cf = c8 if is_f else c8.to(torch.float64)
+                cnt = nn if nn is not None else add(None, None, K.AGG_COUNT)
+                plan.append((a.output_name, "avg", add(cf, m, K.AGG_SUM_F64), pa.float64(), cnt))
+            else:
+                raise NotImplementedError(f"aggregation {fn}")
+        assert_or_throw(len(ops) <= K.MAX_AGGS, NotImplementedError(
+            f"{len(ops)} accumulators needed, one kernel call handles {K.MAX_AGGS}"))
+        gkeys, gvalid, gaggs, ng = K.groupby_u64(key64, kvalid, vals, vvalid, ops)
+        if len(keys) == 0 and ng == 0:  # SQL: a global aggregate of an empty table is one row
+            gaggs = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in ops]
+            ng = 1
+        # ---- assemble the output table
+        fields, cols, valids = [], [], []
+        if len(keys) == 1:
+            kc = t.columns[ki]
+            if kc.dtype == torch.float64:
+                out_k = gkeys.view(torch.float64)
+            elif kc.dtype == torch.float32:
+                out_k = gkeys.to(torch.int32).view(torch.float32)
+            else:
+                out_k = gkeys if kc.dtype == torch.int64 else gkeys.to(kc.dtype)
+            fields.append(pa.field(keys[0], ktype))
+            cols.append(out_k.contiguous())
+            valids.append(gvalid)
+        for name, kind, slot, tp, nn in plan:
+            raw = gaggs[slot]
+            v = None if nn is None else (gaggs[nn] > 0).to(torch.uint8)
+            if kind == "avg":
+                cnt = gaggs[nn].to(torch.float64)
+                col = raw.view(torch.float64) / cnt
+                v = (gaggs[nn] > 0).to(torch.uint8)
+            elif pa.types.is_floating(tp):
+                col = raw.view(torch.float64)
+                if tp == pa.float32():
+                    col = col.to(torch.float32)
+            else:
+                from .table import _storage_dtype
+
+                sd = _storage_dtype(tp)
+                col = raw if sd == torch.int64 else raw.to(sd)
+            fields.append(pa.field(name, tp))
+            cols.append(col.contiguous())
+            valids.append(v)
+        dicts = {keys[0]: t.dictionaries[keys[0]]} if len(keys) == 1 and keys[0] in t.dictionaries else {}
+        return B200DataFrame(B200Table(Schema(fields), cols, valids, dicts))

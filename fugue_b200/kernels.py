@@ -174,3 +174,62 @@ def copy_segments(src_cols: Sequence[torch.Tensor], dst_cols: Sequence[torch.Ten
     _lib.check(lib.fb_copy_segments(dev.index, _stream_ptr(dev), len(src_cols), ptr_src.data_ptr(),
                                     ptr_dst.data_ptr(), widths.data_ptr(), nseg, src_off.data_ptr(),
                                     dst_off.data_ptr(), seg_len.data_ptr()))
+
+
+AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_MAX_F64 = range(7)
+MAX_AGGS = 8
+
+
+def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
+                vals: Sequence[Optional[torch.Tensor]], val_valid: Sequence[Optional[torch.Tensor]],
+                ops: Sequence[int], capacity: Optional[int] = None, max_capacity: Optional[int] = None
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], List[torch.Tensor], int]:
+    """K6: hash group-by of an 8-byte key column with up to 8 aggregates.
+    Returns (group keys, key validity or None, aggregate columns as int64 bit patterns, ngroups)."""
+    lib = _lib.load()
+    dev, n = _check_cols([keys])
+    assert keys.element_size() == 8 and len(vals) == len(ops) == len(val_valid) <= MAX_AGGS
+    for v in vals:
+        assert v is None or (v.element_size() == 8 and v.is_cuda and v.is_contiguous() and v.shape[0] == n)
+    naggs = len(ops)
+    if n == 0:  # nothing to aggregate: no groups
+        e = torch.empty(0, dtype=torch.int64, device=dev)
+        return (e, None if key_valid is None else torch.empty(0, dtype=torch.uint8, device=dev),
+                [e.clone() for _ in range(naggs)], 0)
+    hard_max = 1 << max(1, (2 * max(n, 1) - 1).bit_length())   # >= 2n: every row may be its own group
+    if max_capacity is not None:
+        hard_max = min(hard_max, max_capacity)
+    if capacity is None:
+        capacity = min(hard_max, 1 << 25)
+    capacity = max(2, 1 << (int(capacity) - 1).bit_length())
+    status = torch.zeros(4, dtype=torch.int64, device=dev)
+    vp = _lib.ptr_array([0 if v is None else v.data_ptr() for v in vals])
+    vv = _lib.ptr_array([0 if v is None else v.data_ptr() for v in val_valid])
+    opa = _lib.i32_array(list(ops))
+    while True:
+        nbytes = int(lib.fb_groupby_table_bytes(capacity, naggs))
+        table = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.fb_groupby_u64(dev.index, _stream_ptr(dev), n, keys.data_ptr(),
+                                      0 if key_valid is None else key_valid.data_ptr(), naggs, vp, vv, opa,
+                                      capacity, table.data_ptr(), status.data_ptr()))
+        if int(status[0].item()) == 0:
+            break
+        if capacity >= hard_max:
+            raise _lib.FugueB200KernelError("group-by hash table overflow at the maximum capacity")
+        del table
+        capacity *= 4
+    # compact: first learn the group count, then allocate exactly
+    out_cap = capacity + 2
+    # upper bound on groups is min(n + 2, capacity + 2); allocate that
+    bound = min(n, capacity) + 2
+    out_keys = torch.empty(bound, dtype=torch.int64, device=dev)
+    out_valid = torch.empty(bound, dtype=torch.uint8, device=dev) if key_valid is not None else None
+    out_aggs = [torch.empty(bound, dtype=torch.int64, device=dev) for _ in range(naggs)]
+    d_ptrs = torch.tensor([a.data_ptr() for a in out_aggs] or [0], dtype=torch.int64, device=dev)
+    _lib.check(lib.fb_groupby_extract(dev.index, _stream_ptr(dev), capacity, naggs, opa, table.data_ptr(),
+                                      out_keys.data_ptr(), 0 if out_valid is None else out_valid.data_ptr(),
+                                      d_ptrs.data_ptr(), status.data_ptr()))
+    ngroups = int(status[1].item())
+    del out_cap
+    return (out_keys[:ngroups], None if out_valid is None else out_valid[:ngroups],
+            [a[:ngroups] for a in out_aggs], ngroups)

@@ -116,6 +116,41 @@ int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_
                      void* const* d_dst_cols, const int32_t* d_widths, int nseg,
                      const int64_t* d_src_off, const int64_t* d_dst_off, const int64_t* d_len);
 
+/* ---------------------------------------------------------------------------
+ * K6  hash group-by with aggregation (single 8-byte key; other key shapes are packed /
+ * dictionary-coded into 8 bytes by the host layer)
+ * Replaces: ExecutionEngine.aggregate -> SQL -> qpd/pandas groupby
+ *             fugue/execution/execution_engine.py:889-939, fugue/column/sql.py:275-334,
+ *             fugue/execution/native_execution_engine.py:59-66
+ * NULL key forms its own group (fugue_test/execution_suite.py:195-200); NULL values are
+ * skipped (SQL semantics), COUNT with a NULL value pointer is COUNT(*).
+ *
+ * fb_groupby_u64     : clears `table` (fb_groupby_table_bytes) and aggregates nrows rows.
+ *                      d_status[0] != 0 afterwards means the table was too small: retry with
+ *                      a larger power-of-two `capacity`.  Value columns are 8 bytes wide.
+ * fb_groupby_extract : compacts the groups into out_keys / out_key_valid / out_aggs[a]
+ *                      (each 8 bytes per group, capacity + 2 entries allocated by the caller);
+ *                      d_status[1] receives the number of groups.  d_out_aggs is a DEVICE array
+ *                      of naggs device pointers.  Group order is unspecified.
+ * --------------------------------------------------------------------------- */
+#define FB_MAX_AGGS 8
+enum {
+  FB_AGG_SUM_F64 = 0,
+  FB_AGG_SUM_I64 = 1,
+  FB_AGG_COUNT = 2,
+  FB_AGG_MIN_I64 = 3,
+  FB_AGG_MAX_I64 = 4,
+  FB_AGG_MIN_F64 = 5,
+  FB_AGG_MAX_F64 = 6
+};
+size_t fb_groupby_table_bytes(int64_t capacity, int naggs);
+int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const uint8_t* key_valid,
+                   int naggs, const void* const* val_ptrs, const uint8_t* const* val_valid,
+                   const int32_t* agg_ops, int64_t capacity, void* table, int64_t* d_status);
+int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const int32_t* agg_ops,
+                       const void* table, void* out_keys, uint8_t* out_key_valid,
+                       void* const* d_out_aggs, int64_t* d_status);
+
 #ifdef __cplusplus
 }
 #endif

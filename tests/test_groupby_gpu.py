@@ -1,0 +1,109 @@
+"""K6 hash group-by vs the oracle (pandas groupby(dropna=False).agg) and the reference's literal
+expectations (fugue_test/execution_suite.py:177-206 test_aggregate, builtin_suite.py:937-949)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from fugue_b200 import api as fa
+from fugue_b200.column import all_cols, col, functions as ff
+from fugue_b200.dataframe import ArrayDataFrame, df_eq
+from oracle import native_engine as ora
+
+
+@pytest.fixture(scope="module")
+def engine():
+    return fa.make_execution_engine("b200")
+
+
+def test_aggregate_reference_literals(engine):
+    a = ArrayDataFrame([[1, 2], [None, 2], [None, 1], [3, 4], [None, 4]], "a:double,b:int")
+    b = fa.aggregate(a, b=ff.max(col("b")), engine=engine)
+    df_eq(b, [[4]], "b:int", throw=True)
+    b = fa.aggregate(a, "a", b=ff.max(col("b")), engine=engine)
+    df_eq(b, [[None, 4], [1, 2], [3, 4]], "a:double,b:int", throw=True)
+    with pytest.raises(ValueError):
+        fa.aggregate(a, "a", b=ff.max(col("b")), x=1, engine=engine)
+    with pytest.raises(ValueError):
+        fa.aggregate(a, "a", engine=engine)
+
+
+def test_sum_count_matches_oracle_1e6(engine):
+    rng = np.random.default_rng(0)
+    n = 1_000_000
+    pdf = pd.DataFrame({"key": rng.integers(-(2**62), 2**62, 200_000)[rng.integers(0, 200_000, n)],
+                        "v0": rng.standard_normal(n), "i": rng.integers(-1000, 1000, n)})
+    res = fa.aggregate(pdf, "key", s=ff.sum(col("v0")), c=ff.count(all_cols()), si=ff.sum(col("i")),
+                       mn=ff.min(col("v0")), mx=ff.max(col("i")), av=ff.avg(col("i")),
+                       engine=engine, as_local=True)
+    exp = ora.aggregate(pdf, ["key"], {"s": ("v0", "sum"), "c": ("*", "count"), "si": ("i", "sum"),
+                                       "mn": ("v0", "min"), "mx": ("i", "max"), "av": ("i", "avg")})
+    got = res.sort_values("key").reset_index(drop=True)
+    exp = exp.sort_values("key").reset_index(drop=True)
+    assert len(got) == len(exp)
+    for c in ("key", "c", "si", "mx"):
+        assert np.array_equal(got[c].to_numpy(), exp[c].to_numpy()), c       # integers: bit exact
+    assert np.array_equal(got["mn"].to_numpy(), exp["mn"].to_numpy())          # min moves a value: exact
+    rel = np.abs(got["s"].to_numpy() - exp["s"].to_numpy()) / np.maximum(np.abs(exp["s"].to_numpy()), 1e-300)
+    assert rel.max() <= 1e-9, rel.max()                                         # fp64 SUM within 1e-9 relative
+    assert np.allclose(got["av"].to_numpy(), exp["av"].to_numpy(), rtol=1e-12, atol=0)
+
+
+def test_null_keys_null_values_and_special_key(engine):
+    a = ArrayDataFrame([[None, 1.0], [None, None], [-1, 2.0], [-1, None], [5, None], [5, None], [7, 4.5]],
+                       "k:long,v:double")
+    res = fa.aggregate(a, "k", s=ff.sum(col("v")), c=ff.count(all_cols()), cv=ff.count(col("v")),
+                       m=ff.max(col("v")), engine=engine)
+    # key -1 is the all-ones bit pattern (the table's EMPTY marker) and must still be a group;
+    # SUM/MAX over only-NULL values is NULL; COUNT(v) skips NULLs
+    df_eq(res, [[None, 1.0, 2, 1, 1.0], [-1, 2.0, 2, 1, 2.0], [5, None, 2, 0, None], [7, 4.5, 1, 1, 4.5]],
+          "k:long,s:double,c:long,cv:long,m:double", throw=True)
+
+
+def test_low_cardinality_and_skew(engine):
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    pdf = pd.DataFrame({"key": np.minimum(rng.zipf(1.3, n), 1000).astype("int64"), "v0": rng.standard_normal(n)})
+    res = fa.aggregate(pdf, "key", s=ff.sum(col("v0")), c=ff.count(all_cols()), engine=engine, as_local=True)
+    exp = ora.aggregate_sum_count(pdf, ["key"], "v0")
+    got = res.sort_values("key").reset_index(drop=True)
+    assert np.array_equal(got["key"].to_numpy(), exp["key"].to_numpy())
+    assert np.array_equal(got["c"].to_numpy(), exp["c"].to_numpy())
+    assert np.max(np.abs(got["s"].to_numpy() - exp["s"].to_numpy()) / np.abs(exp["s"].to_numpy())) <= 1e-9
+
+
+def test_other_key_types_and_empty(engine):
+    a = ArrayDataFrame([[1.5, 1], [0.0, 2], [-0.0, 3], [None, 4], [1.5, 5]], "k:double,v:int")
+    res = fa.aggregate(a, "k", s=ff.sum(col("v")), engine=engine)
+    df_eq(res, [[None, 4], [0.0, 5], [1.5, 6]], "k:double,s:long", throw=True)
+    a = ArrayDataFrame([["x", 1], ["y", 2], ["x", 3], [None, 9]], "k:str,v:int")
+    res = fa.aggregate(a, "k", s=ff.sum(col("v")), c=ff.count(all_cols()), engine=engine)
+    df_eq(res, [["x", 4, 2], ["y", 2, 1], [None, 9, 1]], "k:str,s:long,c:long", throw=True)
+    e = ArrayDataFrame([], "k:long,v:double")
+    res = fa.aggregate(e, "k", s=ff.sum(col("v")), engine=engine)
+    df_eq(res, [], "k:long,s:double", throw=True)
+    a = ArrayDataFrame([[1, 2], [3, 4]], "k:int,v:short")
+    res = fa.aggregate(a, "k", m=ff.min(col("v")), engine=engine)
+    df_eq(res, [[1, 2], [3, 4]], "k:int,m:short", throw=True)
+
+
+def test_full_size_properties_100m_rows_10m_keys():
+    """BASELINE config 4 shape per GPU (100 M rows, 10 M distinct keys): checksum properties."""
+    from fugue_b200 import kernels as K
+
+    dev = torch.device("cuda", 0)
+    n, nk = 100_000_000, 10_000_000
+    g = torch.Generator(device=dev).manual_seed(1)
+    idx = torch.randint(0, nk, (n,), dtype=torch.int64, device=dev, generator=g)
+    keys = idx * 0x9E3779B97F4A7C15 % (1 << 62)           # a fixed bijection-ish scramble of dense ids
+    v = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    gk, _, (s, c), ng = K.groupby_u64(keys, None, [v.view(torch.int64), None], [None, None],
+                                      [K.AGG_SUM_F64, K.AGG_COUNT])
+    assert ng == int(torch.unique(keys).numel())
+    assert int(c.sum()) == n                                # COUNT(*) adds up to the row count
+    total = float(s.view(torch.float64).sum())
+    ref = float(v.sum())
+    assert abs(total - ref) <= 1e-9 * max(1.0, float(v.abs().sum())) # sum of sums == sum
+    assert int(torch.unique(gk).numel()) == ng              # every group appears once
