@@ -33,6 +33,7 @@ SIGNATURES = {
                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fb_partition_ids": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                    C.c_uint32, _vp]),
+    "fb_row_hash64": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp, _vp]),
     "fb_debug_fastmod_host": (C.c_uint32, [C.c_uint64, C.c_uint32]),
     "fb_partition_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int64, C.c_uint32]),
     "fb_partition_plan": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
@@ -48,6 +49,15 @@ SIGNATURES = {
     "fb_groupby_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int, _vpp, _vpp, _i32p, C.c_int64,
                                  _vp, _vp]),
     "fb_groupby_extract": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _i32p, _vp, _vp, _vp, _vp, _vp]),
+    "fb_join_table_bytes": (C.c_size_t, [C.c_int64]),
+    "fb_join_build_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp]),
+    "fb_join_probe_count_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int, _vp]),
+    "fb_join_probe_write_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int, _vp,
+                                          _vp, _vp]),
+    "fb_join_mark_matched": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp]),
+    "fb_exclusive_scan_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "fb_exclusive_scan_i64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_size_t]),
+    "fb_gather_rows": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
     "fb_copy_segments": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
 }
 

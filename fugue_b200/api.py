@@ -276,3 +276,44 @@ def aggregate(df: Any, partition_by: Any = None, engine: Any = None, engine_conf
     if as_fugue or isinstance(df, DataFrame):
         return res
     return res.as_pandas() if res.is_local else res.native
+
+
+def join(df1: Any, df2: Any, *dfs: Any, how: str, on: Optional[Iterable[str]] = None, engine: Any = None,
+         engine_conf: Any = None, as_fugue: bool = False, as_local: bool = False) -> Any:
+    """``fa.join`` (fugue/execution/api.py:541-588): joins two or more dataframes left to right."""
+    e = make_execution_engine(engine, engine_conf, infer_by=[df1, df2, *dfs])
+    res: DataFrame = e.join(e.to_df(df1), e.to_df(df2), how=how, on=None if on is None else list(on))
+    for odf in dfs:
+        res = e.join(res, e.to_df(odf), how=how, on=None if on is None else list(on))
+    res = e.convert_yield_dataframe(res, as_local)
+    if as_fugue or any(isinstance(x, DataFrame) for x in (df1, df2, *dfs)):
+        return res
+    return res.as_pandas() if res.is_local else res.native
+
+
+def inner_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="inner", **kwargs)
+
+
+def semi_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="semi", **kwargs)
+
+
+def anti_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="anti", **kwargs)
+
+
+def left_outer_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="left_outer", **kwargs)
+
+
+def right_outer_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="right_outer", **kwargs)
+
+
+def full_outer_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="full_outer", **kwargs)
+
+
+def cross_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
+    return join(df1, df2, *dfs, how="cross", **kwargs)

@@ -98,6 +98,12 @@ __global__ void fb_pid_kernel(FbKeys keys, FbDiv dv, int64_t nrows, uint32_t* __
   for (; i < nrows; i += stride) out[i] = compute_pid<kSingleU64>(keys, dv, i);
 }
 
+__global__ void fb_row_hash_kernel(FbKeys keys, int64_t nrows, uint64_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nrows; i += stride) out[i] = fb_row_hash(keys, i);
+}
+
 // ---------------------------------------------------------------------------
 // Warp-level "which lanes hold my value": kBits ballots instead of the hardware
 // MATCH instruction (MATCH.ANY runs on the ADU pipe at ~70 cycles per warp
@@ -967,6 +973,22 @@ int fb_partition_ids(int dev, void* stream, int64_t nrows, int nkeys, const void
     fb_pid_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(k, dv, nrows, out_pids);
   else
     fb_pid_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(k, dv, nrows, out_pids);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fb_row_hash64(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                  const int32_t* key_widths, const uint8_t* const* key_valid, uint64_t* out_hash) {
+  FB_CHECK(nrows >= 0, "nrows < 0");
+  if (nrows == 0) return 0;
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  int64_t blocks = (nrows + 255) / 256;
+  int64_t maxb = (int64_t)fb_sm_count(dev) * 16;
+  if (blocks > maxb) blocks = maxb;
+  fb_row_hash_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, nrows, out_hash);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -401,3 +401,11 @@ class B200ExecutionEngine:
             valids.append(v)
         dicts = {keys[0]: t.dictionaries[keys[0]]} if len(keys) == 1 and keys[0] in t.dictionaries else {}
         return B200DataFrame(B200Table(Schema(fields), cols, valids, dicts))
+
+    # ---- join (K7) ----------------------------------------------------------------------
+    def join(self, df1: Any, df2: Any, how: str, on: Optional[List[str]] = None) -> B200DataFrame:
+        """``ExecutionEngine.join`` (execution_engine.py:539-561; native :230-241): equi-join on the
+        common columns, NULL keys never match, output schema ``df1.schema`` U (``df2.schema`` - keys)."""
+        from .join import device_join
+
+        return device_join(self, self.to_df(df1), self.to_df(df2), how, on)

@@ -233,3 +233,100 @@ def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
     del out_cap
     return (out_keys[:ngroups], None if out_valid is None else out_valid[:ngroups],
             [a[:ngroups] for a in out_aggs], ngroups)
+
+
+def exclusive_scan(counts: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Exclusive prefix sum of an int64 device vector (own kernels); returns (offsets, total)."""
+    lib = _lib.load()
+    dev = counts.device
+    n = int(counts.shape[0])
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    nb = int(lib.fb_exclusive_scan_scratch_bytes(n))
+    scratch = torch.empty(max(nb, 8), dtype=torch.uint8, device=dev)
+    _lib.check(lib.fb_exclusive_scan_i64(dev.index, _stream_ptr(dev), n, counts.data_ptr(), out.data_ptr(),
+                                         total.data_ptr(), scratch.data_ptr(), scratch.numel()))
+    return out, int(total.item())
+
+
+class JoinTable:
+    """Hash multimap of the build side of a join (K7)."""
+
+    def __init__(self, keys: torch.Tensor, valid: Optional[torch.Tensor]):
+        lib = _lib.load()
+        dev, n = _check_cols([keys])
+        assert keys.element_size() == 8
+        self.nbuild = n
+        self.capacity = max(2, 1 << (2 * max(n, 1)).bit_length())  # load factor <= 0.5
+        self.table = torch.empty(int(lib.fb_join_table_bytes(self.capacity)), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(4, dtype=torch.int64, device=dev)
+        _lib.check(lib.fb_join_build_u64(dev.index, _stream_ptr(dev), n, keys.data_ptr(),
+                                         0 if valid is None else valid.data_ptr(), self.capacity,
+                                         self.table.data_ptr(), self.status.data_ptr()))
+        self.device = dev
+
+    def probe_counts(self, keys: torch.Tensor, valid: Optional[torch.Tensor], outer: bool) -> torch.Tensor:
+        lib = _lib.load()
+        n = int(keys.shape[0])
+        counts = torch.empty(n, dtype=torch.int64, device=self.device)
+        _lib.check(lib.fb_join_probe_count_u64(self.device.index, _stream_ptr(self.device), n, keys.data_ptr(),
+                                               0 if valid is None else valid.data_ptr(), self.capacity,
+                                               self.table.data_ptr(), 1 if outer else 0, counts.data_ptr()))
+        return counts
+
+    def probe(self, keys: torch.Tensor, valid: Optional[torch.Tensor], outer: bool
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(probe_row, build_row) pairs of all matches, probe-row major; build_row == -1 marks the
+        NULL-extended row of an outer join."""
+        lib = _lib.load()
+        n = int(keys.shape[0])
+        counts = self.probe_counts(keys, valid, outer)
+        offsets, total = exclusive_scan(counts)
+        pi = torch.empty(total, dtype=torch.int64, device=self.device)
+        bi = torch.empty(total, dtype=torch.int64, device=self.device)
+        _lib.check(lib.fb_join_probe_write_u64(self.device.index, _stream_ptr(self.device), n, keys.data_ptr(),
+                                               0 if valid is None else valid.data_ptr(), self.capacity,
+                                               self.table.data_ptr(), 1 if outer else 0, offsets.data_ptr(),
+                                               pi.data_ptr(), bi.data_ptr()))
+        return pi, bi
+
+    def matched_mask(self, build_idx: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        m = torch.zeros(self.nbuild, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.fb_join_mark_matched(self.device.index, _stream_ptr(self.device), build_idx.data_ptr(),
+                                            int(build_idx.shape[0]), m.data_ptr()))
+        return m
+
+
+def gather_rows(cols: Sequence[torch.Tensor], valid: Sequence[Optional[torch.Tensor]], idx: torch.Tensor,
+                want_valid: bool) -> Tuple[List[torch.Tensor], List[Optional[torch.Tensor]]]:
+    """out[c][o] = cols[c][idx[o]]; idx < 0 gives NULL (needs want_valid)."""
+    lib = _lib.load()
+    if len(cols) == 0:
+        return [], []
+    dev = idx.device
+    n = int(idx.shape[0])
+    outs = [torch.empty(n, dtype=c.dtype, device=dev) for c in cols]
+    need_v = [want_valid or v is not None for v in valid]
+    outv = [torch.empty(n, dtype=torch.uint8, device=dev) if nv else None for nv in need_v]
+    sp = torch.tensor([c.data_ptr() for c in cols], dtype=torch.int64, device=dev)
+    dp = torch.tensor([c.data_ptr() for c in outs], dtype=torch.int64, device=dev)
+    w = torch.tensor([c.element_size() for c in cols], dtype=torch.int32, device=dev)
+    sv = torch.tensor([0 if v is None else v.data_ptr() for v in valid], dtype=torch.int64, device=dev)
+    dv = torch.tensor([0 if v is None else v.data_ptr() for v in outv], dtype=torch.int64, device=dev)
+    _lib.check(lib.fb_gather_rows(dev.index, _stream_ptr(dev), len(cols), sp.data_ptr(), dp.data_ptr(),
+                                  w.data_ptr(), sv.data_ptr(), dv.data_ptr(), idx.data_ptr(), n))
+    return outs, outv
+
+
+def row_hash64(keys: Sequence[torch.Tensor], valid: Optional[Sequence[Optional[torch.Tensor]]] = None
+               ) -> torch.Tensor:
+    """64-bit hash of each row's key tuple (same function as the partitioner, before ``% num``)."""
+    lib = _lib.load()
+    dev, n = _check_cols(keys)
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    vp = _valid_ptrs(valid, len(keys))
+    _lib.check(lib.fb_row_hash64(dev.index, _stream_ptr(dev), n, len(keys),
+                                 _lib.ptr_array([k.data_ptr() for k in keys]),
+                                 _lib.i32_array([k.element_size() for k in keys]), vp, out.data_ptr()))
+    return out

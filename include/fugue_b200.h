@@ -55,6 +55,11 @@ int fb_partition_ids(int dev, void* stream, int64_t nrows, int nkeys,
                      const uint8_t* const* key_valid, uint32_t num_partitions,
                      uint32_t* out_pids);
 
+/* The 64-bit row hash itself (before `% num`): used to join / group on key tuples wider than
+ * 8 bytes (hash as surrogate key, equality verified afterwards). */
+int fb_row_hash64(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                  const int32_t* key_widths, const uint8_t* const* key_valid, uint64_t* out_hash);
+
 /* Host-side evaluation of the device's division-free `hash % num` (for tests). */
 uint32_t fb_debug_fastmod_host(uint64_t hash, uint32_t num_partitions);
 
@@ -150,6 +155,40 @@ int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const
 int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const int32_t* agg_ops,
                        const void* table, void* out_keys, uint8_t* out_key_valid,
                        void* const* d_out_aggs, int64_t* d_status);
+
+/* ---------------------------------------------------------------------------
+ * K7  hash equi-join on one 8-byte key (other key shapes are packed by the host layer)
+ * Replaces: NativeExecutionEngine.join -> triad PandasUtils.join -> pd.merge
+ *             fugue/execution/native_execution_engine.py:230-241
+ *           schema rule: fugue/dataframe/utils.py:152-226 (host side)
+ * NULL keys never match (fugue_test/execution_suite.py:533-543).
+ *
+ *   fb_join_build_u64        multimap of the build side (capacity: power of two > nbuild,
+ *                            table: fb_join_table_bytes(capacity)); d_status[0] != 0: overflow
+ *   fb_join_probe_count_u64  matches per probe row (outer != 0: unmatched rows count 1)
+ *   fb_exclusive_scan_i64    counts -> output offsets (out[n] entries) and the total
+ *   fb_join_probe_write_u64  (probe_row, build_row) index pairs; build_row = -1 for the
+ *                            NULL-extended row of an outer join
+ *   fb_join_mark_matched     matched[build_row] = 1 (right / full outer joins)
+ *   fb_gather_rows           dst[c][o] = src[c][idx[o]] (idx < 0 -> NULL): all pointer tables
+ *                            and widths are DEVICE arrays
+ * --------------------------------------------------------------------------- */
+size_t fb_join_table_bytes(int64_t capacity);
+int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
+                      int64_t capacity, void* table, int64_t* d_status);
+int fb_join_probe_count_u64(int dev, void* stream, int64_t nprobe, const void* keys,
+                            const uint8_t* key_valid, int64_t capacity, const void* table, int outer,
+                            int64_t* out_counts);
+int fb_join_probe_write_u64(int dev, void* stream, int64_t nprobe, const void* keys,
+                            const uint8_t* key_valid, int64_t capacity, const void* table, int outer,
+                            const int64_t* offsets, int64_t* out_probe_idx, int64_t* out_build_idx);
+int fb_join_mark_matched(int dev, void* stream, const int64_t* build_idx, int64_t n, uint8_t* matched);
+size_t fb_exclusive_scan_scratch_bytes(int64_t n);
+int fb_exclusive_scan_i64(int dev, void* stream, int64_t n, const int64_t* in, int64_t* out,
+                          int64_t* out_total, void* scratch, size_t scratch_bytes);
+int fb_gather_rows(int dev, void* stream, int ncols, const void* const* d_src_cols, void* const* d_dst_cols,
+                   const int32_t* d_widths, const uint8_t* const* d_src_valid, uint8_t* const* d_dst_valid,
+                   const int64_t* idx, int64_t n);
 
 #ifdef __cplusplus
 }
