@@ -245,11 +245,21 @@ def transform(
     e = make_execution_engine(engine, engine_conf, infer_by=[df])
     tf = _FuncAsTransformer(using, schema, params)
     spec = PartitionSpec(partition)
-    edf = e.to_df(df)
-    out_schema = tf.get_output_schema(edf)
-    runner = tf.make_runner(out_schema, list(ignore_errors or []))
-    res: DataFrame = e.map_engine.map_dataframe(edf, runner, out_schema, spec,
-                                                map_func_format_hint=tf.get_format_hint())
+    res: Optional[DataFrame] = None
+    if (as_local and tf.get_format_hint() == "b200" and not isinstance(df, (B200DataFrame, B200Table))
+            and not e.is_distributed):
+        # host input, host output, device function: overlap H2D / partition / D2H column by column
+        from .streaming import streaming_transform
+
+        ldf = as_fugue_df(df)
+        out_schema = tf.get_output_schema(ldf)
+        res = streaming_transform(e, ldf, tf.make_runner(out_schema, list(ignore_errors or [])), out_schema, spec)
+    if res is None:
+        edf = e.to_df(df)
+        out_schema = tf.get_output_schema(edf)
+        runner = tf.make_runner(out_schema, list(ignore_errors or []))
+        res = e.map_engine.map_dataframe(edf, runner, out_schema, spec,
+                                         map_func_format_hint=tf.get_format_hint())
     if persist:
         res = e.persist(res)
     res = e.convert_yield_dataframe(res, as_local)
@@ -317,3 +327,26 @@ def full_outer_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
 
 def cross_join(df1: Any, df2: Any, *dfs: Any, **kwargs: Any) -> Any:
     return join(df1, df2, *dfs, how="cross", **kwargs)
+
+
+def raw_sql(*statements: Any, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+            as_local: bool = False) -> Any:
+    """``fa.raw_sql`` (fugue/sql/api.py): strings and dataframes interleaved, e.g.
+    ``fa.raw_sql("SELECT key, SUM(v0) AS s, COUNT(*) AS c FROM", df, "GROUP BY key")``."""
+    from .sql import StructuredRawSQL
+
+    e = make_execution_engine(engine, engine_conf, infer_by=[s for s in statements if not isinstance(s, str)])
+    dfs: Dict[str, Any] = {}
+    pieces = []
+    for s in statements:
+        if isinstance(s, str):
+            pieces.append((False, s))
+        else:
+            name = f"_{len(dfs)}"
+            dfs[name] = e.to_df(s)
+            pieces.append((True, name))
+    res: DataFrame = e.sql_engine.select(dfs, StructuredRawSQL(pieces))
+    res = e.convert_yield_dataframe(res, as_local)
+    if as_fugue or any(isinstance(s, DataFrame) for s in statements):
+        return res
+    return res.as_pandas() if res.is_local else res.native

@@ -210,6 +210,17 @@ class B200ExecutionEngine:
     def create_default_map_engine(self) -> B200MapEngine:
         return B200MapEngine(self)
 
+    @property
+    def sql_engine(self) -> Any:
+        if getattr(self, "_sql_engine", None) is None:
+            self._sql_engine = self.create_default_sql_engine()
+        return self._sql_engine
+
+    def create_default_sql_engine(self) -> Any:
+        from .sql import B200SQLEngine
+
+        return B200SQLEngine(self)
+
     def get_current_parallelism(self) -> int:
         return 1
 

@@ -208,3 +208,37 @@ def test_multi_gpu_repartition_if_two_gpus_visible():
                         os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and "dist_gpu_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_streaming_transform_matches_plain_path(engine):
+    """Host in / host out with a device function takes the pipelined path; same result as the
+    step-by-step path (to_df -> map_dataframe -> as_local)."""
+    def identity(t: B200Table) -> B200Table:
+        return t
+
+    def add_col(t: B200Table) -> B200Table:
+        from fugue_b200.schema import Schema
+
+        return B200Table(Schema(t.schema, "w:double"), list(t.columns) + [t.column("v0") * 2.0])
+
+    rng = np.random.default_rng(4)
+    n = 300_001
+    pdf = pd.DataFrame({"key": rng.integers(0, 1 << 16, n), "i1": rng.integers(-2**62, 2**62, n),
+                        "v0": rng.standard_normal(n), "f": rng.standard_normal(n).astype("float32")})
+    spec = PartitionSpec(by="key", algo="hash", num=256)
+    tbl = pa.Table.from_pandas(pdf, preserve_index=False)
+    tbl = pa.concat_tables([tbl.slice(0, 100_000), tbl.slice(100_000)])      # two chunks
+    got = fa.transform(tbl, identity, schema="*", partition=spec, engine=engine, as_local=True)
+    pid = pd.util.hash_pandas_object(pdf[["key"]], index=False).mod(256).to_numpy()
+    exp = pdf.iloc[np.argsort(pid, kind="stable")].reset_index(drop=True)
+    pd.testing.assert_frame_equal(got, exp, check_exact=True)
+    got2 = fa.transform(tbl, add_col, schema="*,w:double", partition=spec, engine=engine, as_local=True)
+    exp2 = exp.assign(w=exp.v0 * 2.0)
+    pd.testing.assert_frame_equal(got2, exp2, check_exact=True)
+    # a table with NULLs is not eligible and silently takes the plain path
+    pdf3 = pdf.copy()
+    pdf3.loc[5, "v0"] = np.nan
+    t3 = pa.Table.from_pandas(pdf3, preserve_index=False)
+    t3 = t3.set_column(2, "v0", pa.array(pdf3.v0.where(pdf3.v0.notna(), None).tolist(), type=pa.float64()))
+    got3 = fa.transform(t3, identity, schema="*", partition=spec, engine=engine, as_local=True)
+    assert len(got3) == n and int(got3.v0.isna().sum()) == 1

@@ -107,3 +107,31 @@ def test_full_size_properties_100m_rows_10m_keys():
     ref = float(v.sum())
     assert abs(total - ref) <= 1e-9 * max(1.0, float(v.abs().sum())) # sum of sums == sum
     assert int(torch.unique(gk).numel()) == ng              # every group appears once
+
+
+def test_sql_engine_group_by_and_join(engine):
+    """BASELINE configs 4/5 as SQL text (fugue/sql/_visitors.py:743-766 forwards exactly such text)."""
+    from fugue_b200.sql import StructuredRawSQL
+
+    rng = np.random.default_rng(5)
+    n = 100_000
+    pdf = pd.DataFrame({"key": rng.integers(0, 5000, n), "v0": rng.standard_normal(n)})
+    res = fa.raw_sql("SELECT key, SUM(v0) AS s, COUNT(*) AS c FROM", pdf, "GROUP BY key", engine=engine,
+                     as_local=True)
+    exp = ora.aggregate_sum_count(pdf, ["key"], "v0")
+    got = res.sort_values("key").reset_index(drop=True)
+    assert list(got.columns) == ["key", "s", "c"]
+    assert np.array_equal(got["key"], exp["key"]) and np.array_equal(got["c"], exp["c"])
+    assert np.max(np.abs(got["s"] - exp["s"]) / np.abs(exp["s"])) <= 1e-9
+    # pieces form (fugue/collections/sql.py:48-151) and a join
+    l = pd.DataFrame({"key": rng.integers(0, 1000, 3000), "lv": rng.standard_normal(3000)})
+    r = pd.DataFrame({"key": rng.permutation(1000), "rv": rng.standard_normal(1000)})
+    st = StructuredRawSQL([(False, "SELECT * FROM"), (True, "a"), (False, "INNER JOIN"), (True, "b"),
+                           (False, "ON a.key = b.key")])
+    out = engine.sql_engine.select({"a": l, "b": r}, st)
+    exp = ora.join(l, r, "inner")
+    df_eq(out, exp.values.tolist(), "key:long,lv:double,rv:double", throw=True)
+    out = fa.raw_sql("SELECT COUNT(*) AS n, MAX(lv) AS m FROM", l, engine=engine, as_local=True)
+    assert out.values.tolist() == [[3000, l.lv.max()]]
+    with pytest.raises(NotImplementedError):
+        fa.raw_sql("SELECT key FROM", l, "WHERE key > 3", engine=engine)
