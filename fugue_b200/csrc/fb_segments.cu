@@ -1,63 +1,83 @@
-// Segment copy: out[dst_off[s] .. +len[s]) = in[src_off[s] .. +len[s]) for every column.
-// Used after the multi-GPU exchange to turn the received (source, partition) runs into
-// (partition, source) order so that every owned partition is contiguous;
-// the reference has no counterpart (its shuffles are Dask/Spark/Ray's, fugue_dask/_utils.py:124-130).
-// Pure HBM copy: 2 x width bytes per row per column.
+// Segment copy: out[dst_off[s] .. +len[s]) = table[src_tab[s]][src_off[s] .. +len[s]) for every column.
+//
+// Multi-GPU exchange epilogue (SURVEY.md 8e steps 3+4 in one kernel): the source tables are the
+// hash-partitioned column buffers of ALL ranks, mapped into this process through symmetric memory
+// (NVLink peer pointers), so the kernel PULLS every (source rank, partition) run straight from the
+// peer's HBM over NVLink 5 into its final place in the owned, partition-contiguous output - no
+// NCCL all-to-all, no staging pass.  With one source table it is a plain local segment copy.
+// The reference has no counterpart (its shuffles are Dask/Spark/Ray's, fugue_dask/_utils.py:124-130).
+// Pure byte movement: 2 x width bytes per row per column; peer loads need many bytes in flight
+// (NVLink latency ~3x HBM), hence 8 independent 8-byte loads per thread and piece-parallel CTAs.
 #include "fb_common.cuh"
 
 namespace {
 
+constexpr int kCopyBlock = 256;
+constexpr int kCopyUnroll = 8;
+constexpr int kPieceRows = kCopyBlock * kCopyUnroll * 4;  // rows one CTA handles per piece step
+
 template <typename T>
-__device__ __forceinline__ void copy_run(const T* __restrict__ src, T* __restrict__ dst, int64_t n) {
-  const int64_t step = (int64_t)blockDim.x * 4;
-  int64_t i = threadIdx.x;
-  for (; i + 3 * (int64_t)blockDim.x < n; i += step) {  // 4 independent loads in flight per thread
-    T a = src[i], b = src[i + blockDim.x], c = src[i + 2 * blockDim.x], d = src[i + 3 * blockDim.x];
-    dst[i] = a; dst[i + blockDim.x] = b; dst[i + 2 * blockDim.x] = c; dst[i + 3 * blockDim.x] = d;
+__device__ __forceinline__ void copy_run(const T* __restrict__ src, T* __restrict__ dst, int64_t n,
+                                         int piece, int npieces) {
+  for (int64_t base = (int64_t)piece * kPieceRows; base < n; base += (int64_t)npieces * kPieceRows) {
+    const int64_t end = base + kPieceRows < n ? base + kPieceRows : n;
+    int64_t i = base + threadIdx.x;
+    for (; i + (kCopyUnroll - 1) * kCopyBlock < end; i += kCopyUnroll * kCopyBlock) {
+      T v[kCopyUnroll];
+#pragma unroll
+      for (int k = 0; k < kCopyUnroll; ++k) v[k] = src[i + k * kCopyBlock];
+#pragma unroll
+      for (int k = 0; k < kCopyUnroll; ++k) dst[i + k * kCopyBlock] = v[k];
+    }
+    for (; i < end; i += kCopyBlock) dst[i] = src[i];
   }
-  for (; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCopyBlock)
 fb_copy_segments_kernel(const void* const* __restrict__ src_cols, void* const* __restrict__ dst_cols,
-                        const int32_t* __restrict__ widths, const int64_t* __restrict__ src_off,
-                        const int64_t* __restrict__ dst_off, const int64_t* __restrict__ len, int nseg,
-                        int rows_per_cta) {
+                        const int32_t* __restrict__ widths, int ncols, const int32_t* __restrict__ src_tab,
+                        const int64_t* __restrict__ src_off, const int64_t* __restrict__ dst_off,
+                        const int64_t* __restrict__ len, int nseg) {
   const int c = blockIdx.y;
   const int w = widths[c];
-  const uint8_t* s = (const uint8_t*)src_cols[c];
   uint8_t* d = (uint8_t*)dst_cols[c];
-  // blockIdx.x enumerates (segment, piece) pairs: pieces of rows_per_cta rows, found by a walk
-  // over the segment table is avoided by launching ceil(len/rows_per_cta) pieces per segment on
-  // the host side via a piece table; here: one CTA per segment with an inner loop.
+  const int piece = blockIdx.z, npieces = gridDim.z;
   for (int sgi = blockIdx.x; sgi < nseg; sgi += gridDim.x) {
     const int64_t n = len[sgi];
     if (n <= 0) continue;
+    const int tab = src_tab != nullptr ? src_tab[sgi] : 0;
+    const uint8_t* s = (const uint8_t*)src_cols[(size_t)tab * ncols + c];
     const int64_t so = src_off[sgi], dof = dst_off[sgi];
     switch (w) {
-      case 8: copy_run((const uint64_t*)s + so, (uint64_t*)d + dof, n); break;
-      case 4: copy_run((const uint32_t*)s + so, (uint32_t*)d + dof, n); break;
-      case 2: copy_run((const uint16_t*)s + so, (uint16_t*)d + dof, n); break;
-      default: copy_run(s + so, d + dof, n); break;
+      case 8: copy_run((const uint64_t*)s + so, (uint64_t*)d + dof, n, piece, npieces); break;
+      case 4: copy_run((const uint32_t*)s + so, (uint32_t*)d + dof, n, piece, npieces); break;
+      case 2: copy_run((const uint16_t*)s + so, (uint16_t*)d + dof, n, piece, npieces); break;
+      default: copy_run(s + so, d + dof, n, piece, npieces); break;
     }
   }
-  (void)rows_per_cta;
 }
 
 }  // namespace
 
 extern "C" int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_cols,
                                 void* const* d_dst_cols, const int32_t* d_widths, int nseg,
-                                const int64_t* d_src_off, const int64_t* d_dst_off,
-                                const int64_t* d_len) {
+                                const int32_t* d_src_table, const int64_t* d_src_off,
+                                const int64_t* d_dst_off, const int64_t* d_len, int64_t max_len) {
   FB_CHECK(ncols >= 0 && nseg >= 0, "negative count");
   if (ncols == 0 || nseg == 0) return 0;
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
-  int gx = nseg < 148 * 8 ? nseg : 148 * 8;
-  dim3 grid((unsigned)gx, (unsigned)ncols);
-  fb_copy_segments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src_cols, d_dst_cols, d_widths, d_src_off,
-                                                                 d_dst_off, d_len, nseg, 0);
+  const int sms = fb_sm_count(dev);
+  int gx = nseg < 65535 ? nseg : 65535;
+  // enough pieces to give every SM several CTAs even with few, long segments
+  int64_t pieces = max_len > 0 ? (max_len + kPieceRows - 1) / kPieceRows : 1;
+  const int64_t want = (int64_t)sms * 16 / ((int64_t)gx * ncols) + 1;
+  if (pieces > want) pieces = want;
+  if (pieces > 64) pieces = 64;
+  if (pieces < 1) pieces = 1;
+  dim3 grid((unsigned)gx, (unsigned)ncols, (unsigned)pieces);
+  fb_copy_segments_kernel<<<grid, kCopyBlock, 0, (cudaStream_t)stream>>>(
+      d_src_cols, d_dst_cols, d_widths, ncols, d_src_table, d_src_off, d_dst_off, d_len, nseg);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,6 +14,7 @@ the contract honoured is SURVEY.md 3.3: equal keys land in the same physical par
 The planning functions work on CPU tensors with any torch.distributed backend, so the
 world-size-2 ``gloo`` tests (tests/test_dist_cpu.py) cover this logic without a GPU.
 """
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -53,6 +54,12 @@ class ExchangePlan:
         flat_pm = mine.t().contiguous().reshape(-1)               # partition-major lengths
         dst_off = torch.cumsum(flat_pm, 0) - flat_pm
         self.seg_src_off = src_off.t().contiguous().reshape(-1)   # partition-major order
+        # pull exchange: the same runs addressed inside every SOURCE rank's partitioned table
+        src_part_off = torch.cumsum(counts, 1) - counts            # [world, num] offset of p in src table
+        self.pull_src_off = src_part_off[:, lo:hi].t().contiguous().reshape(-1)
+        self.pull_src_rank = torch.arange(world, dtype=torch.int32).repeat(hi - lo)
+        self.rows_per_rank = counts.sum(1)                        # local row count of every rank
+        self.max_seg = int(flat_pm.max()) if flat_pm.numel() > 0 else 0
         self.seg_dst_off = dst_off
         self.seg_len = flat_pm
         part_counts = mine.sum(0)
@@ -102,33 +109,103 @@ class DistributedB200Engine(B200ExecutionEngine):
     def get_current_parallelism(self) -> int:
         return self._world
 
+    # ---- symmetric arena: this rank's partitioned columns, readable by every peer over NVLink
+    def _ensure_arena(self, nbytes: int) -> None:
+        """All ranks call this with the same ``nbytes`` (derived from the gathered counts)."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if getattr(self, "_arena", None) is not None and self._arena.numel() >= nbytes:
+            return
+        cap = ((int(nbytes * 1.25) + (1 << 21) - 1) >> 21) << 21
+        self._arena = symm_mem.empty(cap, dtype=torch.uint8, device=self._device)
+        self._arena_hdl = symm_mem.rendezvous(self._arena, group=self._group or dist.group.WORLD)
+
+    @staticmethod
+    def _col_offsets(nrows: int, widths: List[int]) -> List[int]:
+        off, out = 0, []
+        for w in widths:
+            out.append(off)
+            off += (nrows * w + 255) & ~255
+        out.append(off)
+        return out
+
     def repartition(self, df: Any, partition_spec: PartitionSpec) -> B200DataFrame:
+        """Shuffle = local K1-K3 into a symmetric arena + ONE pull kernel over NVLink:
+        pass 1 -> count all-gather -> scatter into the arena -> barrier -> every rank copies the
+        (source rank, partition) runs it owns straight from the peers' arenas into its final,
+        partition-contiguous output (fb_copy_segments with peer pointers) -> barrier."""
         from . import kernels as K
 
-        local = super().repartition(df, partition_spec)  # K1-K3 on this GPU's row shard
         keys = partition_spec.partition_by
+        edf = self.to_df(df)
         if len(keys) == 0 or self._world == 1:
-            return local
-        t: B200Table = local.native
-        num = t.num_partitions
+            return super().repartition(edf, partition_spec)
+        t: B200Table = edf.native
+        for k in keys:
+            assert_or_throw(k in t.schema, lambda: KeyError(f"{k} not in {t.schema}"))
+        num = self._num_partitions(partition_spec, t.num_rows)
+        assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
+            f"num_partitions={num}: one radix pass handles up to {K.MAX_PARTITIONS} partitions"))
         assert_or_throw(num >= self._world, ValueError(
             f"num_partitions={num} must be >= the number of GPUs ({self._world})"))
         assert_or_throw(len(t.dictionaries) == 0, NotImplementedError(
             "string (dictionary-encoded) columns need a global dictionary before a multi-GPU shuffle"))
-        counts = gather_counts(t.offsets[1:] - t.offsets[:-1], self._group)
-        plan = ExchangePlan(counts, self._rank)
+        dev = t.device
+        kidx = [t.schema.index_of_key(k) for k in keys]
+        kvalid = [t.valid[i] for i in kidx]
         cols = list(t.columns)
         vpos: Dict[int, int] = {}
         for i, v in enumerate(t.valid):
             if v is not None:
                 vpos[i] = len(cols)
                 cols.append(v)
-        recv = [exchange_column(c, plan, self._group) for c in cols]  # NCCL all-to-all per column
-        outs = [torch.empty_like(c) for c in recv]
-        dev = t.device
-        K.copy_segments(recv, outs, plan.seg_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev))
+        widths = [c.element_size() for c in cols]
+        # ---- pass 1 on the local shard, counts to everybody
+        scratch = self._pool.scratch(dev, K.partition_scratch_bytes(dev, t.num_rows, num))
+        plan_local = K.partition_plan([t.columns[i] for i in kidx], num, kvalid, scratch=scratch)
+        counts = gather_counts(plan_local.offsets[1:] - plan_local.offsets[:-1], self._group)
+        plan = ExchangePlan(counts, self._rank)
+        if os.environ.get("FB_DIST_EXCHANGE", "pull") == "nccl":
+            return self._repartition_nccl(t, keys, cols, vpos, plan_local, plan)
+        rows = [int(x) for x in plan.rows_per_rank.tolist()]
+        self._ensure_arena(max(self._col_offsets(r, widths)[-1] for r in rows))
+        # ---- pass 2: scatter my rows into my arena (peers' pulls of the previous call are over:
+        #      every call ends with a barrier)
+        my_off = self._col_offsets(t.num_rows, widths)
+        parts = [self._arena[my_off[i]:my_off[i] + t.num_rows * w].view(c.dtype)
+                 for i, (c, w) in enumerate(zip(cols, widths))]
+        K.partition_apply(plan_local, cols, parts)
+        dist.barrier(group=self._group)  # stream-ordered: all ranks' arenas are complete
+        # ---- pull my partitions from every rank's arena into their final place
+        base = self._arena_hdl.buffer_ptrs
+        src_ptrs: List[int] = []
+        for s in range(self._world):
+            so = self._col_offsets(rows[s], widths)
+            src_ptrs += [int(base[s]) + so[i] for i in range(len(cols))]
+        outs = [torch.empty(plan.total_recv, dtype=c.dtype, device=dev) for c in cols]
+        K.copy_segments(None, outs, plan.pull_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev),
+                        max_len=plan.max_seg, src_table=plan.pull_src_rank.to(dev), src_ptrs=src_ptrs)
+        dist.barrier(group=self._group)  # nobody overwrites an arena that is still being read
         ncol = len(t.columns)
         valid = [outs[vpos[i]] if i in vpos else None for i in range(ncol)]
         res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
         res.global_partition_range = (plan.lo, plan.hi)  # which physical partitions this GPU owns
+        return B200DataFrame(res)
+
+    def _repartition_nccl(self, t: B200Table, keys: List[str], cols: List[torch.Tensor],
+                          vpos: Dict[int, int], plan_local: Any, plan: ExchangePlan) -> B200DataFrame:
+        """Baseline exchange (FB_DIST_EXCHANGE=nccl): one NCCL all-to-all per column + local
+        segment copy.  Kept for comparison; the pull kernel above is the product path."""
+        from . import kernels as K
+
+        dev = t.device
+        parts = K.partition_apply(plan_local, cols)
+        recv = [exchange_column(c, plan, self._group) for c in parts]
+        outs = [torch.empty_like(c) for c in recv]
+        K.copy_segments(recv, outs, plan.seg_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev),
+                        max_len=plan.max_seg)
+        ncol = len(t.columns)
+        valid = [outs[vpos[i]] if i in vpos else None for i in range(ncol)]
+        res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
+        res.global_partition_range = (plan.lo, plan.hi)
         return B200DataFrame(res)

@@ -159,21 +159,30 @@ def bytes_to_bits(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def copy_segments(src_cols: Sequence[torch.Tensor], dst_cols: Sequence[torch.Tensor],
-                  src_off: torch.Tensor, dst_off: torch.Tensor, seg_len: torch.Tensor) -> None:
-    """For every column: dst[dst_off[s]:+len[s]] = src[src_off[s]:+len[s]] (all tables on device)."""
+                  src_off: torch.Tensor, dst_off: torch.Tensor, seg_len: torch.Tensor,
+                  max_len: Optional[int] = None, src_table: Optional[torch.Tensor] = None,
+                  src_ptrs: Optional[Sequence[int]] = None) -> None:
+    """For every column: dst[dst_off[s]:+len[s]] = table[src_table[s]][src_off[s]:+len[s]].
+    ``src_ptrs`` (ntables x ncols raw device pointers, [table][col]) replaces ``src_cols`` when the
+    sources are peer-GPU buffers mapped through symmetric memory."""
     lib = _lib.load()
-    dev = src_cols[0].device
+    dev = dst_cols[0].device
     nseg = int(seg_len.shape[0])
-    if nseg == 0 or len(src_cols) == 0:
+    ncols = len(dst_cols)
+    if nseg == 0 or ncols == 0:
         return
-    ptr_src = torch.tensor([c.data_ptr() for c in src_cols], dtype=torch.int64, device=dev)
+    ptrs = list(src_ptrs) if src_ptrs is not None else [c.data_ptr() for c in src_cols]
+    ptr_src = torch.tensor(ptrs, dtype=torch.int64, device=dev)
     ptr_dst = torch.tensor([c.data_ptr() for c in dst_cols], dtype=torch.int64, device=dev)
-    widths = torch.tensor([c.element_size() for c in src_cols], dtype=torch.int32, device=dev)
+    widths = torch.tensor([c.element_size() for c in dst_cols], dtype=torch.int32, device=dev)
     for t in (src_off, dst_off, seg_len):
         assert t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
-    _lib.check(lib.fb_copy_segments(dev.index, _stream_ptr(dev), len(src_cols), ptr_src.data_ptr(),
-                                    ptr_dst.data_ptr(), widths.data_ptr(), nseg, src_off.data_ptr(),
-                                    dst_off.data_ptr(), seg_len.data_ptr()))
+    if max_len is None:
+        max_len = int(seg_len.max().item())
+    _lib.check(lib.fb_copy_segments(dev.index, _stream_ptr(dev), ncols, ptr_src.data_ptr(),
+                                    ptr_dst.data_ptr(), widths.data_ptr(), nseg,
+                                    0 if src_table is None else src_table.data_ptr(), src_off.data_ptr(),
+                                    dst_off.data_ptr(), seg_len.data_ptr(), int(max_len)))
 
 
 AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_MAX_F64 = range(7)

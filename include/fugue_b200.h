@@ -111,15 +111,19 @@ int fb_bytes_to_bits(int dev, void* stream, const uint8_t* bytes, int64_t nrows,
                      uint8_t* out_bits, int64_t* out_null_count);
 
 /* ---------------------------------------------------------------------------
- * Segment copy (multi-GPU exchange epilogue): for every column,
- * out[dst_off[s] .. +len[s]) = in[src_off[s] .. +len[s]).  ALL pointer arguments
- * (pointer tables, widths, offset tables) are DEVICE memory.  No reference
- * counterpart: the reference delegates shuffles to Dask/Spark/Ray
- * (fugue_dask/_utils.py:124-130).
+ * Segment copy / multi-GPU pull exchange: for every column c,
+ *   out[c][dst_off[s] .. +len[s]) = table[src_table[s]][c][src_off[s] .. +len[s])
+ * d_src_cols is a DEVICE array of (ntables x ncols) column pointers laid out [table][col]; with
+ * d_src_table == NULL every segment reads table 0.  The tables may be peer-GPU buffers mapped
+ * through symmetric memory: the kernel then pulls the runs over NVLink straight into their final
+ * place (no NCCL all-to-all, no staging pass).  ALL pointer arguments are DEVICE memory; max_len
+ * (host) is the longest segment, used to size the grid.  No reference counterpart: the reference
+ * delegates shuffles to Dask/Spark/Ray (fugue_dask/_utils.py:124-130).
  * --------------------------------------------------------------------------- */
 int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_cols,
                      void* const* d_dst_cols, const int32_t* d_widths, int nseg,
-                     const int64_t* d_src_off, const int64_t* d_dst_off, const int64_t* d_len);
+                     const int32_t* d_src_table, const int64_t* d_src_off, const int64_t* d_dst_off,
+                     const int64_t* d_len, int64_t max_len);
 
 /* ---------------------------------------------------------------------------
  * K6  hash group-by with aggregation (single 8-byte key; other key shapes are packed /
