@@ -483,10 +483,12 @@ fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, int chunk0,
 // ---------------------------------------------------------------------------
 constexpr int kTmaThreads = kBlock + 32;   // 16 consumer warps + 1 producer warp
 constexpr int kMaxUnits = FB_MAX_COLS + 1;
-constexpr uint32_t kStageBytes = (uint32_t)kTile * 8;
 constexpr int kSwcMaxCols = 8;             // payload columns per launch (carry buffers in smem)
 constexpr uint32_t kSwcMaxNum = 256;
-constexpr int kSwcG = 4;                   // rows per write-combining group (4 x 8 B = one 32 B sector)
+// Two tunings of the same kernel (chosen by FB_SWC_MODE, default 0: smaller tiles double the per-tile overhead):
+//   mode 0: tile 4096 rows, G = 4 rows (32 B groups)      mode 1: tile 2048 rows, G = 8 rows (64 B groups)
+constexpr int kSwcItemsA = 8, kSwcGA = 4;
+constexpr int kSwcItemsB = 4, kSwcGB = 8;
 
 struct TmaUnits {
   const uint64_t* src[kMaxUnits];  // unit 0 is the key column
@@ -494,13 +496,14 @@ struct TmaUnits {
   int32_t nunits;
 };
 
-template <int G>
+template <int G, int ITEMS>
 __host__ __device__ inline size_t swc_book_bytes(uint32_t num, int ncols) {
+  constexpr size_t kT = (size_t)kBlock * ITEMS;
   const size_t nbp = nb_padded(num);
   const size_t E = (size_t)num * (G - 1);
   size_t b = 2 * 8 * 16;                       // mbarriers (up to 16 stages)
   b += (size_t)(ncols + 1) * E * 8;            // carry buffers
-  b += ((size_t)kTile + E) * 4;                // slotinfo
+  b += (kT + E) * 4;                           // slotinfo
   b += 6 * nbp * 4 + 64 * 4;                   // per-partition arrays + scanw
   b += (size_t)kWarps * nbp * 2;               // cnt
   b += ((E * 2 + 15) / 16) * 16;               // carryinfo
@@ -548,13 +551,14 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, 
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory"); }
 
-template <int kBits, int G>
+template <int kBits, int G, int ITEMS>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols,
                       const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
-  constexpr uint32_t T = kTile;
+  constexpr uint32_t T = (uint32_t)kBlock * ITEMS;
+  constexpr uint32_t kStageBytes = T * 8;
   constexpr uint32_t GM = G - 1;
-  constexpr int kSlotRounds = (kTile + (int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
+  constexpr int kSlotRounds = ((int)T + (int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
   constexpr int kEntryRounds = ((int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
   extern __shared__ __align__(128) uint64_t smem64[];
   const uint32_t nbp = nb_padded(num);
@@ -630,15 +634,15 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
       // ---- unit 0: the key tile -> partition ids (warp-striped rows: warp*256 + r*32 + lane)
       mbar_wait(bar_full + 8 * s, ph);
       const uint64_t* __restrict__ kst = ring + (size_t)s * T;
-      uint32_t pid[kItems];
+      uint32_t pid[ITEMS];
 #pragma unroll
-      for (int r = 0; r < kItems; ++r)
-        pid[r] = fb_fastmod(fb_hash_single_u64(kst[warp * (32 * kItems) + r * 32 + lane]), dv);
+      for (int r = 0; r < ITEMS; ++r)
+        pid[r] = fb_fastmod(fb_hash_single_u64(kst[warp * (32 * ITEMS) + r * 32 + lane]), dv);
 
       // ---- stable rank inside (warp, partition)
-      uint32_t pos[kItems];
+      uint32_t pos[ITEMS];
 #pragma unroll
-      for (int r = 0; r < kItems; ++r) {
+      for (int r = 0; r < ITEMS; ++r) {
         const unsigned m = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
         const unsigned before = __popc(m & lt);
         uint32_t old = 0;
@@ -715,12 +719,12 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
       // ---- every new row and every old carry entry finds its place: an output slot of this
       //      tile or an entry of the new carry
 #pragma unroll
-      for (int r = 0; r < kItems; ++r) {
+      for (int r = 0; r < ITEMS; ++r) {
         const uint32_t b = pid[r];
         const uint32_t bi = binfo[b];
         const uint32_t i = (bi & 0xFu) + pos[r] + my_cnt[b];  // index in the partition's pending list
         const uint32_t w = bi >> 8;
-        const uint32_t row = warp * (32 * kItems) + r * 32 + lane;
+        const uint32_t row = warp * (32 * ITEMS) + r * 32 + lane;
         if (i < w) slotinfo[wstart[b] + i] = (b << 16) | row;
         else carryinfo[b * GM + (i - w)] = (uint16_t)row;
       }
@@ -902,8 +906,10 @@ cudaError_t ensure_smem_optin(int dev) {
   {
     int smem_max = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcG>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcG>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGA, kSwcItemsA>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcGA, kSwcItemsA>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGB, kSwcItemsB>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcGB, kSwcItemsB>, (size_t)smem_max);
   }
   FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
   FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
@@ -1126,17 +1132,25 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
           ++units.nunits;
         }
       }
-      const size_t book = swc_book_bytes<kSwcG>(num_partitions, nb);
-      int nstages = (int)(((size_t)smem_max - book) / kStageBytes);
+      const int mode = getenv("FB_SWC_MODE") ? atoi(getenv("FB_SWC_MODE")) : 0;  // measured: mode 0 3.49 ms, mode 1 4.59 ms
+      const size_t book = mode == 0 ? swc_book_bytes<kSwcGA, kSwcItemsA>(num_partitions, nb)
+                                    : swc_book_bytes<kSwcGB, kSwcItemsB>(num_partitions, nb);
+      const size_t stage_bytes = (size_t)kBlock * (mode == 0 ? kSwcItemsA : kSwcItemsB) * 8;
+      int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
       if (nstages > 16) nstages = 16;
       FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
-      const size_t tsmem = (size_t)nstages * kStageBytes + book;
-      if (bits == 4)
-        fb_scatter_swc_kernel<4, kSwcG><<<grid, kTmaThreads, tsmem, st>>>(
-            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
-      else
-        fb_scatter_swc_kernel<8, kSwcG><<<grid, kTmaThreads, tsmem, st>>>(
-            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
+      const size_t tsmem = (size_t)nstages * stage_bytes + book;
+#define FB_LAUNCH_SWC(B, G, I)                                                              \
+  fb_scatter_swc_kernel<B, G, I><<<grid, kTmaThreads, tsmem, st>>>(                         \
+      units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets)
+      if (mode == 0) {
+        if (bits == 4) FB_LAUNCH_SWC(4, kSwcGA, kSwcItemsA);
+        else FB_LAUNCH_SWC(8, kSwcGA, kSwcItemsA);
+      } else {
+        if (bits == 4) FB_LAUNCH_SWC(4, kSwcGB, kSwcItemsB);
+        else FB_LAUNCH_SWC(8, kSwcGB, kSwcItemsB);
+      }
+#undef FB_LAUNCH_SWC
       FB_CUDA(cudaGetLastError());
     }
     // the partial tail tile of the fast columns

@@ -1,0 +1,41 @@
+"""Secondary measurements: BASELINE configs 4 (GROUP BY) and 5 (JOIN) at single-GPU scale."""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fugue_b200 import kernels as K
+
+def timeit(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+def main():
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = {}
+    n, nk = 125_000_000, 10_000_000      # config 4 per-GPU share of 1B rows / 8 GPUs
+    keys = torch.randint(0, nk, (n,), dtype=torch.int64, device=dev, generator=g) * 0x9E3779B97F4A7C15 % (1 << 62)
+    v = torch.randn(n, dtype=torch.float64, device=dev, generator=g).view(torch.int64)
+    ms = timeit(lambda: K.groupby_u64(keys, None, [v, None], [None, None], [K.AGG_SUM_F64, K.AGG_COUNT]))
+    out["groupby_sum_count"] = {"rows": n, "distinct_keys": nk, "ms": ms, "rows_per_s": n / ms * 1e3,
+                                "alg_GBps": 16 * n / ms / 1e6}
+    del keys, v
+    n = 62_500_000                        # config 5 per-GPU share: 500M x 500M / 8
+    lk = torch.randint(0, n, (n,), dtype=torch.int64, device=dev, generator=g)
+    rk = torch.randperm(n, dtype=torch.int64, device=dev, generator=g)
+    lv = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    rv = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    def join():
+        tab = K.JoinTable(rk, None)
+        li, ri = tab.probe(lk, None, outer=False)
+        K.gather_rows([lk, lv], [None, None], li, False)
+        K.gather_rows([rv], [None], ri, False)
+    ms = timeit(join)
+    out["inner_join"] = {"left_rows": n, "right_rows": n, "out_rows": n, "ms": ms, "out_rows_per_s": n / ms * 1e3,
+                         "alg_GBps": 56 * n / ms / 1e6}
+    print(json.dumps(out))
+
+main()
