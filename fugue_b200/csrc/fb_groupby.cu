@@ -101,19 +101,28 @@ __device__ __forceinline__ void apply_aggs(uint64_t* __restrict__ slot, const Ag
   }
 }
 
-// slot of `key` (inserting it if absent); -1 on overflow
+// slot of `key` (inserting it if absent); -1 on overflow.  With num_parts > 0 the table is cut
+// into num_parts equal regions and a key lives in the region of its partition id (the same
+// hash % num_parts as the partitioner): on hash-partitioned input the kernel then sweeps the
+// table region by region and the atomics stay L2-resident instead of going to HBM.
 __device__ __forceinline__ int64_t find_or_insert(uint64_t* __restrict__ table, int words, int64_t mask,
-                                                  uint64_t key) {
-  int64_t s = (int64_t)(fb_fmix64(key) & (uint64_t)mask);
+                                                  uint64_t key, const FbDiv& dv, int64_t region_base_shift) {
+  int64_t base = 0;
+  uint64_t h = fb_fmix64(key);
+  if (region_base_shift >= 0) {
+    base = (int64_t)fb_fastmod(fb_hash_single_u64(key), dv) << region_base_shift;
+    h >>= 7;
+  }
+  int64_t s = (int64_t)(h & (uint64_t)mask);
 #pragma unroll 1
   for (int probe = 0; probe < kMaxProbe; ++probe) {
-    uint64_t* slot = table + s * words;
+    uint64_t* slot = table + (base + s) * words;
     uint64_t cur = *(volatile uint64_t*)slot;
-    if (cur == key) return s;
+    if (cur == key) return base + s;
     if (cur == kEmpty) {
       const uint64_t old = atomicCAS((unsigned long long*)slot, (unsigned long long)kEmpty,
                                      (unsigned long long)key);
-      if (old == kEmpty || old == key) return s;
+      if (old == kEmpty || old == key) return base + s;
     }
     s = (s + 1) & mask;
   }
@@ -123,8 +132,9 @@ __device__ __forceinline__ int64_t find_or_insert(uint64_t* __restrict__ table, 
 __global__ void __launch_bounds__(256)
 fb_groupby_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ key_valid, int64_t nrows,
                   uint64_t* __restrict__ table, int64_t capacity, int words, AggSpec spec,
-                  int64_t* __restrict__ status) {
-  const int64_t mask = capacity - 1;
+                  int64_t* __restrict__ status, FbDiv dv, int64_t region_shift) {
+  // region_shift < 0: one region = the whole table; else region size = 1 << region_shift
+  const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt = fb_lanemask_lt();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -156,7 +166,7 @@ fb_groupby_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__
     int leader = need ? (__ffs(peers) - 1) : (int)lane;
     const uint64_t lkey = __shfl_sync(0xFFFFFFFFu, key, leader);
     const bool follow = need && leader != (int)lane && lkey == key;
-    if (need && !follow) s = find_or_insert(table, words, mask, key);
+    if (need && !follow) s = find_or_insert(table, words, mask, key, dv, region_shift);
     const int64_t ls = __shfl_sync(0xFFFFFFFFu, s, leader);
     if (follow) s = ls;
     if (ok) {
@@ -229,7 +239,8 @@ size_t fb_groupby_table_bytes(int64_t capacity, int naggs) {
 
 int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const uint8_t* key_valid,
                    int naggs, const void* const* val_ptrs, const uint8_t* const* val_valid,
-                   const int32_t* agg_ops, int64_t capacity, void* table, int64_t* d_status) {
+                   const int32_t* agg_ops, int64_t capacity, uint32_t num_parts, void* table,
+                   int64_t* d_status) {
   FB_CHECK(nrows >= 0, "nrows < 0");
   FB_CHECK(capacity >= 2 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 2");
   FB_CHECK(table != nullptr && d_status != nullptr, "table/status is NULL");
@@ -237,6 +248,14 @@ int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   AggSpec spec;
   if (int rc = fill_spec(spec, naggs, val_ptrs, val_valid, agg_ops)) return rc;
+  int64_t region_shift = -1;
+  if (num_parts > 1) {
+    FB_CHECK((num_parts & (num_parts - 1)) == 0 && (int64_t)num_parts * 2 <= capacity,
+             "num_parts must be a power of two <= capacity / 2");
+    region_shift = 0;
+    while (((int64_t)num_parts << region_shift) < capacity) ++region_shift;
+  }
+  const FbDiv dv = fb_make_div(num_parts > 1 ? num_parts : 1);
   cudaStream_t st = (cudaStream_t)stream;
   const int words = slot_words(naggs);
   const int sms = fb_sm_count(dev);
@@ -245,7 +264,7 @@ int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const
   if (nrows > 0) {
     FB_CHECK(keys != nullptr, "keys is NULL");
     fb_groupby_kernel<<<sms * 8, 256, 0, st>>>((const uint64_t*)keys, key_valid, nrows, (uint64_t*)table,
-                                              capacity, words, spec, d_status);
+                                              capacity, words, spec, d_status, dv, region_shift);
     FB_CUDA(cudaGetLastError());
   }
   return 0;

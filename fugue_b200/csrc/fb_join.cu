@@ -32,18 +32,27 @@ __global__ void fb_join_clear_kernel(Slot* __restrict__ table, int64_t capacity,
 
 __global__ void __launch_bounds__(256)
 fb_join_build_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ valid, int64_t n,
-                     Slot* __restrict__ table, int64_t capacity, int64_t* __restrict__ status) {
-  const int64_t mask = capacity - 1;
+                     Slot* __restrict__ table, int64_t capacity, int64_t* __restrict__ status, FbDiv dv,
+                     int64_t region_shift) {
+  // region_shift >= 0: the table is cut into regions of 1 << region_shift slots, one per hash
+  // partition of the (hash-partitioned) inputs, so build and probe sweep it region by region
+  const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     if (valid != nullptr && valid[i] == 0) continue;  // NULL keys never match: not inserted
     const uint64_t key = keys[i];
-    int64_t s = (int64_t)(fb_fmix64(key) & (uint64_t)mask);
+    uint64_t h = fb_fmix64(key);
+    int64_t base = 0;
+    if (region_shift >= 0) {
+      base = (int64_t)fb_fastmod(fb_hash_single_u64(key), dv) << region_shift;
+      h >>= 7;
+    }
+    int64_t s = (int64_t)(h & (uint64_t)mask);
     bool done = false;
-    for (int64_t probe = 0; probe < capacity; ++probe) {
-      if (table[s].rowp1 == 0 &&
-          atomicCAS(&table[s].rowp1, 0ULL, (unsigned long long)(i + 1)) == 0ULL) {
-        table[s].key = key;
+    for (int64_t probe = 0; probe <= mask; ++probe) {
+      if (table[base + s].rowp1 == 0 &&
+          atomicCAS(&table[base + s].rowp1, 0ULL, (unsigned long long)(i + 1)) == 0ULL) {
+        table[base + s].key = key;
         done = true;
         break;
       }
@@ -61,19 +70,26 @@ __global__ void __launch_bounds__(256)
 fb_join_probe_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ valid, int64_t n,
                      const Slot* __restrict__ table, int64_t capacity, int outer,
                      int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
-                     int64_t* __restrict__ out_probe, int64_t* __restrict__ out_build) {
-  const int64_t mask = capacity - 1;
+                     int64_t* __restrict__ out_probe, int64_t* __restrict__ out_build, FbDiv dv,
+                     int64_t region_shift) {
+  const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t c = 0;
     int64_t o = kWrite ? offsets[i] : 0;
     if (valid == nullptr || valid[i] != 0) {
       const uint64_t key = keys[i];
-      int64_t s = (int64_t)(fb_fmix64(key) & (uint64_t)mask);
-      for (int64_t probe = 0; probe < capacity; ++probe) {
-        const unsigned long long r = table[s].rowp1;
+      uint64_t h = fb_fmix64(key);
+      int64_t base = 0;
+      if (region_shift >= 0) {
+        base = (int64_t)fb_fastmod(fb_hash_single_u64(key), dv) << region_shift;
+        h >>= 7;
+      }
+      int64_t s = (int64_t)(h & (uint64_t)mask);
+      for (int64_t probe = 0; probe <= mask; ++probe) {
+        const unsigned long long r = table[base + s].rowp1;
         if (r == 0) break;
-        if (table[s].key == key) {
+        if (table[base + s].key == key) {
           if (kWrite) {
             out_probe[o + c] = i;
             out_build[o + c] = (int64_t)r - 1;
@@ -202,6 +218,13 @@ fb_gather_rows_kernel(const void* const* __restrict__ src_cols, void* const* __r
   }
 }
 
+inline int64_t region_shift_of(int64_t capacity, uint32_t num_parts) {
+  if (num_parts <= 1) return -1;
+  int64_t sh = 0;
+  while (((int64_t)num_parts << sh) < capacity) ++sh;
+  return sh;
+}
+
 inline unsigned grid_for(int dev, int64_t n, int per_sm = 8) {
   int64_t b = (n + 255) / 256;
   int64_t m = (int64_t)fb_sm_count(dev) * per_sm;
@@ -217,48 +240,54 @@ extern "C" {
 size_t fb_join_table_bytes(int64_t capacity) { return capacity > 0 ? (size_t)capacity * sizeof(Slot) : 0; }
 
 int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
-                      int64_t capacity, void* table, int64_t* d_status) {
+                      int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status) {
   FB_CHECK(nbuild >= 0, "nbuild < 0");
   FB_CHECK(capacity >= 2 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 2");
   FB_CHECK(capacity > nbuild, "capacity must exceed the number of build rows");
   FB_CHECK(table != nullptr && d_status != nullptr, "table/status is NULL");
+  FB_CHECK(num_parts <= 1 || ((num_parts & (num_parts - 1)) == 0 && (int64_t)num_parts * 2 <= capacity),
+           "num_parts must be a power of two <= capacity / 2");
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   cudaStream_t st = (cudaStream_t)stream;
+  const FbDiv dv = fb_make_div(num_parts > 1 ? num_parts : 1);
+  const int64_t rs = region_shift_of(capacity, num_parts);
   fb_join_clear_kernel<<<grid_for(dev, capacity), 256, 0, st>>>((Slot*)table, capacity, d_status);
   FB_CUDA(cudaGetLastError());
   if (nbuild > 0) {
     fb_join_build_kernel<<<grid_for(dev, nbuild), 256, 0, st>>>((const uint64_t*)keys, key_valid, nbuild,
-                                                                (Slot*)table, capacity, d_status);
+                                                                (Slot*)table, capacity, d_status, dv, rs);
     FB_CUDA(cudaGetLastError());
   }
   return 0;
 }
 
 int fb_join_probe_count_u64(int dev, void* stream, int64_t nprobe, const void* keys,
-                            const uint8_t* key_valid, int64_t capacity, const void* table, int outer,
-                            int64_t* out_counts) {
+                            const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
+                            const void* table, int outer, int64_t* out_counts) {
   FB_CHECK(nprobe >= 0, "nprobe < 0");
   if (nprobe == 0) return 0;
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   fb_join_probe_kernel<false><<<grid_for(dev, nprobe), 256, 0, (cudaStream_t)stream>>>(
       (const uint64_t*)keys, key_valid, nprobe, (const Slot*)table, capacity, outer, out_counts, nullptr,
-      nullptr, nullptr);
+      nullptr, nullptr, fb_make_div(num_parts > 1 ? num_parts : 1), region_shift_of(capacity, num_parts));
   FB_CUDA(cudaGetLastError());
   return 0;
 }
 
 int fb_join_probe_write_u64(int dev, void* stream, int64_t nprobe, const void* keys,
-                            const uint8_t* key_valid, int64_t capacity, const void* table, int outer,
-                            const int64_t* offsets, int64_t* out_probe_idx, int64_t* out_build_idx) {
+                            const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
+                            const void* table, int outer, const int64_t* offsets, int64_t* out_probe_idx,
+                            int64_t* out_build_idx) {
   FB_CHECK(nprobe >= 0, "nprobe < 0");
   if (nprobe == 0) return 0;
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   fb_join_probe_kernel<true><<<grid_for(dev, nprobe), 256, 0, (cudaStream_t)stream>>>(
       (const uint64_t*)keys, key_valid, nprobe, (const Slot*)table, capacity, outer, nullptr, offsets,
-      out_probe_idx, out_build_idx);
+      out_probe_idx, out_build_idx, fb_make_div(num_parts > 1 ? num_parts : 1),
+      region_shift_of(capacity, num_parts));
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -189,9 +189,14 @@ AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_
 MAX_AGGS = 8
 
 
+GROUPBY_PARTITION_MIN_ROWS = 4_000_000   # below this the table fits in L2 anyway
+GROUPBY_PARTITIONS = 256
+
+
 def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
                 vals: Sequence[Optional[torch.Tensor]], val_valid: Sequence[Optional[torch.Tensor]],
-                ops: Sequence[int], capacity: Optional[int] = None, max_capacity: Optional[int] = None
+                ops: Sequence[int], capacity: Optional[int] = None, max_capacity: Optional[int] = None,
+                partition: Optional[bool] = None
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor], List[torch.Tensor], int]:
     """K6: hash group-by of an 8-byte key column with up to 8 aggregates.
     Returns (group keys, key validity or None, aggregate columns as int64 bit patterns, ngroups)."""
@@ -201,6 +206,23 @@ def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
     for v in vals:
         assert v is None or (v.element_size() == 8 and v.is_cuda and v.is_contiguous() and v.shape[0] == n)
     naggs = len(ops)
+    num_parts = 0
+    if partition is None:
+        partition = n >= GROUPBY_PARTITION_MIN_ROWS
+    if partition and n > 0:
+        # radix-partition (key, values, masks) on the key first: rows of one partition are then
+        # contiguous and the aggregation sweeps the hash table region by region (L2-resident)
+        uniq: List[torch.Tensor] = [keys]
+        for t in list(vals) + [key_valid] + list(val_valid):
+            if t is not None and all(t.data_ptr() != u.data_ptr() for u in uniq):
+                uniq.append(t)
+        pout, _ = partition_columns(uniq, [0], GROUPBY_PARTITIONS, [key_valid])
+        remap = {u.data_ptr(): o for u, o in zip(uniq, pout)}
+        keys = remap[keys.data_ptr()]
+        key_valid = None if key_valid is None else remap[key_valid.data_ptr()]
+        vals = [None if v is None else remap[v.data_ptr()] for v in vals]
+        val_valid = [None if v is None else remap[v.data_ptr()] for v in val_valid]
+        num_parts = GROUPBY_PARTITIONS
     if n == 0:  # nothing to aggregate: no groups
         e = torch.empty(0, dtype=torch.int64, device=dev)
         return (e, None if key_valid is None else torch.empty(0, dtype=torch.uint8, device=dev),
@@ -220,7 +242,8 @@ def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
         table = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.fb_groupby_u64(dev.index, _stream_ptr(dev), n, keys.data_ptr(),
                                       0 if key_valid is None else key_valid.data_ptr(), naggs, vp, vv, opa,
-                                      capacity, table.data_ptr(), status.data_ptr()))
+                                      capacity, num_parts if capacity >= 2 * max(num_parts, 1) else 0,
+                                      table.data_ptr(), status.data_ptr()))
         if int(status[0].item()) == 0:
             break
         if capacity >= hard_max:
@@ -261,17 +284,22 @@ def exclusive_scan(counts: torch.Tensor) -> Tuple[torch.Tensor, int]:
 class JoinTable:
     """Hash multimap of the build side of a join (K7)."""
 
-    def __init__(self, keys: torch.Tensor, valid: Optional[torch.Tensor]):
+    def __init__(self, keys: torch.Tensor, valid: Optional[torch.Tensor], num_parts: int = 0):
+        """num_parts > 1: ``keys`` (and later the probe keys) were hash-partitioned into that many
+        partitions with ``partition_columns``; the table is then used region by region."""
         lib = _lib.load()
         dev, n = _check_cols([keys])
         assert keys.element_size() == 8
         self.nbuild = n
         self.capacity = max(2, 1 << (2 * max(n, 1)).bit_length())  # load factor <= 0.5
+        if num_parts > 1:
+            self.capacity = max(self.capacity, 4 * num_parts)
+        self.num_parts = num_parts if num_parts > 1 else 0
         self.table = torch.empty(int(lib.fb_join_table_bytes(self.capacity)), dtype=torch.uint8, device=dev)
         self.status = torch.zeros(4, dtype=torch.int64, device=dev)
         _lib.check(lib.fb_join_build_u64(dev.index, _stream_ptr(dev), n, keys.data_ptr(),
                                          0 if valid is None else valid.data_ptr(), self.capacity,
-                                         self.table.data_ptr(), self.status.data_ptr()))
+                                         self.num_parts, self.table.data_ptr(), self.status.data_ptr()))
         self.device = dev
 
     def probe_counts(self, keys: torch.Tensor, valid: Optional[torch.Tensor], outer: bool) -> torch.Tensor:
@@ -280,7 +308,8 @@ class JoinTable:
         counts = torch.empty(n, dtype=torch.int64, device=self.device)
         _lib.check(lib.fb_join_probe_count_u64(self.device.index, _stream_ptr(self.device), n, keys.data_ptr(),
                                                0 if valid is None else valid.data_ptr(), self.capacity,
-                                               self.table.data_ptr(), 1 if outer else 0, counts.data_ptr()))
+                                               self.num_parts, self.table.data_ptr(), 1 if outer else 0,
+                                               counts.data_ptr()))
         return counts
 
     def probe(self, keys: torch.Tensor, valid: Optional[torch.Tensor], outer: bool
@@ -295,8 +324,8 @@ class JoinTable:
         bi = torch.empty(total, dtype=torch.int64, device=self.device)
         _lib.check(lib.fb_join_probe_write_u64(self.device.index, _stream_ptr(self.device), n, keys.data_ptr(),
                                                0 if valid is None else valid.data_ptr(), self.capacity,
-                                               self.table.data_ptr(), 1 if outer else 0, offsets.data_ptr(),
-                                               pi.data_ptr(), bi.data_ptr()))
+                                               self.num_parts, self.table.data_ptr(), 1 if outer else 0,
+                                               offsets.data_ptr(), pi.data_ptr(), bi.data_ptr()))
         return pi, bi
 
     def matched_mask(self, build_idx: torch.Tensor) -> torch.Tensor:

@@ -135,6 +135,9 @@ int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_
  * skipped (SQL semantics), COUNT with a NULL value pointer is COUNT(*).
  *
  * fb_groupby_u64     : clears `table` (fb_groupby_table_bytes) and aggregates nrows rows.
+ *                      num_parts > 1 (power of two): the input was hash-partitioned on the key into
+ *                      num_parts partitions with fb_partition_cols; keys of partition p then live in
+ *                      table region p, so the table is swept region by region (L2-resident atomics).
  *                      d_status[0] != 0 afterwards means the table was too small: retry with
  *                      a larger power-of-two `capacity`.  Value columns are 8 bytes wide.
  * fb_groupby_extract : compacts the groups into out_keys / out_key_valid / out_aggs[a]
@@ -155,7 +158,8 @@ enum {
 size_t fb_groupby_table_bytes(int64_t capacity, int naggs);
 int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const uint8_t* key_valid,
                    int naggs, const void* const* val_ptrs, const uint8_t* const* val_valid,
-                   const int32_t* agg_ops, int64_t capacity, void* table, int64_t* d_status);
+                   const int32_t* agg_ops, int64_t capacity, uint32_t num_parts, void* table,
+                   int64_t* d_status);
 int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const int32_t* agg_ops,
                        const void* table, void* out_keys, uint8_t* out_key_valid,
                        void* const* d_out_aggs, int64_t* d_status);
@@ -167,6 +171,9 @@ int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const
  *           schema rule: fugue/dataframe/utils.py:152-226 (host side)
  * NULL keys never match (fugue_test/execution_suite.py:533-543).
  *
+ *   num_parts > 1 (power of two, same value in build and probe): both inputs were hash-partitioned
+ *   on the key with fb_partition_cols into num_parts partitions; the table is then used region by
+ *   region (one region per partition) and stays L2-resident (radix join).
  *   fb_join_build_u64        multimap of the build side (capacity: power of two > nbuild,
  *                            table: fb_join_table_bytes(capacity)); d_status[0] != 0: overflow
  *   fb_join_probe_count_u64  matches per probe row (outer != 0: unmatched rows count 1)
@@ -179,13 +186,14 @@ int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const
  * --------------------------------------------------------------------------- */
 size_t fb_join_table_bytes(int64_t capacity);
 int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
-                      int64_t capacity, void* table, int64_t* d_status);
+                      int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status);
 int fb_join_probe_count_u64(int dev, void* stream, int64_t nprobe, const void* keys,
-                            const uint8_t* key_valid, int64_t capacity, const void* table, int outer,
-                            int64_t* out_counts);
+                            const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
+                            const void* table, int outer, int64_t* out_counts);
 int fb_join_probe_write_u64(int dev, void* stream, int64_t nprobe, const void* keys,
-                            const uint8_t* key_valid, int64_t capacity, const void* table, int outer,
-                            const int64_t* offsets, int64_t* out_probe_idx, int64_t* out_build_idx);
+                            const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
+                            const void* table, int outer, const int64_t* offsets, int64_t* out_probe_idx,
+                            int64_t* out_build_idx);
 int fb_join_mark_matched(int dev, void* stream, const int64_t* build_idx, int64_t n, uint8_t* matched);
 size_t fb_exclusive_scan_scratch_bytes(int64_t n);
 int fb_exclusive_scan_i64(int dev, void* stream, int64_t n, const int64_t* in, int64_t* out,

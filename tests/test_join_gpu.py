@@ -147,3 +147,22 @@ def test_full_size_properties_unique_build_side():
     assert torch.equal(li, torch.arange(n, device=dev))      # probe-row-major output
     assert torch.equal(rk[ri], lk)                           # every pair really matches
     assert int(tab.status[0]) == 0
+
+
+@pytest.mark.parametrize("how", ["inner", "left_outer", "full_outer", "semi", "anti"])
+def test_radix_join_path_matches_oracle(e, how, monkeypatch):
+    """Force the radix (partition-first) path on a mid-size input and compare with pandas."""
+    import fugue_b200.join as J
+
+    monkeypatch.setattr(J, "RADIX_JOIN_MIN_ROWS", 1000)
+    rng = np.random.default_rng(21)
+    n1, n2 = 120_000, 90_000
+    l = pd.DataFrame({"key": rng.integers(0, 60_000, n1), "lv": rng.standard_normal(n1), "li": np.arange(n1)})
+    r = pd.DataFrame({"key": rng.integers(30_000, 100_000, n2), "rv": rng.standard_normal(n2)})
+    l.loc[rng.integers(0, n1, 300), "key"] = np.nan
+    r.loc[rng.integers(0, n2, 300), "key"] = np.nan
+    got = fa.join(fa.as_fugue_engine_df(e, l, "key:double,lv:double,li:long"),
+                  fa.as_fugue_engine_df(e, r, "key:double,rv:double"), how=how, engine=e)
+    exp = ora.join(l, r, how)
+    assert got.count() == len(exp)
+    df_eq(got, exp.values.tolist(), got.schema, throw=True)
