@@ -318,6 +318,17 @@ def run_b200(args):
                              f"{KEY_CARDINALITY} keys (1526 rows per key as in the full workload), 2 timed passes of the restated "
                              "NativeExecutionEngine.map_dataframe (pandas groupby-iterate + concat); "
                              "the reference is single-threaded (get_current_parallelism() == 1)"}
+        extras = None
+        if world == 1 and not args.no_extras:
+            # secondary metrics: BASELINE configs 4 (GROUP BY) and 5 (JOIN) at their per-GPU sizes
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import relational_bench
+
+                torch.cuda.empty_cache()
+                extras = relational_bench.measure(local_rank)
+            except Exception as ex:  # pragma: no cover
+                extras = {"error": repr(ex)}
         launches_per_step = 4 + (1 if n % 4096 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps,
@@ -330,7 +341,7 @@ def run_b200(args):
                        "l2": "inputs (6.4 GB/GPU) are larger than L2 (126 MB); no flush needed",
                        "rows_out": nrows_out},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }
         print(json.dumps(line))
     if world > 1:
@@ -346,6 +357,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default: BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,8 +12,8 @@ def timeit(fn, reps=3):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts) // 2]
 
-def main():
-    dev = torch.device("cuda", 0)
+def measure(device_index: int = 0):
+    dev = torch.device("cuda", device_index)
     g = torch.Generator(device=dev).manual_seed(0)
     out = {}
     n, nk = 125_000_000, 10_000_000      # config 4 per-GPU share of 1B rows / 8 GPUs
@@ -46,6 +46,9 @@ def main():
     out["inner_join_flat_table_ms"] = ms_flat
     out["inner_join"] = {"left_rows": n, "right_rows": n, "out_rows": n, "ms": ms, "out_rows_per_s": n / ms * 1e3,
                          "alg_GBps": 56 * n / ms / 1e6}
-    print(json.dumps(out))
+    del lk, rk, lv, rv, L, R, res
+    return out
 
-main()
+
+if __name__ == "__main__":
+    print(json.dumps(measure()))
