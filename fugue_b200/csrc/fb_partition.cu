@@ -553,7 +553,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 
 template <int kBits, int G, int ITEMS>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols,
+fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols, int store_mode,
                       const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
   constexpr uint32_t T = (uint32_t)kBlock * ITEMS;
   constexpr uint32_t kStageBytes = T * 8;
@@ -789,9 +789,23 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
 #pragma unroll
           for (int q = 0; q < kEntryRounds; ++q)
             if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : oldc[csrc[q] - T];
+          if (store_mode == 0) {
 #pragma unroll
-          for (int k = 0; k < kSlotRounds; ++k)
-            if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
+            for (int k = 0; k < kSlotRounds; ++k)
+              if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
+          } else if (store_mode == 1) {
+#pragma unroll
+            for (int k = 0; k < kSlotRounds; ++k)
+              if (srcd[k] != 0xFFFFu) __stcs((unsigned long long*)out + dst[k], (unsigned long long)v[k]);
+          } else if (store_mode == 2) {
+#pragma unroll
+            for (int k = 0; k < kSlotRounds; ++k)
+              if (srcd[k] != 0xFFFFu) __stcg((unsigned long long*)out + dst[k], (unsigned long long)v[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kSlotRounds; ++k)
+              if (srcd[k] != 0xFFFFu) __stwt((unsigned long long*)out + dst[k], (unsigned long long)v[k]);
+          }
           consumer_sync();  // every warp has read this column's old carry (= the next spare)
 #pragma unroll
           for (int q = 0; q < kEntryRounds; ++q) {
@@ -1132,6 +1146,7 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
           ++units.nunits;
         }
       }
+      const int store_mode = getenv("FB_STORE_MODE") ? atoi(getenv("FB_STORE_MODE")) : 0;
       const int mode = getenv("FB_SWC_MODE") ? atoi(getenv("FB_SWC_MODE")) : 0;  // measured: mode 0 3.49 ms, mode 1 4.59 ms
       const size_t book = mode == 0 ? swc_book_bytes<kSwcGA, kSwcItemsA>(num_partitions, nb)
                                     : swc_book_bytes<kSwcGB, kSwcItemsB>(num_partitions, nb);
@@ -1142,7 +1157,7 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
       const size_t tsmem = (size_t)nstages * stage_bytes + book;
 #define FB_LAUNCH_SWC(B, G, I)                                                              \
   fb_scatter_swc_kernel<B, G, I><<<grid, kTmaThreads, tsmem, st>>>(                         \
-      units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets)
+      units, dv, num_partitions, g, nstages, nb, store_mode, (const uint32_t*)scratch, part_offsets)
       if (mode == 0) {
         if (bits == 4) FB_LAUNCH_SWC(4, kSwcGA, kSwcItemsA);
         else FB_LAUNCH_SWC(8, kSwcGA, kSwcItemsA);
