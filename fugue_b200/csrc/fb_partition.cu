@@ -132,7 +132,8 @@ constexpr int kHistRows = kHistBlock * kItems;
 
 template <bool kSingleU64, int kBits>
 __global__ void __launch_bounds__(kHistBlock, 2)
-fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist) {
+fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist,
+               uint8_t* __restrict__ pid_plane) {
   extern __shared__ uint32_t s_cnt[];
   for (uint32_t i = threadIdx.x; i < (uint32_t)kHistWarps * num; i += kHistBlock) s_cnt[i] = 0;
   __syncthreads();
@@ -147,6 +148,8 @@ fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __res
     for (int r = 0; r < kItems; ++r) {
       int64_t row = base + (int64_t)r * kHistBlock + threadIdx.x;
       pid[r] = (full || row < row1) ? compute_pid<kSingleU64>(keys, dv, row) : 0xFFFFFFFFu;
+      // 1-byte partition id plane for pass 2 (num <= 256): pass 2 never hashes again
+      if (pid_plane != nullptr && pid[r] != 0xFFFFFFFFu) pid_plane[row] = (uint8_t)pid[r];
     }
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
@@ -848,6 +851,404 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
 }
 
 // ---------------------------------------------------------------------------
+// pass 2, fast path v5: warp-specialised scatter (producer / rankers / movers).
+//
+// Measured on v4 (profiles/r1_notes.md): one third of the kernel is the per-tile ranking
+// (hash, match, scans), during which no byte moves; the column phase itself runs near the HBM
+// peak.  Here the two run concurrently on different warps of the same persistent CTA:
+//   warp 24      producer : TMA bulk loads - the 1-byte partition ids of tile t+1 (written by pass 1,
+//                           so nothing is hashed here and ANY key shape takes this path) and the
+//                           payload column tiles of tile t into the ring
+//   warps 16-23  rankers  : rank tile t+1 (ballot match + warp-private counters + scans), advance
+//                           the write-combining state, build the slot list of the tile
+//   warps 0-15   movers   : tile t: per column gather from the staged tile / carry, store whole
+//                           sector groups, save the new carry (in place: the per-column barrier
+//                           separates the reads of the old carry from the writes of the new one)
+// Hand-off through mbarriers: slots_ready (rankers -> movers), slots_free (movers -> rankers, as
+// soon as the slot list sits in mover registers), flush_done at chunk ends, full/empty per ring
+// stage and per pid buffer.
+// Shared memory (one CTA per SM), T = 4096, E = num * (G - 1):
+//   ring[S][T] u64 | mbarriers | carry[ncols][E] u64 | slotinfo[T+E] u32 | wpos kcnt binfo
+//   bin_start wstart wdelta [nbp] u32 | scanw[64] | cnt[8][nbp] u16 | carryinfo[E] u16 | pid[2][T] u8
+// ---------------------------------------------------------------------------
+constexpr int kWsMoverWarps = 16, kWsRankWarps = 8;
+constexpr int kWsMovers = kWsMoverWarps * 32, kWsRankers = kWsRankWarps * 32;
+constexpr int kWsThreads = kWsMovers + kWsRankers + 128;  // + producer warpgroup (1 active warp)
+constexpr int kWsG = 4;
+
+struct WsUnits {
+  const uint64_t* src[kSwcMaxCols];
+  uint64_t* dst[kSwcMaxCols];
+  int32_t nunits;
+};
+
+template <int G, int RI>
+__host__ __device__ inline size_t ws_book_bytes(uint32_t num, int ncols) {
+  constexpr size_t kT = (size_t)kWsRankers * RI;
+  const size_t nbp = nb_padded(num);
+  const size_t E = (size_t)num * (G - 1);
+  size_t b = 64 * 8;                           // mbarriers
+  b += (size_t)ncols * E * 8;                  // carry buffers (in place)
+  b += (kT + E) * 4;                           // slotinfo
+  b += 6 * nbp * 4 + 64 * 4;                   // per-partition arrays + scanw
+  b += (size_t)kWsRankWarps * nbp * 2;         // cnt
+  b += ((E * 2 + 15) / 16) * 16;               // carryinfo
+  b += 2 * kT + 32;                            // pid buffers (+ alignment slack)
+  return b;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {  // release.cta: publishes prior smem writes
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mover_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWsMovers) : "memory"); }
+__device__ __forceinline__ void ranker_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kWsRankers) : "memory"); }
+
+template <int kBits, int G, int kWsRankItems>
+__global__ void __launch_bounds__(kWsThreads, 1)
+fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages, int use_hw_match,
+                     const uint8_t* __restrict__ pid_plane,
+                     const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
+  constexpr uint32_t T = (uint32_t)kWsRankers * kWsRankItems;  // rows per tile
+  constexpr uint32_t GM = G - 1;
+  constexpr uint32_t kStageBytes = T * 8;
+  constexpr int kSlotRounds = ((int)T + (int)kSwcMaxNum * (G - 1) + kWsMovers - 1) / kWsMovers;
+  constexpr int kEntryRoundsM = ((int)kSwcMaxNum * (G - 1) + kWsMovers - 1) / kWsMovers;
+  constexpr int kEntryRoundsR = ((int)kSwcMaxNum * (G - 1) + kWsRankers - 1) / kWsRankers;
+  extern __shared__ __align__(128) uint64_t smem64[];
+  const uint32_t nbp = nb_padded(num);
+  const uint32_t E = num * GM;
+  const int ncols = units.nunits;
+  uint64_t* ring = smem64;
+  uint64_t* bars = ring + (size_t)nstages * T;
+  uint64_t* carry = bars + 64;
+  uint32_t* slotinfo = (uint32_t*)(carry + (size_t)ncols * E);
+  uint32_t* wpos = slotinfo + T + E;
+  uint32_t* kcnt = wpos + nbp;
+  uint32_t* binfo = kcnt + nbp;
+  uint32_t* bin_start = binfo + nbp;
+  uint32_t* wstart = bin_start + nbp;
+  uint32_t* wdelta = wstart + nbp;
+  uint32_t* scanw = wdelta + nbp;  // [0,8) counts, [8,16) written, [40] W
+  uint16_t* cnt = (uint16_t*)(scanw + 64);
+  uint16_t* carryinfo = cnt + (size_t)kWsRankWarps * nbp;
+  uint8_t* pidbuf = (uint8_t*)(((uintptr_t)(carryinfo + E) + 15) & ~(uintptr_t)15);  // TMA dst: 16 B aligned
+
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 16);
+  const uint32_t bar_pid_full = smem_u32(bars + 32), bar_pid_empty = smem_u32(bars + 34);
+  const uint32_t bar_slots_ready = smem_u32(bars + 36), bar_slots_free = smem_u32(bars + 37);
+  const uint32_t bar_flush_done = smem_u32(bars + 38);
+  // per column step: "all movers have read the old carry".  Two barriers used alternately: the wait
+  // for step k happens during step k+1, after this warp's arrival for step k+1, so a single barrier
+  // could run two phases ahead of a pending parity wait (deadlock); with two, at most one.
+  const uint32_t bar_carry_read = smem_u32(bars + 40);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kWsMoverWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_pid_full + 8 * i, 1);
+      mbar_init(bar_pid_empty + 8 * i, kWsRankWarps);
+    }
+    mbar_init(bar_slots_ready, kWsRankWarps);
+    mbar_init(bar_slots_free, kWsMoverWarps);
+    mbar_init(bar_flush_done, kWsMoverWarps);
+    mbar_init(bar_carry_read, kWsMoverWarps);
+    mbar_init(bar_carry_read + 8, kWsMoverWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= kWsMoverWarps + kWsRankWarps) {
+    // ============================ producer =============================================
+#ifdef FB_WS_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+#endif
+    if (warp == kWsMoverWarps + kWsRankWarps && lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      const uint32_t ring_s = smem_u32(ring), pid_s = smem_u32(pidbuf);
+      uint32_t s = 0, ph = 0, seq = 0;
+      // pids of the very first tile
+      int chunk = (int)blockIdx.x;
+      int64_t r0 = 0, r1 = 0, t0 = 0;
+      bool have = chunk < g.nchunks_full;
+      if (have) { chunk_range(g, chunk, r0, r1); t0 = r0; }
+      auto load_pid = [&](int64_t row0, uint32_t q) {
+        const uint32_t b = q & 1, pp = (q >> 1) & 1;
+        mbar_wait(bar_pid_empty + 8 * b, pp ^ 1);
+        mbar_expect_tx(bar_pid_full + 8 * b, T);
+        tma_load_1d(pid_s + b * T, pid_plane + row0, T, bar_pid_full + 8 * b, pol);
+      };
+      if (have) load_pid(t0, 0);
+      while (have) {
+        // next tile of this CTA's sequence (for the pid look-ahead)
+        int nchunk = chunk;
+        int64_t nr0 = r0, nr1 = r1, nt0 = t0 + T;
+        bool nhave = true;
+        if (nt0 >= r1) {
+          nchunk = chunk + (int)gridDim.x;
+          nhave = nchunk < g.nchunks_full;
+          if (nhave) { chunk_range(g, nchunk, nr0, nr1); nt0 = nr0; }
+        }
+        if (nhave) load_pid(nt0, seq + 1);
+        for (int u = 0; u < ncols; ++u) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, kStageBytes);
+          tma_load_1d(ring_s + s * kStageBytes, units.src[u] + t0, kStageBytes, bar_full + 8 * s, pol);
+          if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+        }
+        chunk = nchunk; r0 = nr0; r1 = nr1; t0 = nt0; have = nhave;
+        ++seq;
+      }
+    }
+    return;
+  }
+
+  if (warp >= kWsMoverWarps) {
+    // ============================ rankers (8 warps) ====================================
+#ifdef FB_WS_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+#endif
+    const unsigned rw = warp - kWsMoverWarps;          // ranker warp 0..7
+    const unsigned rtid = threadIdx.x - kWsMovers;     // 0..255
+    const unsigned lt = fb_lanemask_lt();
+    uint16_t* __restrict__ my_cnt = cnt + (size_t)rw * nbp;
+    for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
+    uint32_t seq = 0, cseq = 0;
+    for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x, ++cseq) {
+      int64_t r0, r1;
+      chunk_range(g, chunk, r0, r1);
+      if (cseq > 0) mbar_wait(bar_flush_done, (cseq - 1) & 1);  // movers flushed the previous chunk
+      ranker_sync();
+      for (uint32_t b = rtid; b < nbp; b += kWsRankers) {
+        const uint32_t p0 = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)chunk * num + b] : 0u;
+        wpos[b] = p0 & ~GM;
+        kcnt[b] = (p0 & GM) | ((p0 & GM) << 8);
+      }
+      // (visibility: barrier A below)
+      for (int64_t t0 = r0; t0 < r1; t0 += T, ++seq) {
+        const uint32_t pb = seq & 1, pph = (seq >> 1) & 1;
+        mbar_wait(bar_pid_full + 8 * pb, pph);
+        const uint8_t* __restrict__ pt = pidbuf + pb * T + rw * (32 * kWsRankItems);
+        uint32_t pid[kWsRankItems];
+#pragma unroll
+        for (int r = 0; r < kWsRankItems; ++r) pid[r] = pt[r * 32 + lane];
+        // ---- stable rank inside (warp, partition); rows of this warp: rw*512 + r*32 + lane
+        uint32_t pos[kWsRankItems];
+#pragma unroll
+        for (int r = 0; r < kWsRankItems; ++r) {
+          // rankers are off the critical path and the ADU pipe is idle in this kernel, so the
+          // hardware MATCH.ANY (~70 cycles/warp on the ADU) beats 8 ballots on the shared ALU pipe
+          const unsigned m = use_hw_match ? __match_any_sync(0xFFFFFFFFu, pid[r])
+                                          : match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
+          const unsigned before = __popc(m & lt);
+          uint32_t old = 0;
+          if (before == 0) {
+            old = my_cnt[pid[r]];
+            my_cnt[pid[r]] = (uint16_t)(old + __popc(m));
+          }
+          __syncwarp();
+          old = __shfl_sync(0xFFFFFFFFu, old, __ffs(m) - 1);
+          pos[r] = old + before;
+        }
+        if (lane == 0) mbar_arrive_relaxed(bar_pid_empty + 8 * pb);  // pids are in registers
+        ranker_sync();  // A
+        // ---- per partition (thread b < num): tile count, rows to write, new pending state
+        const uint32_t b = rtid;
+        uint32_t n = 0, w = 0, kold = 0, phold = 0, wp_old = 0;
+        if (b < num) {
+#pragma unroll
+          for (int wi = 0; wi < kWsRankWarps; ++wi) {
+            const uint32_t t = cnt[wi * nbp + b];
+            cnt[wi * nbp + b] = (uint16_t)n;
+            n += t;
+          }
+          const uint32_t kc = kcnt[b];
+          kold = kc & 0xFFu;
+          phold = kc >> 8;
+          wp_old = wpos[b];
+          const uint32_t end = wp_old + kold + n;
+          const uint32_t aend = end & ~GM;
+          if (aend > wp_old) {
+            w = aend - wp_old;
+            wpos[b] = aend;
+            kcnt[b] = end - aend;  // phantoms are consumed by the first write
+          } else {
+            kcnt[b] = (kold + n) | (phold << 8);
+          }
+          binfo[b] = kold | (phold << 4) | (w << 8);
+        }
+        uint32_t xn = n, xw = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t yn = __shfl_up_sync(0xFFFFFFFFu, xn, o);
+          const uint32_t yw = __shfl_up_sync(0xFFFFFFFFu, xw, o);
+          if (lane >= (unsigned)o) { xn += yn; xw += yw; }
+        }
+        if (lane == 31) { scanw[rw] = xn; scanw[8 + rw] = xw; }
+        ranker_sync();  // B
+        uint32_t bn = xn - n, bw = xw - w;
+        {
+          const uint32_t tn = lane < kWsRankWarps ? scanw[lane] : 0;
+          const uint32_t tw = lane < kWsRankWarps ? scanw[8 + lane] : 0;
+#pragma unroll
+          for (int wi = 0; wi < kWsRankWarps; ++wi) {
+            const uint32_t vn = __shfl_sync(0xFFFFFFFFu, tn, wi);
+            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, tw, wi);
+            if ((unsigned)wi < rw) { bn += vn; bw += vw; }
+          }
+        }
+        if (b < num) {
+          bin_start[b] = bn;
+          wstart[b] = bw;
+        }
+        // ---- hand-off arrays may be rewritten once the movers hold the previous slot list
+        if (seq > 0) mbar_wait(bar_slots_free, (seq - 1) & 1);
+        if (b < num) wdelta[b] = wp_old - bw;  // slot j lands at output row wdelta + j
+        if (rtid == kWsRankers - 1) scanw[40] = bw + w;  // W: slots to store this tile
+        ranker_sync();  // C
+        // ---- every new row / old carry entry finds its place
+#pragma unroll
+        for (int r = 0; r < kWsRankItems; ++r) {
+          const uint32_t pb2 = pid[r];
+          const uint32_t bi = binfo[pb2];
+          const uint32_t i = (bi & 0xFu) + pos[r] + my_cnt[pb2];
+          const uint32_t ww = bi >> 8;
+          const uint32_t row = rw * (32 * kWsRankItems) + r * 32 + lane;
+          if (i < ww) slotinfo[wstart[pb2] + i] = (pb2 << 16) | row;
+          else carryinfo[pb2 * GM + (i - ww)] = (uint16_t)row;
+        }
+#pragma unroll
+        for (int q = 0; q < kEntryRoundsR; ++q) {
+          const uint32_t e = q * kWsRankers + rtid;
+          if (e < E) {
+            const uint32_t eb = e / GM, i = e - eb * GM;
+            const uint32_t bi = binfo[eb];
+            const uint32_t ko = bi & 0xFu, po = (bi >> 4) & 0xFu, ww = bi >> 8;
+            const uint32_t nn = (eb + 1 < num ? bin_start[eb + 1] : T) - bin_start[eb];
+            const uint32_t desc = i < po ? 0xFFFFu : T + e;
+            if (i < ko) {
+              if (i < ww) slotinfo[wstart[eb] + i] = (eb << 16) | desc;
+              else carryinfo[e] = (uint16_t)desc;
+            }
+            if (ww + i >= ko + nn) carryinfo[e] = 0xFFFFu;
+          }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
+        ranker_sync();  // D: the slot list of this tile is complete
+        if (lane == 0) mbar_arrive(bar_slots_ready);
+      }
+    }
+    return;
+  }
+
+  // ================================ movers (16 warps) ====================================
+#ifdef FB_WS_SETMAXNREG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+#endif
+  uint32_t s = 0, ph = 0, seq = 0, astep = 0, wstep = 0;
+  for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
+    int64_t r0, r1;
+    chunk_range(g, chunk, r0, r1);
+    for (int64_t t0 = r0; t0 < r1; t0 += T, ++seq) {
+      mbar_wait(bar_slots_ready, seq & 1);
+      const uint32_t W = scanw[40];
+      uint32_t srcd[kSlotRounds], dst[kSlotRounds];
+#pragma unroll
+      for (int k = 0; k < kSlotRounds; ++k) {
+        const uint32_t j = k * kWsMovers + threadIdx.x;
+        srcd[k] = 0xFFFFu;
+        dst[k] = 0;
+        if (j < W) {
+          const uint32_t info = slotinfo[j];
+          srcd[k] = info & 0xFFFFu;
+          dst[k] = wdelta[info >> 16] + j;
+        }
+      }
+      uint32_t csrc[kEntryRoundsM];
+#pragma unroll
+      for (int q = 0; q < kEntryRoundsM; ++q) {
+        const uint32_t e = q * kWsMovers + threadIdx.x;
+        csrc[q] = e < E ? (uint32_t)carryinfo[e] : 0xFFFFu;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_slots_free);  // the slot list sits in registers now
+
+      // The new carry of column u is written one step late (while column u+1 moves): by then every
+      // mover has long finished reading the old carry of column u, so nobody waits at a barrier.
+      uint64_t cv_prev[kEntryRoundsM];
+      for (int u = 0; u < ncols; ++u) {
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint64_t* __restrict__ st = ring + (size_t)s * T;
+        uint64_t* __restrict__ out = units.dst[u];
+        const uint64_t* __restrict__ cbuf = carry + (size_t)u * E;
+        uint64_t v[kSlotRounds], cv[kEntryRoundsM];
+#pragma unroll
+        for (int k = 0; k < kSlotRounds; ++k)
+          if (srcd[k] != 0xFFFFu) v[k] = srcd[k] < T ? st[srcd[k]] : cbuf[srcd[k] - T];
+#pragma unroll
+        for (int q = 0; q < kEntryRoundsM; ++q)
+          if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : cbuf[csrc[q] - T];
+#pragma unroll
+        for (int k = 0; k < kSlotRounds; ++k)
+          if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
+        // all my reads of the stage and of the old carry have completed (their values were
+        // consumed by the stores above / are in cv): release the stage, publish "carry read"
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_relaxed(bar_empty + 8 * s);
+          mbar_arrive_relaxed(bar_carry_read + 8 * (astep & 1));
+        }
+        ++astep;
+        if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+        if (u > 0) {  // write the previous column's new carry
+          mbar_wait(bar_carry_read + 8 * (wstep & 1), (wstep >> 1) & 1);
+          ++wstep;
+          uint64_t* __restrict__ pbuf = carry + (size_t)(u - 1) * E;
+#pragma unroll
+          for (int q = 0; q < kEntryRoundsM; ++q) {
+            const uint32_t e = q * kWsMovers + threadIdx.x;
+            if (csrc[q] != 0xFFFFu) pbuf[e] = cv_prev[q];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kEntryRoundsM; ++q) cv_prev[q] = cv[q];
+      }
+      {  // the last column's new carry
+        mbar_wait(bar_carry_read + 8 * (wstep & 1), (wstep >> 1) & 1);
+        ++wstep;
+        uint64_t* __restrict__ pbuf = carry + (size_t)(ncols - 1) * E;
+#pragma unroll
+        for (int q = 0; q < kEntryRoundsM; ++q) {
+          const uint32_t e = q * kWsMovers + threadIdx.x;
+          if (csrc[q] != 0xFFFFu) pbuf[e] = cv_prev[q];
+        }
+      }
+    }
+    // ---- chunk end: flush the pending rows (partial sector groups)
+    mover_sync();
+    for (int u = 0; u < ncols; ++u) {
+      uint64_t* __restrict__ out = units.dst[u];
+      const uint64_t* __restrict__ cbuf = carry + (size_t)u * E;
+#pragma unroll
+      for (int q = 0; q < kEntryRoundsM; ++q) {
+        const uint32_t e = q * kWsMovers + threadIdx.x;
+        if (e < E) {
+          const uint32_t b = e / GM, i = e - b * GM;
+          const uint32_t kc = kcnt[b];
+          if (i < (kc & 0xFFu) && i >= (kc >> 8)) out[wpos[b] + i] = cbuf[e];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_flush_done);  // rankers may start the next chunk
+  }
+}
+
+// ---------------------------------------------------------------------------
 // validity bitmap <-> byte mask
 // ---------------------------------------------------------------------------
 __global__ void fb_bits_to_bytes_kernel(const uint8_t* __restrict__ bits, int64_t bit_offset,
@@ -920,6 +1321,10 @@ cudaError_t ensure_smem_optin(int dev) {
   {
     int smem_max = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, 16>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, 16>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, 8>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, 8>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGA, kSwcItemsA>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcGA, kSwcItemsA>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGB, kSwcItemsB>, (size_t)smem_max);
@@ -954,13 +1359,15 @@ int fill_keys(FbKeys& k, int nkeys, const void* const* ptrs, const int32_t* widt
 
 struct PlanLayout {
   size_t hist_bytes;     // uint32 [nchunks][num]
+  size_t pid_offset;     // uint8 [nrows] partition id plane (num <= 256), 256-byte aligned
   size_t total_bytes;
 };
 
 PlanLayout plan_layout(const ChunkGeom& g, uint32_t num) {
   PlanLayout l;
   l.hist_bytes = (((size_t)g.nchunks * num * sizeof(uint32_t)) + 255) & ~(size_t)255;
-  l.total_bytes = l.hist_bytes + 256;
+  l.pid_offset = l.hist_bytes + 256;
+  l.total_bytes = l.pid_offset + (num <= kSwcMaxNum ? (((size_t)g.nrows + 255) & ~(size_t)255) : 0) + 256;
   return l;
 }
 
@@ -1038,12 +1445,13 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   FbDiv dv = fb_make_div(num_partitions);
   uint32_t* hist = (uint32_t*)scratch;
+  uint8_t* pid_plane = num_partitions <= kSwcMaxNum ? (uint8_t*)scratch + l.pid_offset : nullptr;
   size_t smem = (size_t)kHistWarps * num_partitions * sizeof(uint32_t);
   FB_CUDA(ensure_smem_optin(dev));
   const bool single = single_u64_key(nkeys, key_widths, key_valid);
   const int bits = bits_for(num_partitions);
 #define FB_LAUNCH_HIST(S, B) \
-  fb_hist_kernel<S, B><<<g.nchunks, kHistBlock, smem, st>>>(k, dv, num_partitions, g, hist)
+  fb_hist_kernel<S, B><<<g.nchunks, kHistBlock, smem, st>>>(k, dv, num_partitions, g, hist, pid_plane)
   FB_DISPATCH_SB(single, bits, FB_LAUNCH_HIST);
 #undef FB_LAUNCH_HIST
   FB_CUDA(cudaGetLastError());
@@ -1113,9 +1521,15 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
     return 0;
   };
 
-  // ---- split the columns: fast path (TMA + write combining) vs generic
-  const bool fast_ok = single && num_partitions <= kSwcMaxNum && g.nchunks_full > 0 &&
-                       ((uintptr_t)k.ptr[0] % 16 == 0) && getenv("FB_DISABLE_TMA") == nullptr;
+  // ---- split the columns: fast path (TMA ring + write combining) vs generic
+  // v5 (warp-specialised, reads the partition-id plane written by pass 1): any key shape;
+  // v4 (FB_SCATTER=swc, hashes in pass 2): single 8-byte key only.  Both: 8-byte columns, num <= 256.
+  const char* sel = getenv("FB_SCATTER");
+  const bool use_ws = sel == nullptr || strcmp(sel, "ws") == 0;
+  const bool use_swc = sel != nullptr && strcmp(sel, "swc") == 0;
+  const bool fast_ok = num_partitions <= kSwcMaxNum && g.nchunks_full > 0 &&
+                       ((use_ws) || (use_swc && single && ((uintptr_t)k.ptr[0] % 16 == 0))) &&
+                       getenv("FB_DISABLE_TMA") == nullptr;
   int* fast_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
   int* gen_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
   int nfast = 0, ngen = 0;
@@ -1129,8 +1543,47 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
     int smem_max = 0;
     FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
-    for (int c0 = 0; c0 < nfast; c0 += kSwcMaxCols) {
-      const int nb = nfast - c0 < kSwcMaxCols ? nfast - c0 : kSwcMaxCols;
+    const uint8_t* pid_plane = (const uint8_t*)scratch + l.pid_offset;
+    // measured (100 M rows x 8 cols): 8 columns per launch 3.43 ms, 4 per launch 3.14-3.23 ms (fewer open
+    // write streams -> half-written lines meet their other half while still in L2), 2 per launch 5 ms
+    int cols_per_launch = use_ws ? 4 : kSwcMaxCols;
+    if (use_ws && getenv("FB_WS_COLS")) {
+      cols_per_launch = atoi(getenv("FB_WS_COLS"));
+      if (cols_per_launch < 1 || cols_per_launch > kSwcMaxCols) cols_per_launch = kSwcMaxCols;
+    }
+    for (int c0 = 0; c0 < nfast; c0 += cols_per_launch) {
+      const int nb = nfast - c0 < cols_per_launch ? nfast - c0 : cols_per_launch;
+      if (use_ws) {
+        WsUnits wu;
+        memset(&wu, 0, sizeof(wu));
+        wu.nunits = nb;
+        for (int c = 0; c < nb; ++c) {
+          wu.src[c] = (const uint64_t*)col_ptrs[fast_idx[c0 + c]];
+          wu.dst[c] = (uint64_t*)out_col_ptrs[fast_idx[c0 + c]];
+        }
+        const int hw_match = getenv("FB_WS_HWMATCH") ? atoi(getenv("FB_WS_HWMATCH")) : 0;
+        const int small_tile = getenv("FB_WS_TILE") ? (atoi(getenv("FB_WS_TILE")) == 2048) : 0;
+        const size_t book = small_tile ? ws_book_bytes<kWsG, 8>(num_partitions, nb)
+                                       : ws_book_bytes<kWsG, 16>(num_partitions, nb);
+        const size_t stage_bytes = (size_t)(small_tile ? 2048 : 4096) * 8;
+        int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
+        if (nstages > 16) nstages = 16;
+        FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
+        const size_t tsmem = (size_t)nstages * stage_bytes + book;
+#define FB_LAUNCH_WS(B, RI)                                                                   \
+  fb_scatter_ws_kernel<B, kWsG, RI><<<grid, kWsThreads, tsmem, st>>>(                         \
+      wu, num_partitions, g, nstages, hw_match, pid_plane, (const uint32_t*)scratch, part_offsets)
+        if (small_tile) {
+          if (bits == 4) FB_LAUNCH_WS(4, 8);
+          else FB_LAUNCH_WS(8, 8);
+        } else {
+          if (bits == 4) FB_LAUNCH_WS(4, 16);
+          else FB_LAUNCH_WS(8, 16);
+        }
+#undef FB_LAUNCH_WS
+        FB_CUDA(cudaGetLastError());
+        continue;
+      }
       TmaUnits units;
       memset(&units, 0, sizeof(units));
       units.src[0] = (const uint64_t*)k.ptr[0];
