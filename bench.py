@@ -255,7 +255,8 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         pms = e0.elapsed_time(e1) / reps
         achieved = ALG_BYTES_PER_ROW * n / (kms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "fb_scatter_swc_kernel (pass 2: gather + write-combined scatter)",
+        roofline = {"bound": "hbm", "kernel": "fb_scatter_ws_kernel (pass 2: TMA ring + ranking + write-combined scatter; "
+                                              "2 launches x 4 columns, timed together)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "traffic": _profile_traffic(),
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_ROW * n,
@@ -329,7 +330,7 @@ def run_b200(args):
                 extras = relational_bench.measure(local_rank)
             except Exception as ex:  # pragma: no cover
                 extras = {"error": repr(ex)}
-        launches_per_step = 4 + (1 if n % 4096 else 0)
+        launches_per_step = 5 + (1 if n % 4096 else 0)  # hist, 2 scans, 2 x scatter (4 cols each), tail tile
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
