@@ -209,3 +209,103 @@ class DistributedB200Engine(B200ExecutionEngine):
         res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
         res.global_partition_range = (plan.lo, plan.hi)
         return B200DataFrame(res)
+
+    # ---- distributed relational operators (BASELINE configs 4 and 5) -------------------------
+    def _shuffle_partitions(self) -> int:
+        from .execution_engine import FUGUE_B200_CONF_DEFAULT_PARTITIONS, FUGUE_B200_DEFAULT_PARTITIONS
+
+        n = int(self._conf.get(FUGUE_B200_CONF_DEFAULT_PARTITIONS, FUGUE_B200_DEFAULT_PARTITIONS))
+        return max(n, self._world)
+
+    def aggregate(self, df: Any, partition_spec: Optional[PartitionSpec], agg_cols: List[Any]) -> B200DataFrame:
+        """GROUP BY across GPUs: local partial aggregation (K6) -> shuffle of the partials by key
+        (pull exchange) -> final aggregation of the partials.  Every group ends up on exactly one
+        rank; the result stays sharded.  SUM/COUNT/MIN/MAX decompose directly, AVG as SUM + COUNT."""
+        from .column import AggFuncExpr, col
+
+        keys = [] if partition_spec is None else list(partition_spec.partition_by)
+        if self._world == 1:
+            return super().aggregate(df, partition_spec, agg_cols)
+        partial: List[Any] = []
+        final: List[Any] = []
+        post: List[Any] = []
+        for i, a in enumerate(agg_cols):
+            assert_or_throw(isinstance(a, AggFuncExpr) and a.output_name != "",
+                            lambda: ValueError(f"{a} must be a named aggregation"))
+            tmp = f"__p{i}"
+            if a.func in ("SUM", "MIN", "MAX"):
+                partial.append(AggFuncExpr(a.func, a.arg, tmp))
+                final.append(AggFuncExpr(a.func, col(tmp), a.output_name))
+            elif a.func == "COUNT":
+                partial.append(AggFuncExpr("COUNT", a.arg, tmp))
+                final.append(AggFuncExpr("SUM", col(tmp), a.output_name))
+            elif a.func == "AVG":
+                partial.append(AggFuncExpr("SUM", a.arg, tmp + "s"))
+                partial.append(AggFuncExpr("COUNT", a.arg, tmp + "c"))
+                final.append(AggFuncExpr("SUM", col(tmp + "s"), tmp + "s"))
+                final.append(AggFuncExpr("SUM", col(tmp + "c"), tmp + "c"))
+                post.append((a.output_name, tmp + "s", tmp + "c"))
+            else:
+                raise NotImplementedError(f"distributed {a.func}")
+        local = super().aggregate(df, partition_spec, partial)
+        if len(keys) == 0:
+            # global aggregate: every rank reduces its partial row; gather the W partial rows everywhere
+            shuffled = self._allgather_rows(local)
+        else:
+            shuffled = self.repartition(local, PartitionSpec(by=keys, num=self._shuffle_partitions()))
+        res = super().aggregate(shuffled, partition_spec, final)
+        if post:
+            t: B200Table = res.native
+            names, cols, valid = [], [], []
+            import pyarrow as pa
+
+            fields = []
+            drop = {x for p_ in post for x in p_[1:]}
+            avg_at = {p_[1]: p_ for p_ in post}
+            for name, tp, c, v in zip(t.schema.names, t.schema.types, t.columns, t.valid):
+                if name in avg_at:
+                    out, sname, cname = avg_at[name]
+                    sc, cc = t.column(sname), t.column(cname)
+                    fields.append(pa.field(out, pa.float64()))
+                    cols.append((sc.to(torch.float64) / cc.to(torch.float64)).contiguous())
+                    valid.append((cc > 0).to(torch.uint8))
+                elif name not in drop:
+                    fields.append(pa.field(name, tp))
+                    cols.append(c)
+                    valid.append(v)
+            from .schema import Schema
+
+            res = B200DataFrame(B200Table(Schema(fields), cols, valid, t.dictionaries))
+            want = keys + [a.output_name for a in agg_cols]
+            if res.columns != want:
+                res = res[want]
+        return res
+
+    def _allgather_rows(self, df: B200DataFrame) -> B200DataFrame:
+        t: B200Table = df.native
+        cols, valid = [], []
+        for c, v in zip(t.columns, t.valid):
+            out = torch.empty(c.shape[0] * self._world, dtype=c.dtype, device=c.device)
+            dist.all_gather_into_tensor(out, c.contiguous(), group=self._group)
+            cols.append(out)
+            if v is None:
+                v = torch.ones(c.shape[0], dtype=torch.uint8, device=c.device)
+            vo = torch.empty(c.shape[0] * self._world, dtype=torch.uint8, device=c.device)
+            dist.all_gather_into_tensor(vo, v.contiguous(), group=self._group)
+            valid.append(vo)
+        return B200DataFrame(B200Table(t.schema, cols, valid, t.dictionaries))
+
+    def join(self, df1: Any, df2: Any, how: str, on: Optional[List[str]] = None) -> B200DataFrame:
+        """Equi-join across GPUs: co-partition both sides on the join keys with the same hash and the
+        same partition -> rank ownership (two pull exchanges), then join locally (K7).  Rows with equal
+        keys of both tables are on the same rank; NULL keys are co-located too (they never match, but
+        outer joins must still emit them exactly once).  Cross joins are not distributed."""
+        from .join import get_join_schemas
+
+        if self._world == 1:
+            return super().join(df1, df2, how, on)
+        e1, e2 = self.to_df(df1), self.to_df(df2)
+        key_schema, _ = get_join_schemas(e1, e2, how, on)
+        assert_or_throw(how.lower() != "cross", NotImplementedError("distributed cross join"))
+        spec = PartitionSpec(by=key_schema.names, num=self._shuffle_partitions())
+        return super().join(self.repartition(e1, spec), self.repartition(e2, spec), how, on)

@@ -29,6 +29,47 @@ def shard(rank: int, n: int):
             (np.arange(n) + rank * 10_000_000).astype("int64"), rng.integers(0, 255, n).astype("uint8")]
 
 
+def check_relational(eng, rank, world, dev):
+    """Distributed GROUP BY and JOIN vs the pandas oracle on the concatenated tables."""
+    import pandas as pd
+
+    from fugue_b200.column import all_cols, col, functions as ff
+    from oracle import native_engine as ora
+
+    def frames(r):
+        rng = np.random.default_rng(1000 + r)
+        n = 40_000 + 1000 * r
+        fact = pd.DataFrame({"key": rng.integers(0, 5000, n), "v0": rng.standard_normal(n)})
+        dim = pd.DataFrame({"key": rng.integers(0, 8000, 3000), "rv": rng.standard_normal(3000)})
+        return fact, dim
+
+    fact, dim = frames(rank)
+    agg = eng.aggregate(eng.to_df(fact), PartitionSpec(by=["key"]),
+                        [ff.sum(col("v0")).alias("s"), ff.count(all_cols()).alias("c"),
+                         ff.avg(col("v0")).alias("a"), ff.max(col("v0")).alias("m")])
+    jn = eng.join(eng.to_df(fact), eng.to_df(dim), "inner", ["key"])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (agg.as_pandas(), jn.as_pandas()))
+    if rank == 0:
+        facts, dims = zip(*[frames(r) for r in range(world)])
+        F, D = pd.concat(facts, ignore_index=True), pd.concat(dims, ignore_index=True)
+        got = pd.concat([g[0] for g in gathered], ignore_index=True).sort_values("key").reset_index(drop=True)
+        exp = ora.aggregate(F, ["key"], {"s": ("v0", "sum"), "c": ("*", "count"), "a": ("v0", "avg"),
+                                         "m": ("v0", "max")}).sort_values("key").reset_index(drop=True)
+        assert len(got) == len(exp) and got["key"].is_unique
+        assert np.array_equal(got["key"], exp["key"]) and np.array_equal(got["c"], exp["c"])
+        assert np.array_equal(got["m"], exp["m"])
+        assert np.max(np.abs(got["s"] - exp["s"]) / np.maximum(np.abs(exp["s"]), 1e-300)) <= 1e-9
+        assert np.allclose(got["a"], exp["a"], rtol=1e-9)
+        gj = pd.concat([g[1] for g in gathered], ignore_index=True)
+        ej = ora.join(F, D, "inner")
+        cols = list(ej.columns)
+        a = gj.sort_values(cols).reset_index(drop=True)
+        b = ej.sort_values(cols).reset_index(drop=True)
+        pd.testing.assert_frame_equal(a, b, check_exact=True, check_dtype=False)
+        print(f"dist relational ok: {len(got)} groups, {len(gj)} joined rows")
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -62,6 +103,7 @@ def main():
                 total += b - a
         assert total == sum(x[4] for x in gathered)
         print(f"dist_gpu_check ok: world={world}, {total} rows, bit-exact vs oracle (stable order)")
+    check_relational(eng, rank, world, dev)
     dist.barrier()
     dist.destroy_process_group()
 
