@@ -8,15 +8,15 @@
 // The reference has no counterpart (its shuffles are Dask/Spark/Ray's, fugue_dask/_utils.py:124-130).
 // Pure byte movement: 2 x width bytes per row per column; peer loads need many bytes in flight
 // (NVLink latency ~3x HBM), hence 8 independent 8-byte loads per thread and piece-parallel CTAs.
+#include <stdlib.h>
+
 #include "fb_common.cuh"
 
 namespace {
 
-constexpr int kCopyBlock = 256;
-constexpr int kCopyUnroll = 8;
-constexpr int kPieceRows = kCopyBlock * kCopyUnroll * 4;  // rows one CTA handles per piece step
+constexpr int kPieceRows = 8192;  // rows one CTA handles per piece step
 
-template <typename T>
+template <typename T, int kCopyBlock, int kCopyUnroll>
 __device__ __forceinline__ void copy_run(const T* __restrict__ src, T* __restrict__ dst, int64_t n,
                                          int piece, int npieces) {
   for (int64_t base = (int64_t)piece * kPieceRows; base < n; base += (int64_t)npieces * kPieceRows) {
@@ -33,6 +33,42 @@ __device__ __forceinline__ void copy_run(const T* __restrict__ src, T* __restric
   }
 }
 
+// 8-byte elements with 16-byte loads: peer (NVLink) reads are measured ~35 % faster with 16-byte
+// requests per lane than with 8-byte ones.  The source run is aligned to 16 bytes by peeling one
+// element; the destination is local HBM and is written with 8-byte stores (its alignment is free).
+template <int kCopyBlock, int kCopyUnroll>
+__device__ __forceinline__ void copy_run_u64_v2(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+                                                int64_t n, int piece, int npieces) {
+  int64_t head = ((uintptr_t)src & 8) ? 1 : 0;
+  if (head > n) head = n;
+  if (piece == 0 && head == 1 && threadIdx.x == 0) dst[0] = src[0];
+  const ulonglong2* __restrict__ s2 = (const ulonglong2*)(src + head);
+  uint64_t* __restrict__ d = dst + head;
+  const int64_t npairs = (n - head) >> 1;
+  constexpr int64_t kPiecePairs = kPieceRows / 2;
+  for (int64_t base = (int64_t)piece * kPiecePairs; base < npairs; base += (int64_t)npieces * kPiecePairs) {
+    const int64_t end = base + kPiecePairs < npairs ? base + kPiecePairs : npairs;
+    int64_t i = base + threadIdx.x;
+    for (; i + (kCopyUnroll - 1) * kCopyBlock < end; i += kCopyUnroll * kCopyBlock) {
+      ulonglong2 v[kCopyUnroll];
+#pragma unroll
+      for (int k = 0; k < kCopyUnroll; ++k) v[k] = s2[i + k * kCopyBlock];
+#pragma unroll
+      for (int k = 0; k < kCopyUnroll; ++k) {
+        d[2 * (i + k * kCopyBlock)] = v[k].x;
+        d[2 * (i + k * kCopyBlock) + 1] = v[k].y;
+      }
+    }
+    for (; i < end; i += kCopyBlock) {
+      const ulonglong2 v = s2[i];
+      d[2 * i] = v.x;
+      d[2 * i + 1] = v.y;
+    }
+  }
+  if (piece == 0 && ((n - head) & 1) && threadIdx.x == 0) dst[n - 1] = src[n - 1];
+}
+
+template <int kCopyBlock, int kCopyUnroll>
 __global__ void __launch_bounds__(kCopyBlock)
 fb_copy_segments_kernel(const void* const* __restrict__ src_cols, void* const* __restrict__ dst_cols,
                         const int32_t* __restrict__ widths, int ncols, const int32_t* __restrict__ src_tab,
@@ -49,10 +85,10 @@ fb_copy_segments_kernel(const void* const* __restrict__ src_cols, void* const* _
     const uint8_t* s = (const uint8_t*)src_cols[(size_t)tab * ncols + c];
     const int64_t so = src_off[sgi], dof = dst_off[sgi];
     switch (w) {
-      case 8: copy_run((const uint64_t*)s + so, (uint64_t*)d + dof, n, piece, npieces); break;
-      case 4: copy_run((const uint32_t*)s + so, (uint32_t*)d + dof, n, piece, npieces); break;
-      case 2: copy_run((const uint16_t*)s + so, (uint16_t*)d + dof, n, piece, npieces); break;
-      default: copy_run(s + so, d + dof, n, piece, npieces); break;
+      case 8: copy_run_u64_v2<kCopyBlock, kCopyUnroll>((const uint64_t*)s + so, (uint64_t*)d + dof, n, piece, npieces); break;
+      case 4: copy_run<uint32_t, kCopyBlock, kCopyUnroll>((const uint32_t*)s + so, (uint32_t*)d + dof, n, piece, npieces); break;
+      case 2: copy_run<uint16_t, kCopyBlock, kCopyUnroll>((const uint16_t*)s + so, (uint16_t*)d + dof, n, piece, npieces); break;
+      default: copy_run<uint8_t, kCopyBlock, kCopyUnroll>(s + so, d + dof, n, piece, npieces); break;
     }
   }
 }
@@ -75,9 +111,21 @@ extern "C" int fb_copy_segments(int dev, void* stream, int ncols, const void* co
   if (pieces > want) pieces = want;
   if (pieces > 64) pieces = 64;
   if (pieces < 1) pieces = 1;
+  const int variant = getenv("FB_COPY_VARIANT") ? atoi(getenv("FB_COPY_VARIANT")) : 0;
+  if (getenv("FB_COPY_PIECES")) pieces = atoi(getenv("FB_COPY_PIECES"));
   dim3 grid((unsigned)gx, (unsigned)ncols, (unsigned)pieces);
-  fb_copy_segments_kernel<<<grid, kCopyBlock, 0, (cudaStream_t)stream>>>(
-      d_src_cols, d_dst_cols, d_widths, ncols, d_src_table, d_src_off, d_dst_off, d_len, nseg);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FB_COPY_LAUNCH(B, U)                                                                         \
+  fb_copy_segments_kernel<B, U><<<grid, B, 0, st>>>(d_src_cols, d_dst_cols, d_widths, ncols, d_src_table, \
+                                                    d_src_off, d_dst_off, d_len, nseg)
+  switch (variant) {
+    case 1: FB_COPY_LAUNCH(256, 16); break;
+    case 2: FB_COPY_LAUNCH(512, 8); break;
+    case 3: FB_COPY_LAUNCH(1024, 8); break;
+    case 4: FB_COPY_LAUNCH(128, 16); break;
+    default: FB_COPY_LAUNCH(256, 8); break;
+  }
+#undef FB_COPY_LAUNCH
   FB_CUDA(cudaGetLastError());
   return 0;
 }
