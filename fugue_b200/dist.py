@@ -169,23 +169,38 @@ class DistributedB200Engine(B200ExecutionEngine):
             return self._repartition_nccl(t, keys, cols, vpos, plan_local, plan)
         rows = [int(x) for x in plan.rows_per_rank.tolist()]
         self._ensure_arena(max(self._col_offsets(r, widths)[-1] for r in rows))
-        # ---- pass 2: scatter my rows into my arena (peers' pulls of the previous call are over:
-        #      every call ends with a barrier)
+        # ---- pass 2 + pull, in two column groups so that the NVLink pull of group A overlaps the
+        #      HBM-bound scatter of group B (peers' pulls of the previous call are over: every call
+        #      ends with a barrier)
         my_off = self._col_offsets(t.num_rows, widths)
         parts = [self._arena[my_off[i]:my_off[i] + t.num_rows * w].view(c.dtype)
                  for i, (c, w) in enumerate(zip(cols, widths))]
-        K.partition_apply(plan_local, cols, parts)
-        dist.barrier(group=self._group)  # stream-ordered: all ranks' arenas are complete
-        # ---- pull my partitions from every rank's arena into their final place
         base = self._arena_hdl.buffer_ptrs
-        src_ptrs: List[int] = []
-        for s in range(self._world):
-            so = self._col_offsets(rows[s], widths)
-            src_ptrs += [int(base[s]) + so[i] for i in range(len(cols))]
+        peer_off = [self._col_offsets(rows[s], widths) for s in range(self._world)]
         outs = [torch.empty(plan.total_recv, dtype=c.dtype, device=dev) for c in cols]
-        K.copy_segments(None, outs, plan.pull_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev),
-                        max_len=plan.max_seg, src_table=plan.pull_src_rank.to(dev), src_ptrs=src_ptrs)
-        dist.barrier(group=self._group)  # nobody overwrites an arena that is still being read
+        seg_src, seg_dst, seg_len = plan.pull_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev)
+        seg_rank = plan.pull_src_rank.to(dev)
+        s_main = torch.cuda.current_stream(dev)
+        if getattr(self, "_pull_stream", None) is None:
+            self._pull_stream = torch.cuda.Stream(dev)
+        s_pull = self._pull_stream
+        half = (len(cols) + 1) // 2 if len(cols) >= 4 else len(cols)
+        groups = [list(range(0, half))] + ([list(range(half, len(cols)))] if half < len(cols) else [])
+        for gi, idx in enumerate(groups):
+            K.partition_apply(plan_local, [cols[i] for i in idx], [parts[i] for i in idx])
+            ev = torch.cuda.Event()
+            ev.record(s_main)
+            with torch.cuda.stream(s_pull):
+                s_pull.wait_event(ev)
+                dist.barrier(group=self._group)  # stream-ordered: this group is complete on all ranks
+                src_ptrs = [int(base[s]) + peer_off[s][i] for s in range(self._world) for i in idx]
+                K.copy_segments(None, [outs[i] for i in idx], seg_src, seg_dst, seg_len, max_len=plan.max_seg,
+                                src_table=seg_rank, src_ptrs=src_ptrs)
+        with torch.cuda.stream(s_pull):
+            dist.barrier(group=self._group)  # nobody overwrites an arena that is still being read
+        s_main.wait_stream(s_pull)
+        for o in outs:
+            o.record_stream(s_pull)
         ncol = len(t.columns)
         valid = [outs[vpos[i]] if i in vpos else None for i in range(ncol)]
         res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
