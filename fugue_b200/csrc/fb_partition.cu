@@ -488,10 +488,8 @@ constexpr int kTmaThreads = kBlock + 32;   // 16 consumer warps + 1 producer war
 constexpr int kMaxUnits = FB_MAX_COLS + 1;
 constexpr int kSwcMaxCols = 8;             // payload columns per launch (carry buffers in smem)
 constexpr uint32_t kSwcMaxNum = 256;
-// Two tunings of the same kernel (chosen by FB_SWC_MODE, default 0: smaller tiles double the per-tile overhead):
-//   mode 0: tile 4096 rows, G = 4 rows (32 B groups)      mode 1: tile 2048 rows, G = 8 rows (64 B groups)
+// tile 4096 rows, G = 4 rows (32 B groups); tile 2048 / G = 8 was measured slower (4.59 vs 3.49 ms)
 constexpr int kSwcItemsA = 8, kSwcGA = 4;
-constexpr int kSwcItemsB = 4, kSwcGB = 8;
 
 struct TmaUnits {
   const uint64_t* src[kMaxUnits];  // unit 0 is the key column
@@ -556,7 +554,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 
 template <int kBits, int G, int ITEMS>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols, int store_mode,
+fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols,
                       const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
   constexpr uint32_t T = (uint32_t)kBlock * ITEMS;
   constexpr uint32_t kStageBytes = T * 8;
@@ -792,23 +790,9 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
 #pragma unroll
           for (int q = 0; q < kEntryRounds; ++q)
             if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : oldc[csrc[q] - T];
-          if (store_mode == 0) {
 #pragma unroll
-            for (int k = 0; k < kSlotRounds; ++k)
-              if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
-          } else if (store_mode == 1) {
-#pragma unroll
-            for (int k = 0; k < kSlotRounds; ++k)
-              if (srcd[k] != 0xFFFFu) __stcs((unsigned long long*)out + dst[k], (unsigned long long)v[k]);
-          } else if (store_mode == 2) {
-#pragma unroll
-            for (int k = 0; k < kSlotRounds; ++k)
-              if (srcd[k] != 0xFFFFu) __stcg((unsigned long long*)out + dst[k], (unsigned long long)v[k]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < kSlotRounds; ++k)
-              if (srcd[k] != 0xFFFFu) __stwt((unsigned long long*)out + dst[k], (unsigned long long)v[k]);
-          }
+          for (int k = 0; k < kSlotRounds; ++k)
+            if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
           consumer_sync();  // every warp has read this column's old carry (= the next spare)
 #pragma unroll
           for (int q = 0; q < kEntryRounds; ++q) {
@@ -875,6 +859,7 @@ constexpr int kWsMoverWarps = 16, kWsRankWarps = 8;
 constexpr int kWsMovers = kWsMoverWarps * 32, kWsRankers = kWsRankWarps * 32;
 constexpr int kWsThreads = kWsMovers + kWsRankers + 128;  // + producer warpgroup (1 active warp)
 constexpr int kWsG = 4;
+constexpr int kWsRankItems = 16;  // rows per ranker thread per tile: tile = 256 x 16 = 4096 rows (2048: no faster)
 
 struct WsUnits {
   const uint64_t* src[kSwcMaxCols];
@@ -905,7 +890,7 @@ __device__ __forceinline__ void ranker_sync() { asm volatile("bar.sync 2, %0;" :
 
 template <int kBits, int G, int kWsRankItems>
 __global__ void __launch_bounds__(kWsThreads, 1)
-fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages, int use_hw_match,
+fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
                      const uint8_t* __restrict__ pid_plane,
                      const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
   constexpr uint32_t T = (uint32_t)kWsRankers * kWsRankItems;  // rows per tile
@@ -963,9 +948,6 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages, int 
 
   if (warp >= kWsMoverWarps + kWsRankWarps) {
     // ============================ producer =============================================
-#ifdef FB_WS_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-#endif
     if (warp == kWsMoverWarps + kWsRankWarps && lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
       const uint32_t ring_s = smem_u32(ring), pid_s = smem_u32(pidbuf);
@@ -1008,9 +990,6 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages, int 
 
   if (warp >= kWsMoverWarps) {
     // ============================ rankers (8 warps) ====================================
-#ifdef FB_WS_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-#endif
     const unsigned rw = warp - kWsMoverWarps;          // ranker warp 0..7
     const unsigned rtid = threadIdx.x - kWsMovers;     // 0..255
     const unsigned lt = fb_lanemask_lt();
@@ -1039,10 +1018,8 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages, int 
         uint32_t pos[kWsRankItems];
 #pragma unroll
         for (int r = 0; r < kWsRankItems; ++r) {
-          // rankers are off the critical path and the ADU pipe is idle in this kernel, so the
-          // hardware MATCH.ANY (~70 cycles/warp on the ADU) beats 8 ballots on the shared ALU pipe
-          const unsigned m = use_hw_match ? __match_any_sync(0xFFFFFFFFu, pid[r])
-                                          : match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
+          // (hardware MATCH.ANY was measured slower here too, even with the ADU pipe otherwise idle)
+          const unsigned m = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
           const unsigned before = __popc(m & lt);
           uint32_t old = 0;
           if (before == 0) {
@@ -1146,9 +1123,6 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages, int 
   }
 
   // ================================ movers (16 warps) ====================================
-#ifdef FB_WS_SETMAXNREG
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-#endif
   uint32_t s = 0, ph = 0, seq = 0, astep = 0, wstep = 0;
   for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
     int64_t r0, r1;
@@ -1321,14 +1295,10 @@ cudaError_t ensure_smem_optin(int dev) {
   {
     int smem_max = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, 16>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, 16>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, 8>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, 8>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGA, kSwcItemsA>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcGA, kSwcItemsA>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGB, kSwcItemsB>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcGB, kSwcItemsB>, (size_t)smem_max);
   }
   FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
   FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
@@ -1561,26 +1531,18 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
           wu.src[c] = (const uint64_t*)col_ptrs[fast_idx[c0 + c]];
           wu.dst[c] = (uint64_t*)out_col_ptrs[fast_idx[c0 + c]];
         }
-        const int hw_match = getenv("FB_WS_HWMATCH") ? atoi(getenv("FB_WS_HWMATCH")) : 0;
-        const int small_tile = getenv("FB_WS_TILE") ? (atoi(getenv("FB_WS_TILE")) == 2048) : 0;
-        const size_t book = small_tile ? ws_book_bytes<kWsG, 8>(num_partitions, nb)
-                                       : ws_book_bytes<kWsG, 16>(num_partitions, nb);
-        const size_t stage_bytes = (size_t)(small_tile ? 2048 : 4096) * 8;
+        const size_t book = ws_book_bytes<kWsG, kWsRankItems>(num_partitions, nb);
+        const size_t stage_bytes = (size_t)kWsRankers * kWsRankItems * 8;
         int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
         if (nstages > 16) nstages = 16;
         FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
         const size_t tsmem = (size_t)nstages * stage_bytes + book;
-#define FB_LAUNCH_WS(B, RI)                                                                   \
-  fb_scatter_ws_kernel<B, kWsG, RI><<<grid, kWsThreads, tsmem, st>>>(                         \
-      wu, num_partitions, g, nstages, hw_match, pid_plane, (const uint32_t*)scratch, part_offsets)
-        if (small_tile) {
-          if (bits == 4) FB_LAUNCH_WS(4, 8);
-          else FB_LAUNCH_WS(8, 8);
-        } else {
-          if (bits == 4) FB_LAUNCH_WS(4, 16);
-          else FB_LAUNCH_WS(8, 16);
-        }
-#undef FB_LAUNCH_WS
+        if (bits == 4)
+          fb_scatter_ws_kernel<4, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
+              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
+        else
+          fb_scatter_ws_kernel<8, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
+              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
         FB_CUDA(cudaGetLastError());
         continue;
       }
@@ -1599,26 +1561,18 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
           ++units.nunits;
         }
       }
-      const int store_mode = getenv("FB_STORE_MODE") ? atoi(getenv("FB_STORE_MODE")) : 0;
-      const int mode = getenv("FB_SWC_MODE") ? atoi(getenv("FB_SWC_MODE")) : 0;  // measured: mode 0 3.49 ms, mode 1 4.59 ms
-      const size_t book = mode == 0 ? swc_book_bytes<kSwcGA, kSwcItemsA>(num_partitions, nb)
-                                    : swc_book_bytes<kSwcGB, kSwcItemsB>(num_partitions, nb);
-      const size_t stage_bytes = (size_t)kBlock * (mode == 0 ? kSwcItemsA : kSwcItemsB) * 8;
+      const size_t book = swc_book_bytes<kSwcGA, kSwcItemsA>(num_partitions, nb);
+      const size_t stage_bytes = (size_t)kBlock * kSwcItemsA * 8;
       int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
       if (nstages > 16) nstages = 16;
       FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
       const size_t tsmem = (size_t)nstages * stage_bytes + book;
-#define FB_LAUNCH_SWC(B, G, I)                                                              \
-  fb_scatter_swc_kernel<B, G, I><<<grid, kTmaThreads, tsmem, st>>>(                         \
-      units, dv, num_partitions, g, nstages, nb, store_mode, (const uint32_t*)scratch, part_offsets)
-      if (mode == 0) {
-        if (bits == 4) FB_LAUNCH_SWC(4, kSwcGA, kSwcItemsA);
-        else FB_LAUNCH_SWC(8, kSwcGA, kSwcItemsA);
-      } else {
-        if (bits == 4) FB_LAUNCH_SWC(4, kSwcGB, kSwcItemsB);
-        else FB_LAUNCH_SWC(8, kSwcGB, kSwcItemsB);
-      }
-#undef FB_LAUNCH_SWC
+      if (bits == 4)
+        fb_scatter_swc_kernel<4, kSwcGA, kSwcItemsA><<<grid, kTmaThreads, tsmem, st>>>(
+            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
+      else
+        fb_scatter_swc_kernel<8, kSwcGA, kSwcItemsA><<<grid, kTmaThreads, tsmem, st>>>(
+            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
       FB_CUDA(cudaGetLastError());
     }
     // the partial tail tile of the fast columns

@@ -198,3 +198,18 @@ def test_full_size_properties_100m_rows():
     # permutation: every row id appears exactly once (checksum of checksums)
     assert int(rid.sum()) == n * (n - 1) // 2
     assert int((rid ^ (rid >> 7)).sum()) == int((rowid ^ (rowid >> 7)).sum())
+
+
+@pytest.mark.parametrize("env", [{}, {"FB_SCATTER": "swc"}, {"FB_DISABLE_TMA": "1"}, {"FB_WS_COLS": "8"},
+                                 {"FB_WS_COLS": "1"}])
+def test_all_scatter_kernel_paths_agree(env, monkeypatch):
+    """warp-specialised (default), single-role write-combining (v4) and generic kernels: same bits."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(23)
+    n = 1_234_567
+    cols = [rng.integers(0, 1 << 16, n).astype("int64")] + \
+           [rng.integers(-(2**62), 2**62, n).astype("int64") for _ in range(4)] + \
+           [rng.standard_normal(n) for _ in range(5)]          # 10 columns: more than one launch
+    _check_partition(cols, [0], 256)
+    _check_partition(cols, [0, 5], 200)                           # two key columns, num not a power of two

@@ -21,7 +21,7 @@ outs = [torch.empty(nseg * seglen, dtype=torch.int64, device=dev) for _ in range
 src_ptrs = [int(hdl.buffer_ptrs[peer]) + c * n * 8 for c in range(ncols)]
 tab = torch.zeros(nseg, dtype=torch.int32, device=dev)
 tot = nseg * seglen * 8 * ncols
-for variant in (0, 2):
+for variant in (0,):
     for pieces in ("", "4", "16"):
         os.environ["FB_COPY_VARIANT"] = str(variant)
         if pieces: os.environ["FB_COPY_PIECES"] = pieces
