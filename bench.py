@@ -26,7 +26,7 @@ SCHEMA = "key:long,i1:long,i2:long,i3:long,v0:double,v1:double,v2:double,v3:doub
 ALG_BYTES_PER_ROW = 128  # read every column once + write every column once
 # CPU sample: the logical partitions of 1/100 of the keys, at the workload's rows-per-key ratio
 # (100M rows / 65536 keys = 1526 rows per logical partition): 1M rows over 655 keys.
-REF_SAMPLE_ROWS = 1_000_000
+REF_SAMPLE_ROWS = int(os.environ.get("FB_BENCH_REF_ROWS", "1000000"))
 REF_SAMPLE_KEYS = KEY_CARDINALITY * REF_SAMPLE_ROWS // ROWS_PER_GPU
 METRIC = "transform() rows/sec, hash-partitioned (num=256) identity map, 8-col table"
 

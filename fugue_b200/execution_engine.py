@@ -317,19 +317,28 @@ class B200ExecutionEngine:
         n = t.num_rows
         dev = t.device
         # ---- the 8-byte group key
-        assert_or_throw(len(keys) <= 1, NotImplementedError(
-            "group-by on more than one key column: pack the keys into one 8-byte column first"))
+        multi = len(keys) > 1
+        kidx = [t.schema.index_of_key(k) for k in keys]
+
+        def key_bits64(c: torch.Tensor) -> torch.Tensor:
+            if c.dtype == torch.float64:
+                return torch.where(c == 0, torch.zeros_like(c), c).view(torch.int64)  # -0.0 groups with 0.0
+            if c.dtype == torch.float32:
+                return torch.where(c == 0, torch.zeros_like(c), c).view(torch.int32).to(torch.int64)
+            return c if c.dtype == torch.int64 else c.to(torch.int64)
+
         if len(keys) == 1:
-            ki = t.schema.index_of_key(keys[0])
+            ki = kidx[0]
             kcol, kvalid, ktype = t.columns[ki], t.valid[ki], t.schema.types[ki]
-            if kcol.dtype == torch.float64:
-                kcol = torch.where(kcol == 0, torch.zeros_like(kcol), kcol)  # -0.0 groups with 0.0
-                key64 = kcol.view(torch.int64)
-            elif kcol.dtype == torch.float32:
-                kcol = torch.where(kcol == 0, torch.zeros_like(kcol), kcol)
-                key64 = kcol.view(torch.int32).to(torch.int64)
-            else:
-                key64 = kcol if kcol.dtype == torch.int64 else kcol.to(torch.int64)
+            key64 = key_bits64(kcol)
+        elif multi:
+            # several key columns: group on the 64-bit hash of the key tuple (same hash as the
+            # partitioner) and carry MIN/MAX of every key column as hidden aggregates: a group whose
+            # MIN != MAX (or that mixes NULL and non-NULL) is a hash collision -> error instead of a
+            # silently merged group.  The key values of the output are the MINs.
+            kb = [key_bits64(t.columns[i]).contiguous() for i in kidx]
+            key64 = K.row_hash64(kb, [t.valid[i] for i in kidx])
+            kvalid, ktype = None, None
         else:
             key64, kvalid, ktype = torch.zeros(n, dtype=torch.int64, device=dev), None, None
         # ---- aggregates
@@ -344,6 +353,13 @@ class B200ExecutionEngine:
             ops.append(op)
             return len(ops) - 1
 
+        key_slots: List[Any] = []
+        if multi:
+            for i, kbits in zip(kidx, kb):
+                m = t.valid[i]
+                key_slots.append((add(kbits, m, K.AGG_MIN_I64), add(kbits, m, K.AGG_MAX_I64),
+                                  add(None, m, K.AGG_COUNT) if m is not None else None))
+            rows_slot = add(None, None, K.AGG_COUNT)
         for a in agg_cols:
             fn, arg = a.func, a.arg.name
             if fn == "COUNT":
@@ -380,6 +396,27 @@ class B200ExecutionEngine:
             ng = 1
         # ---- assemble the output table
         fields, cols, valids = [], [], []
+        if multi:
+            from .table import _storage_dtype
+
+            bad = torch.zeros((), dtype=torch.bool, device=dev)
+            for k, i, (smin, smax, scnt) in zip(keys, kidx, key_slots):
+                bad |= (gaggs[smin] != gaggs[smax]).any() if scnt is None else \
+                    (((gaggs[scnt] > 0) & (gaggs[smin] != gaggs[smax])) |
+                     ((gaggs[scnt] > 0) & (gaggs[scnt] != gaggs[rows_slot]))).any()
+                kc = t.columns[i]
+                raw = gaggs[smin]
+                if kc.dtype == torch.float64:
+                    out_k = raw.view(torch.float64)
+                elif kc.dtype == torch.float32:
+                    out_k = raw.to(torch.int32).view(torch.float32)
+                else:
+                    out_k = raw if kc.dtype == torch.int64 else raw.to(kc.dtype)
+                fields.append(pa.field(k, t.schema.types[i]))
+                cols.append(out_k.contiguous())
+                valids.append(None if scnt is None else (gaggs[scnt] > 0).to(torch.uint8))
+            assert_or_throw(not bool(bad), RuntimeError(
+                "64-bit hash collision between two distinct key tuples in a multi-column GROUP BY"))
         if len(keys) == 1:
             kc = t.columns[ki]
             if kc.dtype == torch.float64:
@@ -410,7 +447,7 @@ class B200ExecutionEngine:
             fields.append(pa.field(name, tp))
             cols.append(col.contiguous())
             valids.append(v)
-        dicts = {keys[0]: t.dictionaries[keys[0]]} if len(keys) == 1 and keys[0] in t.dictionaries else {}
+        dicts = {k: t.dictionaries[k] for k in keys if k in t.dictionaries}
         return B200DataFrame(B200Table(Schema(fields), cols, valids, dicts))
 
     # ---- join (K7) ----------------------------------------------------------------------

@@ -186,7 +186,7 @@ def copy_segments(src_cols: Sequence[torch.Tensor], dst_cols: Sequence[torch.Ten
 
 
 AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_MAX_F64 = range(7)
-MAX_AGGS = 8
+MAX_AGGS = 16
 
 
 GROUPBY_PARTITION_MIN_ROWS = 4_000_000   # below this the table fits in L2 anyway

@@ -145,7 +145,7 @@ int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_
  *                      d_status[1] receives the number of groups.  d_out_aggs is a DEVICE array
  *                      of naggs device pointers.  Group order is unspecified.
  * --------------------------------------------------------------------------- */
-#define FB_MAX_AGGS 8
+#define FB_MAX_AGGS 16
 enum {
   FB_AGG_SUM_F64 = 0,
   FB_AGG_SUM_I64 = 1,

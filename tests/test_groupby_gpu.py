@@ -135,3 +135,26 @@ def test_sql_engine_group_by_and_join(engine):
     assert out.values.tolist() == [[3000, l.lv.max()]]
     with pytest.raises(NotImplementedError):
         fa.raw_sql("SELECT key FROM", l, "WHERE key > 3", engine=engine)
+
+
+def test_multi_column_group_by(engine):
+    rng = np.random.default_rng(9)
+    n = 300_000
+    pdf = pd.DataFrame({"a": rng.integers(0, 300, n), "b": rng.integers(-5, 5, n).astype("int32"),
+                        "c": np.round(rng.standard_normal(n), 1), "v": rng.standard_normal(n)})
+    pdf.loc[rng.integers(0, n, 2000), "c"] = np.nan                  # NULLs in one of the key columns
+    res = fa.aggregate(fa.as_fugue_engine_df(engine, pdf, "a:long,b:int,c:double,v:double"), ["a", "b", "c"],
+                       s=ff.sum(col("v")), n=ff.count(all_cols()), engine=engine, as_local=True)
+    got = res.as_pandas().sort_values(["a", "b", "c"]).reset_index(drop=True)
+    exp = ora.aggregate(pdf, ["a", "b", "c"], {"s": ("v", "sum"), "n": ("*", "count")})
+    exp = exp.sort_values(["a", "b", "c"]).reset_index(drop=True)
+    assert len(got) == len(exp)
+    for k in ("a", "b", "n"):
+        assert np.array_equal(got[k].to_numpy(), exp[k].to_numpy()), k
+    assert np.array_equal(got["c"].isna().to_numpy(), exp["c"].isna().to_numpy())
+    assert np.allclose(got["c"].fillna(0), exp["c"].fillna(0), rtol=0, atol=0)
+    assert np.max(np.abs(got["s"] - exp["s"]) / np.maximum(np.abs(exp["s"]), 1e-300)) <= 1e-9
+    # string + int keys
+    a = ArrayDataFrame([["x", 1, 1.0], ["x", 2, 2.0], ["y", 1, 3.0], ["x", 1, 4.0], [None, 1, 5.0]], "k:str,j:int,v:double")
+    res = fa.aggregate(a, ["k", "j"], s=ff.sum(col("v")), engine=engine)
+    df_eq(res, [["x", 1, 5.0], ["x", 2, 2.0], ["y", 1, 3.0], [None, 1, 5.0]], "k:str,j:int,s:double", throw=True)
