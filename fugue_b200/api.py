@@ -350,3 +350,70 @@ def raw_sql(*statements: Any, engine: Any = None, engine_conf: Any = None, as_fu
     if as_fugue or any(isinstance(s, DataFrame) for s in statements):
         return res
     return res.as_pandas() if res.is_local else res.native
+
+
+def _run_engine_function(name: str, dfs: List[Any], engine: Any, engine_conf: Any, as_fugue: bool,
+                         as_local: bool, **kwargs: Any) -> Any:
+    """fugue/execution/api.py:145-179 (run_engine_function)."""
+    e = make_execution_engine(engine, engine_conf, infer_by=dfs)
+    fn = getattr(e, name)
+    res = fn(e.to_df(dfs[0]), **kwargs) if len(dfs) == 1 else fn(e.to_df(dfs[0]), e.to_df(dfs[1]), **kwargs)
+    for odf in dfs[2:]:
+        res = fn(res, e.to_df(odf), **kwargs)
+    res = e.convert_yield_dataframe(res, as_local)
+    if as_fugue or any(isinstance(x, DataFrame) for x in dfs):
+        return res
+    return res.as_pandas() if res.is_local else res.native
+
+
+def union(df1: Any, df2: Any, *dfs: Any, distinct: bool = True, engine: Any = None, engine_conf: Any = None,
+          as_fugue: bool = False, as_local: bool = False) -> Any:
+    return _run_engine_function("union", [df1, df2, *dfs], engine, engine_conf, as_fugue, as_local, distinct=distinct)
+
+
+def subtract(df1: Any, df2: Any, *dfs: Any, distinct: bool = True, engine: Any = None, engine_conf: Any = None,
+             as_fugue: bool = False, as_local: bool = False) -> Any:
+    return _run_engine_function("subtract", [df1, df2, *dfs], engine, engine_conf, as_fugue, as_local,
+                                distinct=distinct)
+
+
+def intersect(df1: Any, df2: Any, *dfs: Any, distinct: bool = True, engine: Any = None, engine_conf: Any = None,
+              as_fugue: bool = False, as_local: bool = False) -> Any:
+    return _run_engine_function("intersect", [df1, df2, *dfs], engine, engine_conf, as_fugue, as_local,
+                                distinct=distinct)
+
+
+def distinct(df: Any, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+             as_local: bool = False) -> Any:
+    return _run_engine_function("distinct", [df], engine, engine_conf, as_fugue, as_local)
+
+
+def dropna(df: Any, how: str = "any", thresh: Optional[int] = None, subset: Optional[List[str]] = None,
+           engine: Any = None, engine_conf: Any = None, as_fugue: bool = False, as_local: bool = False) -> Any:
+    return _run_engine_function("dropna", [df], engine, engine_conf, as_fugue, as_local, how=how, thresh=thresh,
+                                subset=subset)
+
+
+def fillna(df: Any, value: Any, subset: Optional[List[str]] = None, engine: Any = None, engine_conf: Any = None,
+           as_fugue: bool = False, as_local: bool = False) -> Any:
+    return _run_engine_function("fillna", [df], engine, engine_conf, as_fugue, as_local, value=value, subset=subset)
+
+
+def sample(df: Any, n: Optional[int] = None, frac: Optional[float] = None, replace: bool = False,
+           seed: Optional[int] = None, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+           as_local: bool = False) -> Any:
+    return _run_engine_function("sample", [df], engine, engine_conf, as_fugue, as_local, n=n, frac=frac,
+                                replace=replace, seed=seed)
+
+
+def load(path: Any, format_hint: Any = None, columns: Any = None, engine: Any = None, engine_conf: Any = None,
+         as_fugue: bool = False, **kwargs: Any) -> Any:
+    e = make_execution_engine(engine, engine_conf)
+    res = e.load_df(path, format_hint=format_hint, columns=columns, **kwargs)
+    return res if as_fugue else res.native
+
+
+def save(df: Any, path: str, format_hint: Any = None, mode: str = "overwrite", engine: Any = None,
+         engine_conf: Any = None, **kwargs: Any) -> None:
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    e.save_df(e.to_df(df), path, format_hint=format_hint, mode=mode, **kwargs)

@@ -457,3 +457,52 @@ class B200ExecutionEngine:
         from .join import device_join
 
         return device_join(self, self.to_df(df1), self.to_df(df2), how, on)
+
+    # ---- set operations, NULL handling, sampling, IO (fugue_b200/relational.py) -----------
+    def union(self, df1: Any, df2: Any, distinct: bool = True) -> B200DataFrame:
+        from . import relational as R
+
+        return R.union(self, self.to_df(df1), self.to_df(df2), distinct)
+
+    def subtract(self, df1: Any, df2: Any, distinct: bool = True) -> B200DataFrame:
+        from . import relational as R
+
+        return R.subtract(self, self.to_df(df1), self.to_df(df2), distinct)
+
+    def intersect(self, df1: Any, df2: Any, distinct: bool = True) -> B200DataFrame:
+        from . import relational as R
+
+        return R.intersect(self, self.to_df(df1), self.to_df(df2), distinct)
+
+    def distinct(self, df: Any) -> B200DataFrame:
+        from . import relational as R
+
+        return R.distinct(self, self.to_df(df))
+
+    def dropna(self, df: Any, how: str = "any", thresh: Optional[int] = None,
+               subset: Optional[List[str]] = None) -> B200DataFrame:
+        from . import relational as R
+
+        return R.dropna(self.to_df(df), how, thresh, subset)
+
+    def fillna(self, df: Any, value: Any, subset: Optional[List[str]] = None) -> B200DataFrame:
+        from . import relational as R
+
+        return R.fillna(self.to_df(df), value, subset)
+
+    def sample(self, df: Any, n: Optional[int] = None, frac: Optional[float] = None, replace: bool = False,
+               seed: Optional[int] = None) -> B200DataFrame:
+        from . import relational as R
+
+        return R.sample(self.to_df(df), n, frac, replace, seed)
+
+    def load_df(self, path: Any, format_hint: Any = None, columns: Any = None, **kwargs: Any) -> B200DataFrame:
+        from . import relational as R
+
+        return R.load_df(self, path, format_hint, columns, **kwargs)
+
+    def save_df(self, df: Any, path: str, format_hint: Any = None, mode: str = "overwrite",
+                partition_spec: Optional[PartitionSpec] = None, force_single: bool = False, **kwargs: Any) -> None:
+        from . import relational as R
+
+        R.save_df(self, df, path, format_hint, mode, **kwargs)
