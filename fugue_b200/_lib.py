@@ -43,6 +43,8 @@ SIGNATURES = {
                                      _vpp]),
     "fb_partition_cols": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _i32p,
                                     C.c_int, _vpp, C.c_uint32, _vpp, _vp, _vp, C.c_size_t]),
+    "fb_radix_pass": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vpp, _i32p, _vpp, _vp, C.c_size_t,
+                                _vp]),
     "fb_bits_to_bytes": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "fb_bytes_to_bits": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp, _vp]),
     "fb_groupby_table_bytes": (C.c_size_t, [C.c_int64, C.c_int]),

@@ -417,3 +417,11 @@ def save(df: Any, path: str, format_hint: Any = None, mode: str = "overwrite", e
          engine_conf: Any = None, **kwargs: Any) -> None:
     e = make_execution_engine(engine, engine_conf, infer_by=[df])
     e.save_df(e.to_df(df), path, format_hint=format_hint, mode=mode, **kwargs)
+
+
+def take(df: Any, n: int, presort: Any = None, na_position: str = "last", partition: Any = None,
+         engine: Any = None, engine_conf: Any = None, as_fugue: bool = False, as_local: bool = False) -> Any:
+    """``fa.take`` (fugue/execution/api.py): first n rows (per partition key group) after sorting."""
+    return _run_engine_function("take", [df], engine, engine_conf, as_fugue, as_local, n=n, presort=presort,
+                                na_position=na_position,
+                                partition_spec=None if partition is None else PartitionSpec(partition))

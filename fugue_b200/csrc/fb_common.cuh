@@ -48,6 +48,7 @@ struct FbKeys {
   const uint8_t* valid[FB_MAX_KEYS];
   int32_t width[FB_MAX_KEYS];
   int32_t nkeys;
+  int32_t digit_shift;  // < 0: hash mode; >= 0: radix-sort mode, id = (key[0] >> digit_shift) & (num - 1)
 };
 
 // Division-free `h % d` for a runtime-invariant 32-bit divisor d >= 1

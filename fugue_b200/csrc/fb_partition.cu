@@ -83,6 +83,8 @@ __device__ __forceinline__ uint32_t compute_pid(const FbKeys& keys, const FbDiv&
   if (kSingleU64) {
     h = fb_hash_single_u64(__ldg((const unsigned long long*)keys.ptr[0] + row));
   } else {
+    if (keys.digit_shift >= 0)  // one pass of an LSD radix sort on an 8-byte unsigned sort key
+      return (uint32_t)(__ldg((const unsigned long long*)keys.ptr[0] + row) >> keys.digit_shift) & (dv.d - 1);
     h = fb_row_hash(keys, row);
   }
   return fb_fastmod(h, dv);
@@ -1316,6 +1318,7 @@ int fill_keys(FbKeys& k, int nkeys, const void* const* ptrs, const int32_t* widt
   FB_CHECK(nkeys >= 1 && nkeys <= FB_MAX_KEYS, "nkeys=%d out of range [1,%d]", nkeys, FB_MAX_KEYS);
   memset(&k, 0, sizeof(k));
   k.nkeys = nkeys;
+  k.digit_shift = -1;
   for (int i = 0; i < nkeys; ++i) {
     FB_CHECK(widths[i] == 1 || widths[i] == 2 || widths[i] == 4 || widths[i] == 8,
              "key %d has unsupported width %d", i, widths[i]);
@@ -1390,10 +1393,9 @@ int fb_row_hash64(int dev, void* stream, int64_t nrows, int nkeys, const void* c
   return 0;
 }
 
-int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
-                      const int32_t* key_widths, const uint8_t* const* key_valid,
-                      uint32_t num_partitions, void* scratch, size_t scratch_bytes,
-                      int64_t* out_part_offsets) {
+static int plan_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, bool single,
+                     uint32_t num_partitions, void* scratch, size_t scratch_bytes,
+                     int64_t* out_part_offsets) {
   FB_CHECK(nrows >= 0, "nrows < 0");
   FB_CHECK(nrows < ((int64_t)1 << 32), "nrows=%lld exceeds the 2^32-1 rows one call handles",
            (long long)nrows);
@@ -1411,14 +1413,11 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
   PlanLayout l = plan_layout(g, num_partitions);
   FB_CHECK(scratch != nullptr && scratch_bytes >= l.total_bytes,
            "scratch too small: need %zu bytes, got %zu", l.total_bytes, scratch_bytes);
-  FbKeys k;
-  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   FbDiv dv = fb_make_div(num_partitions);
   uint32_t* hist = (uint32_t*)scratch;
   uint8_t* pid_plane = num_partitions <= kSwcMaxNum ? (uint8_t*)scratch + l.pid_offset : nullptr;
   size_t smem = (size_t)kHistWarps * num_partitions * sizeof(uint32_t);
   FB_CUDA(ensure_smem_optin(dev));
-  const bool single = single_u64_key(nkeys, key_widths, key_valid);
   const int bits = bits_for(num_partitions);
 #define FB_LAUNCH_HIST(S, B) \
   fb_hist_kernel<S, B><<<g.nchunks, kHistBlock, smem, st>>>(k, dv, num_partitions, g, hist, pid_plane)
@@ -1432,11 +1431,20 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
   return 0;
 }
 
-int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
-                       const int32_t* key_widths, const uint8_t* const* key_valid,
-                       uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
-                       const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
-                       const int32_t* col_widths, void* const* out_col_ptrs) {
+int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                      const int32_t* key_widths, const uint8_t* const* key_valid,
+                      uint32_t num_partitions, void* scratch, size_t scratch_bytes,
+                      int64_t* out_part_offsets) {
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  return plan_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
+                   scratch, scratch_bytes, out_part_offsets);
+}
+
+static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, bool single,
+                      uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
+                      const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
+                      const int32_t* col_widths, void* const* out_col_ptrs) {
   FB_CHECK(nrows >= 0 && nrows < ((int64_t)1 << 32), "nrows out of range");
   FB_CHECK(num_partitions >= 1 && num_partitions <= FB_MAX_PARTITIONS,
            "num_partitions=%u out of range [1,%d]", num_partitions, FB_MAX_PARTITIONS);
@@ -1447,11 +1455,8 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
   ChunkGeom g = make_geom(dev, nrows);
   PlanLayout l = plan_layout(g, num_partitions);
   FB_CHECK(scratch != nullptr && scratch_bytes >= l.total_bytes, "scratch too small");
-  FbKeys k;
-  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   FbDiv dv = fb_make_div(num_partitions);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool single = single_u64_key(nkeys, key_widths, key_valid);
   const size_t smem = scatter_smem_bytes(num_partitions);
   FB_CUDA(ensure_smem_optin(dev));
   const int bits = bits_for(num_partitions);
@@ -1579,6 +1584,31 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
     if (int rc = launch_generic(fast_idx, nfast, g.nchunks_full, g.nchunks - g.nchunks_full)) return rc;
   }
   return 0;
+}
+
+int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                       const int32_t* key_widths, const uint8_t* const* key_valid,
+                       uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
+                       const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
+                       const int32_t* col_widths, void* const* out_col_ptrs) {
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
+                    scratch, scratch_bytes, part_offsets, ncols, col_ptrs, col_widths, out_col_ptrs);
+}
+
+int fb_radix_pass(int dev, void* stream, int64_t nrows, const void* sort_key_u64, int shift, int ncols,
+                  const void* const* col_ptrs, const int32_t* col_widths, void* const* out_col_ptrs,
+                  void* scratch, size_t scratch_bytes, int64_t* d_offsets /*257*/) {
+  FB_CHECK(shift >= 0 && shift <= 56, "shift out of range");
+  const void* kp[1] = {sort_key_u64};
+  const int32_t kw[1] = {8};
+  FbKeys k;
+  if (int rc = fill_keys(k, 1, kp, kw, nullptr)) return rc;
+  k.digit_shift = shift;
+  if (int rc = plan_impl(dev, stream, nrows, k, false, 256, scratch, scratch_bytes, d_offsets)) return rc;
+  return apply_impl(dev, stream, nrows, k, false, 256, scratch, scratch_bytes, d_offsets, ncols, col_ptrs,
+                    col_widths, out_col_ptrs);
 }
 
 int fb_partition_cols(int dev, void* stream, int64_t nrows, int ncols, const void* const* col_ptrs,

@@ -99,13 +99,27 @@ class B200MapEngine:
         if on_init is not None:
             on_init(0, edf)
         keyed = len(partition_spec.partition_by) > 0 and not is_coarse
+        if map_func_format_hint == "b200" and len(presort) > 0:
+            # device presort: sort by (partition keys, presort) first; the stable hash partition below
+            # keeps that order inside every physical partition, so logical partitions (distinct key
+            # tuples) come out contiguous and presorted; their boundaries go to table.logical_offsets
+            from collections import OrderedDict
+
+            from . import sort as S
+
+            order = OrderedDict((k, True) for k in (partition_spec.partition_by if keyed else []))
+            for k, v in presort.items():
+                order[k] = v
+            edf = B200DataFrame(S.sort_table(edf.native, order))
         if keyed:
             edf = engine.repartition(edf, partition_spec)  # K1+K2+K3 on the device
         if map_func_format_hint == "b200":
             # device-vectorised map: the function is typed on B200Table and is called once per
             # device table, the physical partitions delimited by table.offsets
-            assert_or_throw(len(presort) == 0, NotImplementedError(
-                "presort with a B200Table-typed function needs the segmented device sort"))
+            if len(presort) > 0 and keyed:
+                from . import sort as S
+
+                edf.native.logical_offsets = S.logical_offsets(edf.native, partition_spec.partition_by)
             cursor.set(lambda: edf.peek_array(), 0, 0)
             out = map_func(cursor, edf)
             res = engine.to_df(out)
@@ -506,3 +520,19 @@ class B200ExecutionEngine:
         from . import relational as R
 
         R.save_df(self, df, path, format_hint, mode, **kwargs)
+
+    def take(self, df: Any, n: int, presort: Any, na_position: str = "last",
+             partition_spec: Optional[PartitionSpec] = None) -> B200DataFrame:
+        """``ExecutionEngine.take`` (execution_engine.py:708-734; native :350-384) on the device."""
+        from . import sort as S
+        from .partition import parse_presort_exp
+
+        partition_spec = partition_spec or PartitionSpec()
+        assert_or_throw(isinstance(n, int) and not isinstance(n, bool), ValueError("n needs to be an integer"))
+        sorts = parse_presort_exp(presort) if presort else None
+        if not sorts:
+            sorts = partition_spec.presort
+        edf = self.to_df(df)
+        for k in list(sorts.keys()) + list(partition_spec.partition_by):
+            assert_or_throw(k in edf.schema, lambda: KeyError(f"{k} not in {edf.schema}"))
+        return B200DataFrame(S.take(edf.native, n, sorts, na_position, list(partition_spec.partition_by)))

@@ -62,6 +62,8 @@ class B200Table:
         # physical partitioning metadata (set by the engine after a hash partition)
         self.offsets = offsets                # int64 [num + 1] on the device
         self.partition_keys = partition_keys  # key column names the offsets refer to
+        self.logical_offsets: Optional[torch.Tensor] = None  # set after a device presort: one segment
+        #                                                      per distinct key tuple (logical partition)
         n = self.columns[0].shape[0] if self.columns else 0
         for c in self.columns:
             assert c.dim() == 1 and c.shape[0] == n and c.is_contiguous()

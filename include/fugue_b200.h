@@ -103,6 +103,19 @@ int fb_partition_cols(int dev, void* stream, int64_t nrows, int ncols,
                       void* const* out_col_ptrs, int64_t* out_part_offsets,
                       void* scratch, size_t scratch_bytes);
 
+/* ---------------------------------------------------------------------------
+ * One stable pass of an LSD radix sort: rows are reordered by the 8-bit digit
+ * (sort_key >> shift) & 255 of an 8-byte UNSIGNED sort key column, keeping the current order
+ * inside a digit (same kernels as the hash partition; d_offsets: 257 int64).  Eight passes sort
+ * by a 64-bit key; the host layer builds order-preserving keys for ints / doubles / NULLS FIRST|LAST
+ * / DESC and sorts (key, row index) pairs, then gathers the payload once (fb_gather_rows).
+ * Replaces: pdf.sort_values(presort_keys, ascending=...) fugue/execution/native_execution_engine.py:
+ * 107-115, 157-160 (presort) and :350-384 (take).
+ * --------------------------------------------------------------------------- */
+int fb_radix_pass(int dev, void* stream, int64_t nrows, const void* sort_key_u64, int shift, int ncols,
+                  const void* const* col_ptrs, const int32_t* col_widths, void* const* out_col_ptrs,
+                  void* scratch, size_t scratch_bytes, int64_t* d_offsets);
+
 /* Arrow validity bitmap (LSB first) <-> byte mask. `bit_offset` is the Arrow
  * array offset. */
 int fb_bits_to_bytes(int dev, void* stream, const uint8_t* bits, int64_t bit_offset,

@@ -119,3 +119,66 @@ def test_save_and_load_parquet_csv_json(e, tmp_path):
     p3 = os.path.join(tmp_path, "x.json")
     fa.save(ArrayDataFrame([[1, 2], [3, 4]], "a:long,b:long"), p3, engine=e)
     df_eq(fa.load(p3, engine=e, as_fugue=True), [[1, 2], [3, 4]], "a:long,b:long", throw=True)
+
+
+def test_take(e):
+    ps = dict(by=["a"], presort="b DESC,c DESC")
+    ps2 = dict(by=["c"], presort="b ASC")
+    s = "a:str,b:int,c:long"
+    a = fa.as_fugue_engine_df(e, [["a", 2, 3], ["a", 3, 4], ["b", 1, 2], ["b", 2, 2], [None, 4, 2], [None, 2, 1]], s)
+    df_eq(fa.take(a, n=1, presort="b desc", engine=e), [[None, 4, 2]], s, throw=True)
+    df_eq(fa.take(a, n=2, presort="a desc", na_position="first", engine=e), [[None, 4, 2], [None, 2, 1]], s, throw=True)
+    df_eq(fa.take(a, n=1, presort="a asc, b desc", partition=ps, engine=e),
+          [["a", 3, 4], ["b", 2, 2], [None, 4, 2]], s, throw=True)
+    df_eq(fa.take(a, n=1, presort=None, partition=ps2, engine=e),
+          [["a", 2, 3], ["a", 3, 4], ["b", 1, 2], [None, 2, 1]], s, throw=True)
+    df_eq(fa.take(a, n=2, presort="a desc", na_position="last", engine=e), [["b", 1, 2], ["b", 2, 2]], s, throw=True)
+    df_eq(fa.take(a, n=2, presort="a", na_position="first", engine=e), [[None, 4, 2], [None, 2, 1]], s, throw=True)
+    a = fa.as_fugue_engine_df(e, [["a", 2, 3], [None, 4, 2], [None, 2, 1]], s)
+    j = fa.take(a, n=2, partition="a", presort=None, engine=e)
+    df_eq(j, [["a", 2, 3], [None, 4, 2], [None, 2, 1]], s, throw=True)
+    i = fa.take(a, n=1, partition="a", presort=None, engine=e)
+    assert i.count() == 2
+    raises(ValueError, lambda: fa.take(a, n=0.5, presort=None, engine=e))
+
+
+def test_device_sort_matches_pandas(e):
+    from collections import OrderedDict
+
+    from fugue_b200 import sort as S
+
+    rng = np.random.default_rng(8)
+    n = 300_000
+    pdf = pd.DataFrame({"i": rng.integers(-10**12, 10**12, n), "f": rng.standard_normal(n),
+                        "s": rng.integers(-3, 3, n).astype("int32"), "u": rng.integers(0, 255, n).astype("uint8")})
+    pdf.loc[rng.integers(0, n, 3000), "f"] = np.nan
+    t = fa.as_fugue_engine_df(e, pdf, "i:long,f:double,s:int,u:ubyte").native
+    for sorts, napos in [(OrderedDict(i=True), "last"), (OrderedDict(f=False), "first"),
+                         (OrderedDict([("s", True), ("u", False), ("f", True)]), "last")]:
+        got = S.sort_table(t, sorts, napos).to_pandas()
+        exp = pdf.sort_values(list(sorts.keys()), ascending=list(sorts.values()), na_position=napos,
+                              kind="stable").reset_index(drop=True)
+        pd.testing.assert_frame_equal(got, exp, check_exact=True)
+
+
+def test_presort_and_logical_partitions_for_device_functions(e):
+    """select-top per logical partition written as a device function (fugue_test/execution_suite.py:
+    225-256 does it with cursor.row on the host)."""
+    from fugue_b200.table import B200Table
+    from fugue_b200.sort import take_rows
+
+    def first_of_each_logical_partition(t: B200Table) -> B200Table:
+        return take_rows(t, t.logical_offsets[:-1])
+
+    o = ArrayDataFrame([[1, 2], [None, 2], [None, 1], [3, 4], [None, 4]], "a:double,b:int")
+    c = fa.transform(o, first_of_each_logical_partition, schema="*", partition=dict(by=["a"], presort="b"), engine=e)
+    df_eq(c, [[None, 1], [1, 2], [3, 4]], "a:double,b:int", throw=True)
+    c = fa.transform(o, first_of_each_logical_partition, schema="*", partition=dict(by=["a"], presort="b DESC", num=3),
+                     engine=e)
+    df_eq(c, [[None, 4], [1, 2], [3, 4]], "a:double,b:int", throw=True)
+    rng = np.random.default_rng(12)
+    pdf = pd.DataFrame({"k": rng.integers(0, 5000, 200_000), "v": rng.standard_normal(200_000)})
+    got = fa.transform(pdf, first_of_each_logical_partition, schema="*", partition=dict(by="k", presort="v desc"),
+                       engine=e, as_local=True)
+    exp = pdf.sort_values("v", ascending=False).groupby("k").head(1)
+    assert sorted(map(tuple, got.values.tolist())) == sorted(map(tuple, exp.values.tolist()))
