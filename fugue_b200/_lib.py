@@ -60,6 +60,8 @@ SIGNATURES = {
     "fb_join_mark_matched": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp]),
     "fb_exclusive_scan_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "fb_exclusive_scan_i64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_size_t]),
+    "fb_compact_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "fb_compact_indices": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_size_t]),
     "fb_gather_rows": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
     "fb_copy_segments": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
                                    C.c_int64]),

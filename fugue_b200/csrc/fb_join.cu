@@ -218,6 +218,41 @@ fb_gather_rows_kernel(const void* const* __restrict__ src_cols, void* const* __r
   }
 }
 
+// ---- stream compaction: indices of the non-zero bytes of a mask, in order ---------------------
+__global__ void __launch_bounds__(kScanBlock)
+fb_mask_tile_counts_kernel(const uint8_t* __restrict__ mask, int64_t n, int64_t* __restrict__ counts) {
+  __shared__ int64_t s_warp[kScanBlock / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  int64_t v = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + (int64_t)k * kScanBlock + threadIdx.x;
+    if (i < n && mask[i] != 0) ++v;
+  }
+  int64_t total;
+  block_exclusive_scan(v, s_warp, total);
+  if (threadIdx.x == 0) counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+fb_mask_write_kernel(const uint8_t* __restrict__ mask, int64_t n, const int64_t* __restrict__ tile_base,
+                     int64_t* __restrict__ out_idx) {
+  __shared__ int64_t s_warp[kScanBlock / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int64_t cnt = 0;
+  uint8_t m[kScanItems];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    m[k] = base + k < n ? mask[base + k] : 0;
+    cnt += m[k] != 0;
+  }
+  int64_t total;
+  int64_t o = tile_base[blockIdx.x] + block_exclusive_scan(cnt, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (m[k] != 0) out_idx[o++] = base + k;
+}
+
 inline int64_t region_shift_of(int64_t capacity, uint32_t num_parts) {
   if (num_parts <= 1) return -1;
   int64_t sh = 0;
@@ -325,6 +360,30 @@ int fb_exclusive_scan_i64(int dev, void* stream, int64_t n, const int64_t* in, i
   fb_scan_sums_kernel<<<1, kScanBlock, 0, st>>>(sums, ntiles, out_total);
   FB_CUDA(cudaGetLastError());
   fb_scan_tiles_kernel<<<(unsigned)ntiles, kScanBlock, 0, st>>>(in, n, sums, out);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t fb_compact_scratch_bytes(int64_t n) { return fb_exclusive_scan_scratch_bytes(n); }
+
+int fb_compact_indices(int dev, void* stream, const uint8_t* mask, int64_t n, int64_t* out_idx,
+                       int64_t* d_count, void* scratch, size_t scratch_bytes) {
+  FB_CHECK(n >= 0 && d_count != nullptr, "bad arguments");
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    FB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    return 0;
+  }
+  FB_CHECK(scratch != nullptr && scratch_bytes >= fb_compact_scratch_bytes(n), "compaction scratch too small");
+  const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  int64_t* counts = (int64_t*)scratch;
+  fb_mask_tile_counts_kernel<<<(unsigned)ntiles, kScanBlock, 0, st>>>(mask, n, counts);
+  FB_CUDA(cudaGetLastError());
+  fb_scan_sums_kernel<<<1, kScanBlock, 0, st>>>(counts, ntiles, d_count);
+  FB_CUDA(cudaGetLastError());
+  fb_mask_write_kernel<<<(unsigned)ntiles, kScanBlock, 0, st>>>(mask, n, counts, out_idx);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1436,6 +1436,12 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
                       uint32_t num_partitions, void* scratch, size_t scratch_bytes,
                       int64_t* out_part_offsets) {
   FbKeys k;
+  if (nrows == 0) {  // empty tables have NULL column pointers: nothing to read, offsets are all zero
+    memset(&k, 0, sizeof(k));
+    k.nkeys = 1;
+    k.digit_shift = -1;
+    return plan_impl(dev, stream, 0, k, false, num_partitions, scratch, scratch_bytes, out_part_offsets);
+  }
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   return plan_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
                    scratch, scratch_bytes, out_part_offsets);
@@ -1591,6 +1597,7 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
                        uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
                        const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
                        const int32_t* col_widths, void* const* out_col_ptrs) {
+  if (nrows == 0 || ncols == 0) return 0;
   FbKeys k;
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
@@ -1601,6 +1608,7 @@ int fb_radix_pass(int dev, void* stream, int64_t nrows, const void* sort_key_u64
                   const void* const* col_ptrs, const int32_t* col_widths, void* const* out_col_ptrs,
                   void* scratch, size_t scratch_bytes, int64_t* d_offsets /*257*/) {
   FB_CHECK(shift >= 0 && shift <= 56, "shift out of range");
+  if (nrows == 0) return 0;
   const void* kp[1] = {sort_key_u64};
   const int32_t kw[1] = {8};
   FbKeys k;

@@ -168,7 +168,7 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
             hit = torch.zeros(n1, dtype=torch.bool, device=dev)
             hit[li[ok]] = True
         keep = hit if how in ("semi", "left_semi") else ~hit
-        li = torch.nonzero(keep).flatten()
+        li = K.compact_indices((keep).contiguous())
         cols, valid = K.gather_rows(t1.columns, t1.valid, li, want_valid=False)
         return B200DataFrame(B200Table(out_schema, cols, valid, t1.dictionaries))
     if how == "right_outer":
@@ -184,7 +184,7 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
         li, ri = _drop_collisions(t1, t2, keys, li, ri, outer_side="left" if how != "inner" else None)
     if how == "full_outer":
         matched = tab.matched_mask(ri) if exact else _matched_mask(n2, ri)
-        extra = torch.nonzero(matched == 0).flatten()
+        extra = K.compact_indices((matched == 0).contiguous())
         li = torch.cat([li, torch.full_like(extra, -1)])
         ri = torch.cat([ri, extra])
     return _assemble(t1, t2, keys, out_schema, li, ri, how)
@@ -213,7 +213,7 @@ def _drop_collisions(t1, t2, keys, li, ri, outer_side):
     first_bad = torch.zeros_like(bad)
     if bool(bad.any()):
         # keep one NULL-extended row for probe rows that lost all their candidates
-        idx = torch.nonzero(bad).flatten()
+        idx = K.compact_indices((bad).contiguous())
         rows = probe[idx]
         lost = ~has[rows]
         uniq, inv = torch.unique(rows[lost], return_inverse=True)

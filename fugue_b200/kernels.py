@@ -368,3 +368,20 @@ def row_hash64(keys: Sequence[torch.Tensor], valid: Optional[Sequence[Optional[t
                                  _lib.ptr_array([k.data_ptr() for k in keys]),
                                  _lib.i32_array([k.element_size() for k in keys]), vp, out.data_ptr()))
     return out
+
+
+def compact_indices(mask: torch.Tensor) -> torch.Tensor:
+    """Row numbers (int64, increasing) where ``mask`` (bool / uint8 device vector) is set."""
+    lib = _lib.load()
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    assert mask.dtype == torch.uint8 and mask.is_cuda and mask.is_contiguous()
+    dev = mask.device
+    n = int(mask.shape[0])
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    nb = int(lib.fb_compact_scratch_bytes(n))
+    scratch = torch.empty(max(nb, 8), dtype=torch.uint8, device=dev)
+    _lib.check(lib.fb_compact_indices(dev.index, _stream_ptr(dev), mask.data_ptr(), n, out.data_ptr(),
+                                      cnt.data_ptr(), scratch.data_ptr(), scratch.numel()))
+    return out[:int(cnt.item())]

@@ -90,7 +90,7 @@ def _tagged_groups(engine: Any, df1: B200DataFrame, df2: B200DataFrame) -> B200D
 def _keep_groups(groups: B200DataFrame, names: List[str], lo: int, hi: int) -> B200DataFrame:
     t: B200Table = groups.native
     keep = (t.column("__fb_lo") == lo) & (t.column("__fb_hi") == hi)
-    idx = torch.nonzero(keep).flatten()
+    idx = K.compact_indices((keep).contiguous())
     return B200DataFrame(_take_rows(t, idx))[names]
 
 
@@ -123,7 +123,7 @@ def dropna(df: B200DataFrame, how: str = "any", thresh: Optional[int] = None,
         v = t.valid[t.schema.index_of_key(n)]
         nn += 1 if v is None else v.to(torch.int32)
     need = thresh if thresh is not None else (len(names) if how == "any" else 1)
-    idx = torch.nonzero(nn >= need).flatten()
+    idx = K.compact_indices((nn >= need).contiguous())
     if idx.numel() == t.num_rows:
         return df
     return B200DataFrame(_take_rows(t, idx))

@@ -137,7 +137,7 @@ def group_starts(t: B200Table, keys: List[str]) -> torch.Tensor:
 
 def logical_offsets(t: B200Table, keys: List[str]) -> torch.Tensor:
     """int64 offsets (length groups + 1) of the logical partitions of a key-sorted table."""
-    starts = torch.nonzero(group_starts(t, keys)).flatten()
+    starts = K.compact_indices((group_starts(t, keys)).contiguous())
     end = torch.tensor([t.num_rows], dtype=torch.int64, device=t.device)
     return torch.cat([starts, end])
 
@@ -166,5 +166,5 @@ def take(t: B200Table, n: int, sorts: "OrderedDict[str, bool]", na_position: str
     first = group_starts(s, partition_by)
     pos = torch.arange(s.num_rows, dtype=torch.int64, device=s.device)
     start_of = torch.cummax(torch.where(first, pos, torch.zeros_like(pos)), 0).values
-    keep = torch.nonzero((pos - start_of) < n).flatten()
+    keep = K.compact_indices(((pos - start_of) < n).contiguous())
     return take_rows(s, keep)

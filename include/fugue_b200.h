@@ -211,6 +211,12 @@ int fb_join_mark_matched(int dev, void* stream, const int64_t* build_idx, int64_
 size_t fb_exclusive_scan_scratch_bytes(int64_t n);
 int fb_exclusive_scan_i64(int dev, void* stream, int64_t n, const int64_t* in, int64_t* out,
                           int64_t* out_total, void* scratch, size_t scratch_bytes);
+/* Stream compaction: out_idx receives, in increasing order, the row numbers whose mask byte is
+ * non-zero (at most n entries); *d_count (device) their number.  Used by semi/anti joins, set
+ * operations, dropna, take. */
+size_t fb_compact_scratch_bytes(int64_t n);
+int fb_compact_indices(int dev, void* stream, const uint8_t* mask, int64_t n, int64_t* out_idx,
+                       int64_t* d_count, void* scratch, size_t scratch_bytes);
 int fb_gather_rows(int dev, void* stream, int ncols, const void* const* d_src_cols, void* const* d_dst_cols,
                    const int32_t* d_widths, const uint8_t* const* d_src_valid, uint8_t* const* d_dst_valid,
                    const int64_t* idx, int64_t n);
