@@ -1017,11 +1017,15 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
 #pragma unroll
         for (int r = 0; r < kWsRankItems; ++r) pid[r] = pt[r * 32 + lane];
         // ---- stable rank inside (warp, partition); rows of this warp: rw*512 + r*32 + lane
+        // all match masks first (16 independent ballot chains: ILP for the two ranker warps per
+        // scheduler), then the serial counter updates
+        unsigned mm[kWsRankItems];
+#pragma unroll
+        for (int r = 0; r < kWsRankItems; ++r) mm[r] = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
         uint32_t pos[kWsRankItems];
 #pragma unroll
         for (int r = 0; r < kWsRankItems; ++r) {
-          // (hardware MATCH.ANY was measured slower here too, even with the ADU pipe otherwise idle)
-          const unsigned m = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
+          const unsigned m = mm[r];
           const unsigned before = __popc(m & lt);
           uint32_t old = 0;
           if (before == 0) {
