@@ -134,13 +134,12 @@ constexpr int kHistRows = kHistBlock * kItems;
 
 template <bool kSingleU64, int kBits>
 __global__ void __launch_bounds__(kHistBlock, 2)
-fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist,
-               uint8_t* __restrict__ pid_plane) {
+fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, int chunk0, uint32_t* __restrict__ hist) {
   extern __shared__ uint32_t s_cnt[];
   for (uint32_t i = threadIdx.x; i < (uint32_t)kHistWarps * num; i += kHistBlock) s_cnt[i] = 0;
   __syncthreads();
   int64_t row0, row1;
-  chunk_range(g, (int)blockIdx.x, row0, row1);
+  chunk_range(g, chunk0 + (int)blockIdx.x, row0, row1);
   const unsigned lt = fb_lanemask_lt();
   uint32_t* my = s_cnt + (size_t)(threadIdx.x >> 5) * num;
   for (int64_t base = row0; base < row1; base += kHistRows) {
@@ -150,8 +149,6 @@ fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __res
     for (int r = 0; r < kItems; ++r) {
       int64_t row = base + (int64_t)r * kHistBlock + threadIdx.x;
       pid[r] = (full || row < row1) ? compute_pid<kSingleU64>(keys, dv, row) : 0xFFFFFFFFu;
-      // 1-byte partition id plane for pass 2 (num <= 256): pass 2 never hashes again
-      if (pid_plane != nullptr && pid[r] != 0xFFFFFFFFu) pid_plane[row] = (uint8_t)pid[r];
     }
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
@@ -162,13 +159,90 @@ fb_hist_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __res
     }
   }
   __syncthreads();
-  uint32_t* out = hist + (size_t)blockIdx.x * num;
+  uint32_t* out = hist + (size_t)(chunk0 + (int)blockIdx.x) * num;
   for (uint32_t b = threadIdx.x; b < num; b += kHistBlock) {
     uint32_t t = 0;
 #pragma unroll 8
     for (int w = 0; w < kHistWarps; ++w) t += s_cnt[(size_t)w * num + b];
     out[b] = t;
   }
+}
+
+// ---------------------------------------------------------------------------
+// pass 1 for num <= 256 (full tiles): histogram AND the complete ranking of every 4096-row tile, so
+// that pass 2 never hashes, matches or counts.  One 12800-byte record per tile in scratch:
+//   [0, 4096)       uint8  partition id of every row
+//   [4096, 12288)   uint16 rank of the row among the rows of the same partition in this tile
+//   [12288, 12800)  uint16 rows per partition in this tile (256 entries)
+// Pass 2 loads one record per tile with a single TMA bulk copy.  This kernel runs at full occupancy
+// (2 x 1024 threads per SM); the same work done by the 8 ranker warps of the pass-2 CTA was the
+// bottleneck of 4-column launches (profiles/r1_notes.md).
+// ---------------------------------------------------------------------------
+constexpr int kRankBlock = 1024, kRankWarps = kRankBlock / 32, kRankItems = kTile / kRankBlock;
+constexpr uint32_t kMetaRank = kTile, kMetaCnt = 3 * kTile, kMetaBytes = 3 * kTile + 512;
+static_assert(kRankItems * kRankBlock == kTile, "tile must be a multiple of the rank block");
+
+template <bool kSingleU64, int kBits>
+__global__ void __launch_bounds__(kRankBlock, 2)
+fb_rank_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, uint32_t* __restrict__ hist,
+               uint8_t* __restrict__ meta) {
+  __shared__ uint16_t s_cnt[kRankWarps * 256];
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kRankWarps * 256; i += kRankBlock) s_cnt[i] = 0;
+  __syncthreads();
+  int64_t row0, row1;
+  chunk_range(g, (int)blockIdx.x, row0, row1);  // launched over the full chunks only
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = fb_lanemask_lt();
+  uint16_t* __restrict__ my = s_cnt + warp * 256;
+  uint32_t acc = 0;  // thread b < num: rows of partition b in this chunk
+  for (int64_t t0 = row0; t0 < row1; t0 += kTile) {
+    uint8_t* __restrict__ rec = meta + (size_t)(t0 / kTile) * kMetaBytes;
+    uint32_t pid[kRankItems], pos[kRankItems];
+#pragma unroll
+    for (int r = 0; r < kRankItems; ++r)
+      pid[r] = compute_pid<kSingleU64>(keys, dv, t0 + warp * (32 * kRankItems) + r * 32 + lane);
+    unsigned mm[kRankItems];
+#pragma unroll
+    for (int r = 0; r < kRankItems; ++r) mm[r] = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
+#pragma unroll
+    for (int r = 0; r < kRankItems; ++r) {
+      const unsigned m = mm[r];
+      const unsigned before = __popc(m & lt);
+      uint32_t old = 0;
+      if (before == 0) {
+        old = my[pid[r]];
+        my[pid[r]] = (uint16_t)(old + __popc(m));
+      }
+      __syncwarp();
+      old = __shfl_sync(0xFFFFFFFFu, old, __ffs(m) - 1);
+      pos[r] = old + before;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {  // exclusive prefix over the warps, per partition
+      const uint32_t b = threadIdx.x;
+      uint32_t n = 0;
+#pragma unroll
+      for (int w = 0; w < kRankWarps; ++w) {
+        const uint32_t t = s_cnt[w * 256 + b];
+        s_cnt[w * 256 + b] = (uint16_t)n;
+        n += t;
+      }
+      acc += n;
+      ((uint16_t*)(rec + kMetaCnt))[b] = (uint16_t)n;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRankItems; ++r) {
+      const uint32_t idx = warp * (32 * kRankItems) + r * 32 + lane;
+      rec[idx] = (uint8_t)pid[r];
+      ((uint16_t*)(rec + kMetaRank))[idx] = (uint16_t)(pos[r] + my[pid[r]]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ((uint32_t*)my)[i * 32 + lane] = 0;
+    __syncwarp();
+  }
+  if (threadIdx.x < num) hist[(size_t)blockIdx.x * num + threadIdx.x] = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -842,11 +916,12 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
 // Measured on v4 (profiles/r1_notes.md): one third of the kernel is the per-tile ranking
 // (hash, match, scans), during which no byte moves; the column phase itself runs near the HBM
 // peak.  Here the two run concurrently on different warps of the same persistent CTA:
-//   warp 24      producer : TMA bulk loads - the 1-byte partition ids of tile t+1 (written by pass 1,
-//                           so nothing is hashed here and ANY key shape takes this path) and the
-//                           payload column tiles of tile t into the ring
-//   warps 16-23  rankers  : rank tile t+1 (ballot match + warp-private counters + scans), advance
-//                           the write-combining state, build the slot list of the tile
+//   warp 24      producer : TMA bulk loads - the rank record of tile t+1 (partition id, rank and
+//                           per-partition counts, written by pass 1: nothing is hashed, matched or
+//                           counted here and ANY key shape takes this path) and the payload column
+//                           tiles of tile t into the ring
+//   warps 16-23  rankers  : place tile t+1: advance the write-combining state of every partition,
+//                           build the slot list of the tile
 //   warps 0-15   movers   : tile t: per column gather from the staged tile / carry, store whole
 //                           sector groups, save the new carry (in place: the per-column barrier
 //                           separates the reads of the old carry from the writes of the new one)
@@ -855,7 +930,7 @@ fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int n
 // stage and per pid buffer.
 // Shared memory (one CTA per SM), T = 4096, E = num * (G - 1):
 //   ring[S][T] u64 | mbarriers | carry[ncols][E] u64 | slotinfo[T+E] u32 | wpos kcnt binfo
-//   bin_start wstart wdelta [nbp] u32 | scanw[64] | cnt[8][nbp] u16 | carryinfo[E] u16 | pid[2][T] u8
+//   bin_n wstart wdelta [nbp] u32 | scanw[64] | carryinfo[E] u16 | rank records [2][12800 B]
 // ---------------------------------------------------------------------------
 constexpr int kWsMoverWarps = 16, kWsRankWarps = 8;
 constexpr int kWsMovers = kWsMoverWarps * 32, kWsRankers = kWsRankWarps * 32;
@@ -878,9 +953,8 @@ __host__ __device__ inline size_t ws_book_bytes(uint32_t num, int ncols) {
   b += (size_t)ncols * E * 8;                  // carry buffers (in place)
   b += (kT + E) * 4;                           // slotinfo
   b += 6 * nbp * 4 + 64 * 4;                   // per-partition arrays + scanw
-  b += (size_t)kWsRankWarps * nbp * 2;         // cnt
   b += ((E * 2 + 15) / 16) * 16;               // carryinfo
-  b += 2 * kT + 32;                            // pid buffers (+ alignment slack)
+  b += 2 * (size_t)kMetaBytes + 128;           // rank records (+ alignment slack)
   return b;
 }
 
@@ -893,9 +967,10 @@ __device__ __forceinline__ void ranker_sync() { asm volatile("bar.sync 2, %0;" :
 template <int kBits, int G, int kWsRankItems>
 __global__ void __launch_bounds__(kWsThreads, 1)
 fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
-                     const uint8_t* __restrict__ pid_plane,
+                     const uint8_t* __restrict__ meta,
                      const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
   constexpr uint32_t T = (uint32_t)kWsRankers * kWsRankItems;  // rows per tile
+  static_assert(T == (uint32_t)kTile, "pass 1 ranks tiles of kTile rows");
   constexpr uint32_t GM = G - 1;
   constexpr uint32_t kStageBytes = T * 8;
   constexpr int kSlotRounds = ((int)T + (int)kSwcMaxNum * (G - 1) + kWsMovers - 1) / kWsMovers;
@@ -912,13 +987,12 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
   uint32_t* wpos = slotinfo + T + E;
   uint32_t* kcnt = wpos + nbp;
   uint32_t* binfo = kcnt + nbp;
-  uint32_t* bin_start = binfo + nbp;
-  uint32_t* wstart = bin_start + nbp;
+  uint32_t* bin_n = binfo + nbp;
+  uint32_t* wstart = bin_n + nbp;
   uint32_t* wdelta = wstart + nbp;
-  uint32_t* scanw = wdelta + nbp;  // [0,8) counts, [8,16) written, [40] W
-  uint16_t* cnt = (uint16_t*)(scanw + 64);
-  uint16_t* carryinfo = cnt + (size_t)kWsRankWarps * nbp;
-  uint8_t* pidbuf = (uint8_t*)(((uintptr_t)(carryinfo + E) + 15) & ~(uintptr_t)15);  // TMA dst: 16 B aligned
+  uint32_t* scanw = wdelta + nbp;  // [8,16) written per ranker warp, [40] W
+  uint16_t* carryinfo = (uint16_t*)(scanw + 64);
+  uint8_t* metabuf = (uint8_t*)(((uintptr_t)(carryinfo + E) + 127) & ~(uintptr_t)127);  // TMA dst
 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 16);
@@ -952,7 +1026,7 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
     // ============================ producer =============================================
     if (warp == kWsMoverWarps + kWsRankWarps && lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
-      const uint32_t ring_s = smem_u32(ring), pid_s = smem_u32(pidbuf);
+      const uint32_t ring_s = smem_u32(ring), meta_s = smem_u32(metabuf);
       uint32_t s = 0, ph = 0, seq = 0;
       // pids of the very first tile
       int chunk = (int)blockIdx.x;
@@ -962,8 +1036,9 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
       auto load_pid = [&](int64_t row0, uint32_t q) {
         const uint32_t b = q & 1, pp = (q >> 1) & 1;
         mbar_wait(bar_pid_empty + 8 * b, pp ^ 1);
-        mbar_expect_tx(bar_pid_full + 8 * b, T);
-        tma_load_1d(pid_s + b * T, pid_plane + row0, T, bar_pid_full + 8 * b, pol);
+        mbar_expect_tx(bar_pid_full + 8 * b, kMetaBytes);
+        tma_load_1d(meta_s + b * kMetaBytes, meta + (size_t)(row0 / T) * kMetaBytes, kMetaBytes,
+                    bar_pid_full + 8 * b, pol);
       };
       if (have) load_pid(t0, 0);
       while (have) {
@@ -994,9 +1069,6 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
     // ============================ rankers (8 warps) ====================================
     const unsigned rw = warp - kWsMoverWarps;          // ranker warp 0..7
     const unsigned rtid = threadIdx.x - kWsMovers;     // 0..255
-    const unsigned lt = fb_lanemask_lt();
-    uint16_t* __restrict__ my_cnt = cnt + (size_t)rw * nbp;
-    for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
     uint32_t seq = 0, cseq = 0;
     for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x, ++cseq) {
       int64_t r0, r1;
@@ -1008,46 +1080,25 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
         wpos[b] = p0 & ~GM;
         kcnt[b] = (p0 & GM) | ((p0 & GM) << 8);
       }
-      // (visibility: barrier A below)
+      ranker_sync();
       for (int64_t t0 = r0; t0 < r1; t0 += T, ++seq) {
         const uint32_t pb = seq & 1, pph = (seq >> 1) & 1;
         mbar_wait(bar_pid_full + 8 * pb, pph);
-        const uint8_t* __restrict__ pt = pidbuf + pb * T + rw * (32 * kWsRankItems);
-        uint32_t pid[kWsRankItems];
-#pragma unroll
-        for (int r = 0; r < kWsRankItems; ++r) pid[r] = pt[r * 32 + lane];
-        // ---- stable rank inside (warp, partition); rows of this warp: rw*512 + r*32 + lane
-        // all match masks first (16 independent ballot chains: ILP for the two ranker warps per
-        // scheduler), then the serial counter updates
-        unsigned mm[kWsRankItems];
-#pragma unroll
-        for (int r = 0; r < kWsRankItems; ++r) mm[r] = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
-        uint32_t pos[kWsRankItems];
+        const uint8_t* __restrict__ rec = metabuf + pb * kMetaBytes;
+        // rows of this thread: r * 256 + rtid; packed (partition id << 16) | rank in tile
+        uint32_t pr[kWsRankItems];
 #pragma unroll
         for (int r = 0; r < kWsRankItems; ++r) {
-          const unsigned m = mm[r];
-          const unsigned before = __popc(m & lt);
-          uint32_t old = 0;
-          if (before == 0) {
-            old = my_cnt[pid[r]];
-            my_cnt[pid[r]] = (uint16_t)(old + __popc(m));
-          }
-          __syncwarp();
-          old = __shfl_sync(0xFFFFFFFFu, old, __ffs(m) - 1);
-          pos[r] = old + before;
+          const uint32_t row = r * kWsRankers + rtid;
+          pr[r] = ((uint32_t)rec[row] << 16) | ((const uint16_t*)(rec + kMetaRank))[row];
         }
-        if (lane == 0) mbar_arrive_relaxed(bar_pid_empty + 8 * pb);  // pids are in registers
-        ranker_sync();  // A
         // ---- per partition (thread b < num): tile count, rows to write, new pending state
         const uint32_t b = rtid;
         uint32_t n = 0, w = 0, kold = 0, phold = 0, wp_old = 0;
+        if (b < num) n = ((const uint16_t*)(rec + kMetaCnt))[b];
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(bar_pid_empty + 8 * pb);  // the record is in registers
         if (b < num) {
-#pragma unroll
-          for (int wi = 0; wi < kWsRankWarps; ++wi) {
-            const uint32_t t = cnt[wi * nbp + b];
-            cnt[wi * nbp + b] = (uint16_t)n;
-            n += t;
-          }
           const uint32_t kc = kcnt[b];
           kold = kc & 0xFFu;
           phold = kc >> 8;
@@ -1062,44 +1113,41 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
             kcnt[b] = (kold + n) | (phold << 8);
           }
           binfo[b] = kold | (phold << 4) | (w << 8);
+          bin_n[b] = n;
         }
-        uint32_t xn = n, xw = w;
+        uint32_t xw = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t yn = __shfl_up_sync(0xFFFFFFFFu, xn, o);
           const uint32_t yw = __shfl_up_sync(0xFFFFFFFFu, xw, o);
-          if (lane >= (unsigned)o) { xn += yn; xw += yw; }
+          if (lane >= (unsigned)o) xw += yw;
         }
-        if (lane == 31) { scanw[rw] = xn; scanw[8 + rw] = xw; }
+        if (lane == 31) scanw[8 + rw] = xw;
         ranker_sync();  // B
-        uint32_t bn = xn - n, bw = xw - w;
+        uint32_t bw = xw - w;
         {
-          const uint32_t tn = lane < kWsRankWarps ? scanw[lane] : 0;
           const uint32_t tw = lane < kWsRankWarps ? scanw[8 + lane] : 0;
 #pragma unroll
           for (int wi = 0; wi < kWsRankWarps; ++wi) {
-            const uint32_t vn = __shfl_sync(0xFFFFFFFFu, tn, wi);
             const uint32_t vw = __shfl_sync(0xFFFFFFFFu, tw, wi);
-            if ((unsigned)wi < rw) { bn += vn; bw += vw; }
+            if ((unsigned)wi < rw) bw += vw;
           }
-        }
-        if (b < num) {
-          bin_start[b] = bn;
-          wstart[b] = bw;
         }
         // ---- hand-off arrays may be rewritten once the movers hold the previous slot list
         if (seq > 0) mbar_wait(bar_slots_free, (seq - 1) & 1);
-        if (b < num) wdelta[b] = wp_old - bw;  // slot j lands at output row wdelta + j
+        if (b < num) {
+          wstart[b] = bw;
+          wdelta[b] = wp_old - bw;  // slot j lands at output row wdelta + j
+        }
         if (rtid == kWsRankers - 1) scanw[40] = bw + w;  // W: slots to store this tile
         ranker_sync();  // C
         // ---- every new row / old carry entry finds its place
 #pragma unroll
         for (int r = 0; r < kWsRankItems; ++r) {
-          const uint32_t pb2 = pid[r];
+          const uint32_t pb2 = pr[r] >> 16;
           const uint32_t bi = binfo[pb2];
-          const uint32_t i = (bi & 0xFu) + pos[r] + my_cnt[pb2];
+          const uint32_t i = (bi & 0xFu) + (pr[r] & 0xFFFFu);
           const uint32_t ww = bi >> 8;
-          const uint32_t row = rw * (32 * kWsRankItems) + r * 32 + lane;
+          const uint32_t row = r * kWsRankers + rtid;
           if (i < ww) slotinfo[wstart[pb2] + i] = (pb2 << 16) | row;
           else carryinfo[pb2 * GM + (i - ww)] = (uint16_t)row;
         }
@@ -1110,7 +1158,7 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
             const uint32_t eb = e / GM, i = e - eb * GM;
             const uint32_t bi = binfo[eb];
             const uint32_t ko = bi & 0xFu, po = (bi >> 4) & 0xFu, ww = bi >> 8;
-            const uint32_t nn = (eb + 1 < num ? bin_start[eb + 1] : T) - bin_start[eb];
+            const uint32_t nn = bin_n[eb];
             const uint32_t desc = i < po ? 0xFFFFu : T + e;
             if (i < ko) {
               if (i < ww) slotinfo[wstart[eb] + i] = (eb << 16) | desc;
@@ -1119,8 +1167,6 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
             if (ww + i >= ko + nn) carryinfo[e] = 0xFFFFu;
           }
         }
-        __syncwarp();
-        for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
         ranker_sync();  // D: the slot list of this tile is complete
         if (lane == 0) mbar_arrive(bar_slots_ready);
       }
@@ -1336,7 +1382,7 @@ int fill_keys(FbKeys& k, int nkeys, const void* const* ptrs, const int32_t* widt
 
 struct PlanLayout {
   size_t hist_bytes;     // uint32 [nchunks][num]
-  size_t pid_offset;     // uint8 [nrows] partition id plane (num <= 256), 256-byte aligned
+  size_t pid_offset;     // rank records, kMetaBytes per full tile (num <= 256), 256-byte aligned
   size_t total_bytes;
 };
 
@@ -1344,7 +1390,7 @@ PlanLayout plan_layout(const ChunkGeom& g, uint32_t num) {
   PlanLayout l;
   l.hist_bytes = (((size_t)g.nchunks * num * sizeof(uint32_t)) + 255) & ~(size_t)255;
   l.pid_offset = l.hist_bytes + 256;
-  l.total_bytes = l.pid_offset + (num <= kSwcMaxNum ? (((size_t)g.nrows + 255) & ~(size_t)255) : 0) + 256;
+  l.total_bytes = l.pid_offset + (num <= kSwcMaxNum ? (size_t)(g.full_rows / kTile) * kMetaBytes : 0) + 256;
   return l;
 }
 
@@ -1419,15 +1465,32 @@ static int plan_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, bool
            "scratch too small: need %zu bytes, got %zu", l.total_bytes, scratch_bytes);
   FbDiv dv = fb_make_div(num_partitions);
   uint32_t* hist = (uint32_t*)scratch;
-  uint8_t* pid_plane = num_partitions <= kSwcMaxNum ? (uint8_t*)scratch + l.pid_offset : nullptr;
   size_t smem = (size_t)kHistWarps * num_partitions * sizeof(uint32_t);
   FB_CUDA(ensure_smem_optin(dev));
   const int bits = bits_for(num_partitions);
-#define FB_LAUNCH_HIST(S, B) \
-  fb_hist_kernel<S, B><<<g.nchunks, kHistBlock, smem, st>>>(k, dv, num_partitions, g, hist, pid_plane)
-  FB_DISPATCH_SB(single, bits, FB_LAUNCH_HIST);
+  // num <= 256: full tiles are ranked completely (fb_rank_kernel); the tail chunk and larger
+  // partition counts only need the histogram
+  int hist_chunk0 = 0;
+  if (num_partitions <= kSwcMaxNum && g.nchunks_full > 0) {
+    uint8_t* meta = (uint8_t*)scratch + l.pid_offset;
+    if (single) {
+      if (bits == 4) fb_rank_kernel<true, 4><<<g.nchunks_full, kRankBlock, 0, st>>>(k, dv, num_partitions, g, hist, meta);
+      else fb_rank_kernel<true, 8><<<g.nchunks_full, kRankBlock, 0, st>>>(k, dv, num_partitions, g, hist, meta);
+    } else {
+      if (bits == 4) fb_rank_kernel<false, 4><<<g.nchunks_full, kRankBlock, 0, st>>>(k, dv, num_partitions, g, hist, meta);
+      else fb_rank_kernel<false, 8><<<g.nchunks_full, kRankBlock, 0, st>>>(k, dv, num_partitions, g, hist, meta);
+    }
+    FB_CUDA(cudaGetLastError());
+    hist_chunk0 = g.nchunks_full;
+  }
+  if (hist_chunk0 < g.nchunks) {
+#define FB_LAUNCH_HIST(S, B)                                                                       \
+  fb_hist_kernel<S, B><<<g.nchunks - hist_chunk0, kHistBlock, smem, st>>>(k, dv, num_partitions, g, \
+                                                                          hist_chunk0, hist)
+    FB_DISPATCH_SB(single, bits, FB_LAUNCH_HIST);
 #undef FB_LAUNCH_HIST
-  FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaGetLastError());
+  }
   fb_scan_chunks_kernel<<<num_partitions, 256, 0, st>>>(hist, num_partitions, g.nchunks, out_part_offsets);
   FB_CUDA(cudaGetLastError());
   fb_scan_parts_kernel<<<1, 1024, 0, st>>>(out_part_offsets, num_partitions);
@@ -1528,13 +1591,18 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
     int smem_max = 0;
     FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
-    const uint8_t* pid_plane = (const uint8_t*)scratch + l.pid_offset;
-    // measured (100 M rows x 8 cols): 8 columns per launch 3.43 ms, 4 per launch 3.14-3.23 ms (fewer open
-    // write streams -> half-written lines meet their other half while still in L2), 2 per launch 5 ms
-    int cols_per_launch = use_ws ? 4 : kSwcMaxCols;
-    if (use_ws && getenv("FB_WS_COLS")) {
-      cols_per_launch = atoi(getenv("FB_WS_COLS"));
-      if (cols_per_launch < 1 || cols_per_launch > kSwcMaxCols) cols_per_launch = kSwcMaxCols;
+    const uint8_t* pid_plane = (const uint8_t*)scratch + l.pid_offset;  // rank records of pass 1
+    // measured (100 M rows x 8 cols, columns per launch): 8 -> 3.45 ms, 4 -> 3.10, 3 -> 3.21, 2 -> 3.33,
+    // 1 -> 4.59 (fewer open write streams: half-written lines meet their other half while still in L2;
+    // a launch costs ~0.15 ms of ramp + rank-record traffic).  Groups of at most 4, evenly sized.
+    int cols_per_launch = kSwcMaxCols;
+    if (use_ws) {
+      const int ngroups = (nfast + 3) / 4;
+      cols_per_launch = (nfast + ngroups - 1) / ngroups;
+      if (getenv("FB_WS_COLS")) {
+        cols_per_launch = atoi(getenv("FB_WS_COLS"));
+        if (cols_per_launch < 1 || cols_per_launch > kSwcMaxCols) cols_per_launch = kSwcMaxCols;
+      }
     }
     for (int c0 = 0; c0 < nfast; c0 += cols_per_launch) {
       const int nb = nfast - c0 < cols_per_launch ? nfast - c0 : cols_per_launch;
