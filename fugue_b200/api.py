@@ -268,24 +268,51 @@ def transform(
     return res.as_pandas() if res.is_local else res.native
 
 
-def aggregate(df: Any, partition_by: Any = None, engine: Any = None, engine_conf: Any = None,
-              as_fugue: bool = False, as_local: bool = False, **agg_kwcols: Any) -> Any:
-    """``fa.aggregate`` (fugue/execution/api.py:1175-1232):
-    ``aggregate(df, "key", s=f.sum(col("v0")), c=f.count(all_cols()))``."""
-    from .column import AggFuncExpr
-
-    assert_or_throw(len(agg_kwcols) > 0, ValueError("at least one aggregation is required"))
-    cols = []
-    for k, v in agg_kwcols.items():
-        assert_or_throw(isinstance(v, AggFuncExpr), lambda: ValueError(f"{k}={v!r} is not an aggregation"))
-        cols.append(v.alias(k))
-    e = make_execution_engine(engine, engine_conf, infer_by=[df])
-    spec = None if partition_by is None else PartitionSpec(by=partition_by)
-    res: DataFrame = e.aggregate(e.to_df(df), spec, cols)
+def _finish(e: Any, df: Any, res: DataFrame, as_fugue: bool, as_local: bool) -> Any:
     res = e.convert_yield_dataframe(res, as_local)
     if as_fugue or isinstance(df, DataFrame):
         return res
     return res.as_pandas() if res.is_local else res.native
+
+
+def aggregate(df: Any, partition_by: Any = None, engine: Any = None, engine_conf: Any = None,
+              as_fugue: bool = False, as_local: bool = False, **agg_kwcols: Any) -> Any:
+    """``fa.aggregate`` (fugue/execution/api.py:1175-1232):
+    ``aggregate(df, "key", s=f.sum(col("v0")), c=f.count(all_cols()))``."""
+    from .column import ColumnExpr, lit
+
+    cols = [v.alias(k) if isinstance(v, ColumnExpr) else lit(v).alias(k) for k, v in agg_kwcols.items()]
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    spec = None if partition_by is None else PartitionSpec(by=partition_by)
+    return _finish(e, df, e.aggregate(e.to_df(df), spec, cols), as_fugue, as_local)
+
+
+def select(df: Any, *columns: Any, where: Any = None, having: Any = None, distinct: bool = False,
+           engine: Any = None, engine_conf: Any = None, as_fugue: bool = False, as_local: bool = False) -> Any:
+    """``fa.select`` (fugue/execution/api.py:975-1057): SQL SELECT over one dataframe written with
+    column expressions; strings are column names."""
+    from .column import SelectColumns, col
+
+    cols = SelectColumns(*[col(x) if isinstance(x, str) else x for x in columns], arg_distinct=distinct)
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    return _finish(e, df, e.select(e.to_df(df), cols, where=where, having=having), as_fugue, as_local)
+
+
+def filter(df: Any, condition: Any, engine: Any = None, engine_conf: Any = None,  # noqa: A001
+           as_fugue: bool = False, as_local: bool = False) -> Any:
+    """``fa.filter`` (fugue/execution/api.py:1060-1102)."""
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    return _finish(e, df, e.filter(e.to_df(df), condition), as_fugue, as_local)
+
+
+def assign(df: Any, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+           as_local: bool = False, **columns: Any) -> Any:
+    """``fa.assign`` (fugue/execution/api.py:1105-1172): ``assign(df, x=1, c=col("b") + 1)``."""
+    from .column import ColumnExpr, lit
+
+    cols = [v.alias(k) if isinstance(v, ColumnExpr) else lit(v).alias(k) for k, v in columns.items()]
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    return _finish(e, df, e.assign(e.to_df(df), cols), as_fugue, as_local)
 
 
 def join(df1: Any, df2: Any, *dfs: Any, how: str, on: Optional[Iterable[str]] = None, engine: Any = None,

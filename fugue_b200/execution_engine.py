@@ -315,16 +315,32 @@ class B200ExecutionEngine:
     # ---- aggregate (K6) -----------------------------------------------------------------
     def aggregate(self, df: Any, partition_spec: Optional[PartitionSpec], agg_cols: List[Any]) -> B200DataFrame:
         """``ExecutionEngine.aggregate`` (execution_engine.py:889-939): ``partition_spec.partition_by``
-        are the GROUP BY keys, ``agg_cols`` aggregation expressions with names
-        (fugue_b200.column.functions).  Runs the sm_100a hash group-by kernel."""
-        import pyarrow as pa
-
-        from .column import AggFuncExpr
+        are the GROUP BY keys, ``agg_cols`` named aggregation expressions.  Plain ``FUNC(column)``
+        aggregations go straight to the sm_100a hash group-by kernel; anything richer
+        (``(max(b) * 2).cast("int32")``, aggregations of expressions) goes through :meth:`select`,
+        which evaluates the inner / outer expressions with the device evaluator around that kernel."""
+        from .column import AggFuncExpr, SelectColumns, _NamedColumnExpr, _WildcardExpr, col, is_agg
 
         assert_or_throw(len(agg_cols) > 0, ValueError("agg_cols can't be empty"))
         for a in agg_cols:
-            assert_or_throw(isinstance(a, AggFuncExpr), lambda: ValueError(f"{a} is not an aggregation"))
+            assert_or_throw(is_agg(a), lambda: ValueError(f"{a} is not an aggregation"))
+        agg_cols = [a.infer_alias() for a in agg_cols]
+        for a in agg_cols:
             assert_or_throw(a.output_name != "", lambda: ValueError(f"{a} must have an alias"))
+        plain = all(isinstance(a, AggFuncExpr) and a.as_type is None and not a.is_distinct
+                    and a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG")
+                    and isinstance(a.arg, (_NamedColumnExpr, _WildcardExpr)) and a.arg.as_type is None
+                    for a in agg_cols)
+        if plain:
+            return self._aggregate_named(df, partition_spec, agg_cols)
+        keys = [] if partition_spec is None else list(partition_spec.partition_by)
+        return self.select(df, SelectColumns(*[col(k) for k in keys], *agg_cols))
+
+    def _aggregate_named(self, df: Any, partition_spec: Optional[PartitionSpec],
+                         agg_cols: List[Any]) -> B200DataFrame:
+        """GROUP BY on named key columns with ``SUM/COUNT/MIN/MAX/AVG`` of named columns."""
+        import pyarrow as pa
+
         edf = self.to_df(df)
         t: B200Table = edf.native
         keys = [] if partition_spec is None else list(partition_spec.partition_by)
@@ -463,6 +479,140 @@ class B200ExecutionEngine:
             valids.append(v)
         dicts = {k: t.dictionaries[k] for k in keys if k in t.dictionaries}
         return B200DataFrame(B200Table(Schema(fields), cols, valids, dicts))
+
+    # ---- select / filter / assign (K8) ---------------------------------------------------
+    def select(self, df: Any, cols: Any, where: Any = None, having: Any = None) -> B200DataFrame:
+        """``ExecutionEngine.select`` (execution_engine.py:736-806): ``SELECT cols FROM df [WHERE ...]
+        [GROUP BY inferred keys] [HAVING ...]``.  Row-wise expressions run in the device evaluator
+        (one pass per SELECT list), aggregations in the hash group-by kernel; nothing goes through
+        SQL text.  Pins: fugue_test/execution_suite.py:98-155."""
+        from . import expr as X
+        from . import relational as R
+        from .column import (AggFuncExpr, SelectColumns, _LiteralColumnExpr, _NamedColumnExpr,
+                             _WildcardExpr, col, is_agg, to_uuid)
+
+        edf = self.to_df(df)
+        t: B200Table = edf.native
+        sel: SelectColumns = cols.replace_wildcard(t.schema).assert_all_with_names()
+        if where is not None:
+            assert_or_throw(not is_agg(where), lambda: ValueError(f"{where} has aggregation functions"))
+            t = X.filter_table(t, where)
+        if not sel.has_agg:
+            assert_or_throw(having is None, ValueError("HAVING needs an aggregation"))
+            res = B200DataFrame(X.project(t, sel.all_cols))
+            return R.distinct(self, res) if sel.is_distinct else res
+        # ---- aggregation: pre-project (group keys, aggregation arguments) -> group-by -> post-project
+        pre: List[Any] = []        # expressions of the temporary table
+        pre_names: Dict[str, str] = {}
+        key_names: List[str] = []
+
+        def temp(e: Any, prefix: str) -> str:
+            """Name of the temporary column holding ``e`` (plain columns keep their name)."""
+            if isinstance(e, _NamedColumnExpr) and e.as_type is None:
+                if e.name not in pre_names:
+                    pre_names[e.name] = e.name
+                    pre.append(col(e.name))
+                return e.name
+            uid = to_uuid(e)
+            if uid not in pre_names:
+                pre_names[uid] = f"__fb_{prefix}{len(pre_names)}"
+                pre.append(e.alias(pre_names[uid]))
+            return pre_names[uid]
+
+        key_of: Dict[str, str] = {}  # uuid of a group-key expression -> its column in the group table
+        for k in sel.group_keys:
+            nm = temp(k, "k")
+            key_of[to_uuid(k)] = nm
+            if nm not in key_names:
+                key_names.append(nm)
+        aggs: List[AggFuncExpr] = []
+        for c in sel.all_cols:
+            X.find_aggs(c, aggs)
+        if having is not None:
+            X.find_aggs(having, aggs)
+        agg_col: Dict[str, str] = {}  # uuid of FUNC(arg) -> its column in the group table
+        named_aggs: List[AggFuncExpr] = []
+        for a in aggs:
+            bare = a.alias("").cast(None)
+            uid = to_uuid(bare)
+            if uid in agg_col:
+                continue
+            assert_or_throw(not a.is_distinct, NotImplementedError(f"DISTINCT aggregation {a}"))
+            assert_or_throw(a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG"),
+                            NotImplementedError(f"aggregation {a.func}"))
+            assert_or_throw(not is_agg(a.arg), ValueError(f"nested aggregation {a}"))
+            out = f"__fb_a{len(agg_col)}"
+            agg_col[uid] = out
+            if isinstance(a.arg, _WildcardExpr):
+                named_aggs.append(AggFuncExpr(a.func, col("*"), out))
+            elif isinstance(a.arg, _LiteralColumnExpr):
+                nm = temp(a.arg.alias("").cast(a.arg.as_type), "l")
+                named_aggs.append(AggFuncExpr(a.func, col(nm), out))
+            else:
+                named_aggs.append(AggFuncExpr(a.func, col(temp(a.arg, "v")), out))
+        if len(pre) == 0:  # e.g. SELECT COUNT(*) FROM t
+            tmp = t
+        else:
+            tmp = X.project(t, pre)
+        g = self._aggregate_named(B200DataFrame(tmp), PartitionSpec(by=key_names) if key_names else None,
+                                  named_aggs).native
+
+        def to_group_table(e: Any) -> Any:
+            def mapper(node: Any) -> Any:
+                if isinstance(node, AggFuncExpr):
+                    return col(agg_col[to_uuid(node.alias("").cast(None))])
+                if isinstance(node, _LiteralColumnExpr):
+                    return None
+                uid = to_uuid(node.alias("").cast(None))
+                if uid in key_of:
+                    return col(key_of[uid])
+                return None
+            return X.rewrite(e, mapper)
+
+        if having is not None:
+            g = X.filter_table(g, to_group_table(having.alias("")))
+        outs = [to_group_table(c).alias(c.output_name) for c in sel.all_cols]
+        res = B200DataFrame(X.project(g, outs))
+        # MIN/MAX/plain keys keep the input type when the expression says so (correct_select_schema)
+        fix = {}
+        for c in sel.all_cols:
+            tp = c.infer_type(edf.schema)
+            if tp is not None and tp != res.schema[c.output_name].type:
+                fix[c.output_name] = tp
+        if fix:
+            res = B200DataFrame(X.project(res.native, [col(n).cast(fix[n]) if n in fix else col(n)
+                                                       for n in res.schema.names]))
+        return R.distinct(self, res) if sel.is_distinct else res
+
+    def filter(self, df: Any, condition: Any) -> B200DataFrame:
+        """``ExecutionEngine.filter`` (execution_engine.py:808-834): rows where ``condition`` is TRUE
+        (predicate evaluated on the device, stream compaction + gather).  Pins: execution_suite.py:85-95."""
+        from . import expr as X
+        from .column import is_agg
+
+        assert_or_throw(not is_agg(condition), lambda: ValueError(f"{condition} has aggregation functions"))
+        edf = self.to_df(df)
+        res = B200DataFrame(X.filter_table(edf.native, condition))
+        if edf.has_metadata:
+            res.reset_metadata(edf.metadata)
+        return res
+
+    def assign(self, df: Any, columns: List[Any]) -> B200DataFrame:
+        """``ExecutionEngine.assign`` (execution_engine.py:836-887): replace / append columns.
+        Pins: execution_suite.py:157-174."""
+        from .column import SelectColumns, col
+
+        SelectColumns(*columns).assert_no_wildcard().assert_all_with_names().assert_no_agg()
+        edf = self.to_df(df)
+        pos = {n: i for i, n in enumerate(edf.schema.names)}
+        cols: List[Any] = [col(n) for n in pos]
+        for c in columns:
+            c = c.infer_alias()
+            if c.output_name in pos:
+                cols[pos[c.output_name]] = c
+            else:
+                cols.append(c)
+        return self.select(edf, SelectColumns(*cols))
 
     # ---- join (K7) ----------------------------------------------------------------------
     def join(self, df1: Any, df2: Any, how: str, on: Optional[List[str]] = None) -> B200DataFrame:

@@ -221,6 +221,50 @@ int fb_gather_rows(int dev, void* stream, int ncols, const void* const* d_src_co
                    const int32_t* d_widths, const uint8_t* const* d_src_valid, uint8_t* const* d_dst_valid,
                    const int64_t* idx, int64_t n);
 
+/* ---------------------------------------------------------------------------
+ * K8  column-expression evaluator (SELECT list / WHERE predicate / assign)
+ * Replaces: ExecutionEngine.select / filter / assign -> SQLExpressionGenerator -> SQLEngine.select
+ *             fugue/execution/execution_engine.py:736-887, fugue/column/sql.py:275-347,
+ *             fugue/execution/native_execution_engine.py:59-66 (qpd on pandas)
+ *           expression semantics: fugue/column/expressions.py:219-434; pins
+ *             fugue_test/execution_suite.py:85-174 (test_filter / test_select / test_assign)
+ *
+ * One pass evaluates a whole register-machine program over all rows: FB_EXPR_NREGS vector registers
+ * of canonical 64-bit values (int64 / float64 bits / bool as 0|1) + a validity lane each.
+ *   FB_X_LOAD   dst <- column a (converted from its storage type), validity from its byte mask
+ *   FB_X_LIT    dst <- imm (raw 64 bits)            FB_X_NULL  dst <- NULL
+ *   arithmetic / comparison ops: dst <- a op b, NULL if either side is NULL
+ *   FB_X_AND / FB_X_OR: Kleene three-valued logic;  FB_X_IS_NULL / FB_X_NOT_NULL / FB_X_COALESCE
+ * Outputs: register out_regs[o] is converted to out_types[o] and stored to out_ptrs[o]; its
+ * validity to out_valid[o] when that pointer is non-NULL.  `program`, the pointer tables and the
+ * type arrays are HOST arrays (copied into the launch); column / output pointers are device memory.
+ * --------------------------------------------------------------------------- */
+#define FB_EXPR_MAX_COLS 16
+#define FB_EXPR_MAX_OUTS 16
+#define FB_EXPR_MAX_INS 64
+#define FB_EXPR_NREGS 8
+enum fb_expr_type { FB_T_I8 = 0, FB_T_I16 = 1, FB_T_I32 = 2, FB_T_I64 = 3, FB_T_U8 = 4, FB_T_F32 = 5, FB_T_F64 = 6 };
+enum fb_expr_op {
+  FB_X_LOAD = 0, FB_X_LIT = 1, FB_X_NULL = 2, FB_X_MOV = 3, FB_X_I2F = 4, FB_X_F2I = 5,
+  FB_X_ADD_I = 6, FB_X_SUB_I = 7, FB_X_MUL_I = 8, FB_X_NEG_I = 9,
+  FB_X_ADD_F = 10, FB_X_SUB_F = 11, FB_X_MUL_F = 12, FB_X_DIV_F = 13, FB_X_NEG_F = 14,
+  FB_X_LT_I = 15, FB_X_LE_I = 16, FB_X_EQ_I = 17, FB_X_NE_I = 18,
+  FB_X_LT_F = 19, FB_X_LE_F = 20, FB_X_EQ_F = 21, FB_X_NE_F = 22,
+  FB_X_AND = 23, FB_X_OR = 24, FB_X_NOT = 25, FB_X_IS_NULL = 26, FB_X_NOT_NULL = 27,
+  FB_X_COALESCE = 28, FB_X_TOBOOL_I = 29, FB_X_TOBOOL_F = 30
+};
+typedef struct fb_expr_ins {
+  int32_t op;  /* enum fb_expr_op */
+  int32_t dst; /* destination register */
+  int32_t a;   /* source register (FB_X_LOAD: column index) */
+  int32_t b;   /* second source register */
+  int64_t imm; /* FB_X_LIT: the value's raw 64 bits */
+} fb_expr_ins;
+int fb_eval_expr(int dev, void* stream, int64_t nrows, int ncols, const void* const* col_ptrs,
+                 const int32_t* col_types, const uint8_t* const* col_valid, int nins,
+                 const fb_expr_ins* program, int nouts, const int32_t* out_regs,
+                 const int32_t* out_types, void* const* out_ptrs, uint8_t* const* out_valid);
+
 #ifdef __cplusplus
 }
 #endif

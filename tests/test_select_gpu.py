@@ -1,0 +1,218 @@
+"""select / filter / assign / expression aggregates on the B200 engine.
+
+* literal expectations of fugue_test/execution_suite.py:85-206 (test_filter, test_select, test_assign,
+  test_aggregate) through the fa.* API;
+* the device evaluator (fb_eval_expr through the C ABI) against numpy on random programs' building
+  blocks, and whole selects against oracle/expressions.py on random nullable tables."""
+import numpy as np
+import pandas as pd
+import pytest
+from pytest import raises
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from fugue_b200 import api as fa
+from fugue_b200 import kernels as K
+from fugue_b200.column import SelectColumns, all_cols, col, functions as ff, lit, null
+from fugue_b200.dataframe import ArrayDataFrame, df_eq
+from oracle import expressions as OX
+
+
+@pytest.fixture(scope="module")
+def e():
+    return fa.make_execution_engine("b200")
+
+
+def _a():
+    return ArrayDataFrame([[1, 2], [None, 2], [None, 1], [3, 4], [None, 4]], "a:double,b:int")
+
+
+def test_filter(e):
+    a = _a()
+    df_eq(fa.filter(a, col("a").not_null(), engine=e), [[1, 2], [3, 4]], "a:double,b:int", throw=True)
+    df_eq(fa.filter(a, col("a").not_null() & (col("b") < 3), engine=e), [[1, 2]], "a:double,b:int", throw=True)
+    df_eq(fa.filter(a, col("a") + col("b") == 3, engine=e), [[1, 2]], "a:double,b:int", throw=True)
+    with raises(ValueError):
+        fa.filter(a, ff.max(col("a")) > 1, engine=e)
+
+
+def test_select(e):
+    a = _a()
+    b = fa.select(a, col("b"), (col("b") + 1).alias("c").cast(str), engine=e)
+    df_eq(b, [[2, "3"], [2, "3"], [1, "2"], [4, "5"], [4, "5"]], "b:int,c:str", throw=True)
+    b = fa.select(a, col("b"), (col("b") + 1).alias("c").cast(str), distinct=True, engine=e)
+    df_eq(b, [[2, "3"], [1, "2"], [4, "5"]], "b:int,c:str", throw=True)
+    b = fa.select(a, all_cols(), where=col("a") + col("b") == 3, engine=e)
+    df_eq(b, [[1, 2]], "a:double,b:int", throw=True)
+    b = fa.select(a, col("a"), ff.sum(col("b")).cast(float).alias("b"), engine=e)
+    df_eq(b, [[1, 2], [3, 4], [None, 7]], "a:double,b:double", throw=True)
+    col_b = ff.sum(col("b"))
+    b = fa.select(a, col("a"), col_b.cast(float).alias("c"), having=(col_b >= 7) | (col("a") == 1), engine=e)
+    df_eq(b, [[1, 2], [None, 7]], "a:double,c:double", throw=True)
+    b = fa.select(a, col("a"), lit(1, "o").cast(str), col_b.cast(float).alias("c"),
+                  having=(col_b >= 7) | (col("a") == 1), engine=e)
+    df_eq(b, [[1, "1", 2], [None, "1", 7]], "a:double,o:str,c:double", throw=True)
+
+
+def test_assign(e):
+    b = fa.assign(_a(), x=1, b=col("b").cast(str), c=(col("b") + 1).cast(int), engine=e)
+    df_eq(b, [[1, "2", 1, 3], [None, "2", 1, 3], [None, "1", 1, 2], [3, "4", 1, 5], [None, "4", 1, 5]],
+          "a:double,b:str,x:long,c:long", throw=True)
+
+
+def test_aggregate_expressions(e):
+    a = _a()
+    b = fa.aggregate(a, b=ff.max(col("b")), c=(ff.max(col("b")) * 2).cast("int32").alias("c"), engine=e)
+    df_eq(b, [[4, 8]], "b:int,c:int", throw=True)
+    b = fa.aggregate(a, "a", b=ff.max(col("b")), c=(ff.max(col("b")) * 2).cast("int32").alias("c"), engine=e)
+    df_eq(b, [[None, 4, 8], [1, 2, 4], [3, 4, 8]], "a:double,b:int,c:int", throw=True)
+    with raises(ValueError):
+        fa.aggregate(a, "a", b=ff.max(col("b")), x=1, engine=e)
+    with raises(ValueError):
+        fa.aggregate(a, "a", engine=e)
+
+
+def test_strings_and_literals(e):
+    s = ArrayDataFrame([["x", 1], ["y", 2], [None, 3], ["x", 4]], "k:str,v:long")
+    df_eq(fa.filter(s, col("k") == "x", engine=e), [["x", 1], ["x", 4]], "k:str,v:long", throw=True)
+    df_eq(fa.filter(s, col("k") != "x", engine=e), [["y", 2]], "k:str,v:long", throw=True)
+    df_eq(fa.filter(s, col("k") == "zz", engine=e), [], "k:str,v:long", throw=True)
+    df_eq(fa.filter(s, col("k").is_null() | (col("v") >= 4), engine=e), [[None, 3], ["x", 4]], "k:str,v:long",
+          throw=True)
+    b = fa.select(s, col("k"), lit("c", "t"), null().cast("double").alias("n"), (col("v") * 1.5).alias("w"), engine=e)
+    df_eq(b, [["x", "c", None, 1.5], ["y", "c", None, 3.0], [None, "c", None, 4.5], ["x", "c", None, 6.0]],
+          "k:str,t:str,n:double,w:double", throw=True)
+    with raises(NotImplementedError):
+        fa.filter(s, col("k") < "x", engine=e)
+
+
+def test_eval_expr_kernel_blocks():
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(5)
+    n = 100_003  # not a multiple of the 1024-row tile
+    a = rng.integers(-1000, 1000, n).astype(np.int32)
+    b = rng.standard_normal(n)
+    bm = (rng.random(n) > 0.3).astype(np.uint8)
+    ta, tb, tm = (torch.from_numpy(x).to(dev) for x in (a, b, bm))
+    # r0 = a (int32 -> i64), r1 = b (f64, nullable); out0 = a * 3 - 7 (int16 store); out1 = (a -> f64) / b;
+    # out2 = (a < 10) AND (b IS NOT NULL and b > 0)  [Kleene]; out3 = COALESCE(b, 2.5)
+    f64 = lambda v: int(np.float64(v).view(np.uint64))
+    prog = [
+        (K.X_LOAD, 0, 0, 0, 0), (K.X_LIT, 1, 0, 0, 3), (K.X_MUL_I, 1, 0, 1, 0), (K.X_LIT, 2, 0, 0, 7),
+        (K.X_SUB_I, 1, 1, 2, 0),                                    # r1 = a*3-7
+        (K.X_LOAD, 2, 1, 0, 0), (K.X_MOV, 3, 0, 0, 0), (K.X_I2F, 3, 3, 0, 0), (K.X_DIV_F, 3, 3, 2, 0),   # r3 = a/b
+        (K.X_LIT, 4, 0, 0, 10), (K.X_LT_I, 4, 0, 4, 0),             # r4 = a < 10
+        (K.X_LIT, 5, 0, 0, f64(0.0)), (K.X_LT_F, 5, 5, 2, 0),       # r5 = 0 < b (NULL when b NULL)
+        (K.X_AND, 4, 4, 5, 0),                                      # r4 = r4 AND r5
+        (K.X_LIT, 5, 0, 0, f64(2.5)), (K.X_COALESCE, 5, 2, 5, 0),   # r5 = COALESCE(b, 2.5)
+    ]
+    outs, valids = K.eval_expr(n, dev, [ta, tb], [None, tm], prog, [1, 3, 4, 5],
+                               [torch.int16, torch.float64, torch.uint8, torch.float64], [False, True, True, True])
+    assert (outs[0].cpu().numpy() == (a.astype(np.int64) * 3 - 7).astype(np.int16)).all()
+    v = bm.astype(bool)
+    assert (valids[1].cpu().numpy().astype(bool) == v).all()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = a.astype(np.float64) / b
+    got = outs[1].cpu().numpy()
+    assert (got[v].view(np.uint64) == ref[v].view(np.uint64)).all() and (got[~v] == 0).all()
+    lt, pos = a < 10, b > 0
+    is_false = (~lt) | (v & ~pos)
+    k_valid = is_false | v
+    assert (valids[2].cpu().numpy().astype(bool) == k_valid).all()
+    assert (outs[2].cpu().numpy().astype(bool) == (lt & v & pos)).all()
+    assert (outs[3].cpu().numpy() == np.where(v, b, 2.5)).all() and valids[3].cpu().numpy().all()
+    with raises(Exception):
+        K.eval_expr(n, dev, [ta], [None], [(99, 0, 0, 0, 0)], [0], [torch.int64], [False])
+
+
+def _random_table(rng, n):
+    a = rng.integers(-50, 50, n).astype(np.int64)
+    b = rng.integers(0, 7, n).astype(np.int32)
+    x = rng.standard_normal(n)
+    x[rng.random(n) < 0.2] = np.nan
+    y = rng.standard_normal(n) * 10
+    g = pd.array(np.where(rng.random(n) < 0.1, None, rng.integers(0, 20, n)), dtype="Int64")
+    p = pd.array(np.where(rng.random(n) < 0.15, None, rng.random(n) < 0.5), dtype="boolean")
+    return pd.DataFrame({"a": a, "b": b, "x": x, "y": y, "g": g, "p": p})
+
+
+def _frames_equal(got: pd.DataFrame, want: pd.DataFrame, sort: bool):
+    assert list(got.columns) == list(want.columns)
+    assert len(got) == len(want), (len(got), len(want))
+    if sort:
+        got = got.sort_values(list(got.columns)).reset_index(drop=True)
+        want = want.sort_values(list(want.columns)).reset_index(drop=True)
+    for c in want.columns:
+        w, gt = want[c], got[c]
+        wn = w.isna().to_numpy()
+        gn = gt.isna().to_numpy()
+        assert (wn == gn).all(), c
+        if pd.api.types.is_numeric_dtype(w.dtype) or pd.api.types.is_bool_dtype(w.dtype):
+            wv = w.to_numpy(dtype="float64", na_value=0.0)[~wn]
+            gv = pd.to_numeric(gt[~gn]).to_numpy(dtype="float64")
+            if pd.api.types.is_float_dtype(w.dtype):
+                assert np.allclose(wv, gv, rtol=1e-12, atol=1e-12, equal_nan=True), c
+            else:
+                assert (wv == gv).all(), c
+        else:
+            assert (w[~wn].astype(str).to_numpy() == gt[~gn].astype(str).to_numpy()).all(), c
+
+
+def test_random_selects_match_oracle(e):
+    rng = np.random.default_rng(11)
+    pdf = _random_table(rng, 200_000)
+    edf = e.to_df(pdf)
+    cases = [
+        SelectColumns(col("a"), (col("a") * col("b") - 3).alias("m"), (col("x") / col("y")).alias("d"),
+                      (col("a") / col("b")).alias("q"), (-col("x")).alias("nx"), (-col("b")).alias("nb")),
+        SelectColumns(((col("x") > 0) & col("p")).alias("k1"), ((col("x") > 0) | col("p")).alias("k2"),
+                      (~col("p")).alias("k3"), (col("x").is_null() | (col("a") >= col("b"))).alias("k4"),
+                      (col("g") == col("b")).alias("k5"), (col("g") != 3).alias("k6")),
+        SelectColumns(ff.coalesce(col("x"), col("y")).alias("c1"), ff.coalesce(col("g"), -1).alias("c2"),
+                      ff.coalesce(col("g"), col("x"), 0.5).alias("c3"), (col("a") + 1.5).cast(int).alias("c4"),
+                      col("x").cast("int").alias("c5"), col("b").cast(float).alias("c6"),
+                      (col("a") > 0).cast(int).alias("c7"), col("g").cast(bool).alias("c8")),
+    ]
+    for sel in cases:
+        got = e.select(edf, sel).as_pandas()
+        want = OX.select(pdf, sel)
+        _frames_equal(got, want, sort=False)
+    # filters (row order preserved)
+    for cond in [(col("x") > 0.5) & (col("g") < 10), col("p") | col("x").is_null(), ~(col("a") * 2 <= col("b")),
+                 (col("x") + col("y") > 0) | (col("g").is_null() & col("p"))]:
+        got = e.filter(edf, cond).as_pandas()
+        want = OX.filter_rows(pdf, cond)
+        assert len(got) == len(want)
+        _frames_equal(got, want, sort=False)
+
+
+def test_random_aggregating_selects_match_oracle(e):
+    rng = np.random.default_rng(12)
+    pdf = _random_table(rng, 300_000)
+    edf = e.to_df(pdf)
+    s = ff.sum(col("x"))
+    cases = [
+        (SelectColumns(col("g"), col("b"), ff.sum(col("x") * col("y")).alias("sxy"), ff.count(all_cols()).alias("n"),
+                       ff.count(col("x")).alias("nx"), ff.max(col("a") + col("b")).alias("mx"),
+                       ff.avg(col("y")).alias("av")), None, None),
+        (SelectColumns((col("a") - col("a") / 10 * 10 + col("b")).cast(int).alias("k"), ff.min(col("y")).alias("lo"),
+                       (ff.max(col("y")) - ff.min(col("y"))).alias("span")), col("x").not_null(), None),
+        (SelectColumns(col("g"), (s / ff.count(col("x"))).alias("mean"), lit(7, "seven")), None,
+         (s > 0) & col("g").not_null()),
+        (SelectColumns(ff.sum(col("a")).alias("sa"), ff.count(all_cols()).alias("n"), ff.avg(col("x")).alias("ax")),
+         col("p"), None),
+    ]
+    for sel, where, having in cases:
+        got = e.select(edf, sel, where=where, having=having).as_pandas()
+        want = OX.select(pdf, sel, where=where, having=having)
+        _frames_equal(got, want, sort=True)
+
+
+def test_large_expression_is_split_over_launches(e):
+    pdf = pd.DataFrame({"a": np.arange(5000, dtype=np.int64), "x": np.linspace(0, 1, 5000)})
+    cols = [((col("a") + i) * (col("x") - i) + (col("a") - i) * 2).alias(f"c{i}") for i in range(20)]
+    got = e.select(e.to_df(pdf), SelectColumns(*cols)).as_pandas()
+    for i in range(20):
+        ref = (pdf["a"] + i) * (pdf["x"] - i) + (pdf["a"] - i) * 2
+        assert np.allclose(got[f"c{i}"].to_numpy(), ref.to_numpy(), rtol=1e-13)
