@@ -7,19 +7,22 @@ fugue/workflow/workflow.py:2109-2166) and ``ExecutionEngine.aggregate`` reaches 
 ``SQLExpressionGenerator`` (fugue/column/sql.py:275-334).  The native engine hands the text to qpd
 (native_execution_engine.py:59-66); here:
 
-    SELECT k[, ...], AGG(x) [AS a], COUNT(*) [AS c] FROM t [GROUP BY k]      -> hash group-by kernel
+    SELECT [DISTINCT] <expr [AS a], ...> FROM t [WHERE <expr>] [GROUP BY <expr, ...>] [HAVING <expr>]
+             [ORDER BY c [ASC|DESC], ...] [LIMIT n]
+        -> parsed into column expressions (fugue_b200.column) and run by ``engine.select``: row-wise
+           parts in the device expression evaluator, SUM/COUNT/MIN/MAX/AVG in the hash group-by kernel
     SELECT * FROM a [INNER|LEFT|RIGHT|FULL [OUTER]|LEFT SEMI|LEFT ANTI|CROSS] JOIN b
              [USING (k, ...) | ON a.k = b.k [AND ...]]                        -> hash join kernels
-    SELECT c1, c2 FROM t  /  SELECT * FROM t                                  -> column projection
 
+Expressions: + - * /, comparisons (= == != <> < <= > >=), AND / OR / NOT, IS [NOT] NULL, [NOT] IN (...),
+[NOT] BETWEEN, CAST(x AS type), COALESCE, literals, `quoted` and table-qualified names.
 Anything else raises NotImplementedError (there is no host SQL fallback in this package).
 """
 import re
 from typing import Any, Dict, List, Tuple
 
-from .column import AggFuncExpr, col
+from .column import ColumnExpr, SelectColumns, all_cols, col, function, functions, is_agg, lit, null, to_uuid
 from .dataframe import DataFrame
-from .partition import PartitionSpec
 
 _AGG = r"(SUM|COUNT|MIN|MAX|AVG|MEAN)\s*\(\s*(\*|[A-Za-z_][\w]*)\s*\)"
 _IDENT = r"[A-Za-z_][\w]*"
@@ -84,48 +87,48 @@ class B200SQLEngine:
         return tables[name]
 
     def _single(self, items: str, rest: str, tables: Dict[str, DataFrame], sql: str) -> DataFrame:
-        m = re.match(rf"(?is)^(`?{_IDENT}`?)(?:\s+GROUP BY (.+))?$", rest)
-        if m is None:
-            raise NotImplementedError(f"unsupported SQL (WHERE/HAVING/ORDER BY are not on the GPU path): {sql}")
-        df = self._table(m.group(1), tables, sql)
-        group = [g.strip().strip("`") for g in m.group(2).split(",")] if m.group(2) else []
-        plain: List[Tuple[str, str]] = []
-        aggs: List[AggFuncExpr] = []
-        order: List[str] = []
-        for raw in _split_commas(items):
-            it = raw.strip()
-            ma = re.match(rf"(?is)^{_AGG}(?:\s+AS\s+(`?{_IDENT}`?))?$", it)
-            if ma:
-                func = "AVG" if ma.group(1).upper() == "MEAN" else ma.group(1).upper()
-                alias = (ma.group(3) or "").strip("`")
-                if alias == "":
-                    alias = ma.group(2) if ma.group(2) != "*" else func.lower()
-                aggs.append(AggFuncExpr(func, col(ma.group(2)), alias))
-                order.append(alias)
-                continue
-            mc = re.match(rf"(?is)^(\*|`?{_IDENT}`?)(?:\s+AS\s+(`?{_IDENT}`?))?$", it)
-            if mc is None:
-                raise NotImplementedError(f"unsupported select item {it!r} in: {sql}")
-            name = mc.group(1).strip("`")
-            plain.append((name, (mc.group(2) or name).strip("`")))
-            order.append((mc.group(2) or name).strip("`"))
-        if not aggs:
-            if group:
+        st = _parse_select(items, rest, sql)
+        df = self._table(st.table, tables, sql)
+        cols = list(st.columns)
+        hidden: List[str] = []
+        if st.group_by:
+            # Fugue infers the GROUP BY keys from the select list (SelectColumns.group_keys); the SQL
+            # text must agree with that, extra keys ride along as hidden columns
+            probe = SelectColumns(*cols)
+            if not probe.has_agg:
                 raise NotImplementedError(f"GROUP BY without aggregates: {sql}")
-            if len(plain) == 1 and plain[0][0] == "*":
-                return df
-            res = df[[p[0] for p in plain]]
-            ren = {a: b for a, b in plain if a != b}
-            return res.rename(ren) if ren else res
-        for name, _ in plain:
-            if name not in group:
-                raise ValueError(f"{name} is neither aggregated nor in GROUP BY: {sql}")
-        res = self._engine.aggregate(df, PartitionSpec(by=group) if group else None, aggs)
-        ren = {a: b for a, b in plain if a != b}
-        if ren:
-            res = res.rename(ren)
-        want = [o for o in order if o in res.schema]
-        return res[want] if want != res.columns else res
+            inferred = {to_uuid(k) for k in probe.group_keys}
+            listed = set()
+            for g in st.group_by:
+                uid = to_uuid(g.alias("").cast(None))
+                listed.add(uid)
+                if uid not in inferred:
+                    name = f"__fb_g{len(hidden)}"
+                    hidden.append(name)
+                    cols.append(g.alias(name))
+            for k in probe.group_keys:
+                if to_uuid(k) not in listed:
+                    raise ValueError(f"{k} is neither aggregated nor in GROUP BY: {sql}")
+        res = self._engine.select(df, SelectColumns(*cols, arg_distinct=st.distinct), where=st.where,
+                                  having=st.having)
+        if hidden:
+            res = res[[n for n in res.columns if n not in hidden]]
+        if st.order_by:
+            from collections import OrderedDict
+
+            from .dataframe import B200DataFrame
+            from .sort import sort_table
+
+            sorts = OrderedDict((n, asc) for n, asc in st.order_by)
+            for n in sorts:
+                if n not in res.schema:
+                    raise ValueError(f"ORDER BY {n}: not an output column of: {sql}")
+            res = B200DataFrame(sort_table(res.native, sorts, "last"))
+        if st.limit is not None:
+            from .dataframe import B200DataFrame
+
+            res = B200DataFrame(res.native.slice(0, min(st.limit, res.native.num_rows)))
+        return res
 
     def _join(self, items: str, rest: str, tables: Dict[str, DataFrame], sql: str) -> DataFrame:
         if items.strip() != "*":
@@ -170,3 +173,339 @@ def _split_commas(text: str) -> List[str]:
             cur.append(ch)
     out.append("".join(cur))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# SELECT statement parser (single table) -> column expressions
+# ---------------------------------------------------------------------------------------------
+class _Select:
+    def __init__(self) -> None:
+        self.distinct = False
+        self.columns: List[ColumnExpr] = []
+        self.table = ""
+        self.where: Any = None
+        self.group_by: List[ColumnExpr] = []
+        self.having: Any = None
+        self.order_by: List[Tuple[str, bool]] = []
+        self.limit: Any = None
+
+
+_TOKEN = re.compile(r"""\s*(?:
+    (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?)
+  | (?P<str>'(?:[^'\\]|\\.|'')*')
+  | (?P<bq>`(?:[^`]|``)*`)
+  | (?P<id>[A-Za-z_]\w*)
+  | (?P<op><=|>=|<>|!=|==|=|<|>|\+|-|\*|/|\(|\)|,|\.)
+)""", re.X)
+
+_AGG_FUNCS = {"SUM": functions.sum, "COUNT": functions.count, "MIN": functions.min, "MAX": functions.max,
+              "AVG": functions.avg, "MEAN": functions.avg, "FIRST": functions.first, "LAST": functions.last}
+_CLAUSES = ("WHERE", "GROUP", "HAVING", "ORDER", "LIMIT")
+
+
+def _tokenize(text: str, sql: str) -> List[Tuple[str, str]]:
+    out: List[Tuple[str, str]] = []
+    pos = 0
+    text = text.rstrip()
+    while pos < len(text):
+        m = _TOKEN.match(text, pos)
+        if m is None or m.end() == pos:
+            raise NotImplementedError(f"can't tokenize {text[pos:pos + 20]!r} in: {sql}")
+        kind = m.lastgroup
+        out.append((kind, m.group(kind)))
+        pos = m.end()
+    return out
+
+
+class _Parser:
+    """Recursive descent over the token list; precedence OR < AND < NOT < comparison < + - < * / < unary."""
+
+    def __init__(self, tokens: List[Tuple[str, str]], sql: str):
+        self.t = tokens
+        self.i = 0
+        self.sql = sql
+
+    def peek(self, k: int = 0) -> Tuple[str, str]:
+        return self.t[self.i + k] if self.i + k < len(self.t) else ("end", "")
+
+    def kw(self, *words: str) -> bool:
+        """Consume the keyword sequence if it is next."""
+        for k, w in enumerate(words):
+            kind, val = self.peek(k)
+            if kind != "id" or val.upper() != w:
+                return False
+        self.i += len(words)
+        return True
+
+    def at_kw(self, word: str) -> bool:
+        kind, val = self.peek()
+        return kind == "id" and val.upper() == word
+
+    def op(self, sym: str) -> bool:
+        if self.peek() == ("op", sym):
+            self.i += 1
+            return True
+        return False
+
+    def expect(self, sym: str) -> None:
+        if not self.op(sym):
+            raise NotImplementedError(f"expected {sym!r} near token {self.i} in: {self.sql}")
+
+    def fail(self, what: str) -> Any:
+        raise NotImplementedError(f"{what} in: {self.sql}")
+
+    # ---- expressions
+    def expr(self) -> ColumnExpr:
+        e = self.and_expr()
+        while self.kw("OR"):
+            e = e | self.and_expr()
+        return e
+
+    def and_expr(self) -> ColumnExpr:
+        e = self.not_expr()
+        while self.kw("AND"):
+            e = e & self.not_expr()
+        return e
+
+    def not_expr(self) -> ColumnExpr:
+        if self.kw("NOT"):
+            return ~self.not_expr()
+        return self.comparison()
+
+    def comparison(self) -> ColumnExpr:
+        e = self.additive()
+        while True:
+            if self.kw("IS", "NOT", "NULL"):
+                e = e.not_null()
+            elif self.kw("IS", "NULL"):
+                e = e.is_null()
+            elif self.at_kw("NOT") and self.peek(1)[1].upper() in ("IN", "BETWEEN"):
+                self.i += 1
+                e = ~self._in_or_between(e)
+            elif self.at_kw("IN") or self.at_kw("BETWEEN"):
+                e = self._in_or_between(e)
+            else:
+                kind, val = self.peek()
+                if kind == "op" and val in ("=", "==", "!=", "<>", "<", "<=", ">", ">="):
+                    self.i += 1
+                    r = self.additive()
+                    e = {"=": e == r, "==": e == r, "!=": e != r, "<>": e != r, "<": e < r, "<=": e <= r,
+                         ">": e > r, ">=": e >= r}[val]
+                else:
+                    return e
+
+    def _in_or_between(self, e: ColumnExpr) -> ColumnExpr:
+        if self.kw("IN"):
+            self.expect("(")
+            res: Any = None
+            while True:
+                c = e == self.additive()
+                res = c if res is None else (res | c)
+                if not self.op(","):
+                    break
+            self.expect(")")
+            return res
+        self.kw("BETWEEN")
+        lo = self.additive()
+        if not self.kw("AND"):
+            self.fail("BETWEEN without AND")
+        hi = self.additive()
+        return (e >= lo) & (e <= hi)
+
+    def additive(self) -> ColumnExpr:
+        e = self.multiplicative()
+        while True:
+            if self.op("+"):
+                e = e + self.multiplicative()
+            elif self.op("-"):
+                e = e - self.multiplicative()
+            else:
+                return e
+
+    def multiplicative(self) -> ColumnExpr:
+        e = self.unary()
+        while True:
+            if self.op("*"):
+                e = e * self.unary()
+            elif self.op("/"):
+                e = e / self.unary()
+            else:
+                return e
+
+    def unary(self) -> ColumnExpr:
+        if self.op("-"):
+            kind, val = self.peek()
+            if kind == "num":  # a negative literal, not a negated expression
+                self.i += 1
+                return lit(-_number(val))
+            return -self.unary()
+        if self.op("+"):
+            return self.unary()
+        return self.primary()
+
+    def primary(self) -> ColumnExpr:
+        kind, val = self.peek()
+        if kind == "num":
+            self.i += 1
+            return lit(_number(val))
+        if kind == "str":
+            self.i += 1
+            body = val[1:-1].replace("''", "'")
+            return lit(re.sub(r"\\(.)", r"\1", body))
+        if kind == "op" and val == "(":
+            self.i += 1
+            e = self.expr()
+            self.expect(")")
+            return e
+        if kind == "bq":
+            self.i += 1
+            return self._maybe_qualified(val[1:-1].replace("``", "`"))
+        if kind == "id":
+            up = val.upper()
+            if up == "NULL":
+                self.i += 1
+                return null()
+            if up in ("TRUE", "FALSE"):
+                self.i += 1
+                return lit(up == "TRUE")
+            if up == "CAST" and self.peek(1) == ("op", "("):
+                self.i += 2
+                e = self.expr()
+                if not self.kw("AS"):
+                    self.fail("CAST without AS")
+                tp = []
+                while self.peek() != ("op", ")") and self.peek()[0] != "end":
+                    tp.append(self.peek()[1])
+                    self.i += 1
+                self.expect(")")
+                return e.cast("".join(tp).lower())
+            if self.peek(1) == ("op", "("):
+                return self._call(up)
+            self.i += 1
+            return self._maybe_qualified(val)
+        return self.fail(f"unexpected token {val!r}")
+
+    def _maybe_qualified(self, name: str) -> ColumnExpr:
+        if self.peek() == ("op", ".") and self.peek(1)[0] in ("id", "bq"):  # table.column
+            kind, val = self.peek(1)
+            self.i += 2
+            name = val[1:-1].replace("``", "`") if kind == "bq" else val
+        return col(name)
+
+    def _call(self, fn: str) -> ColumnExpr:
+        self.i += 2  # name (
+        if fn in _AGG_FUNCS:
+            distinct = self.kw("DISTINCT")
+            if self.op("*"):
+                arg: ColumnExpr = all_cols()
+            else:
+                arg = self.expr()
+            self.expect(")")
+            if distinct:
+                if fn != "COUNT":
+                    self.fail(f"{fn}(DISTINCT ...)")
+                return functions.count_distinct(arg)
+            return _AGG_FUNCS[fn](arg)
+        args: List[Any] = []
+        if not self.op(")"):
+            while True:
+                args.append(self.expr())
+                if not self.op(","):
+                    break
+            self.expect(")")
+        if fn == "COALESCE":
+            return functions.coalesce(*args)
+        return function(fn, *args)
+
+    # ---- select items / lists
+    def item(self) -> ColumnExpr:
+        if self.peek() == ("op", "*"):
+            self.i += 1
+            return all_cols()
+        e = self.expr()
+        if self.kw("AS"):
+            kind, val = self.peek()
+            if kind not in ("id", "bq"):
+                self.fail("AS without a name")
+            self.i += 1
+            return e.alias(val[1:-1].replace("``", "`") if kind == "bq" else val)
+        kind, val = self.peek()
+        if kind == "bq" or (kind == "id" and val.upper() not in _CLAUSES + ("FROM",)):
+            self.i += 1  # implicit alias
+            return e.alias(val[1:-1].replace("``", "`") if kind == "bq" else val)
+        return e
+
+
+def _number(text: str) -> Any:
+    return int(text) if re.fullmatch(r"\d+", text) else float(text)
+
+
+def _default_alias(e: ColumnExpr) -> ColumnExpr:
+    """Name an unnamed select item the way the SQL engines do for the common cases."""
+    from .column import AggFuncExpr, _WildcardExpr
+
+    if isinstance(e, _WildcardExpr) or e.output_name != "":
+        return e
+    if isinstance(e, AggFuncExpr) and isinstance(e.arg, _WildcardExpr):
+        return e.alias(e.func.lower())          # COUNT(*) -> "count"
+    named = e.infer_alias()
+    return named
+
+
+def _parse_select(items: str, rest: str, sql: str) -> _Select:
+    st = _Select()
+    p = _Parser(_tokenize(items, sql), sql)
+    st.distinct = p.kw("DISTINCT")
+    while True:
+        st.columns.append(_default_alias(p.item()))
+        if not p.op(","):
+            break
+    if p.peek()[0] != "end":
+        p.fail(f"unexpected token {p.peek()[1]!r} in the select list")
+    p = _Parser(_tokenize(rest, sql), sql)
+    kind, val = p.peek()
+    if kind == "op" and val == "(":
+        p.fail("sub-queries are not on the GPU path")
+    if kind not in ("id", "bq"):
+        p.fail("FROM needs a table name")
+    p.i += 1
+    st.table = val.strip("`")
+    kind, val = p.peek()  # optional alias
+    if p.kw("AS"):
+        p.i += 1
+    elif kind == "id" and val.upper() not in _CLAUSES:
+        p.i += 1
+    if p.kw("WHERE"):
+        st.where = p.expr()
+    if p.kw("GROUP", "BY"):
+        while True:
+            st.group_by.append(p.expr())
+            if not p.op(","):
+                break
+    if p.kw("HAVING"):
+        st.having = p.expr()
+    if p.kw("ORDER", "BY"):
+        while True:
+            kind, val = p.peek()
+            if kind not in ("id", "bq"):
+                p.fail("ORDER BY takes output column names")
+            p.i += 1
+            asc = True
+            if p.kw("DESC"):
+                asc = False
+            else:
+                p.kw("ASC")
+            st.order_by.append((val.strip("`"), asc))
+            if not p.op(","):
+                break
+    if p.kw("LIMIT"):
+        kind, val = p.peek()
+        if kind != "num" or not val.isdigit():
+            p.fail("LIMIT takes an integer")
+        p.i += 1
+        st.limit = int(val)
+    if p.peek()[0] != "end":
+        p.fail(f"unsupported SQL near {p.peek()[1]!r}")
+    if st.where is not None and is_agg(st.where):
+        raise ValueError(f"aggregation in WHERE: {sql}")
+    return st

@@ -133,8 +133,10 @@ def test_sql_engine_group_by_and_join(engine):
     df_eq(out, exp.values.tolist(), "key:long,lv:double,rv:double", throw=True)
     out = fa.raw_sql("SELECT COUNT(*) AS n, MAX(lv) AS m FROM", l, engine=engine, as_local=True)
     assert out.values.tolist() == [[3000, l.lv.max()]]
+    out = fa.raw_sql("SELECT key FROM", l, "WHERE key > 3", engine=engine, as_local=True)
+    assert np.array_equal(out["key"].to_numpy(), l.key[l.key > 3].to_numpy())
     with pytest.raises(NotImplementedError):
-        fa.raw_sql("SELECT key FROM", l, "WHERE key > 3", engine=engine)
+        fa.raw_sql("SELECT key FROM (SELECT * FROM", l, ")", engine=engine)
 
 
 def test_multi_column_group_by(engine):

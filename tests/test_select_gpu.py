@@ -216,3 +216,35 @@ def test_large_expression_is_split_over_launches(e):
     for i in range(20):
         ref = (pdf["a"] + i) * (pdf["x"] - i) + (pdf["a"] - i) * 2
         assert np.allclose(got[f"c{i}"].to_numpy(), ref.to_numpy(), rtol=1e-13)
+
+
+def test_sql_text_reaches_the_device_path(e):
+    rng = np.random.default_rng(21)
+    n = 200_000
+    pdf = pd.DataFrame({"key": rng.integers(0, 300, n), "v0": rng.standard_normal(n), "v1": rng.standard_normal(n),
+                        "tag": rng.choice(["x", "y", "z"], n)})
+    got = fa.raw_sql("SELECT key, SUM(v0 * 2) AS s, COUNT(*) AS c, AVG(v1) a FROM", pdf,
+                     "WHERE v1 > 0 AND tag <> 'z' GROUP BY key HAVING COUNT(*) > 5 ORDER BY key DESC LIMIT 50",
+                     engine=e, as_local=True)
+    f = pdf[(pdf.v1 > 0) & (pdf.tag != "z")]
+    want = f.assign(v02=f.v0 * 2).groupby("key").agg(s=("v02", "sum"), c=("v0", "size"), a=("v1", "mean")).reset_index()
+    want = want[want.c > 5].sort_values("key", ascending=False).head(50).reset_index(drop=True)
+    assert list(got.columns) == ["key", "s", "c", "a"]
+    assert np.array_equal(got.key.to_numpy(), want.key.to_numpy()) and np.array_equal(got.c.to_numpy(), want.c.to_numpy())
+    assert np.allclose(got.s.to_numpy(), want.s.to_numpy(), rtol=1e-9) and np.allclose(got.a.to_numpy(), want.a.to_numpy(), rtol=1e-9)
+    # projection with expressions, CAST, IN / BETWEEN, IS NULL, DISTINCT
+    got = fa.raw_sql("SELECT key, CAST(v0 * 10 AS long) AS q, v0 IS NULL AS isn FROM", pdf,
+                     "WHERE key IN (1, 2, 3) AND v1 NOT BETWEEN -0.5 AND 0.5", engine=e, as_local=True)
+    f = pdf[pdf.key.isin([1, 2, 3]) & ~pdf.v1.between(-0.5, 0.5)]
+    assert np.array_equal(got.key.to_numpy(), f.key.to_numpy())
+    assert np.array_equal(got.q.to_numpy(), np.trunc(f.v0.to_numpy() * 10).astype(np.int64))
+    assert not got.isn.any()
+    got = fa.raw_sql("SELECT DISTINCT tag, key - key AS z FROM", pdf, engine=e, as_local=True)
+    assert sorted(got.tag.tolist()) == ["x", "y", "z"] and (got.z == 0).all()
+    # GROUP BY key that is not selected rides along as a hidden column
+    got = fa.raw_sql("SELECT MAX(v0) AS m FROM", pdf, "GROUP BY key", engine=e, as_local=True)
+    assert np.allclose(np.sort(got.m.to_numpy()), np.sort(pdf.groupby("key").v0.max().to_numpy()))
+    with raises(ValueError):
+        fa.raw_sql("SELECT key, tag, SUM(v0) AS s FROM", pdf, "GROUP BY key", engine=e)
+    with raises(NotImplementedError):
+        fa.raw_sql("SELECT key FROM", pdf, "UNION SELECT key FROM", pdf, engine=e)
