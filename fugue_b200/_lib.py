@@ -24,7 +24,8 @@ _lib: Optional[C.CDLL] = None
 
 class ExprIns(C.Structure):
     """``fb_expr_ins`` of include/fugue_b200.h."""
-    _fields_ = [("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("imm", C.c_int64)]
+    _fields_ = [("op", C.c_int32), ("kind", C.c_int32), ("b", C.c_int32), ("flags", C.c_int32),
+                ("imm", C.c_int64)]
 
 
 _vp = C.c_void_p
@@ -70,7 +71,7 @@ SIGNATURES = {
     "fb_compact_indices": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_size_t]),
     "fb_gather_rows": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
     "fb_eval_expr": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp, C.c_int, _vp, C.c_int,
-                               _i32p, _i32p, _vpp, _vpp]),
+                               _i32p, _vpp, _vpp]),
     "fb_copy_segments": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
                                    C.c_int64]),
 }

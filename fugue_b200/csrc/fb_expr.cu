@@ -1,21 +1,22 @@
-// Vectorised column-expression evaluator for sm_100a.
+// Column-expression evaluator for sm_100a: one pass over HBM per SELECT list.
 //
 // ExecutionEngine.select / filter / assign (fugue/execution/execution_engine.py:736-887) evaluate
-// expression trees (fugue/column/expressions.py) row by row; the reference turns them into SQL text and
-// hands them to qpd/pandas, which materialises one temporary column per operator.  Here a whole
-// SELECT list (+ WHERE predicate) is compiled on the host into one short register-machine program and
-// evaluated in ONE pass over the input columns:
+// expression trees (fugue/column/expressions.py); the reference turns them into SQL text and hands
+// them to qpd/pandas, which materialises one temporary column per operator.  Here the host compiles
+// the whole SELECT list (or WHERE predicate) into one short accumulator-machine program:
 //
-//   * a CTA owns a tile of 1024 rows (256 threads x 4 rows); the machine's vector registers live in
-//     shared memory ([reg][1024] 8-byte values + [reg][1024] validity bytes), each thread only ever
-//     touches its own 4 lanes of every register, so instructions need no barriers;
-//   * the interpreter dispatches once per instruction per thread and then runs the 4 rows, so the
-//     switch is amortised and the kernel stays HBM-bound: every referenced column is read once,
-//     every output written once, no temporaries in global memory;
-//   * values are canonical 64-bit (int64 or float64, bool as int64 0/1); the host compiler types
-//     every instruction, inserts the int->float conversions and allocates registers;
-//   * SQL NULL semantics: arithmetic and comparisons propagate NULL, AND/OR are Kleene three-valued,
-//     IS NULL / IS NOT NULL / COALESCE read the validity lane.
+//   * a thread owns kExprItems rows; the accumulator (their current values + a validity bit each)
+//     sits in hardware registers for the whole program;
+//   * the second operand of an instruction is fetched straight from its source: a column in HBM
+//     (coalesced, converted from its storage type on the fly), an immediate, or a temporary in
+//     shared memory - temporaries are only needed when both sides of an operator are compound, so
+//     typical expressions never touch shared memory (a first version that kept every intermediate
+//     in shared-memory vector registers ran at 1.0 TB/s, bound by shared-memory wavefronts);
+//   * the interpreter dispatches once per instruction per thread and then runs its rows unrolled,
+//     so the switch is amortised; every output is written by its own FB_X_OUT instruction;
+//   * SQL NULL semantics: arithmetic and comparisons propagate NULL (validity bits are ANDed for
+//     all rows of the thread at once), AND / OR are Kleene three-valued, IS NULL / IS NOT NULL /
+//     COALESCE read the validity bits.
 #include <mutex>
 
 #include "fb_common.cuh"
@@ -23,8 +24,9 @@
 namespace {
 
 constexpr int kExprThreads = 256;
-constexpr int kExprItems = 4;
+constexpr int kExprItems = 8;
 constexpr int kExprTile = kExprThreads * kExprItems;
+constexpr unsigned kAllValid = (1u << kExprItems) - 1;
 
 struct ExprProgram {
   const void* col_ptr[FB_EXPR_MAX_COLS];
@@ -32,142 +34,195 @@ struct ExprProgram {
   int32_t col_type[FB_EXPR_MAX_COLS];
   void* out_ptr[FB_EXPR_MAX_OUTS];
   uint8_t* out_valid[FB_EXPR_MAX_OUTS];
-  int32_t out_reg[FB_EXPR_MAX_OUTS];
   int32_t out_type[FB_EXPR_MAX_OUTS];
-  int32_t nins, nouts;
+  int32_t nins;
   fb_expr_ins ins[FB_EXPR_MAX_INS];
 };
-
-__device__ __forceinline__ uint64_t load_as_bits(const void* p, int32_t type, int64_t row) {
-  switch (type) {
-    case FB_T_I8: return (uint64_t)(int64_t)((const int8_t*)p)[row];
-    case FB_T_I16: return (uint64_t)(int64_t)((const int16_t*)p)[row];
-    case FB_T_I32: return (uint64_t)(int64_t)((const int32_t*)p)[row];
-    case FB_T_I64: return (uint64_t)((const int64_t*)p)[row];
-    case FB_T_U8: return (uint64_t)((const uint8_t*)p)[row];
-    case FB_T_F32: return (uint64_t)__double_as_longlong((double)((const float*)p)[row]);
-    default: return (uint64_t)((const int64_t*)p)[row];  // FB_T_F64: raw bits
-  }
-}
-
-__device__ __forceinline__ void store_from_bits(void* p, int32_t type, int64_t row, uint64_t bits) {
-  switch (type) {
-    case FB_T_I8: ((int8_t*)p)[row] = (int8_t)(int64_t)bits; break;
-    case FB_T_I16: ((int16_t*)p)[row] = (int16_t)(int64_t)bits; break;
-    case FB_T_I32: ((int32_t*)p)[row] = (int32_t)(int64_t)bits; break;
-    case FB_T_I64: ((int64_t*)p)[row] = (int64_t)bits; break;
-    case FB_T_U8: ((uint8_t*)p)[row] = (uint8_t)bits; break;
-    case FB_T_F32: ((float*)p)[row] = (float)__longlong_as_double((long long)bits); break;
-    default: ((int64_t*)p)[row] = (int64_t)bits; break;  // FB_T_F64
-  }
-}
+static_assert(sizeof(ExprProgram) <= 4000, "program must fit the kernel parameter space");
 
 __device__ __forceinline__ double as_f(uint64_t b) { return __longlong_as_double((long long)b); }
 __device__ __forceinline__ uint64_t f_bits(double d) { return (uint64_t)__double_as_longlong(d); }
 
+template <typename T, bool kFloat>
+__device__ __forceinline__ void load_col(const void* p, int64_t row0, int tid, int nk, uint64_t (&v)[kExprItems]) {
+  const T* __restrict__ q = (const T*)p + row0;
+#pragma unroll
+  for (int k = 0; k < kExprItems; ++k) {
+    const int i = k * kExprThreads + tid;
+    if (i < nk) {
+      if (kFloat) v[k] = f_bits((double)q[i]);
+      else v[k] = (uint64_t)(int64_t)q[i];
+    }
+  }
+}
+
+template <typename T, bool kFloat>
+__device__ __forceinline__ void store_col(void* p, int64_t row0, int tid, int nk, const uint64_t (&v)[kExprItems],
+                                          unsigned valid) {
+  T* __restrict__ q = (T*)p + row0;
+#pragma unroll
+  for (int k = 0; k < kExprItems; ++k) {
+    const int i = k * kExprThreads + tid;
+    if (i < nk) {
+      const uint64_t bits = (valid >> k) & 1u ? v[k] : 0ull;  // NULL rows store 0
+      if (kFloat) q[i] = (T)as_f(bits);
+      else q[i] = (T)(int64_t)bits;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kExprThreads, 3)
 fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
   extern __shared__ __align__(16) uint64_t s_expr[];
-  uint64_t* vals = s_expr;                                           // [FB_EXPR_NREGS][kExprTile]
-  uint8_t* valid = (uint8_t*)(vals + (size_t)FB_EXPR_NREGS * kExprTile);  // [FB_EXPR_NREGS][kExprTile]
+  uint64_t* tmp_v = s_expr;                                              // [FB_EXPR_NREGS][kExprTile]
+  uint8_t* tmp_m = (uint8_t*)(tmp_v + (size_t)FB_EXPR_NREGS * kExprTile);  // [FB_EXPR_NREGS][kExprThreads] bits
   const int tid = threadIdx.x;
   const int64_t ntiles = (nrows + kExprTile - 1) / kExprTile;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * kExprTile;
     const int nk = (int)(nrows - row0 < kExprTile ? nrows - row0 : kExprTile);  // rows in this tile
+    uint64_t acc[kExprItems];
+    unsigned accv = kAllValid;
+#pragma unroll
+    for (int k = 0; k < kExprItems; ++k) acc[k] = 0;
     for (int pc = 0; pc < P.nins; ++pc) {
       const fb_expr_ins in = P.ins[pc];
-      uint64_t* dv = vals + (size_t)in.dst * kExprTile;
-      uint8_t* dm = valid + (size_t)in.dst * kExprTile;
-      const uint64_t* av = vals + (size_t)in.a * kExprTile;
-      const uint8_t* am = valid + (size_t)in.a * kExprTile;
-      const uint64_t* bv = vals + (size_t)in.b * kExprTile;
-      const uint8_t* bm = valid + (size_t)in.b * kExprTile;
-#define FB_EACH(...)                                  \
-  _Pragma("unroll") for (int k = 0; k < kExprItems; ++k) { \
-    const int i = k * kExprThreads + tid;             \
-    if (i < nk) { __VA_ARGS__ }                       \
-  }
-#define FB_BIN(EXPR) FB_EACH(const uint64_t x = av[i], y = bv[i]; dv[i] = (EXPR); dm[i] = am[i] & bm[i];)
-#define FB_UN(EXPR) FB_EACH(const uint64_t x = av[i]; dv[i] = (EXPR); dm[i] = am[i];)
+      // ---- operand B
+      uint64_t b[kExprItems];
+      unsigned bv = kAllValid;
+#pragma unroll
+      for (int k = 0; k < kExprItems; ++k) b[k] = (uint64_t)in.imm;  // FB_XK_IMM (and a defined value otherwise)
+      if (in.kind == FB_XK_COL) {
+        const void* p = P.col_ptr[in.b];
+        switch (P.col_type[in.b]) {
+          case FB_T_I8: load_col<int8_t, false>(p, row0, tid, nk, b); break;
+          case FB_T_I16: load_col<int16_t, false>(p, row0, tid, nk, b); break;
+          case FB_T_I32: load_col<int32_t, false>(p, row0, tid, nk, b); break;
+          case FB_T_I64: load_col<int64_t, false>(p, row0, tid, nk, b); break;
+          case FB_T_U8: load_col<uint8_t, false>(p, row0, tid, nk, b); break;
+          case FB_T_F32: load_col<float, true>(p, row0, tid, nk, b); break;
+          default: load_col<int64_t, false>(p, row0, tid, nk, b); break;  // FB_T_F64: raw bits
+        }
+        const uint8_t* m = P.col_valid[in.b];
+        if (m != nullptr) {
+          bv = 0;
+#pragma unroll
+          for (int k = 0; k < kExprItems; ++k) {
+            const int i = k * kExprThreads + tid;
+            if (i < nk && m[row0 + i] != 0) bv |= 1u << k;
+          }
+        }
+      } else if (in.kind == FB_XK_REG) {
+        const uint64_t* r = tmp_v + (size_t)in.b * kExprTile;
+#pragma unroll
+        for (int k = 0; k < kExprItems; ++k) b[k] = r[k * kExprThreads + tid];
+        bv = tmp_m[in.b * kExprThreads + tid];
+      } else if (in.kind == FB_XK_NULL) {
+        bv = 0;
+      }
+      if (in.flags & FB_XF_B_I2F) {
+#pragma unroll
+        for (int k = 0; k < kExprItems; ++k) b[k] = f_bits((double)(int64_t)b[k]);
+      }
+#define FB_ROWS(...) _Pragma("unroll") for (int k = 0; k < kExprItems; ++k) { __VA_ARGS__ }
+#define FB_BIN(EXPR) FB_ROWS(const uint64_t x = acc[k], y = b[k]; acc[k] = (EXPR);) accv &= bv;
+#define FB_UN(EXPR) FB_ROWS(const uint64_t x = acc[k]; acc[k] = (EXPR);)
       switch (in.op) {
-        case FB_X_LOAD: {
-          const void* p = P.col_ptr[in.a];
-          const uint8_t* m = P.col_valid[in.a];
-          const int32_t t = P.col_type[in.a];
-          FB_EACH(dv[i] = load_as_bits(p, t, row0 + i); dm[i] = m ? (uint8_t)(m[row0 + i] != 0) : (uint8_t)1;)
+        case FB_X_MOV: FB_ROWS(acc[k] = b[k];) accv = bv; break;
+        case FB_X_ST: {
+          uint64_t* r = tmp_v + (size_t)in.b * kExprTile;
+          FB_ROWS(r[k * kExprThreads + tid] = acc[k];)
+          tmp_m[in.b * kExprThreads + tid] = (uint8_t)accv;
           break;
         }
-        case FB_X_LIT: FB_EACH(dv[i] = (uint64_t)in.imm; dm[i] = 1;) break;
-        case FB_X_NULL: FB_EACH(dv[i] = 0; dm[i] = 0;) break;
-        case FB_X_MOV: FB_UN(x) break;
+        case FB_X_OUT: {
+          void* p = P.out_ptr[in.b];
+          switch (P.out_type[in.b]) {
+            case FB_T_I8: store_col<int8_t, false>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_I16: store_col<int16_t, false>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_I32: store_col<int32_t, false>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_I64: store_col<int64_t, false>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_U8: store_col<uint8_t, false>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_F32: store_col<float, true>(p, row0, tid, nk, acc, accv); break;
+            default: store_col<int64_t, false>(p, row0, tid, nk, acc, accv); break;  // FB_T_F64
+          }
+          uint8_t* m = P.out_valid[in.b];
+          if (m != nullptr) {
+            FB_ROWS(const int i = k * kExprThreads + tid; if (i < nk) m[row0 + i] = (uint8_t)((accv >> k) & 1u);)
+          }
+          break;
+        }
         case FB_X_I2F: FB_UN(f_bits((double)(int64_t)x)) break;
         case FB_X_F2I: FB_UN((uint64_t)(int64_t)as_f(x)) break;
+        case FB_X_NEG_I: FB_UN(0 - x) break;
+        case FB_X_NEG_F: FB_UN(x ^ 0x8000000000000000ull) break;
+        case FB_X_NOT: FB_UN((uint64_t)(x == 0)) break;
+        case FB_X_IS_NULL: FB_ROWS(acc[k] = (uint64_t)(((accv >> k) & 1u) == 0);) accv = kAllValid; break;
+        case FB_X_NOT_NULL: FB_ROWS(acc[k] = (uint64_t)((accv >> k) & 1u);) accv = kAllValid; break;
+        case FB_X_TOBOOL_I: FB_UN((uint64_t)(x != 0)) break;
+        case FB_X_TOBOOL_F: FB_UN((uint64_t)(as_f(x) != 0.0)) break;
         case FB_X_ADD_I: FB_BIN(x + y) break;
         case FB_X_SUB_I: FB_BIN(x - y) break;
+        case FB_X_RSUB_I: FB_BIN(y - x) break;
         case FB_X_MUL_I: FB_BIN(x * y) break;
-        case FB_X_NEG_I: FB_UN(0 - x) break;
         case FB_X_ADD_F: FB_BIN(f_bits(as_f(x) + as_f(y))) break;
         case FB_X_SUB_F: FB_BIN(f_bits(as_f(x) - as_f(y))) break;
+        case FB_X_RSUB_F: FB_BIN(f_bits(as_f(y) - as_f(x))) break;
         case FB_X_MUL_F: FB_BIN(f_bits(as_f(x) * as_f(y))) break;
         case FB_X_DIV_F: FB_BIN(f_bits(as_f(x) / as_f(y))) break;
-        case FB_X_NEG_F: FB_UN(x ^ 0x8000000000000000ull) break;
+        case FB_X_RDIV_F: FB_BIN(f_bits(as_f(y) / as_f(x))) break;
         case FB_X_LT_I: FB_BIN((uint64_t)((int64_t)x < (int64_t)y)) break;
         case FB_X_LE_I: FB_BIN((uint64_t)((int64_t)x <= (int64_t)y)) break;
+        case FB_X_GT_I: FB_BIN((uint64_t)((int64_t)x > (int64_t)y)) break;
+        case FB_X_GE_I: FB_BIN((uint64_t)((int64_t)x >= (int64_t)y)) break;
         case FB_X_EQ_I: FB_BIN((uint64_t)(x == y)) break;
         case FB_X_NE_I: FB_BIN((uint64_t)(x != y)) break;
         case FB_X_LT_F: FB_BIN((uint64_t)(as_f(x) < as_f(y))) break;
         case FB_X_LE_F: FB_BIN((uint64_t)(as_f(x) <= as_f(y))) break;
+        case FB_X_GT_F: FB_BIN((uint64_t)(as_f(x) > as_f(y))) break;
+        case FB_X_GE_F: FB_BIN((uint64_t)(as_f(x) >= as_f(y))) break;
         case FB_X_EQ_F: FB_BIN((uint64_t)(as_f(x) == as_f(y))) break;
         case FB_X_NE_F: FB_BIN((uint64_t)(as_f(x) != as_f(y))) break;
-        case FB_X_AND:  // Kleene: FALSE wins over NULL
-          FB_EACH(const bool va = am[i], vb = bm[i]; const bool fa = va && av[i] == 0, fb = vb && bv[i] == 0;
-                  const bool isf = fa || fb; dm[i] = (uint8_t)(isf || (va && vb));
-                  dv[i] = (uint64_t)(!isf && va && vb);)
+        case FB_X_AND: {  // Kleene: FALSE wins over NULL
+          unsigned nv = 0;
+          FB_ROWS(const bool va = (accv >> k) & 1u, vb = (bv >> k) & 1u;
+                  const bool fa = va && acc[k] == 0, fb = vb && b[k] == 0; const bool isf = fa || fb;
+                  if (isf || (va && vb)) nv |= 1u << k; acc[k] = (uint64_t)(!isf && va && vb);)
+          accv = nv;
           break;
-        case FB_X_OR:  // Kleene: TRUE wins over NULL
-          FB_EACH(const bool va = am[i], vb = bm[i]; const bool ta = va && av[i] != 0, tb = vb && bv[i] != 0;
-                  const bool ist = ta || tb; dm[i] = (uint8_t)(ist || (va && vb)); dv[i] = (uint64_t)ist;)
+        }
+        case FB_X_OR: {  // Kleene: TRUE wins over NULL
+          unsigned nv = 0;
+          FB_ROWS(const bool va = (accv >> k) & 1u, vb = (bv >> k) & 1u;
+                  const bool ta = va && acc[k] != 0, tb = vb && b[k] != 0; const bool ist = ta || tb;
+                  if (ist || (va && vb)) nv |= 1u << k; acc[k] = (uint64_t)ist;)
+          accv = nv;
           break;
-        case FB_X_NOT: FB_UN((uint64_t)(x == 0)) break;
-        case FB_X_IS_NULL: FB_EACH(dv[i] = (uint64_t)(am[i] == 0); dm[i] = 1;) break;
-        case FB_X_NOT_NULL: FB_EACH(dv[i] = (uint64_t)(am[i] != 0); dm[i] = 1;) break;
-        case FB_X_COALESCE:
-          FB_EACH(const bool va = am[i]; dv[i] = va ? av[i] : bv[i]; dm[i] = (uint8_t)(va | bm[i]);)
-          break;
-        case FB_X_TOBOOL_I: FB_UN((uint64_t)(x != 0)) break;
-        case FB_X_TOBOOL_F: FB_UN((uint64_t)(as_f(x) != 0.0)) break;
+        }
+        case FB_X_COALESCE: FB_ROWS(if (!((accv >> k) & 1u)) acc[k] = b[k];) accv |= bv; break;
+        case FB_X_RCOALESCE: FB_ROWS(if ((bv >> k) & 1u) acc[k] = b[k];) accv |= bv; break;
         default: break;
       }
 #undef FB_BIN
 #undef FB_UN
+#undef FB_ROWS
     }
-    for (int o = 0; o < P.nouts; ++o) {
-      const uint64_t* __restrict__ rv = vals + (size_t)P.out_reg[o] * kExprTile;
-      const uint8_t* __restrict__ rm = valid + (size_t)P.out_reg[o] * kExprTile;
-      void* op = P.out_ptr[o];
-      uint8_t* om = P.out_valid[o];
-      const int32_t t = P.out_type[o];
-      FB_EACH(store_from_bits(op, t, row0 + i, rm[i] ? rv[i] : 0ull); if (om) om[row0 + i] = rm[i];)
-    }
-#undef FB_EACH
   }
 }
 
-constexpr size_t kExprSmem = (size_t)FB_EXPR_NREGS * kExprTile * 9;
+constexpr size_t kExprSmem = (size_t)FB_EXPR_NREGS * kExprTile * 8 + (size_t)FB_EXPR_NREGS * kExprThreads;
 
 }  // namespace
 
 extern "C" int fb_eval_expr(int dev, void* stream, int64_t nrows, int ncols, const void* const* col_ptrs,
                             const int32_t* col_types, const uint8_t* const* col_valid, int nins,
-                            const fb_expr_ins* program, int nouts, const int32_t* out_regs,
-                            const int32_t* out_types, void* const* out_ptrs, uint8_t* const* out_valid) {
+                            const fb_expr_ins* program, int nouts, const int32_t* out_types,
+                            void* const* out_ptrs, uint8_t* const* out_valid) {
   FB_CHECK(nrows >= 0, "nrows < 0");
   FB_CHECK(ncols >= 0 && ncols <= FB_EXPR_MAX_COLS, "ncols=%d out of range [0,%d]", ncols, FB_EXPR_MAX_COLS);
   FB_CHECK(nins >= 1 && nins <= FB_EXPR_MAX_INS, "nins=%d out of range [1,%d]", nins, FB_EXPR_MAX_INS);
   FB_CHECK(nouts >= 1 && nouts <= FB_EXPR_MAX_OUTS, "nouts=%d out of range [1,%d]", nouts, FB_EXPR_MAX_OUTS);
-  FB_CHECK(program != nullptr && out_regs != nullptr && out_types != nullptr && out_ptrs != nullptr,
-           "NULL argument");
+  FB_CHECK(program != nullptr && out_types != nullptr && out_ptrs != nullptr, "NULL argument");
   ExprProgram P;
   memset(&P, 0, sizeof(P));
   for (int c = 0; c < ncols; ++c) {
@@ -177,30 +232,33 @@ extern "C" int fb_eval_expr(int dev, void* stream, int64_t nrows, int ncols, con
     P.col_type[c] = col_types[c];
     P.col_valid[c] = col_valid ? col_valid[c] : nullptr;
   }
-  for (int i = 0; i < nins; ++i) {
-    const fb_expr_ins& in = program[i];
-    FB_CHECK(in.op >= FB_X_LOAD && in.op <= FB_X_TOBOOL_F, "instruction %d: unknown op %d", i, in.op);
-    FB_CHECK(in.dst >= 0 && in.dst < FB_EXPR_NREGS, "instruction %d: dst register %d out of range", i, in.dst);
-    if (in.op == FB_X_LOAD) {
-      FB_CHECK(in.a >= 0 && in.a < ncols, "instruction %d: column %d out of range", i, in.a);
-    } else {
-      FB_CHECK(in.a >= 0 && in.a < FB_EXPR_NREGS && in.b >= 0 && in.b < FB_EXPR_NREGS,
-               "instruction %d: source register out of range", i);
-    }
-    P.ins[i] = in;
-    if (in.op == FB_X_LOAD) P.ins[i].b = 0;  // the kernel forms (unused) register pointers from a and b
-  }
   for (int o = 0; o < nouts; ++o) {
-    FB_CHECK(out_regs[o] >= 0 && out_regs[o] < FB_EXPR_NREGS, "output %d: register out of range", o);
     FB_CHECK(out_types[o] >= FB_T_I8 && out_types[o] <= FB_T_F64, "output %d: unknown type", o);
     FB_CHECK(nrows == 0 || out_ptrs[o] != nullptr, "output %d pointer is NULL", o);
-    P.out_reg[o] = out_regs[o];
     P.out_type[o] = out_types[o];
     P.out_ptr[o] = out_ptrs[o];
     P.out_valid[o] = out_valid ? out_valid[o] : nullptr;
   }
+  for (int i = 0; i < nins; ++i) {
+    const fb_expr_ins& in = program[i];
+    FB_CHECK(in.op >= FB_X_MOV && in.op <= FB_X_RCOALESCE, "instruction %d: unknown op %d", i, in.op);
+    FB_CHECK(in.kind >= FB_XK_NONE && in.kind <= FB_XK_NULL, "instruction %d: unknown operand kind %d", i, in.kind);
+    if (in.op == FB_X_ST) {
+      FB_CHECK(in.b >= 0 && in.b < FB_EXPR_NREGS, "instruction %d: temporary %d out of range", i, in.b);
+      FB_CHECK(in.kind == FB_XK_NONE, "instruction %d: FB_X_ST takes no operand", i);
+    } else if (in.op == FB_X_OUT) {
+      FB_CHECK(in.b >= 0 && in.b < nouts, "instruction %d: output %d out of range", i, in.b);
+      FB_CHECK(in.kind == FB_XK_NONE, "instruction %d: FB_X_OUT takes no operand", i);
+    } else if (in.kind == FB_XK_REG) {
+      FB_CHECK(in.b >= 0 && in.b < FB_EXPR_NREGS, "instruction %d: temporary %d out of range", i, in.b);
+    } else if (in.kind == FB_XK_COL) {
+      FB_CHECK(in.b >= 0 && in.b < ncols, "instruction %d: column %d out of range", i, in.b);
+    }
+    const bool binary = in.op == FB_X_MOV || in.op >= FB_X_ADD_I;
+    FB_CHECK(!binary || in.kind != FB_XK_NONE, "instruction %d: op %d needs an operand", i, in.op);
+    P.ins[i] = in;
+  }
   P.nins = nins;
-  P.nouts = nouts;
   if (nrows == 0) return 0;
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
@@ -215,7 +273,7 @@ extern "C" int fb_eval_expr(int dev, void* stream, int64_t nrows, int ncols, con
     }
   }
   const int64_t ntiles = (nrows + kExprTile - 1) / kExprTile;
-  int64_t grid = (int64_t)fb_sm_count(dev) * 3;  // 72 KB of registers per CTA: 3 CTAs per SM
+  int64_t grid = (int64_t)fb_sm_count(dev) * 3;  // 65 KB of temporaries per CTA: 3 CTAs per SM
   if (grid > ntiles) grid = ntiles;
   fb_eval_expr_kernel<<<(unsigned)grid, kExprThreads, kExprSmem, (cudaStream_t)stream>>>(P, nrows);
   FB_CUDA(cudaGetLastError());

@@ -47,28 +47,39 @@ class _OutOfResources(Exception):
 
 
 class _Program:
-    """One ``fb_eval_expr`` launch: instructions, referenced columns, pending outputs."""
+    """One ``fb_eval_expr`` launch.  Code generation for the accumulator machine: ``compile`` leaves the
+    value of an expression in the accumulator; the right-hand side of an operator is used in place
+    when it is a leaf (column / literal), otherwise the left value waits in a temporary."""
+
+    _REVERSE = {"+": "+", "*": "*", "-": "r-", "/": "r/", "<": ">", "<=": ">=", ">": "<", ">=": "<=",
+                "==": "==", "!=": "!=", "&": "&", "|": "|"}
+    _OPS = {  # (int opcode, float opcode)
+        "+": (K.X_ADD_I, K.X_ADD_F), "-": (K.X_SUB_I, K.X_SUB_F), "r-": (K.X_RSUB_I, K.X_RSUB_F),
+        "*": (K.X_MUL_I, K.X_MUL_F), "/": (None, K.X_DIV_F), "r/": (None, K.X_RDIV_F),
+        "<": (K.X_LT_I, K.X_LT_F), "<=": (K.X_LE_I, K.X_LE_F), ">": (K.X_GT_I, K.X_GT_F),
+        ">=": (K.X_GE_I, K.X_GE_F), "==": (K.X_EQ_I, K.X_EQ_F), "!=": (K.X_NE_I, K.X_NE_F),
+    }
 
     def __init__(self, table: B200Table):
         self.t = table
         self.ins: List[Tuple[int, int, int, int, int]] = []
         self.cols: List[int] = []          # table column indices, in load order
         self.free = list(range(K.EXPR_NREGS - 1, -1, -1))
-        self.outs: List[Tuple[int, torch.dtype, bool]] = []  # (reg, dtype, want_valid)
+        self.outs: List[Tuple[torch.dtype, bool]] = []  # (dtype, want_valid) per FB_X_OUT
 
     # -- resources
     def alloc(self) -> int:
         if not self.free:
-            raise _OutOfResources("registers")
+            raise _OutOfResources("temporaries")
         return self.free.pop()
 
     def release(self, r: int) -> None:
         self.free.append(r)
 
-    def emit(self, op: int, dst: int, a: int = 0, b: int = 0, imm: int = 0) -> None:
+    def emit(self, op: int, kind: int = K.XK_NONE, b: int = 0, flags: int = 0, imm: int = 0) -> None:
         if len(self.ins) >= K.EXPR_MAX_INS:
             raise _OutOfResources("instructions")
-        self.ins.append((op, dst, a, b, imm))
+        self.ins.append((op, kind, b, flags, imm))
 
     def col_slot(self, ci: int) -> int:
         if ci in self.cols:
@@ -78,88 +89,110 @@ class _Program:
         self.cols.append(ci)
         return len(self.cols) - 1
 
-    # -- compilation: returns (register, class, nullable)
-    def compile(self, e: ColumnExpr, top: bool = False) -> Tuple[int, str, bool]:
-        r, cls, nullable = self._node(e)
+    def output(self, dtype: torch.dtype, want_valid: bool) -> None:
+        if len(self.outs) >= K.EXPR_MAX_OUTS:
+            raise _OutOfResources("outputs")
+        self.emit(K.X_OUT, K.XK_NONE, len(self.outs))
+        self.outs.append((dtype, want_valid))
+
+    def mark(self) -> Any:
+        return (len(self.ins), list(self.cols), list(self.free), len(self.outs))
+
+    def rollback(self, m: Any) -> None:
+        del self.ins[m[0]:]
+        self.cols, self.free = m[1], m[2]
+        del self.outs[m[3]:]
+
+    # -- leaves: usable directly as operand B.  Returns (kind, b, imm, cls, nullable) or None
+    def _leaf(self, e: Any) -> Optional[Tuple[int, int, int, str, bool]]:
         if e.as_type is not None:
-            if _is_str(e.as_type) and not top and cls != "s":
-                raise NotImplementedError(f"cast to str inside an expression (only on a whole column): {e}")
-            r, cls = self._cast(r, cls, _cls_of(e.as_type), e)
-        return r, cls, nullable
-
-    def _cast(self, r: int, cls: str, want: str, e: ColumnExpr) -> Tuple[int, str]:
-        if want == "s":
-            return r, cls  # applied to the stored column (top level only, checked by the caller)
-        if cls == "s":
-            raise NotImplementedError(f"cast of a string expression to {e.as_type}: {e}")
-        if want == cls:
-            return r, cls
-        if want == "f":
-            self.emit(K.X_I2F, r, r)
-        elif want == "i":
-            if cls == "f":
-                self.emit(K.X_F2I, r, r)
-        elif want == "b":
-            self.emit(K.X_TOBOOL_F if cls == "f" else K.X_TOBOOL_I, r, r)
-        return r, want
-
-    def _to_float(self, r: int, cls: str) -> None:
-        if cls != "f":
-            self.emit(K.X_I2F, r, r)
-
-    def _to_bool(self, r: int, cls: str) -> None:
-        if cls == "f":
-            self.emit(K.X_TOBOOL_F, r, r)
-        elif cls == "i":
-            self.emit(K.X_TOBOOL_I, r, r)
-
-    def _node(self, e: ColumnExpr) -> Tuple[int, str, bool]:  # noqa: C901
-        t = self.t
+            return None
         if isinstance(e, _NamedColumnExpr):
+            t = self.t
             if e.name not in t.schema:
                 raise KeyError(f"column {e.name} is not in {t.schema}")
             ci = t.schema.index_of_key(e.name)
             cls = _cls_of(t.schema.types[ci])
-            r = self.alloc()
-            self.emit(K.X_LOAD, r, self.col_slot(ci))
-            return r, cls, t.valid[ci] is not None
+            return (K.XK_COL, ci, 0, cls, t.valid[ci] is not None)  # b = table column, slot assigned on use
         if isinstance(e, _LiteralColumnExpr):
             v = e.value
-            r = self.alloc()
             if v is None:
-                self.emit(K.X_NULL, r)
-                return r, "n", True
+                return (K.XK_NULL, 0, 0, "n", True)
             if isinstance(v, bool):
-                self.emit(K.X_LIT, r, imm=int(v))
-                return r, "b", False
+                return (K.XK_IMM, 0, int(v), "b", False)
             if isinstance(v, int):
-                self.emit(K.X_LIT, r, imm=v & ((1 << 64) - 1))
-                return r, "i", False
+                return (K.XK_IMM, 0, v & ((1 << 64) - 1), "i", False)
             if isinstance(v, float):
-                self.emit(K.X_LIT, r, imm=_f64_bits(v))
-                return r, "f", False
-            raise NotImplementedError(f"string literal {e} outside a comparison with a string column")
+                return (K.XK_IMM, 0, _f64_bits(v), "f", False)
+        return None
+
+    def _emit_with(self, op: int, leaf: Tuple[int, int, int, str, bool], ctx: str) -> None:
+        """``acc <- acc op leaf`` with the leaf converted to the context class ('i', 'f' or 'b')."""
+        kind, b, imm, cls, _ = leaf
+        flags = 0
+        if kind == K.XK_COL:
+            b = self.col_slot(b)
+            if ctx == "f" and cls != "f":
+                flags = K.XF_B_I2F
+        elif kind == K.XK_IMM and ctx == "f" and cls != "f":
+            v = imm - (1 << 64) if imm >= (1 << 63) else imm
+            imm = _f64_bits(float(v))
+        self.emit(op, kind, b, flags, imm)
+
+    def _acc_to(self, cls: str, ctx: str) -> None:
+        if cls == "n" or cls == ctx:
+            return
+        if ctx == "f":
+            self.emit(K.X_I2F)
+        elif ctx == "b":
+            self.emit(K.X_TOBOOL_F if cls == "f" else K.X_TOBOOL_I)
+        elif ctx == "i" and cls == "f":
+            self.emit(K.X_F2I)
+
+    # -- compilation: value ends up in the accumulator; returns (class, nullable)
+    def compile(self, e: ColumnExpr, top: bool = False) -> Tuple[str, bool]:
+        cls, nullable = self._node(e)
+        if e.as_type is not None:
+            want = _cls_of(e.as_type)
+            if want == "s":
+                if not top and cls != "s":
+                    raise NotImplementedError(f"cast to str inside an expression (only on a whole column): {e}")
+            elif cls == "s":
+                raise NotImplementedError(f"cast of a string expression to {e.as_type}: {e}")
+            elif cls != "n":
+                self._acc_to(cls, want)
+                cls = want
+        return cls, nullable
+
+    def _node(self, e: ColumnExpr) -> Tuple[str, bool]:  # noqa: C901
         if isinstance(e, _WildcardExpr):
             raise ValueError("'*' can't be evaluated as a value")
         if isinstance(e, AggFuncExpr):
             raise ValueError(f"aggregation {e} in a row-wise expression")
+        if isinstance(e, (_NamedColumnExpr, _LiteralColumnExpr)):
+            if isinstance(e, _LiteralColumnExpr) and isinstance(e.value, str):
+                raise NotImplementedError(f"string literal {e} outside a comparison with a string column")
+            bare = e.cast(None) if e.as_type is not None else e
+            leaf = self._leaf(bare)
+            assert leaf is not None
+            self._emit_with(K.X_MOV, leaf, leaf[3])
+            return leaf[3], leaf[4]
         if isinstance(e, _UnaryOpExpr):
-            if e.op in ("IS_NULL", "NOT_NULL"):
-                r, _, _ = self._string_or_value(e.col)
-                self.emit(K.X_IS_NULL if e.op == "IS_NULL" else K.X_NOT_NULL, r, r)
-                return r, "b", False
-            r, cls, nullable = self.compile(e.col)
+            cls, nullable = self.compile(e.col)
+            if e.op in ("IS_NULL", "NOT_NULL"):  # string columns are fine here: only validity is read
+                self.emit(K.X_IS_NULL if e.op == "IS_NULL" else K.X_NOT_NULL)
+                return "b", False
             if cls == "s":
                 raise NotImplementedError(f"{e.op} on a string expression: {e}")
             if e.op == "-":
                 if cls == "n":
-                    return r, cls, True
-                self.emit(K.X_NEG_F if cls == "f" else K.X_NEG_I, r, r)
-                return r, ("i" if cls == "b" else cls), nullable
+                    return cls, True
+                self.emit(K.X_NEG_F if cls == "f" else K.X_NEG_I)
+                return ("i" if cls == "b" else cls), nullable
             if e.op == "~":
-                self._to_bool(r, cls)
-                self.emit(K.X_NOT, r, r)
-                return r, "b", nullable
+                self._acc_to(cls, "b")
+                self.emit(K.X_NOT)
+                return "b", nullable
             raise NotImplementedError(f"unary operator {e.op}")
         if isinstance(e, _BinaryOpExpr):
             return self._binary(e)
@@ -169,55 +202,51 @@ class _Program:
             raise NotImplementedError(f"function {e.func} has no device implementation")
         raise NotImplementedError(f"can't evaluate {e!r}")
 
-    def _string_or_value(self, e: ColumnExpr) -> Tuple[int, str, bool]:
-        """Operand of IS NULL / NOT NULL: string columns are fine here (only validity is read)."""
-        return self.compile(e)
-
-    def _binary(self, e: _BinaryOpExpr) -> Tuple[int, str, bool]:  # noqa: C901
+    def _binary(self, e: _BinaryOpExpr) -> Tuple[str, bool]:
         op = e.op
+        if op not in self._REVERSE:
+            raise NotImplementedError(f"operator {op}")
         str_cmp = self._string_compare(e)
         if str_cmp is not None:
             return str_cmp
-        ra, ca, na = self.compile(e.left)
-        rb, cb, nb = self.compile(e.right)
-        if "s" in (ca, cb):
+        cl, cr = self._static_cls(e.left), self._static_cls(e.right)
+        if "s" in (cl, cr):
             raise NotImplementedError(f"operator {op} on string operands: {e}")
-        nullable = na or nb
-        if op in ("&", "|"):
-            if ca != "n":
-                self._to_bool(ra, ca)
-            if cb != "n":
-                self._to_bool(rb, cb)
-            self.emit(K.X_AND if op == "&" else K.X_OR, ra, ra, rb)
-            self.release(rb)
-            return ra, "b", nullable
-        is_f = "f" in (ca, cb) or op == "/"
-        if is_f:
-            if ca != "n":
-                self._to_float(ra, ca)
-            if cb != "n":
-                self._to_float(rb, cb)
-        table = {
-            "+": (K.X_ADD_I, K.X_ADD_F, False), "-": (K.X_SUB_I, K.X_SUB_F, False),
-            "*": (K.X_MUL_I, K.X_MUL_F, False), "/": (None, K.X_DIV_F, False),
-            "<": (K.X_LT_I, K.X_LT_F, False), "<=": (K.X_LE_I, K.X_LE_F, False),
-            ">": (K.X_LT_I, K.X_LT_F, True), ">=": (K.X_LE_I, K.X_LE_F, True),
-            "==": (K.X_EQ_I, K.X_EQ_F, False), "!=": (K.X_NE_I, K.X_NE_F, False),
-        }
-        if op not in table:
-            raise NotImplementedError(f"operator {op}")
-        oi, of, swap = table[op]
-        code = of if is_f else oi
-        if swap:
-            self.emit(code, ra, rb, ra)
-        else:
-            self.emit(code, ra, ra, rb)
-        self.release(rb)
-        if op in ("+", "-", "*", "/"):
-            return ra, ("f" if is_f else "i"), nullable
-        return ra, "b", nullable
+        logical = op in ("&", "|")
+        ctx = "b" if logical else ("f" if (op == "/" or "f" in (cl, cr)) else "i")
+        res = "b" if (logical or op in ("<", "<=", ">", ">=", "==", "!=")) else ctx
 
-    def _string_compare(self, e: _BinaryOpExpr) -> Optional[Tuple[int, str, bool]]:
+        def usable(leaf: Any) -> bool:  # a leaf whose class needs no instruction of its own in this context
+            return leaf is not None and (not logical or leaf[3] in ("b", "n"))
+
+        def code(o: str) -> int:
+            if logical:
+                return K.X_AND if o == "&" else K.X_OR
+            oi, of = self._OPS[o]
+            return of if ctx == "f" else oi
+
+        lr, ll = self._leaf(e.right), self._leaf(e.left)
+        if usable(lr):
+            ca, na = self.compile(e.left)
+            self._acc_to(ca, ctx)
+            self._emit_with(code(op), lr, ctx)
+            return res, na or lr[4]
+        if usable(ll):
+            cb, nb = self.compile(e.right)
+            self._acc_to(cb, ctx)
+            self._emit_with(code(self._REVERSE[op]), ll, ctx)
+            return res, nb or ll[4]
+        ca, na = self.compile(e.left)
+        self._acc_to(ca, ctx)
+        tmp = self.alloc()
+        self.emit(K.X_ST, K.XK_NONE, tmp)
+        cb, nb = self.compile(e.right)
+        self._acc_to(cb, ctx)
+        self.emit(code(self._REVERSE[op]), K.XK_REG, tmp)
+        self.release(tmp)
+        return res, na or nb
+
+    def _string_compare(self, e: _BinaryOpExpr) -> Optional[Tuple[str, bool]]:
         """``strcol == 'lit'`` / ``!=``: compare dictionary codes."""
         t = self.t
         sides = [e.left, e.right]
@@ -237,43 +266,43 @@ class _Program:
         ci = t.schema.index_of_key(c.name)
         d = t.dictionaries[c.name]
         code = d.index(lit_.value).as_py() if len(d) > 0 else -1  # -1: value not in the dictionary
-        r = self.alloc()
-        self.emit(K.X_LOAD, r, self.col_slot(ci))
-        rl = self.alloc()
-        self.emit(K.X_LIT, rl, imm=(code if code is not None else -1) & ((1 << 64) - 1))
-        self.emit(K.X_EQ_I if e.op == "==" else K.X_NE_I, r, r, rl)
-        self.release(rl)
-        return r, "b", t.valid[ci] is not None
+        self.emit(K.X_MOV, K.XK_COL, self.col_slot(ci))
+        self.emit(K.X_EQ_I if e.op == "==" else K.X_NE_I, K.XK_IMM, 0, 0,
+                  (code if code is not None else -1) & ((1 << 64) - 1))
+        return "b", t.valid[ci] is not None
 
-    def _coalesce(self, e: _FuncExpr) -> Tuple[int, str, bool]:
+    def _coalesce(self, e: _FuncExpr) -> Tuple[str, bool]:
         args = [a if isinstance(a, ColumnExpr) else _LiteralColumnExpr(a) for a in e.args]
         if len(args) == 0:
             raise ValueError("COALESCE needs arguments")
-        # the result class: float if any argument is float, else int / bool
         probe = [self._static_cls(a) for a in args]
         if "s" in probe:
             raise NotImplementedError(f"COALESCE on strings: {e}")
         want = "f" if "f" in probe else ("b" if all(p in ("b", "n") for p in probe) and "b" in probe else "i")
-        acc: Optional[int] = None
-        nullable = True
-        for a in args:
-            r, cls, n = self.compile(a)
-            if cls != "n" and want == "f":
-                self._to_float(r, cls)
-            if acc is None:
-                acc, nullable = r, n
-            else:
-                self.emit(K.X_COALESCE, acc, acc, r)
-                self.release(r)
-                nullable = nullable and n
-        assert acc is not None
-        return acc, want, nullable
+        cls, nullable = self.compile(args[0])
+        self._acc_to(cls, want)
+        for a in args[1:]:
+            leaf = self._leaf(a)
+            if leaf is not None and (want != "b" or leaf[3] in ("b", "n")):
+                self._emit_with(K.X_COALESCE, leaf, want)
+                nullable = nullable and leaf[4]
+                continue
+            tmp = self.alloc()
+            self.emit(K.X_ST, K.XK_NONE, tmp)
+            cls, n = self.compile(a)
+            self._acc_to(cls, want)
+            self.emit(K.X_RCOALESCE, K.XK_REG, tmp)  # acc <- tmp if tmp is not NULL else acc
+            self.release(tmp)
+            nullable = nullable and n
+        return want, nullable
 
     def _static_cls(self, e: ColumnExpr) -> str:
         """Class an expression will evaluate to (without emitting code)."""
         if e.as_type is not None:
             return _cls_of(e.as_type)
         if isinstance(e, _NamedColumnExpr):
+            if e.name not in self.t.schema:
+                raise KeyError(f"column {e.name} is not in {self.t.schema}")
             return _cls_of(self.t.schema[e.name].type)
         if isinstance(e, _LiteralColumnExpr):
             v = e.value
@@ -298,7 +327,7 @@ class _Program:
         t = self.t
         return K.eval_expr(t.num_rows, t.device, [t.columns[i] for i in self.cols],
                            [t.valid[i] for i in self.cols], self.ins, [o[0] for o in self.outs],
-                           [o[1] for o in self.outs], [o[2] for o in self.outs])
+                           [o[1] for o in self.outs])
 
 
 def _default_type(cls: str, e: ColumnExpr, schema: Schema) -> pa.DataType:
@@ -367,32 +396,32 @@ def project(t: B200Table, exprs: Sequence[ColumnExpr]) -> B200Table:
     k = 0
     while k < len(pending):
         prog = _Program(t)
-        batch: List[Tuple[int, ColumnExpr, str, bool]] = []
-        while k < len(pending) and len(batch) < K.EXPR_MAX_OUTS:
+        batch: List[Tuple[int, ColumnExpr, str]] = []
+        while k < len(pending):
             i, e = pending[k]
-            mark = (len(prog.ins), list(prog.cols), list(prog.free))
+            mark = prog.mark()
             try:
-                r, cls, nullable = prog.compile(e, top=True)
+                cls, nullable = prog.compile(e, top=True)
+                if cls == "n":  # a bare NULL-valued expression
+                    cls = _cls_of(e.as_type) if e.as_type is not None and not _is_str(e.as_type) else "i"
+                tp = e.as_type if e.as_type is not None else _default_type(cls, e, t.schema)
+                if _is_str(tp) or _cls_of(tp) != cls:
+                    store_tp = {"i": pa.int64(), "f": pa.float64(), "b": pa.bool_()}[cls]
+                    if not _is_str(tp):
+                        tp = store_tp  # an inferred type of another class than the computed value
+                else:
+                    store_tp = tp
+                prog.output(_storage_dtype(store_tp), nullable)
             except _OutOfResources as ex:
                 if not batch:
                     raise NotImplementedError(f"expression too large for one device program ({ex}): {e}")
-                del prog.ins[mark[0]:]
-                prog.cols, prog.free = mark[1], mark[2]
+                prog.rollback(mark)
                 break
-            if cls == "n":  # a bare NULL-valued expression
-                cls = _cls_of(e.as_type) if e.as_type is not None else "i"
-            tp = e.as_type if e.as_type is not None else _default_type(cls, e, t.schema)
-            store_tp = {"i": pa.int64(), "f": pa.float64(), "b": pa.bool_()}[cls] if _is_str(tp) else tp
-            if _cls_of(store_tp) != cls and not _is_str(tp):
-                # an inferred type of another class (can't happen for casts: _cast converted already)
-                store_tp = {"i": pa.int64(), "f": pa.float64(), "b": pa.bool_()}[cls]
-                tp = store_tp
-            prog.outs.append((r, _storage_dtype(store_tp), nullable))
             out_types[i] = tp
-            batch.append((i, e, cls, nullable))
+            batch.append((i, e, cls))
             k += 1
         cols, valids = prog.run()
-        for (i, e, cls, nullable), c, v in zip(batch, cols, valids):
+        for (i, e, cls), c, v in zip(batch, cols, valids):
             if _is_str(out_types[i]):
                 c, dicts[names[i]] = _to_string_column(c, v, cls)
             out_cols[i], out_valid[i] = c, v
@@ -404,15 +433,15 @@ def predicate_mask(t: B200Table, condition: ColumnExpr) -> torch.Tensor:
     """uint8 mask: 1 where ``condition`` is TRUE (NULL counts as FALSE, like SQL WHERE)."""
     prog = _Program(t)
     try:
-        r, cls, _ = prog.compile(condition.alias("") if condition.as_name else condition)
+        cls, _ = prog.compile(condition.alias("") if condition.as_name else condition)
+        if cls == "s":
+            raise ValueError(f"{condition} is not a boolean expression")
+        if cls == "n":
+            return torch.zeros(t.num_rows, dtype=torch.uint8, device=t.device)
+        prog._acc_to(cls, "b")
+        prog.output(torch.uint8, False)  # FB_X_OUT stores 0 for NULL
     except _OutOfResources as ex:
         raise NotImplementedError(f"condition too large for one device program ({ex}): {condition}")
-    if cls == "s":
-        raise ValueError(f"{condition} is not a boolean expression")
-    if cls == "n":
-        return torch.zeros(t.num_rows, dtype=torch.uint8, device=t.device)
-    prog._to_bool(r, cls)
-    prog.outs.append((r, torch.uint8, False))  # the store writes 0 for NULL
     cols, _ = prog.run()
     return cols[0]
 

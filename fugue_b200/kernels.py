@@ -388,11 +388,14 @@ def compact_indices(mask: torch.Tensor) -> torch.Tensor:
 
 
 # ---- K8: column-expression evaluator -----------------------------------------------------------
-EXPR_MAX_COLS, EXPR_MAX_OUTS, EXPR_MAX_INS, EXPR_NREGS = 16, 16, 64, 8
+EXPR_MAX_COLS, EXPR_MAX_OUTS, EXPR_MAX_INS, EXPR_NREGS = 16, 16, 96, 4
 T_I8, T_I16, T_I32, T_I64, T_U8, T_F32, T_F64 = range(7)
-(X_LOAD, X_LIT, X_NULL, X_MOV, X_I2F, X_F2I, X_ADD_I, X_SUB_I, X_MUL_I, X_NEG_I, X_ADD_F, X_SUB_F, X_MUL_F,
- X_DIV_F, X_NEG_F, X_LT_I, X_LE_I, X_EQ_I, X_NE_I, X_LT_F, X_LE_F, X_EQ_F, X_NE_F, X_AND, X_OR, X_NOT,
- X_IS_NULL, X_NOT_NULL, X_COALESCE, X_TOBOOL_I, X_TOBOOL_F) = range(31)
+XK_NONE, XK_REG, XK_COL, XK_IMM, XK_NULL = range(5)
+XF_B_I2F = 1
+(X_MOV, X_ST, X_OUT, X_I2F, X_F2I, X_NEG_I, X_NEG_F, X_NOT, X_IS_NULL, X_NOT_NULL, X_TOBOOL_I, X_TOBOOL_F,
+ X_ADD_I, X_SUB_I, X_RSUB_I, X_MUL_I, X_ADD_F, X_SUB_F, X_RSUB_F, X_MUL_F, X_DIV_F, X_RDIV_F,
+ X_LT_I, X_LE_I, X_GT_I, X_GE_I, X_EQ_I, X_NE_I, X_LT_F, X_LE_F, X_GT_F, X_GE_F, X_EQ_F, X_NE_F,
+ X_AND, X_OR, X_COALESCE, X_RCOALESCE) = range(38)
 
 _EXPR_TYPE_OF_DTYPE = {torch.int8: T_I8, torch.int16: T_I16, torch.int32: T_I32, torch.int64: T_I64,
                        torch.uint8: T_U8, torch.bool: T_U8, torch.float32: T_F32, torch.float64: T_F64}
@@ -404,18 +407,20 @@ def expr_type_of(dtype: torch.dtype) -> int:
 
 def eval_expr(nrows: int, device: torch.device, cols: Sequence[torch.Tensor],
               valid: Sequence[Optional[torch.Tensor]], program: Sequence[Tuple[int, int, int, int, int]],
-              out_regs: Sequence[int], out_dtypes: Sequence[torch.dtype], want_valid: Sequence[bool]
+              out_dtypes: Sequence[torch.dtype], want_valid: Sequence[bool]
               ) -> Tuple[List[torch.Tensor], List[Optional[torch.Tensor]]]:
-    """Run one register-machine ``program`` (tuples ``(op, dst, a, b, imm_bits)``) over all rows;
-    returns the output columns and (where asked for) their validity byte masks."""
+    """Run one accumulator-machine ``program`` (tuples ``(op, operand_kind, b, flags, imm_bits)``, see
+    include/fugue_b200.h K8) over all rows; ``X_OUT b`` writes output ``b``.  Returns the output
+    columns and (where asked for) their validity byte masks."""
     lib = _lib.load()
     outs = [torch.empty(nrows, dtype=dt, device=device) for dt in out_dtypes]
     outv = [torch.empty(nrows, dtype=torch.uint8, device=device) if w else None for w in want_valid]
     if nrows == 0:
         return outs, outv
     prog = (_lib.ExprIns * len(program))()
-    for i, (op, dst, a, b, imm) in enumerate(program):
-        prog[i].op, prog[i].dst, prog[i].a, prog[i].b = op, dst, a, b
+    for i, (op, kind, b, flags, imm) in enumerate(program):
+        prog[i].op, prog[i].kind, prog[i].b, prog[i].flags = op, kind, b, flags
+        imm &= (1 << 64) - 1
         prog[i].imm = imm - (1 << 64) if imm >= (1 << 63) else imm
     for c in cols:
         assert c.is_cuda and c.is_contiguous() and c.shape[0] == nrows
@@ -423,7 +428,7 @@ def eval_expr(nrows: int, device: torch.device, cols: Sequence[torch.Tensor],
         device.index, _stream_ptr(device), nrows, len(cols), _lib.ptr_array([c.data_ptr() for c in cols]),
         _lib.i32_array([expr_type_of(c.dtype) for c in cols]),
         _lib.ptr_array([0 if v is None else v.data_ptr() for v in valid]), len(program), prog, len(outs),
-        _lib.i32_array(list(out_regs)), _lib.i32_array([expr_type_of(dt) for dt in out_dtypes]),
+        _lib.i32_array([expr_type_of(dt) for dt in out_dtypes]),
         _lib.ptr_array([o.data_ptr() for o in outs]),
         _lib.ptr_array([0 if v is None else v.data_ptr() for v in outv])))
     return outs, outv

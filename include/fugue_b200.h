@@ -229,41 +229,48 @@ int fb_gather_rows(int dev, void* stream, int ncols, const void* const* d_src_co
  *           expression semantics: fugue/column/expressions.py:219-434; pins
  *             fugue_test/execution_suite.py:85-174 (test_filter / test_select / test_assign)
  *
- * One pass evaluates a whole register-machine program over all rows: FB_EXPR_NREGS vector registers
- * of canonical 64-bit values (int64 / float64 bits / bool as 0|1) + a validity lane each.
- *   FB_X_LOAD   dst <- column a (converted from its storage type), validity from its byte mask
- *   FB_X_LIT    dst <- imm (raw 64 bits)            FB_X_NULL  dst <- NULL
- *   arithmetic / comparison ops: dst <- a op b, NULL if either side is NULL
- *   FB_X_AND / FB_X_OR: Kleene three-valued logic;  FB_X_IS_NULL / FB_X_NOT_NULL / FB_X_COALESCE
- * Outputs: register out_regs[o] is converted to out_types[o] and stored to out_ptrs[o]; its
- * validity to out_valid[o] when that pointer is non-NULL.  `program`, the pointer tables and the
- * type arrays are HOST arrays (copied into the launch); column / output pointers are device memory.
+ * One pass evaluates a whole SELECT list: an accumulator-machine program, compiled on the host, runs
+ * over every row.  The accumulator (a row's current value + validity) lives in hardware registers;
+ * the second operand of an instruction is a column (read straight from HBM, converted from its
+ * storage type), an immediate, or one of FB_EXPR_NREGS temporaries (shared memory, only needed when
+ * both sides of an operator are compound).  Values are canonical 64-bit: int64, float64 bits, bool
+ * as 0|1.
+ *   FB_X_MOV    acc <- B                         FB_X_ST   temp[b] <- acc
+ *   FB_X_OUT    output[b] <- acc (converted to out_types[b]; validity to out_valid[b] if non-NULL)
+ *   arithmetic / comparisons: acc <- acc op B (FB_X_R*: B op acc), NULL if either side is NULL
+ *   FB_X_AND / FB_X_OR: Kleene three-valued logic; FB_X_IS_NULL / FB_X_NOT_NULL / FB_X_COALESCE
+ *   flags & FB_XF_B_I2F: convert operand B from int64 to float64 first
+ * `program`, the pointer tables and the type arrays are HOST arrays (copied into the launch);
+ * column / output pointers are device memory.
  * --------------------------------------------------------------------------- */
 #define FB_EXPR_MAX_COLS 16
 #define FB_EXPR_MAX_OUTS 16
-#define FB_EXPR_MAX_INS 64
-#define FB_EXPR_NREGS 8
+#define FB_EXPR_MAX_INS 96
+#define FB_EXPR_NREGS 4
 enum fb_expr_type { FB_T_I8 = 0, FB_T_I16 = 1, FB_T_I32 = 2, FB_T_I64 = 3, FB_T_U8 = 4, FB_T_F32 = 5, FB_T_F64 = 6 };
+enum fb_expr_operand { FB_XK_NONE = 0, FB_XK_REG = 1, FB_XK_COL = 2, FB_XK_IMM = 3, FB_XK_NULL = 4 };
+#define FB_XF_B_I2F 1
 enum fb_expr_op {
-  FB_X_LOAD = 0, FB_X_LIT = 1, FB_X_NULL = 2, FB_X_MOV = 3, FB_X_I2F = 4, FB_X_F2I = 5,
-  FB_X_ADD_I = 6, FB_X_SUB_I = 7, FB_X_MUL_I = 8, FB_X_NEG_I = 9,
-  FB_X_ADD_F = 10, FB_X_SUB_F = 11, FB_X_MUL_F = 12, FB_X_DIV_F = 13, FB_X_NEG_F = 14,
-  FB_X_LT_I = 15, FB_X_LE_I = 16, FB_X_EQ_I = 17, FB_X_NE_I = 18,
-  FB_X_LT_F = 19, FB_X_LE_F = 20, FB_X_EQ_F = 21, FB_X_NE_F = 22,
-  FB_X_AND = 23, FB_X_OR = 24, FB_X_NOT = 25, FB_X_IS_NULL = 26, FB_X_NOT_NULL = 27,
-  FB_X_COALESCE = 28, FB_X_TOBOOL_I = 29, FB_X_TOBOOL_F = 30
+  FB_X_MOV = 0, FB_X_ST = 1, FB_X_OUT = 2,
+  FB_X_I2F = 3, FB_X_F2I = 4, FB_X_NEG_I = 5, FB_X_NEG_F = 6, FB_X_NOT = 7, FB_X_IS_NULL = 8,
+  FB_X_NOT_NULL = 9, FB_X_TOBOOL_I = 10, FB_X_TOBOOL_F = 11,
+  FB_X_ADD_I = 12, FB_X_SUB_I = 13, FB_X_RSUB_I = 14, FB_X_MUL_I = 15,
+  FB_X_ADD_F = 16, FB_X_SUB_F = 17, FB_X_RSUB_F = 18, FB_X_MUL_F = 19, FB_X_DIV_F = 20, FB_X_RDIV_F = 21,
+  FB_X_LT_I = 22, FB_X_LE_I = 23, FB_X_GT_I = 24, FB_X_GE_I = 25, FB_X_EQ_I = 26, FB_X_NE_I = 27,
+  FB_X_LT_F = 28, FB_X_LE_F = 29, FB_X_GT_F = 30, FB_X_GE_F = 31, FB_X_EQ_F = 32, FB_X_NE_F = 33,
+  FB_X_AND = 34, FB_X_OR = 35, FB_X_COALESCE = 36, FB_X_RCOALESCE = 37
 };
 typedef struct fb_expr_ins {
-  int32_t op;  /* enum fb_expr_op */
-  int32_t dst; /* destination register */
-  int32_t a;   /* source register (FB_X_LOAD: column index) */
-  int32_t b;   /* second source register */
-  int64_t imm; /* FB_X_LIT: the value's raw 64 bits */
+  int32_t op;    /* enum fb_expr_op */
+  int32_t kind;  /* enum fb_expr_operand: what operand B is */
+  int32_t b;     /* temporary / column / output index */
+  int32_t flags; /* FB_XF_* */
+  int64_t imm;   /* FB_XK_IMM: the value's raw 64 bits */
 } fb_expr_ins;
 int fb_eval_expr(int dev, void* stream, int64_t nrows, int ncols, const void* const* col_ptrs,
                  const int32_t* col_types, const uint8_t* const* col_valid, int nins,
-                 const fb_expr_ins* program, int nouts, const int32_t* out_regs,
-                 const int32_t* out_types, void* const* out_ptrs, uint8_t* const* out_valid);
+                 const fb_expr_ins* program, int nouts, const int32_t* out_types, void* const* out_ptrs,
+                 uint8_t* const* out_valid);
 
 #ifdef __cplusplus
 }

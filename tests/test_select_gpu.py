@@ -90,25 +90,23 @@ def test_strings_and_literals(e):
 def test_eval_expr_kernel_blocks():
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(5)
-    n = 100_003  # not a multiple of the 1024-row tile
+    n = 100_003  # not a multiple of the 2048-row tile
     a = rng.integers(-1000, 1000, n).astype(np.int32)
     b = rng.standard_normal(n)
     bm = (rng.random(n) > 0.3).astype(np.uint8)
     ta, tb, tm = (torch.from_numpy(x).to(dev) for x in (a, b, bm))
-    # r0 = a (int32 -> i64), r1 = b (f64, nullable); out0 = a * 3 - 7 (int16 store); out1 = (a -> f64) / b;
-    # out2 = (a < 10) AND (b IS NOT NULL and b > 0)  [Kleene]; out3 = COALESCE(b, 2.5)
     f64 = lambda v: int(np.float64(v).view(np.uint64))
+    N, C, I, R = K.XK_NONE, K.XK_COL, K.XK_IMM, K.XK_REG
     prog = [
-        (K.X_LOAD, 0, 0, 0, 0), (K.X_LIT, 1, 0, 0, 3), (K.X_MUL_I, 1, 0, 1, 0), (K.X_LIT, 2, 0, 0, 7),
-        (K.X_SUB_I, 1, 1, 2, 0),                                    # r1 = a*3-7
-        (K.X_LOAD, 2, 1, 0, 0), (K.X_MOV, 3, 0, 0, 0), (K.X_I2F, 3, 3, 0, 0), (K.X_DIV_F, 3, 3, 2, 0),   # r3 = a/b
-        (K.X_LIT, 4, 0, 0, 10), (K.X_LT_I, 4, 0, 4, 0),             # r4 = a < 10
-        (K.X_LIT, 5, 0, 0, f64(0.0)), (K.X_LT_F, 5, 5, 2, 0),       # r5 = 0 < b (NULL when b NULL)
-        (K.X_AND, 4, 4, 5, 0),                                      # r4 = r4 AND r5
-        (K.X_LIT, 5, 0, 0, f64(2.5)), (K.X_COALESCE, 5, 2, 5, 0),   # r5 = COALESCE(b, 2.5)
+        (K.X_MOV, C, 0, 0, 0), (K.X_MUL_I, I, 0, 0, 3), (K.X_SUB_I, I, 0, 0, 7), (K.X_OUT, N, 0, 0, 0),  # a*3-7
+        (K.X_MOV, C, 0, 0, 0), (K.X_I2F, N, 0, 0, 0), (K.X_DIV_F, C, 1, 0, 0), (K.X_OUT, N, 1, 0, 0),    # a/b
+        (K.X_MOV, C, 0, 0, 0), (K.X_LT_I, I, 0, 0, 10), (K.X_ST, N, 2, 0, 0),                            # t2 = a<10
+        (K.X_MOV, C, 1, 0, 0), (K.X_GT_F, I, 0, 0, f64(0.0)), (K.X_AND, R, 2, 0, 0), (K.X_OUT, N, 2, 0, 0),
+        (K.X_MOV, C, 1, 0, 0), (K.X_COALESCE, I, 0, 0, f64(2.5)), (K.X_OUT, N, 3, 0, 0),
+        (K.X_MOV, C, 0, K.XF_B_I2F, 0), (K.X_RSUB_F, I, 0, 0, f64(0.5)), (K.X_OUT, N, 4, 0, 0),          # 0.5 - a
     ]
-    outs, valids = K.eval_expr(n, dev, [ta, tb], [None, tm], prog, [1, 3, 4, 5],
-                               [torch.int16, torch.float64, torch.uint8, torch.float64], [False, True, True, True])
+    dts = [torch.int16, torch.float64, torch.uint8, torch.float64, torch.float32]
+    outs, valids = K.eval_expr(n, dev, [ta, tb], [None, tm], prog, dts, [False, True, True, True, False])
     assert (outs[0].cpu().numpy() == (a.astype(np.int64) * 3 - 7).astype(np.int16)).all()
     v = bm.astype(bool)
     assert (valids[1].cpu().numpy().astype(bool) == v).all()
@@ -118,12 +116,24 @@ def test_eval_expr_kernel_blocks():
     assert (got[v].view(np.uint64) == ref[v].view(np.uint64)).all() and (got[~v] == 0).all()
     lt, pos = a < 10, b > 0
     is_false = (~lt) | (v & ~pos)
-    k_valid = is_false | v
-    assert (valids[2].cpu().numpy().astype(bool) == k_valid).all()
+    assert (valids[2].cpu().numpy().astype(bool) == (is_false | v)).all()
     assert (outs[2].cpu().numpy().astype(bool) == (lt & v & pos)).all()
     assert (outs[3].cpu().numpy() == np.where(v, b, 2.5)).all() and valids[3].cpu().numpy().all()
-    with raises(Exception):
-        K.eval_expr(n, dev, [ta], [None], [(99, 0, 0, 0, 0)], [0], [torch.int64], [False])
+    assert (outs[4].cpu().numpy() == (0.5 - a).astype(np.float32)).all()
+    # the numpy model of the machine (tests/_expr_sim.py, used by the CPU compiler tests) agrees bit for bit
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _expr_sim as sim
+    souts, svalid = sim.run(n, [a, b], [None, bm], prog, [K.expr_type_of(d) for d in dts])
+    for o, so in zip(outs, souts):
+        assert np.array_equal(o.cpu().numpy().view(np.uint8), so.view(np.uint8))
+    for vv, sv in zip(valids, svalid):
+        assert vv is None or np.array_equal(vv.cpu().numpy(), sv)
+    for bad in ([(99, N, 0, 0, 0)], [(K.X_ADD_I, N, 0, 0, 0), (K.X_OUT, N, 0, 0, 0)], [(K.X_MOV, C, 7, 0, 0)],
+                [(K.X_OUT, N, 3, 0, 0)], [(K.X_ST, N, K.EXPR_NREGS, 0, 0)]):
+        with raises(Exception):
+            K.eval_expr(n, dev, [ta], [None], bad, [torch.int64], [False])
 
 
 def _random_table(rng, n):

@@ -47,6 +47,24 @@ def measure(device_index: int = 0):
     out["inner_join"] = {"left_rows": n, "right_rows": n, "out_rows": n, "ms": ms, "out_rows_per_s": n / ms * 1e3,
                          "alg_GBps": 56 * n / ms / 1e6}
     del lk, rk, lv, rv, L, R, res
+    # K8: one-pass expression evaluation (SELECT list) and a WHERE filter, 100 M rows
+    from fugue_b200.column import SelectColumns, col
+    n = 100_000_000
+    key = torch.randint(0, 1 << 16, (n,), dtype=torch.int64, device=dev, generator=g)
+    v0 = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    v1 = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    T = B200DataFrame(B200Table("key:long,v0:double,v1:double", [key, v0, v1]))
+    sel = SelectColumns((col("v0") * col("v1") + col("key")).alias("x"),
+                        ((col("v0") > 0) & (col("v1") < 0.5)).alias("p"),
+                        (col("key") * 3 - 7).alias("k3"))
+    ms = timeit(lambda: e.select(T, sel))
+    out["select_3_exprs"] = {"rows": n, "ms": ms, "rows_per_s": n / ms * 1e3,
+                             "alg_GBps": (24 + 8 + 1 + 8) * n / ms / 1e6}   # read 3 cols once, write f64 + bool + i64
+    cond = (col("v0") > 0.5) & (col("key") < 60000)
+    kept = e.filter(T, cond).count()
+    ms = timeit(lambda: e.filter(T, cond))
+    out["filter"] = {"rows": n, "kept": kept, "ms": ms, "rows_per_s": n / ms * 1e3,
+                     "alg_GBps": (16 * n + 2 * 24 * kept) / ms / 1e6}      # predicate columns + gather of kept rows
     return out
 
 
