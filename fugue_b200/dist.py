@@ -239,7 +239,9 @@ class DistributedB200Engine(B200ExecutionEngine):
         from .column import AggFuncExpr, col
 
         keys = [] if partition_spec is None else list(partition_spec.partition_by)
-        if self._world == 1:
+        if self._world == 1 or not self._plain_aggs(agg_cols):
+            # aggregations of expressions / expressions of aggregations: the base class evaluates the
+            # row-wise parts locally and comes back here with plain FUNC(column) aggregations
             return super().aggregate(df, partition_spec, agg_cols)
         partial: List[Any] = []
         final: List[Any] = []

@@ -319,7 +319,7 @@ class B200ExecutionEngine:
         aggregations go straight to the sm_100a hash group-by kernel; anything richer
         (``(max(b) * 2).cast("int32")``, aggregations of expressions) goes through :meth:`select`,
         which evaluates the inner / outer expressions with the device evaluator around that kernel."""
-        from .column import AggFuncExpr, SelectColumns, _NamedColumnExpr, _WildcardExpr, col, is_agg
+        from .column import SelectColumns, col, is_agg
 
         assert_or_throw(len(agg_cols) > 0, ValueError("agg_cols can't be empty"))
         for a in agg_cols:
@@ -327,14 +327,21 @@ class B200ExecutionEngine:
         agg_cols = [a.infer_alias() for a in agg_cols]
         for a in agg_cols:
             assert_or_throw(a.output_name != "", lambda: ValueError(f"{a} must have an alias"))
-        plain = all(isinstance(a, AggFuncExpr) and a.as_type is None and not a.is_distinct
-                    and a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG")
-                    and isinstance(a.arg, (_NamedColumnExpr, _WildcardExpr)) and a.arg.as_type is None
-                    for a in agg_cols)
-        if plain:
+        if self._plain_aggs(agg_cols):
             return self._aggregate_named(df, partition_spec, agg_cols)
         keys = [] if partition_spec is None else list(partition_spec.partition_by)
         return self.select(df, SelectColumns(*[col(k) for k in keys], *agg_cols))
+
+    @staticmethod
+    def _plain_aggs(agg_cols: List[Any]) -> bool:
+        """``SUM/COUNT/MIN/MAX/AVG`` of a named column (or ``*``) without casts: what the group-by
+        kernel takes directly (and what the distributed engine decomposes into partial / final)."""
+        from .column import AggFuncExpr, _NamedColumnExpr, _WildcardExpr
+
+        return all(isinstance(a, AggFuncExpr) and a.as_type is None and not a.is_distinct
+                   and a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG")
+                   and isinstance(a.arg, (_NamedColumnExpr, _WildcardExpr)) and a.arg.as_type is None
+                   for a in agg_cols)
 
     def _aggregate_named(self, df: Any, partition_spec: Optional[PartitionSpec],
                          agg_cols: List[Any]) -> B200DataFrame:
@@ -554,8 +561,9 @@ class B200ExecutionEngine:
             tmp = t
         else:
             tmp = X.project(t, pre)
-        g = self._aggregate_named(B200DataFrame(tmp), PartitionSpec(by=key_names) if key_names else None,
-                                  named_aggs).native
+        # (self.aggregate, not the local kernel wrapper: the distributed engine shuffles partials here)
+        g = self.aggregate(B200DataFrame(tmp), PartitionSpec(by=key_names) if key_names else None,
+                           named_aggs).native
 
         def to_group_table(e: Any) -> Any:
             def mapper(node: Any) -> Any:

@@ -68,6 +68,24 @@ def check_relational(eng, rank, world, dev):
         b = ej.sort_values(cols).reset_index(drop=True)
         pd.testing.assert_frame_equal(a, b, check_exact=True, check_dtype=False)
         print(f"dist relational ok: {len(got)} groups, {len(gj)} joined rows")
+    # aggregating select with expressions, WHERE and HAVING: row-wise parts local, partials shuffled
+    from fugue_b200.column import SelectColumns
+    from oracle import expressions as OX
+
+    sel = SelectColumns(col("key"), (ff.sum(col("v0") * 2) / ff.count(all_cols())).alias("m2"),
+                        ff.max(col("v0") + col("key")).alias("mx"))
+    where, having = col("v0") > -1.0, ff.count(all_cols()) > 3
+    part = eng.select(eng.to_df(fact), sel, where=where, having=having)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, part.as_pandas())
+    if rank == 0:
+        got = pd.concat(gathered, ignore_index=True).sort_values("key").reset_index(drop=True)
+        exp = OX.select(F, sel, where=where, having=having).sort_values("key").reset_index(drop=True)
+        assert len(got) == len(exp) and got["key"].is_unique
+        assert np.array_equal(got["key"].to_numpy(), exp["key"].to_numpy(dtype="int64"))
+        assert np.allclose(got["m2"].to_numpy(), exp["m2"].to_numpy(dtype="float64"), rtol=1e-9)
+        assert np.allclose(got["mx"].to_numpy(), exp["mx"].to_numpy(dtype="float64"), rtol=1e-12)
+        print(f"dist select ok: {len(got)} groups")
 
 
 def main():
