@@ -1590,7 +1590,11 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
   if (nfast > 0) {
     int smem_max = 0;
     FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
+    int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
+    if (const char* gs = getenv("FB_WS_GRID")) {  // leave SMs to a concurrent kernel (multi-GPU pull)
+      const int lim = atoi(gs);
+      if (lim >= 1 && lim < grid) grid = lim;
+    }
     const uint8_t* pid_plane = (const uint8_t*)scratch + l.pid_offset;  // rank records of pass 1
     // measured (100 M rows x 8 cols, columns per launch): 8 -> 3.45 ms, 4 -> 3.10, 3 -> 3.21, 2 -> 3.33,
     // 1 -> 4.59 (fewer open write streams: half-written lines meet their other half while still in L2;

@@ -130,10 +130,10 @@ class DistributedB200Engine(B200ExecutionEngine):
         return out
 
     def repartition(self, df: Any, partition_spec: PartitionSpec) -> B200DataFrame:
-        """Shuffle = local K1-K3 into a symmetric arena + ONE pull kernel over NVLink:
+        """Shuffle = local K1-K3 into a symmetric arena + a pull over NVLink peer memory:
         pass 1 -> count all-gather -> scatter into the arena -> barrier -> every rank copies the
         (source rank, partition) runs it owns straight from the peers' arenas into its final,
-        partition-contiguous output (fb_copy_segments with peer pointers) -> barrier."""
+        partition-contiguous output (copy engines, or the fb_copy_segments kernel) -> barrier."""
         from . import kernels as K
 
         keys = partition_spec.partition_by
@@ -165,27 +165,43 @@ class DistributedB200Engine(B200ExecutionEngine):
         plan_local = K.partition_plan([t.columns[i] for i in kidx], num, kvalid, scratch=scratch)
         counts = gather_counts(plan_local.offsets[1:] - plan_local.offsets[:-1], self._group)
         plan = ExchangePlan(counts, self._rank)
-        if os.environ.get("FB_DIST_EXCHANGE", "pull") == "nccl":
+        mode = os.environ.get("FB_DIST_EXCHANGE", "pull")
+        if mode == "nccl":
             return self._repartition_nccl(t, keys, cols, vpos, plan_local, plan)
         rows = [int(x) for x in plan.rows_per_rank.tolist()]
         self._ensure_arena(max(self._col_offsets(r, widths)[-1] for r in rows))
-        # ---- pass 2 + pull, in two column groups so that the NVLink pull of group A overlaps the
-        #      HBM-bound scatter of group B (peers' pulls of the previous call are over: every call
-        #      ends with a barrier)
+        # ---- pass 2 + exchange in column groups, so that moving group A over NVLink overlaps the
+        #      HBM-bound scatter of group B (peers' reads of the previous call are over: every call
+        #      ends with a barrier).
+        #      "dma" (default): the (source rank, partition) runs are copied by the COPY ENGINES
+        #      (fb_copy_runs_dma): the scatter kernel fills every SM's registers and shared memory, so
+        #      a pull *kernel* cannot co-run with it and the two serialise; DMA needs no SM.
+        #      "pull": one fb_copy_segments kernel with peer pointers (16-byte loads over NVLink).
         my_off = self._col_offsets(t.num_rows, widths)
         parts = [self._arena[my_off[i]:my_off[i] + t.num_rows * w].view(c.dtype)
                  for i, (c, w) in enumerate(zip(cols, widths))]
         base = self._arena_hdl.buffer_ptrs
         peer_off = [self._col_offsets(rows[s], widths) for s in range(self._world)]
         outs = [torch.empty(plan.total_recv, dtype=c.dtype, device=dev) for c in cols]
-        seg_src, seg_dst, seg_len = plan.pull_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev)
-        seg_rank = plan.pull_src_rank.to(dev)
         s_main = torch.cuda.current_stream(dev)
         if getattr(self, "_pull_stream", None) is None:
             self._pull_stream = torch.cuda.Stream(dev)
         s_pull = self._pull_stream
-        half = (len(cols) + 1) // 2 if len(cols) >= 4 else len(cols)
-        groups = [list(range(0, half))] + ([list(range(half, len(cols)))] if half < len(cols) else [])
+        per = max(1, int(os.environ.get("FB_DIST_GROUP_COLS", "4")))
+        groups = [list(range(a, min(a + per, len(cols)))) for a in range(0, len(cols), per)]
+        if mode == "dma":
+            import numpy as np
+
+            keep = plan.seg_len.numpy() > 0
+            r_rank = plan.pull_src_rank.numpy()[keep].astype(np.int64)
+            r_src = plan.pull_src_off.numpy()[keep].astype(np.uint64)
+            r_dst = plan.seg_dst_off.numpy()[keep].astype(np.uint64)
+            r_len = plan.seg_len.numpy()[keep].astype(np.uint64)
+            col_base = np.array([[int(base[s]) + peer_off[s][i] for i in range(len(cols))]
+                                 for s in range(self._world)], dtype=np.uint64)   # [rank][column]
+        else:
+            seg_src, seg_dst = plan.pull_src_off.to(dev), plan.seg_dst_off.to(dev)
+            seg_len, seg_rank = plan.seg_len.to(dev), plan.pull_src_rank.to(dev)
         for gi, idx in enumerate(groups):
             K.partition_apply(plan_local, [cols[i] for i in idx], [parts[i] for i in idx])
             ev = torch.cuda.Event()
@@ -193,9 +209,15 @@ class DistributedB200Engine(B200ExecutionEngine):
             with torch.cuda.stream(s_pull):
                 s_pull.wait_event(ev)
                 dist.barrier(group=self._group)  # stream-ordered: this group is complete on all ranks
-                src_ptrs = [int(base[s]) + peer_off[s][i] for s in range(self._world) for i in idx]
-                K.copy_segments(None, [outs[i] for i in idx], seg_src, seg_dst, seg_len, max_len=plan.max_seg,
-                                src_table=seg_rank, src_ptrs=src_ptrs)
+                if mode == "dma":
+                    src = np.concatenate([col_base[r_rank, i] + r_src * np.uint64(widths[i]) for i in idx])
+                    dst = np.concatenate([np.uint64(outs[i].data_ptr()) + r_dst * np.uint64(widths[i]) for i in idx])
+                    nb = np.concatenate([r_len * np.uint64(widths[i]) for i in idx])
+                    K.copy_runs_dma(dev, src, dst, nb)
+                else:
+                    src_ptrs = [int(base[s]) + peer_off[s][i] for s in range(self._world) for i in idx]
+                    K.copy_segments(None, [outs[i] for i in idx], seg_src, seg_dst, seg_len, max_len=plan.max_seg,
+                                    src_table=seg_rank, src_ptrs=src_ptrs)
         with torch.cuda.stream(s_pull):
             dist.barrier(group=self._group)  # nobody overwrites an arena that is still being read
         s_main.wait_stream(s_pull)

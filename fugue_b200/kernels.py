@@ -3,7 +3,7 @@
 torch is used here only as the owner of device memory and streams; every
 operation is a call into ``libfugue_b200.so``.
 """
-from typing import List, Optional, Sequence, Tuple
+from typing import Any, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -183,6 +183,22 @@ def copy_segments(src_cols: Sequence[torch.Tensor], dst_cols: Sequence[torch.Ten
                                     ptr_dst.data_ptr(), widths.data_ptr(), nseg,
                                     0 if src_table is None else src_table.data_ptr(), src_off.data_ptr(),
                                     dst_off.data_ptr(), seg_len.data_ptr(), int(max_len)))
+
+
+def copy_runs_dma(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: Any) -> None:
+    """``nruns`` device-to-device copies on the copy engines (numpy uint64 arrays of raw pointers /
+    byte counts); sources may be peer buffers mapped through symmetric memory."""
+    import numpy as np
+
+    lib = _lib.load()
+    src = np.ascontiguousarray(src_ptrs, dtype=np.uint64)
+    dst = np.ascontiguousarray(dst_ptrs, dtype=np.uint64)
+    nb = np.ascontiguousarray(nbytes, dtype=np.uint64)
+    assert src.shape == dst.shape == nb.shape and src.ndim == 1
+    if src.size == 0:
+        return
+    _lib.check(lib.fb_copy_runs_dma(device.index, _stream_ptr(device), int(src.size), src.ctypes.data,
+                                    dst.ctypes.data, nb.ctypes.data))
 
 
 AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_MAX_F64 = range(7)

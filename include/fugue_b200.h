@@ -137,6 +137,12 @@ int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_
                      void* const* d_dst_cols, const int32_t* d_widths, int nseg,
                      const int32_t* d_src_table, const int64_t* d_src_off, const int64_t* d_dst_off,
                      const int64_t* d_len, int64_t max_len);
+/* The same exchange on the COPY ENGINES: nruns independent device-to-device copies (local or peer
+ * memory mapped into this process), submitted as one batch on `stream`.  Unlike the pull kernel it
+ * needs no SM, so it overlaps completely with the scatter kernel of the next column group (which
+ * fills every SM's registers and shared memory).  src / dst / bytes are HOST arrays. */
+int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void* const* src, void* const* dst,
+                     const size_t* bytes);
 
 /* ---------------------------------------------------------------------------
  * K6  hash group-by with aggregation (single 8-byte key; other key shapes are packed /
