@@ -255,12 +255,12 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         pms = e0.elapsed_time(e1) / reps
         achieved = ALG_BYTES_PER_ROW * n / (kms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "fb_scatter_ws_kernel (pass 2: TMA ring + ranking + write-combined scatter; "
+        roofline = {"bound": "hbm", "kernel": "fb_scatter_ws_kernel (pass 2: TMA ring + placement from rank records + write-combined scatter; "
                                               "2 launches x 4 columns, timed together)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "traffic": _profile_traffic(),
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_ROW * n,
-                    "kernel_ms": kms, "hist_scan_ms": pms,
+                    "kernel_ms": kms, "pass1_rank_scan_ms": pms,
                     "step_frac": ALG_BYTES_PER_ROW * n / (ms_per_step * 1e-3) / 1e9 / peak}
         del outs, plan
 

@@ -43,27 +43,27 @@ static_assert(sizeof(ExprProgram) <= 4000, "program must fit the kernel paramete
 __device__ __forceinline__ double as_f(uint64_t b) { return __longlong_as_double((long long)b); }
 __device__ __forceinline__ uint64_t f_bits(double d) { return (uint64_t)__double_as_longlong(d); }
 
-template <typename T, bool kFloat>
+template <typename T, bool kFloat, bool kFull>
 __device__ __forceinline__ void load_col(const void* p, int64_t row0, int tid, int nk, uint64_t (&v)[kExprItems]) {
   const T* __restrict__ q = (const T*)p + row0;
 #pragma unroll
   for (int k = 0; k < kExprItems; ++k) {
     const int i = k * kExprThreads + tid;
-    if (i < nk) {
+    if (kFull || i < nk) {
       if (kFloat) v[k] = f_bits((double)q[i]);
       else v[k] = (uint64_t)(int64_t)q[i];
     }
   }
 }
 
-template <typename T, bool kFloat>
+template <typename T, bool kFloat, bool kFull>
 __device__ __forceinline__ void store_col(void* p, int64_t row0, int tid, int nk, const uint64_t (&v)[kExprItems],
                                           unsigned valid) {
   T* __restrict__ q = (T*)p + row0;
 #pragma unroll
   for (int k = 0; k < kExprItems; ++k) {
     const int i = k * kExprThreads + tid;
-    if (i < nk) {
+    if (kFull || i < nk) {
       const uint64_t bits = (valid >> k) & 1u ? v[k] : 0ull;  // NULL rows store 0
       if (kFloat) q[i] = (T)as_f(bits);
       else q[i] = (T)(int64_t)bits;
@@ -71,16 +71,11 @@ __device__ __forceinline__ void store_col(void* p, int64_t row0, int tid, int nk
   }
 }
 
-__global__ void __launch_bounds__(kExprThreads, 3)
-fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
-  extern __shared__ __align__(16) uint64_t s_expr[];
-  uint64_t* tmp_v = s_expr;                                              // [FB_EXPR_NREGS][kExprTile]
-  uint8_t* tmp_m = (uint8_t*)(tmp_v + (size_t)FB_EXPR_NREGS * kExprTile);  // [FB_EXPR_NREGS][kExprThreads] bits
-  const int tid = threadIdx.x;
-  const int64_t ntiles = (nrows + kExprTile - 1) / kExprTile;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kExprTile;
-    const int nk = (int)(nrows - row0 < kExprTile ? nrows - row0 : kExprTile);  // rows in this tile
+// one tile of kExprTile rows (kFull: no bounds checks; only the last tile of a table is partial)
+template <bool kFull>
+__device__ __forceinline__ void run_tile(const ExprProgram& P, int64_t row0, int nk, int tid, uint64_t* tmp_v,
+                                         uint8_t* tmp_m) {
+  {
     uint64_t acc[kExprItems];
     unsigned accv = kAllValid;
 #pragma unroll
@@ -90,18 +85,19 @@ fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
       // ---- operand B
       uint64_t b[kExprItems];
       unsigned bv = kAllValid;
+      if (in.kind == FB_XK_IMM) {
 #pragma unroll
-      for (int k = 0; k < kExprItems; ++k) b[k] = (uint64_t)in.imm;  // FB_XK_IMM (and a defined value otherwise)
-      if (in.kind == FB_XK_COL) {
+        for (int k = 0; k < kExprItems; ++k) b[k] = (uint64_t)in.imm;
+      } else if (in.kind == FB_XK_COL) {
         const void* p = P.col_ptr[in.b];
         switch (P.col_type[in.b]) {
-          case FB_T_I8: load_col<int8_t, false>(p, row0, tid, nk, b); break;
-          case FB_T_I16: load_col<int16_t, false>(p, row0, tid, nk, b); break;
-          case FB_T_I32: load_col<int32_t, false>(p, row0, tid, nk, b); break;
-          case FB_T_I64: load_col<int64_t, false>(p, row0, tid, nk, b); break;
-          case FB_T_U8: load_col<uint8_t, false>(p, row0, tid, nk, b); break;
-          case FB_T_F32: load_col<float, true>(p, row0, tid, nk, b); break;
-          default: load_col<int64_t, false>(p, row0, tid, nk, b); break;  // FB_T_F64: raw bits
+          case FB_T_I8: load_col<int8_t, false, kFull>(p, row0, tid, nk, b); break;
+          case FB_T_I16: load_col<int16_t, false, kFull>(p, row0, tid, nk, b); break;
+          case FB_T_I32: load_col<int32_t, false, kFull>(p, row0, tid, nk, b); break;
+          case FB_T_I64: load_col<int64_t, false, kFull>(p, row0, tid, nk, b); break;
+          case FB_T_U8: load_col<uint8_t, false, kFull>(p, row0, tid, nk, b); break;
+          case FB_T_F32: load_col<float, true, kFull>(p, row0, tid, nk, b); break;
+          default: load_col<int64_t, false, kFull>(p, row0, tid, nk, b); break;  // FB_T_F64: raw bits
         }
         const uint8_t* m = P.col_valid[in.b];
         if (m != nullptr) {
@@ -109,7 +105,7 @@ fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
 #pragma unroll
           for (int k = 0; k < kExprItems; ++k) {
             const int i = k * kExprThreads + tid;
-            if (i < nk && m[row0 + i] != 0) bv |= 1u << k;
+            if ((kFull || i < nk) && m[row0 + i] != 0) bv |= 1u << k;
           }
         }
       } else if (in.kind == FB_XK_REG) {
@@ -119,6 +115,11 @@ fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
         bv = tmp_m[in.b * kExprThreads + tid];
       } else if (in.kind == FB_XK_NULL) {
         bv = 0;
+      }
+      if (in.kind == FB_XK_NONE || in.kind == FB_XK_NULL || (!kFull && in.kind == FB_XK_COL)) {
+#pragma unroll
+        for (int k = 0; k < kExprItems; ++k)  // defined values for lanes that were not loaded
+          if (in.kind != FB_XK_COL || k * kExprThreads + tid >= nk) b[k] = 0;
       }
       if (in.flags & FB_XF_B_I2F) {
 #pragma unroll
@@ -138,17 +139,18 @@ fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
         case FB_X_OUT: {
           void* p = P.out_ptr[in.b];
           switch (P.out_type[in.b]) {
-            case FB_T_I8: store_col<int8_t, false>(p, row0, tid, nk, acc, accv); break;
-            case FB_T_I16: store_col<int16_t, false>(p, row0, tid, nk, acc, accv); break;
-            case FB_T_I32: store_col<int32_t, false>(p, row0, tid, nk, acc, accv); break;
-            case FB_T_I64: store_col<int64_t, false>(p, row0, tid, nk, acc, accv); break;
-            case FB_T_U8: store_col<uint8_t, false>(p, row0, tid, nk, acc, accv); break;
-            case FB_T_F32: store_col<float, true>(p, row0, tid, nk, acc, accv); break;
-            default: store_col<int64_t, false>(p, row0, tid, nk, acc, accv); break;  // FB_T_F64
+            case FB_T_I8: store_col<int8_t, false, kFull>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_I16: store_col<int16_t, false, kFull>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_I32: store_col<int32_t, false, kFull>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_I64: store_col<int64_t, false, kFull>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_U8: store_col<uint8_t, false, kFull>(p, row0, tid, nk, acc, accv); break;
+            case FB_T_F32: store_col<float, true, kFull>(p, row0, tid, nk, acc, accv); break;
+            default: store_col<int64_t, false, kFull>(p, row0, tid, nk, acc, accv); break;  // FB_T_F64
           }
           uint8_t* m = P.out_valid[in.b];
           if (m != nullptr) {
-            FB_ROWS(const int i = k * kExprThreads + tid; if (i < nk) m[row0 + i] = (uint8_t)((accv >> k) & 1u);)
+            FB_ROWS(const int i = k * kExprThreads + tid;
+                    if (kFull || i < nk) m[row0 + i] = (uint8_t)((accv >> k) & 1u);)
           }
           break;
         }
@@ -207,6 +209,20 @@ fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
 #undef FB_UN
 #undef FB_ROWS
     }
+  }
+}
+
+__global__ void __launch_bounds__(kExprThreads, 3)
+fb_eval_expr_kernel(const __grid_constant__ ExprProgram P, int64_t nrows) {
+  extern __shared__ __align__(16) uint64_t s_expr[];
+  uint64_t* tmp_v = s_expr;                                              // [FB_EXPR_NREGS][kExprTile]
+  uint8_t* tmp_m = (uint8_t*)(tmp_v + (size_t)FB_EXPR_NREGS * kExprTile);  // [FB_EXPR_NREGS][kExprThreads] bits
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (nrows + kExprTile - 1) / kExprTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kExprTile;
+    if (nrows - row0 >= kExprTile) run_tile<true>(P, row0, kExprTile, tid, tmp_v, tmp_m);
+    else run_tile<false>(P, row0, (int)(nrows - row0), tid, tmp_v, tmp_m);
   }
 }
 
