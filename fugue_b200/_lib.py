@@ -56,14 +56,14 @@ SIGNATURES = {
     "fb_bytes_to_bits": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp, _vp]),
     "fb_groupby_table_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "fb_groupby_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int, _vpp, _vpp, _i32p, C.c_int64,
-                                 C.c_uint32, _vp, _vp]),
+                                 C.c_uint32, _vp, _vp, _vp]),
     "fb_groupby_extract": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _i32p, _vp, _vp, _vp, _vp, _vp]),
     "fb_join_table_bytes": (C.c_size_t, [C.c_int64]),
-    "fb_join_build_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp, _vp]),
+    "fb_join_build_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp, _vp, _vp]),
     "fb_join_probe_count_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp,
-                                          C.c_int, _vp]),
+                                          C.c_int, _vp, _vp]),
     "fb_join_probe_write_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp,
-                                          C.c_int, _vp, _vp, _vp]),
+                                          C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "fb_join_mark_matched": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp]),
     "fb_exclusive_scan_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "fb_exclusive_scan_i64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_size_t]),

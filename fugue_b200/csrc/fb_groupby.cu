@@ -65,8 +65,12 @@ __device__ __forceinline__ uint64_t identity_of(int op) {
   }
 }
 
-__global__ void fb_groupby_init_kernel(uint64_t* __restrict__ table, int64_t nslots, int words,
+// initialises slots [slot0, slot0 + nslots); status is reset when it is passed
+constexpr int64_t kL2BatchBytes = 32ll << 20;  // table bytes worked on at a time (B200 L2: 126 MB)
+
+__global__ void fb_groupby_init_kernel(uint64_t* __restrict__ table_all, int64_t slot0, int64_t nslots, int words,
                                        AggSpec spec, int64_t* __restrict__ status) {
+  uint64_t* __restrict__ table = table_all + slot0 * words;
   const int64_t total = nslots * words;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -76,7 +80,7 @@ __global__ void fb_groupby_init_kernel(uint64_t* __restrict__ table, int64_t nsl
     else if (w <= spec.naggs) v = identity_of(spec.op[w - 1]);
     table[i] = v;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 4) status[threadIdx.x] = 0;
+  if (status != nullptr && blockIdx.x == 0 && threadIdx.x < 4) status[threadIdx.x] = 0;
 }
 
 __device__ __forceinline__ void apply_aggs(uint64_t* __restrict__ slot, const AggSpec& spec, int64_t row) {
@@ -132,16 +136,20 @@ __device__ __forceinline__ int64_t find_or_insert(uint64_t* __restrict__ table, 
 __global__ void __launch_bounds__(256)
 fb_groupby_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ key_valid, int64_t nrows,
                   uint64_t* __restrict__ table, int64_t capacity, int words, AggSpec spec,
-                  int64_t* __restrict__ status, FbDiv dv, int64_t region_shift) {
+                  int64_t* __restrict__ status, FbDiv dv, int64_t region_shift,
+                  const int64_t* __restrict__ part_off, int p0, int p1) {
   // region_shift < 0: one region = the whole table; else region size = 1 << region_shift
+  // part_off != nullptr: only the rows of hash partitions [p0, p1) (one launch per batch of regions)
   const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt = fb_lanemask_lt();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t nround = (nrows + stride - 1) / stride;
+  const int64_t row_lo = part_off != nullptr ? part_off[p0] : 0;
+  const int64_t row_hi = part_off != nullptr ? part_off[p1] : nrows;
+  const int64_t nround = (row_hi - row_lo + stride - 1) / stride;
   for (int64_t it = 0; it < nround; ++it) {
-    const int64_t row = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = row < nrows;
+    const int64_t row = row_lo + it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = row < row_hi;
     uint64_t key = 0;
     int64_t s = -2;
     bool special = false;
@@ -240,7 +248,7 @@ size_t fb_groupby_table_bytes(int64_t capacity, int naggs) {
 int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const uint8_t* key_valid,
                    int naggs, const void* const* val_ptrs, const uint8_t* const* val_valid,
                    const int32_t* agg_ops, int64_t capacity, uint32_t num_parts, void* table,
-                   int64_t* d_status) {
+                   int64_t* d_status, const int64_t* d_part_offsets) {
   FB_CHECK(nrows >= 0, "nrows < 0");
   FB_CHECK(capacity >= 2 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 2");
   FB_CHECK(table != nullptr && d_status != nullptr, "table/status is NULL");
@@ -259,12 +267,39 @@ int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const
   cudaStream_t st = (cudaStream_t)stream;
   const int words = slot_words(naggs);
   const int sms = fb_sm_count(dev);
-  fb_groupby_init_kernel<<<sms * 8, 256, 0, st>>>((uint64_t*)table, capacity + 2, words, spec, d_status);
+  if (nrows > 0) FB_CHECK(keys != nullptr, "keys is NULL");
+  if (num_parts > 1 && d_part_offsets != nullptr && nrows > 0) {
+    // batches of regions small enough to stay in L2 between their initialisation and the last
+    // atomic on them: a table that is initialised as a whole is back in HBM before it is used,
+    // and every probe / atomic then costs a random DRAM sector read plus a write-back
+    // (measured: 3.4 ms for 125 M rows into 10 M groups; batched: see profiles/r1_notes.md)
+    const int64_t region_bytes = ((int64_t)1 << region_shift) * words * (int64_t)sizeof(uint64_t);
+    int64_t per = kL2BatchBytes / region_bytes;
+    if (per < 1) per = 1;
+    fb_groupby_init_kernel<<<1, 64, 0, st>>>((uint64_t*)table, capacity, 2, words, spec, d_status);  // special slots
+    FB_CUDA(cudaGetLastError());
+    for (int64_t p0 = 0; p0 < (int64_t)num_parts; p0 += per) {
+      const int64_t p1 = p0 + per < (int64_t)num_parts ? p0 + per : (int64_t)num_parts;
+      const int64_t nslots = (p1 - p0) << region_shift;
+      int64_t ib = (nslots * words + 256 * 8 - 1) / (256 * 8);
+      if (ib > sms * 8) ib = sms * 8;
+      fb_groupby_init_kernel<<<(unsigned)ib, 256, 0, st>>>((uint64_t*)table, p0 << region_shift, nslots, words, spec,
+                                                          nullptr);
+      const int64_t est = nrows / num_parts * (p1 - p0) * 5 / 4 + 256;
+      int64_t gb = (est + 255) / 256;
+      if (gb > sms * 8) gb = sms * 8;
+      fb_groupby_kernel<<<(unsigned)gb, 256, 0, st>>>((const uint64_t*)keys, key_valid, nrows, (uint64_t*)table,
+                                                     capacity, words, spec, d_status, dv, region_shift,
+                                                     d_part_offsets, (int)p0, (int)p1);
+    }
+    FB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  fb_groupby_init_kernel<<<sms * 8, 256, 0, st>>>((uint64_t*)table, 0, capacity + 2, words, spec, d_status);
   FB_CUDA(cudaGetLastError());
   if (nrows > 0) {
-    FB_CHECK(keys != nullptr, "keys is NULL");
     fb_groupby_kernel<<<sms * 8, 256, 0, st>>>((const uint64_t*)keys, key_valid, nrows, (uint64_t*)table,
-                                              capacity, words, spec, d_status, dv, region_shift);
+                                              capacity, words, spec, d_status, dv, region_shift, nullptr, 0, 0);
     FB_CUDA(cudaGetLastError());
   }
   return 0;

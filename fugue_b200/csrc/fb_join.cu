@@ -21,23 +21,35 @@ struct Slot {
   unsigned long long rowp1;  // 0 = empty
 };
 
-__global__ void fb_join_clear_kernel(Slot* __restrict__ table, int64_t capacity, int64_t* __restrict__ status) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+inline int64_t l2_batch_bytes() {  // table bytes worked on at a time (B200 L2: 126 MB)
+  const char* e = getenv("FB_L2_BATCH_MB");
+  const int64_t mb = e != nullptr ? atoll(e) : 64;  // measured 32 / 64 / 96 MB: join 9.53 / 8.91 / 8.74 ms
+  return (mb > 0 ? mb : 64) << 20;
+}
+
+// clears slots [slot0, slot0 + nslots); status is reset when it is passed
+__global__ void fb_join_clear_kernel(Slot* __restrict__ table_all, int64_t slot0, int64_t nslots,
+                                     int64_t* __restrict__ status) {
+  Slot* __restrict__ table = table_all + slot0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots;
        i += (int64_t)gridDim.x * blockDim.x) {
     table[i].key = 0;
     table[i].rowp1 = 0;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 4) status[threadIdx.x] = 0;
+  if (status != nullptr && blockIdx.x == 0 && threadIdx.x < 4) status[threadIdx.x] = 0;
 }
 
 __global__ void __launch_bounds__(256)
 fb_join_build_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ valid, int64_t n,
                      Slot* __restrict__ table, int64_t capacity, int64_t* __restrict__ status, FbDiv dv,
-                     int64_t region_shift) {
+                     int64_t region_shift, const int64_t* __restrict__ part_off, int p0, int p1) {
   // region_shift >= 0: the table is cut into regions of 1 << region_shift slots, one per hash
   // partition of the (hash-partitioned) inputs, so build and probe sweep it region by region
+  // part_off != nullptr: only the rows of hash partitions [p0, p1) (one launch per batch of regions)
   const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  const int64_t row_lo = part_off != nullptr ? part_off[p0] : 0;
+  const int64_t row_hi = part_off != nullptr ? part_off[p1] : n;
+  for (int64_t i = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_hi;
        i += (int64_t)gridDim.x * blockDim.x) {
     if (valid != nullptr && valid[i] == 0) continue;  // NULL keys never match: not inserted
     const uint64_t key = keys[i];
@@ -71,12 +83,25 @@ fb_join_probe_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restric
                      const Slot* __restrict__ table, int64_t capacity, int outer,
                      int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
                      int64_t* __restrict__ out_probe, int64_t* __restrict__ out_build, FbDiv dv,
-                     int64_t region_shift) {
+                     int64_t region_shift, int64_t* __restrict__ first) {
+  // `first` (optional): the count pass records the build row of the first match (-1: none); the
+  // write pass then emits rows with exactly one output pair straight from it, without walking the
+  // table again (the common foreign-key -> unique-key join never touches the table twice)
   const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t c = 0;
     int64_t o = kWrite ? offsets[i] : 0;
+    int64_t f = -1;
+    if (kWrite && first != nullptr) {
+      const int64_t cnt = counts[i];
+      if (cnt == 0) continue;
+      if (cnt == 1) {
+        out_probe[o] = i;
+        out_build[o] = first[i];
+        continue;
+      }
+    }
     if (valid == nullptr || valid[i] != 0) {
       const uint64_t key = keys[i];
       uint64_t h = fb_fmix64(key);
@@ -93,6 +118,8 @@ fb_join_probe_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restric
           if (kWrite) {
             out_probe[o + c] = i;
             out_build[o + c] = (int64_t)r - 1;
+          } else if (c == 0) {
+            f = (int64_t)r - 1;
           }
           ++c;
         }
@@ -106,7 +133,10 @@ fb_join_probe_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restric
       }
       c = 1;
     }
-    if (!kWrite) counts[i] = c;
+    if (!kWrite) {
+      counts[i] = c;
+      if (first != nullptr) first[i] = f;
+    }
   }
 }
 
@@ -275,7 +305,8 @@ extern "C" {
 size_t fb_join_table_bytes(int64_t capacity) { return capacity > 0 ? (size_t)capacity * sizeof(Slot) : 0; }
 
 int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
-                      int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status) {
+                      int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status,
+                      const int64_t* d_part_offsets) {
   FB_CHECK(nbuild >= 0, "nbuild < 0");
   FB_CHECK(capacity >= 2 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 2");
   FB_CHECK(capacity > nbuild, "capacity must exceed the number of build rows");
@@ -287,11 +318,31 @@ int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, c
   cudaStream_t st = (cudaStream_t)stream;
   const FbDiv dv = fb_make_div(num_parts > 1 ? num_parts : 1);
   const int64_t rs = region_shift_of(capacity, num_parts);
-  fb_join_clear_kernel<<<grid_for(dev, capacity), 256, 0, st>>>((Slot*)table, capacity, d_status);
+  if (num_parts > 1 && d_part_offsets != nullptr && nbuild > 0) {
+    // clear + fill a few regions at a time, so that they are still in L2 when the inserts arrive
+    // (a table cleared as a whole is back in HBM by then: 5.5 ms for 62.5 M rows, one random DRAM
+    // sector read + write-back per insert)
+    const int64_t region_bytes = ((int64_t)1 << rs) * (int64_t)sizeof(Slot);
+    int64_t per = l2_batch_bytes() / region_bytes;
+    if (per < 1) per = 1;
+    FB_CUDA(cudaMemsetAsync(d_status, 0, 4 * sizeof(int64_t), st));
+    for (int64_t p0 = 0; p0 < (int64_t)num_parts; p0 += per) {
+      const int64_t p1 = p0 + per < (int64_t)num_parts ? p0 + per : (int64_t)num_parts;
+      const int64_t nslots = (p1 - p0) << rs;
+      fb_join_clear_kernel<<<grid_for(dev, nslots / 4 + 1), 256, 0, st>>>((Slot*)table, p0 << rs, nslots, nullptr);
+      const int64_t est = nbuild / num_parts * (p1 - p0) * 5 / 4 + 256;
+      fb_join_build_kernel<<<grid_for(dev, est), 256, 0, st>>>((const uint64_t*)keys, key_valid, nbuild, (Slot*)table,
+                                                              capacity, d_status, dv, rs, d_part_offsets, (int)p0,
+                                                              (int)p1);
+    }
+    FB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  fb_join_clear_kernel<<<grid_for(dev, capacity), 256, 0, st>>>((Slot*)table, 0, capacity, d_status);
   FB_CUDA(cudaGetLastError());
   if (nbuild > 0) {
     fb_join_build_kernel<<<grid_for(dev, nbuild), 256, 0, st>>>((const uint64_t*)keys, key_valid, nbuild,
-                                                                (Slot*)table, capacity, d_status, dv, rs);
+                                                                (Slot*)table, capacity, d_status, dv, rs, nullptr, 0, 0);
     FB_CUDA(cudaGetLastError());
   }
   return 0;
@@ -299,14 +350,15 @@ int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, c
 
 int fb_join_probe_count_u64(int dev, void* stream, int64_t nprobe, const void* keys,
                             const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
-                            const void* table, int outer, int64_t* out_counts) {
+                            const void* table, int outer, int64_t* out_counts, int64_t* out_first) {
   FB_CHECK(nprobe >= 0, "nprobe < 0");
   if (nprobe == 0) return 0;
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   fb_join_probe_kernel<false><<<grid_for(dev, nprobe), 256, 0, (cudaStream_t)stream>>>(
       (const uint64_t*)keys, key_valid, nprobe, (const Slot*)table, capacity, outer, out_counts, nullptr,
-      nullptr, nullptr, fb_make_div(num_parts > 1 ? num_parts : 1), region_shift_of(capacity, num_parts));
+      nullptr, nullptr, fb_make_div(num_parts > 1 ? num_parts : 1), region_shift_of(capacity, num_parts),
+      out_first);
   FB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -314,15 +366,16 @@ int fb_join_probe_count_u64(int dev, void* stream, int64_t nprobe, const void* k
 int fb_join_probe_write_u64(int dev, void* stream, int64_t nprobe, const void* keys,
                             const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
                             const void* table, int outer, const int64_t* offsets, int64_t* out_probe_idx,
-                            int64_t* out_build_idx) {
+                            int64_t* out_build_idx, const int64_t* counts, const int64_t* first) {
   FB_CHECK(nprobe >= 0, "nprobe < 0");
   if (nprobe == 0) return 0;
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   fb_join_probe_kernel<true><<<grid_for(dev, nprobe), 256, 0, (cudaStream_t)stream>>>(
-      (const uint64_t*)keys, key_valid, nprobe, (const Slot*)table, capacity, outer, nullptr, offsets,
-      out_probe_idx, out_build_idx, fb_make_div(num_parts > 1 ? num_parts : 1),
-      region_shift_of(capacity, num_parts));
+      (const uint64_t*)keys, key_valid, nprobe, (const Slot*)table, capacity, outer,
+      (counts != nullptr && first != nullptr) ? (int64_t*)counts : nullptr, offsets, out_probe_idx, out_build_idx,
+      fb_make_div(num_parts > 1 ? num_parts : 1), region_shift_of(capacity, num_parts),
+      (counts != nullptr && first != nullptr) ? (int64_t*)first : nullptr);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -132,11 +132,11 @@ def _radix_partition(t: B200Table, key64: torch.Tensor, kvalid: Optional[torch.T
     if kvalid is not None:
         index["kv"] = len(cols)
         cols.append(kvalid)
-    out, _ = K.partition_columns(cols, [0], num, [kvalid])
+    out, part_offsets = K.partition_columns(cols, [0], num, [kvalid])
     pt = B200Table(t.schema, [out[index[("c", i)]] for i in range(len(t.columns))],
                    [out[index[("v", i)]] if ("v", i) in index else None for i in range(len(t.columns))],
                    t.dictionaries)
-    return pt, out[0], (out[index["kv"]] if kvalid is not None else None)
+    return pt, out[0], (out[index["kv"]] if kvalid is not None else None), part_offsets
 
 
 def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
@@ -154,16 +154,17 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
         return _assemble(t1, t2, keys, out_schema, li, ri, how)
     k1, v1, k2, v2, exact = _key64(t1, t2, keys)
     parts = 0
+    po1 = po2 = None
     if min(n1, n2) >= RADIX_JOIN_MIN_ROWS:
         parts = RADIX_JOIN_PARTITIONS
-        t1, k1, v1 = _radix_partition(t1, k1, v1, parts)
-        t2, k2, v2 = _radix_partition(t2, k2, v2, parts)
+        t1, k1, v1, po1 = _radix_partition(t1, k1, v1, parts)
+        t2, k2, v2, po2 = _radix_partition(t2, k2, v2, parts)
     if how in ("semi", "left_semi", "anti", "left_anti"):
         if exact:
-            counts = K.JoinTable(k2, v2, parts).probe_counts(k1, v1, outer=False)
+            counts = K.JoinTable(k2, v2, parts, po2).probe_counts(k1, v1, outer=False)
             hit = counts > 0
         else:
-            li, ri = K.JoinTable(k2, v2, parts).probe(k1, v1, outer=False)
+            li, ri = K.JoinTable(k2, v2, parts, po2).probe(k1, v1, outer=False)
             ok = _verify(t1, t2, keys, li, ri)
             hit = torch.zeros(n1, dtype=torch.bool, device=dev)
             hit[li[ok]] = True
@@ -173,12 +174,12 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
         return B200DataFrame(B200Table(out_schema, cols, valid, t1.dictionaries))
     if how == "right_outer":
         # probe with the right side so that every right row appears
-        tab = K.JoinTable(k1, v1, parts)
+        tab = K.JoinTable(k1, v1, parts, po1)
         ri, li = tab.probe(k2, v2, outer=True)
         if not exact:
             li, ri = _drop_collisions(t1, t2, keys, li, ri, outer_side="right")
         return _assemble(t1, t2, keys, out_schema, li, ri, how)
-    tab = K.JoinTable(k2, v2, parts)
+    tab = K.JoinTable(k2, v2, parts, po2)
     li, ri = tab.probe(k1, v1, outer=how in ("left_outer", "full_outer"))
     if not exact:
         li, ri = _drop_collisions(t1, t2, keys, li, ri, outer_side="left" if how != "inner" else None)

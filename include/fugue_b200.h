@@ -157,6 +157,10 @@ int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void* const* sr
  *                      num_parts > 1 (power of two): the input was hash-partitioned on the key into
  *                      num_parts partitions with fb_partition_cols; keys of partition p then live in
  *                      table region p, so the table is swept region by region (L2-resident atomics).
+ *                      d_part_offsets (device, num_parts + 1 row offsets of the partitions, may be
+ *                      NULL): the table is then initialised and filled a few regions at a time
+ *                      (one launch pair per 32 MB of table), so the regions are still in L2 when
+ *                      their atomics arrive.
  *                      d_status[0] != 0 afterwards means the table was too small: retry with
  *                      a larger power-of-two `capacity`.  Value columns are 8 bytes wide.
  * fb_groupby_extract : compacts the groups into out_keys / out_key_valid / out_aggs[a]
@@ -178,7 +182,7 @@ size_t fb_groupby_table_bytes(int64_t capacity, int naggs);
 int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const uint8_t* key_valid,
                    int naggs, const void* const* val_ptrs, const uint8_t* const* val_valid,
                    const int32_t* agg_ops, int64_t capacity, uint32_t num_parts, void* table,
-                   int64_t* d_status);
+                   int64_t* d_status, const int64_t* d_part_offsets);
 int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const int32_t* agg_ops,
                        const void* table, void* out_keys, uint8_t* out_key_valid,
                        void* const* d_out_aggs, int64_t* d_status);
@@ -194,8 +198,13 @@ int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const
  *   on the key with fb_partition_cols into num_parts partitions; the table is then used region by
  *   region (one region per partition) and stays L2-resident (radix join).
  *   fb_join_build_u64        multimap of the build side (capacity: power of two > nbuild,
- *                            table: fb_join_table_bytes(capacity)); d_status[0] != 0: overflow
- *   fb_join_probe_count_u64  matches per probe row (outer != 0: unmatched rows count 1)
+ *                            table: fb_join_table_bytes(capacity)); d_status[0] != 0: overflow;
+ *                            d_part_offsets (device, num_parts + 1, may be NULL): clear + fill a
+ *                            few regions at a time so that they stay in L2
+ *   fb_join_probe_count_u64  matches per probe row (outer != 0: unmatched rows count 1); out_first
+ *                            (optional): build row of the first match, -1 if none - handed back to
+ *                            fb_join_probe_write_u64 (with the counts) it lets rows with one output
+ *                            pair skip the second walk of the table
  *   fb_exclusive_scan_i64    counts -> output offsets (out[n] entries) and the total
  *   fb_join_probe_write_u64  (probe_row, build_row) index pairs; build_row = -1 for the
  *                            NULL-extended row of an outer join
@@ -205,14 +214,15 @@ int fb_groupby_extract(int dev, void* stream, int64_t capacity, int naggs, const
  * --------------------------------------------------------------------------- */
 size_t fb_join_table_bytes(int64_t capacity);
 int fb_join_build_u64(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
-                      int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status);
+                      int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status,
+                      const int64_t* d_part_offsets);
 int fb_join_probe_count_u64(int dev, void* stream, int64_t nprobe, const void* keys,
                             const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
-                            const void* table, int outer, int64_t* out_counts);
+                            const void* table, int outer, int64_t* out_counts, int64_t* out_first);
 int fb_join_probe_write_u64(int dev, void* stream, int64_t nprobe, const void* keys,
                             const uint8_t* key_valid, int64_t capacity, uint32_t num_parts,
                             const void* table, int outer, const int64_t* offsets, int64_t* out_probe_idx,
-                            int64_t* out_build_idx);
+                            int64_t* out_build_idx, const int64_t* counts, const int64_t* first);
 int fb_join_mark_matched(int dev, void* stream, const int64_t* build_idx, int64_t n, uint8_t* matched);
 size_t fb_exclusive_scan_scratch_bytes(int64_t n);
 int fb_exclusive_scan_i64(int dev, void* stream, int64_t n, const int64_t* in, int64_t* out,

@@ -160,3 +160,22 @@ def test_multi_column_group_by(engine):
     a = ArrayDataFrame([["x", 1, 1.0], ["x", 2, 2.0], ["y", 1, 3.0], ["x", 1, 4.0], [None, 1, 5.0]], "k:str,j:int,v:double")
     res = fa.aggregate(a, ["k", "j"], s=ff.sum(col("v")), engine=engine)
     df_eq(res, [["x", 1, 5.0], ["x", 2, 2.0], ["y", 1, 3.0], [None, 1, 5.0]], "k:str,j:int,s:double", throw=True)
+
+
+def test_batched_table_initialisation_gives_the_same_groups(monkeypatch):
+    """fb_groupby_u64 with partition offsets: init + aggregate in L2-sized batches of regions."""
+    from fugue_b200 import kernels as K
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(3)
+    n = 6_000_000
+    keys = torch.randint(0, 700_000, (n,), dtype=torch.int64, device=dev, generator=g)
+    v = torch.randint(-1000, 1000, (n,), dtype=torch.int64, device=dev, generator=g)
+    ref = K.groupby_u64(keys, None, [v, None], [None, None], [K.AGG_SUM_I64, K.AGG_COUNT])
+    monkeypatch.setattr(K, "GROUPBY_BATCHED", True)
+    got = K.groupby_u64(keys, None, [v, None], [None, None], [K.AGG_SUM_I64, K.AGG_COUNT])
+    assert ref[3] == got[3]
+    o1, o2 = torch.argsort(ref[0][:ref[3]]), torch.argsort(got[0][:got[3]])
+    assert torch.equal(ref[0][:ref[3]][o1], got[0][:got[3]][o2])
+    for a, b in zip(ref[2], got[2]):
+        assert torch.equal(a[:ref[3]][o1], b[:got[3]][o2])
