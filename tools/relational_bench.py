@@ -65,6 +65,23 @@ def measure(device_index: int = 0):
     ms = timeit(lambda: e.filter(T, cond))
     out["filter"] = {"rows": n, "kept": kept, "ms": ms, "rows_per_s": n / ms * 1e3,
                      "alg_GBps": (16 * n + 2 * 24 * kept) / ms / 1e6}      # predicate columns + gather of kept rows
+    del key, v0, v1, T
+    # skewed variant of the headline workload: keys Zipf(s = 1.0) over 2^16 values
+    n = 100_000_000
+    w = 1.0 / torch.arange(1, (1 << 16) + 1, dtype=torch.float64, device=dev)
+    cdf = torch.cumsum(w, 0) / w.sum()
+    zkey = torch.searchsorted(cdf, torch.rand(n, dtype=torch.float64, device=dev, generator=g)).clamp_(max=(1 << 16) - 1)
+    cols = [zkey] + [torch.randint(-(2**62), 2**62, (n,), dtype=torch.int64, device=dev, generator=g) for _ in range(3)] \
+        + [torch.randn(n, dtype=torch.float64, device=dev, generator=g) for _ in range(4)]
+    outs = [torch.empty_like(c) for c in cols]
+    scratch = torch.empty(K.partition_scratch_bytes(dev, n, 256) + 256, dtype=torch.uint8, device=dev)
+    off = torch.empty(257, dtype=torch.int64, device=dev)
+    ms = timeit(lambda: K.partition_columns(cols, [0], 256, out=outs, scratch=scratch, offsets=off), reps=5)
+    sizes = (off[1:] - off[:-1])
+    pid = K.partition_ids([outs[0]], 256).long()
+    ok = bool((pid == torch.repeat_interleave(torch.arange(256, device=dev), sizes)).all()) and int(off[-1]) == n
+    out["transform_zipf_s1"] = {"rows": n, "ms": ms, "rows_per_s": n / ms * 1e3, "largest_partition_share":
+                                float(sizes.max()) / n, "every_row_in_its_partition": ok}
     return out
 
 
