@@ -148,8 +148,7 @@ class DistributedB200Engine(B200ExecutionEngine):
             f"num_partitions={num}: one radix pass handles up to {K.MAX_PARTITIONS} partitions"))
         assert_or_throw(num >= self._world, ValueError(
             f"num_partitions={num} must be >= the number of GPUs ({self._world})"))
-        assert_or_throw(len(t.dictionaries) == 0, NotImplementedError(
-            "string (dictionary-encoded) columns need a global dictionary before a multi-GPU shuffle"))
+        t = self._globalize_dictionaries(t)  # string columns: one code space on all ranks
         dev = t.device
         kidx = [t.schema.index_of_key(k) for k in keys]
         kvalid = [t.valid[i] for i in kidx]
@@ -228,6 +227,32 @@ class DistributedB200Engine(B200ExecutionEngine):
         res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
         res.global_partition_range = (plan.lo, plan.hi)  # which physical partitions this GPU owns
         return B200DataFrame(res)
+
+    def _globalize_dictionaries(self, t: B200Table) -> B200Table:
+        """String columns are dictionary encoded per rank; before rows travel (and before codes are
+        hashed as partition keys) every rank re-codes them against the union dictionary: the
+        dictionaries are gathered on the host (small), the union is taken in first-appearance order
+        over ranks (identical everywhere), and the codes are remapped on the device."""
+        if len(t.dictionaries) == 0:
+            return t
+        import pyarrow as pa
+        import pyarrow.compute as pc
+
+        names = sorted(t.dictionaries)
+        local = {k: t.dictionaries[k].to_pylist() for k in names}
+        gathered: List[Any] = [None] * self._world
+        dist.all_gather_object(gathered, local, group=self._group)
+        cols = list(t.columns)
+        dicts: Dict[str, Any] = {}
+        for k in names:
+            union = pc.unique(pa.array([x for g in gathered for x in g[k]], type=pa.string()))
+            pos = pc.index_in(t.dictionaries[k], value_set=union).to_numpy(zero_copy_only=False).astype("int32")
+            i = t.schema.index_of_key(k)
+            if len(pos) > 0:
+                m = torch.from_numpy(pos).to(t.device)
+                cols[i] = m[cols[i].long().clamp_(min=0)].contiguous()
+            dicts[k] = union
+        return B200Table(t.schema, cols, t.valid, dicts, t.offsets, t.partition_keys)
 
     def _repartition_nccl(self, t: B200Table, keys: List[str], cols: List[torch.Tensor],
                           vpos: Dict[int, int], plan_local: Any, plan: ExchangePlan) -> B200DataFrame:

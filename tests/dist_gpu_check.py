@@ -86,6 +86,22 @@ def check_relational(eng, rank, world, dev):
         assert np.allclose(got["m2"].to_numpy(), exp["m2"].to_numpy(dtype="float64"), rtol=1e-9)
         assert np.allclose(got["mx"].to_numpy(), exp["mx"].to_numpy(dtype="float64"), rtol=1e-12)
         print(f"dist select ok: {len(got)} groups")
+    # string key column: per-rank dictionaries are unified before the shuffle, so equal strings of
+    # different ranks land in the same group
+    words = [f"w{i:03d}" for i in range(50)]
+    rng = np.random.default_rng(77 + rank)
+    sdf = pd.DataFrame({"k": rng.choice(words[rank * 5:rank * 5 + 30], 20_000), "v": rng.integers(0, 100, 20_000)})
+    sagg = eng.aggregate(eng.to_df(sdf), PartitionSpec(by=["k"]), [ff.sum(col("v")).alias("s"),
+                                                                   ff.count(all_cols()).alias("c")])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (sagg.as_pandas(), sdf))
+    if rank == 0:
+        got = pd.concat([g[0] for g in gathered], ignore_index=True).sort_values("k").reset_index(drop=True)
+        allrows = pd.concat([g[1] for g in gathered], ignore_index=True)
+        exp = allrows.groupby("k").agg(s=("v", "sum"), c=("v", "size")).reset_index().sort_values("k").reset_index(drop=True)
+        assert got["k"].is_unique and list(got["k"]) == list(exp["k"])
+        assert np.array_equal(got["s"].to_numpy(), exp["s"].to_numpy()) and np.array_equal(got["c"].to_numpy(), exp["c"].to_numpy())
+        print(f"dist string keys ok: {len(got)} groups")
 
 
 def main():
