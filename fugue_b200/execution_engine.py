@@ -283,11 +283,13 @@ class B200ExecutionEngine:
         single-device table already is one physical partition."""
         edf = self.to_df(df)
         keys = partition_spec.partition_by
-        if len(keys) == 0:
-            return edf
         t: B200Table = edf.native
         for k in keys:
             assert_or_throw(k in t.schema, lambda: KeyError(f"{k} not in {t.schema}"))
+        if partition_spec.algo in ("even", "rand"):
+            return self._repartition_even_rand(edf, partition_spec)
+        if len(keys) == 0:
+            return edf
         num = self._num_partitions(partition_spec, t.num_rows)
         assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
             f"num_partitions={num}: one radix pass handles up to {K.MAX_PARTITIONS} partitions"))
@@ -307,6 +309,57 @@ class B200ExecutionEngine:
         ncol = len(t.columns)
         valid = [out[vpos[i]] if i in vpos else None for i in range(ncol)]
         res = B200Table(t.schema, out[:ncol], valid, t.dictionaries, offsets, list(keys))
+        rdf = B200DataFrame(res)
+        if edf.has_metadata:
+            rdf.reset_metadata(edf.metadata)
+        return rdf
+
+    def _repartition_even_rand(self, edf: B200DataFrame, spec: PartitionSpec) -> B200DataFrame:
+        """``algo="even"`` / ``"rand"`` with the meaning the distributed backends give them
+        (fugue_dask/_utils.py:62-121): without keys the rows are cut into ``num`` equal contiguous
+        ranges (rand: after a random permutation); with keys the distinct key tuples are numbered (in
+        key order; rand: in random order) and spread evenly over ``num`` partitions, ``num <= 0``
+        meaning one partition per group.  Built from the device sort (radix passes) and gathers."""
+        from collections import OrderedDict
+
+        from . import sort as S
+
+        t: B200Table = edf.native
+        keys = list(spec.partition_by)
+        n, dev = t.num_rows, t.device
+        rand = spec.algo == "rand"
+        num = spec.get_num_partitions(**{KEYWORD_ROWCOUNT: lambda: n,
+                                         KEYWORD_PARALLELISM: lambda: self.get_current_parallelism()})
+        gen = torch.Generator(device=dev).manual_seed(int(self._conf.get("fugue.b200.rand.seed", 0)))
+
+        def even_offsets(total: int, parts: int) -> torch.Tensor:
+            return (torch.arange(parts + 1, dtype=torch.int64, device=dev) * total) // max(parts, 1)
+
+        if len(keys) == 0:
+            if num <= 1 or n == 0:
+                return edf if not rand or n == 0 else B200DataFrame(
+                    S.take_rows(t, torch.randperm(n, device=dev, generator=gen)))
+            assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(f"num_partitions={num}"))
+            src = S.take_rows(t, torch.randperm(n, device=dev, generator=gen)) if rand else t
+            res = B200Table(src.schema, src.columns, src.valid, src.dictionaries, even_offsets(n, num), [])
+        else:
+            if n == 0:
+                return edf
+            st = S.sort_table(t, OrderedDict((k, True) for k in keys), "first")
+            gid = torch.cumsum(S.group_starts(st, keys).to(torch.int64), 0) - 1   # dense group number per row
+            ngroups = int(gid[-1].item()) + 1
+            if num <= 0:
+                num = ngroups
+            assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
+                f"num_partitions={num}: at most {K.MAX_PARTITIONS} physical partitions"))
+            if rand:
+                gid = torch.randperm(ngroups, device=dev, generator=gen)[gid]
+            pid = (gid * num) // ngroups
+            if rand:  # groups are no longer in partition order: one stable radix pass per varying byte
+                spid, idx = S._radix_sort_pairs(pid.contiguous(), torch.arange(n, dtype=torch.int64, device=dev))
+                st, pid = S.take_rows(st, idx), spid
+            offsets = torch.searchsorted(pid.contiguous(), torch.arange(num + 1, dtype=torch.int64, device=dev))
+            res = B200Table(st.schema, st.columns, st.valid, st.dictionaries, offsets, keys)
         rdf = B200DataFrame(res)
         if edf.has_metadata:
             rdf.reset_metadata(edf.metadata)

@@ -242,3 +242,55 @@ def test_streaming_transform_matches_plain_path(engine):
     t3 = t3.set_column(2, "v0", pa.array(pdf3.v0.where(pdf3.v0.notna(), None).tolist(), type=pa.float64()))
     got3 = fa.transform(t3, identity, schema="*", partition=spec, engine=engine, as_local=True)
     assert len(got3) == n and int(got3.v0.isna().sum()) == 1
+
+
+def test_even_and_rand_partition_algos():
+    """algo="even"/"rand" (fugue_dask/_utils.py:62-121): equal row ranges without keys; with keys the
+    distinct key tuples are spread evenly over the partitions (num <= 0: one partition per group)."""
+    e = fa.make_execution_engine("b200")
+    rng = np.random.default_rng(4)
+    n = 100_003
+    pdf = pd.DataFrame({"k": rng.integers(0, 37, n), "j": rng.integers(0, 3, n).astype("int32"),
+                        "v": np.arange(n, dtype="int64")})
+    edf = e.to_df(pdf)
+
+    def parts(df):
+        t = df.native
+        off = t.offsets.cpu().numpy()
+        host = df.as_pandas()
+        return [host.iloc[off[i]:off[i + 1]] for i in range(len(off) - 1)], host
+
+    # no keys, even: contiguous equal ranges in input order
+    ps, host = parts(e.repartition(edf, PartitionSpec(algo="even", num=7)))
+    assert len(ps) == 7 and max(len(p) for p in ps) - min(len(p) for p in ps) <= 1
+    assert np.array_equal(host["v"].to_numpy(), pdf["v"].to_numpy())
+    # no keys, rand: same multiset, shuffled, equal sizes, reproducible
+    r1 = e.repartition(edf, PartitionSpec(algo="rand", num=7))
+    ps, host = parts(r1)
+    assert max(len(p) for p in ps) - min(len(p) for p in ps) <= 1
+    assert not np.array_equal(host["v"].to_numpy(), pdf["v"].to_numpy())
+    assert np.array_equal(np.sort(host["v"].to_numpy()), pdf["v"].to_numpy())
+    assert np.array_equal(parts(e.repartition(edf, PartitionSpec(algo="rand", num=7)))[1]["v"].to_numpy(),
+                          host["v"].to_numpy())
+    # keys, even: groups in key order, spread evenly; every key in exactly one partition
+    for algo in ("even", "rand"):
+        ps, host = parts(e.repartition(edf, PartitionSpec(algo=algo, by=["k", "j"], num=10)))
+        assert len(ps) == 10 and sum(len(p) for p in ps) == n
+        groups = [set(map(tuple, p[["k", "j"]].drop_duplicates().to_numpy())) for p in ps]
+        assert sum(len(g) for g in groups) == len(set().union(*groups)) == 37 * 3     # co-located, none lost
+        assert max(len(g) for g in groups) - min(len(g) for g in groups) <= 1        # evenly by group count
+        assert np.array_equal(np.sort(host["v"].to_numpy()), pdf["v"].to_numpy())
+        if algo == "even":
+            firsts = [min(g) for g in groups]
+            assert firsts == sorted(firsts)                                           # key order kept
+    # num <= 0 with keys: one partition per group
+    ps, _ = parts(e.repartition(edf, PartitionSpec(algo="even", by=["k"])))
+    assert len(ps) == 37 and all(p["k"].nunique() == 1 for p in ps)
+    # a keyed transform under algo="even" sees every logical partition once
+    def count(df: pd.DataFrame) -> pd.DataFrame:
+        return pd.DataFrame({"k": [df["k"].iloc[0]], "c": [len(df)]})
+
+    out = fa.transform(pdf, count, schema="k:long,c:long", partition=PartitionSpec(algo="even", by=["k"], num=5),
+                       engine=e, as_local=True)
+    exp = pdf.groupby("k").size().reset_index(name="c")
+    assert np.array_equal(out.sort_values("k")["c"].to_numpy(), exp["c"].to_numpy())
