@@ -392,8 +392,9 @@ class B200ExecutionEngine:
         from .column import AggFuncExpr, _NamedColumnExpr, _WildcardExpr
 
         return all(isinstance(a, AggFuncExpr) and a.as_type is None and not a.is_distinct
-                   and a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG")
+                   and a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST", "LAST")
                    and isinstance(a.arg, (_NamedColumnExpr, _WildcardExpr)) and a.arg.as_type is None
+                   and not (a.func in ("FIRST", "LAST") and isinstance(a.arg, _WildcardExpr))
                    for a in agg_cols)
 
     def _aggregate_named(self, df: Any, partition_spec: Optional[PartitionSpec],
@@ -450,6 +451,7 @@ class B200ExecutionEngine:
                 key_slots.append((add(kbits, m, K.AGG_MIN_I64), add(kbits, m, K.AGG_MAX_I64),
                                   add(None, m, K.AGG_COUNT) if m is not None else None))
             rows_slot = add(None, None, K.AGG_COUNT)
+        rowno: Any = None
         for a in agg_cols:
             fn, arg = a.func, a.arg.name
             if fn == "COUNT":
@@ -461,6 +463,15 @@ class B200ExecutionEngine:
                 continue
             ci = t.schema.index_of_key(arg)
             c, m, tp = t.columns[ci], t.valid[ci], t.schema.types[ci]
+            if fn in ("FIRST", "LAST"):
+                # first / last non-NULL value in input row order: MIN / MAX of the row number over the
+                # rows where the value is not NULL, then one gather (works for every column type)
+                if rowno is None:
+                    rowno = torch.arange(n, dtype=torch.int64, device=dev)
+                cnt = add(None, m, K.AGG_COUNT)
+                plan.append((a.output_name, "pick", add(rowno, m, K.AGG_MIN_I64 if fn == "FIRST" else K.AGG_MAX_I64),
+                             tp, (cnt, ci)))
+                continue
             assert_or_throw(arg not in t.dictionaries, NotImplementedError(f"{fn} on a string column"))
             is_f = pa.types.is_floating(tp)
             c8 = c if c.element_size() == 8 else c.to(torch.float64 if is_f else torch.int64)
@@ -518,8 +529,19 @@ class B200ExecutionEngine:
             fields.append(pa.field(keys[0], ktype))
             cols.append(out_k.contiguous())
             valids.append(gvalid)
+        dicts = {k: t.dictionaries[k] for k in keys if k in t.dictionaries}
         for name, kind, slot, tp, nn in plan:
             raw = gaggs[slot]
+            if kind == "pick":
+                cnt, ci = nn
+                has = gaggs[cnt] > 0
+                idx = torch.where(has, raw, torch.zeros_like(raw))
+                fields.append(pa.field(name, tp))
+                cols.append(t.columns[ci][idx].contiguous() if n > 0 else t.columns[ci][:0])
+                valids.append(has.to(torch.uint8))
+                if t.schema.names[ci] in t.dictionaries:
+                    dicts[name] = t.dictionaries[t.schema.names[ci]]
+                continue
             v = None if nn is None else (gaggs[nn] > 0).to(torch.uint8)
             if kind == "avg":
                 cnt = gaggs[nn].to(torch.float64)
@@ -537,7 +559,6 @@ class B200ExecutionEngine:
             fields.append(pa.field(name, tp))
             cols.append(col.contiguous())
             valids.append(v)
-        dicts = {k: t.dictionaries[k] for k in keys if k in t.dictionaries}
         return B200DataFrame(B200Table(Schema(fields), cols, valids, dicts))
 
     # ---- select / filter / assign (K8) ---------------------------------------------------
@@ -598,7 +619,7 @@ class B200ExecutionEngine:
             if uid in agg_col:
                 continue
             assert_or_throw(not a.is_distinct, NotImplementedError(f"DISTINCT aggregation {a}"))
-            assert_or_throw(a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG"),
+            assert_or_throw(a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST", "LAST"),
                             NotImplementedError(f"aggregation {a.func}"))
             assert_or_throw(not is_agg(a.arg), ValueError(f"nested aggregation {a}"))
             out = f"__fb_a{len(agg_col)}"

@@ -258,3 +258,16 @@ def test_sql_text_reaches_the_device_path(e):
         fa.raw_sql("SELECT key, tag, SUM(v0) AS s FROM", pdf, "GROUP BY key", engine=e)
     with raises(NotImplementedError):
         fa.raw_sql("SELECT key FROM", pdf, "UNION SELECT key FROM", pdf, engine=e)
+
+
+def test_first_last_aggregates(e):
+    a = ArrayDataFrame([[1, None, "x"], [1, 5.0, None], [1, 7.0, "y"], [2, None, None], [None, 3.0, "z"], [None, 4.0, "w"]],
+                       "k:long,v:double,s:str")
+    b = fa.aggregate(a, "k", f=ff.first(col("v")), l=ff.last(col("v")), fs=ff.first(col("s")), ls=ff.last(col("s")),
+                     engine=e)
+    df_eq(b, [[1, 5.0, 7.0, "x", "y"], [2, None, None, None, None], [None, 3.0, 4.0, "z", "w"]],
+          "k:long,f:double,l:double,fs:str,ls:str", throw=True)
+    b = fa.select(a, (ff.last(col("v")) - ff.first(col("v"))).alias("d"), engine=e)
+    df_eq(b, [[-1.0]], "d:double", throw=True)
+    got = fa.raw_sql("SELECT k, FIRST(v) AS f FROM", a, "WHERE v IS NOT NULL GROUP BY k", engine=e, as_fugue=True)
+    df_eq(got, [[1, 5.0], [None, 3.0]], "k:long,f:double", throw=True)
