@@ -9,7 +9,8 @@ entry-point group ``fugue.plugins`` (fugue/constants.py:7, setup.py:99-107).
 Design: subclass ``NativeExecutionEngine`` for everything outside the hot path (exactly how
 ``fugue_duckdb`` reuses ``PandasMapEngine``, fugue_duckdb/execution_engine.py:200-201) and
 override the facets SURVEY.md section 8 puts on the path: ``map_engine`` (map_dataframe),
-``repartition``, ``join`` (inner), ``aggregate``.
+``repartition``, ``join``, ``aggregate`` and ``select`` (hence ``filter`` / ``assign``), translating the
+reference's column expressions node by node into ``fugue_b200.column``.
 """
 from typing import Any, Callable, Dict, List, Optional
 
@@ -187,13 +188,70 @@ class FugueB200ExecutionEngine(NativeExecutionEngine):
         return self.to_df(df)
 
     def join(self, df1: FDataFrame, df2: FDataFrame, how: str, on: Optional[List[str]] = None) -> FDataFrame:
-        if how.lower() == "inner" and hasattr(self._b200, "join"):
-            try:
-                res = self._b200.join(self._to_device(df1), self._to_device(df2), how, on)
-                return FugueB200DataFrame(res.native)
-            except NotImplementedError:
-                pass
-        return super().join(self.to_df(df1).as_local(), self.to_df(df2).as_local(), how, on)
+        try:  # every join type runs on the device (fugue_b200/join.py); exotic column types fall back
+            res = self._b200.join(self._to_device(df1), self._to_device(df2), how, on)
+            return FugueB200DataFrame(res.native)
+        except NotImplementedError:
+            return super().join(self.to_df(df1).as_local(), self.to_df(df2).as_local(), how, on)
+
+    # ``filter`` and ``assign`` of the base class are written in terms of ``select``
+    # (fugue/execution/execution_engine.py:808-887), so these two overrides put all four on the device
+    def select(self, df: FDataFrame, cols: Any, where: Any = None, having: Any = None) -> FDataFrame:
+        from .column import SelectColumns as _SelectColumns
+
+        try:
+            mine = _SelectColumns(*[_translate_expr(c) for c in cols.all_cols], arg_distinct=cols.is_distinct)
+            res = self._b200.select(self._to_device(df), mine,
+                                    where=None if where is None else _translate_expr(where),
+                                    having=None if having is None else _translate_expr(having))
+            return FugueB200DataFrame(res.native)
+        except NotImplementedError:
+            return super().select(self.to_df(df).as_local(), cols, where=where, having=having)
+
+    def aggregate(self, df: FDataFrame, partition_spec: Optional[FPartitionSpec], agg_cols: List[Any]) -> FDataFrame:
+        try:
+            res = self._b200.aggregate(self._to_device(df),
+                                       None if partition_spec is None else _to_spec(partition_spec),
+                                       [_translate_expr(c) for c in agg_cols])
+            return FugueB200DataFrame(res.native)
+        except NotImplementedError:
+            return super().aggregate(self.to_df(df).as_local(), partition_spec, agg_cols)
+
+
+def _translate_expr(e: Any) -> Any:
+    """``fugue.column`` expression tree -> the same tree in ``fugue_b200.column`` (the two DSLs have the
+    same node kinds: named / wildcard / literal / function / unary / binary / aggregation)."""
+    from fugue.column import expressions as fe
+    from fugue.column import functions as ff
+
+    from . import column as bc
+
+    if not isinstance(e, fe.ColumnExpr):
+        return e
+    if isinstance(e, fe._WildcardExpr):
+        return bc.all_cols()
+    if isinstance(e, fe._NamedColumnExpr):
+        res: Any = bc.col(e.name)
+    elif isinstance(e, fe._LiteralColumnExpr):
+        res = bc.lit(e.value)
+    elif isinstance(e, ff._UnaryAggFuncExpr):
+        same = isinstance(e, ff._SameTypeUnaryAggFuncExpr)
+        cls = bc._SameTypeAggFuncExpr if same else bc.AggFuncExpr
+        res = cls(e.func, _translate_expr(e.args[0]), arg_distinct=e.is_distinct)
+    elif isinstance(e, fe._UnaryOpExpr):
+        arg = _translate_expr(e.col)
+        res = {"-": lambda: -arg, "~": lambda: ~arg, "IS_NULL": arg.is_null, "NOT_NULL": arg.not_null}[e.op]()
+    elif isinstance(e, fe._BinaryOpExpr):
+        kind = bc._BoolBinaryOpExpr if isinstance(e, fe._BoolBinaryOpExpr) else bc._BinaryOpExpr
+        res = kind(e.op, _translate_expr(e.left), _translate_expr(e.right))
+    elif isinstance(e, fe._FuncExpr):
+        res = bc.function(e.func, *[_translate_expr(a) for a in e.args], arg_distinct=e.is_distinct,
+                          **{k: _translate_expr(v) for k, v in e.kwargs.items()})
+    else:
+        raise NotImplementedError(f"can't translate {type(e).__name__}")
+    if e.as_type is not None:
+        res = res.cast(e.as_type)
+    return res.alias(e.as_name) if e.as_name != "" else res
 
 
 @infer_execution_engine.candidate(
