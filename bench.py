@@ -268,46 +268,54 @@ def run_b200(args):
     e2e = None
     h2d = d2h = 0
     if not args.no_e2e:
-        import pyarrow as pa
+        try:
+            import pyarrow as pa
 
-        host_cols = []
-        for c in cols:
-            h = torch.empty(c.shape, dtype=c.dtype, pin_memory=True)
-            h.copy_(c)
-            host_cols.append(h)
-        torch.cuda.synchronize(dev)
-        names = Schema(SCHEMA).names
-        pa_types = Schema(SCHEMA).types
-        arrays = [pa.Array.from_buffers(tp, n, [None, pa.py_buffer(h.numpy())])
-                  for h, tp in zip(host_cols, pa_types)]
-        host_table = pa.Table.from_arrays(arrays, names=names)
-        h2d = sum(h.numel() * h.element_size() for h in host_cols)
-        d2h = h2d
-        from fugue_b200.dataframe import ArrowDataFrame
+            host_cols = []
+            for c in cols:
+                h = torch.empty(c.shape, dtype=c.dtype, pin_memory=True)
+                h.copy_(c)
+                host_cols.append(h)
+            torch.cuda.synchronize(dev)
+            names = Schema(SCHEMA).names
+            pa_types = Schema(SCHEMA).types
+            arrays = [pa.Array.from_buffers(tp, n, [None, pa.py_buffer(h.numpy())])
+                      for h, tp in zip(host_cols, pa_types)]
+            host_table = pa.Table.from_arrays(arrays, names=names)
+            h2d = sum(h.numel() * h.element_size() for h in host_cols)
+            d2h = h2d
+            from fugue_b200.dataframe import ArrowDataFrame
 
-        host_df = ArrowDataFrame(host_table)
-        del df_in, table
-        e2e_steps = max(1, min(steps, 3))
+            host_df = ArrowDataFrame(host_table)
+            del df_in, table
+            e2e_steps = max(1, min(steps, 3))
 
-        def e2e_step():
-            res = fa.transform(host_df, identity, schema="*", partition=spec, engine=engine, as_local=True)
-            return res.count()
+            def e2e_step():
+                res = fa.transform(host_df, identity, schema="*", partition=spec, engine=engine, as_local=True)
+                return res.count()
 
-        for _ in range(2):
-            e2e_step()
-        sync()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            cnt = e2e_step()
-        sync()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_rows / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": d2h * world, "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "fugue_b200.api.transform(host pyarrow table in pinned memory, as_local=True)"}
+            for _ in range(2):
+                e2e_step()
+            sync()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                cnt = e2e_step()
+            sync()
+            dt = (time.perf_counter() - t0) / e2e_steps
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": total_rows / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
+                   "d2h_bytes_per_step": d2h * world, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                   "api": "fugue_b200.api.transform(host pyarrow table in pinned memory, as_local=True)"}
+        except Exception as ex:  # the device-resident numbers above stay valid; say why e2e is missing
+            e2e = {"error": repr(ex)[:300]}
+            if world > 1:
+                try:
+                    dist.barrier()
+                except Exception:
+                    pass
 
     if rank == 0:
         cpu = None
