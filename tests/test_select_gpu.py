@@ -271,3 +271,33 @@ def test_first_last_aggregates(e):
     df_eq(b, [[-1.0]], "d:double", throw=True)
     got = fa.raw_sql("SELECT k, FIRST(v) AS f FROM", a, "WHERE v IS NOT NULL GROUP BY k", engine=e, as_fugue=True)
     df_eq(got, [[1, 5.0], [None, 3.0]], "k:long,f:double", throw=True)
+
+
+def test_full_size_properties_100m_rows(e):
+    """Size-independent checks at the BASELINE row count: linearity of an integer projection, the
+    three-way split of a nullable predicate, and filter == mask semantics."""
+    from fugue_b200.dataframe import B200DataFrame
+    from fugue_b200.table import B200Table
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(9)
+    n = 100_000_000
+    a = torch.randint(-1000, 1000, (n,), dtype=torch.int64, device=dev, generator=g)
+    x = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    xv = (torch.rand(n, device=dev, generator=g) > 0.1).to(torch.uint8)        # 10 % NULLs in x
+    t = B200DataFrame(B200Table("a:long,x:double", [a, x], [None, xv]))
+    out = e.select(t, SelectColumns((col("a") * 2 + 1).alias("y"), (col("x") > 0).alias("p"),
+                                    ff.coalesce(col("x"), 0.0).alias("c"))).native
+    assert int(out.column("y").sum()) == 2 * int(a.sum()) + n                    # exact integer arithmetic
+    pv = out.valid[out.schema.index_of_key("p")]
+    assert pv is not None and torch.equal(pv, xv)                                # NULL propagates through >
+    assert out.valid[out.schema.index_of_key("c")] is None                       # COALESCE(x, 0.0) is never NULL
+    assert torch.equal(out.column("c"), torch.where(xv.bool(), x, torch.zeros_like(x)))
+    n_true = e.filter(t, col("x") > 0).count()
+    n_false = e.filter(t, ~(col("x") > 0)).count()
+    n_null = e.filter(t, (col("x") > 0).is_null()).count()
+    assert n_true + n_false + n_null == n and n_null == n - int(xv.sum())
+    assert n_true == int(((x > 0) & xv.bool()).sum())
+    kept = e.filter(t, (col("a") >= 0) & col("x").not_null()).native
+    m = (a >= 0) & xv.bool()
+    assert torch.equal(kept.column("a"), a[m]) and torch.equal(kept.column("x"), x[m])   # order preserved
