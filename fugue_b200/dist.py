@@ -290,27 +290,9 @@ class DistributedB200Engine(B200ExecutionEngine):
             # aggregations of expressions / expressions of aggregations: the base class evaluates the
             # row-wise parts locally and comes back here with plain FUNC(column) aggregations
             return super().aggregate(df, partition_spec, agg_cols)
-        partial: List[Any] = []
-        final: List[Any] = []
-        post: List[Any] = []
-        for i, a in enumerate(agg_cols):
-            assert_or_throw(isinstance(a, AggFuncExpr) and a.output_name != "",
-                            lambda: ValueError(f"{a} must be a named aggregation"))
-            tmp = f"__p{i}"
-            if a.func in ("SUM", "MIN", "MAX"):
-                partial.append(AggFuncExpr(a.func, a.arg, tmp))
-                final.append(AggFuncExpr(a.func, col(tmp), a.output_name))
-            elif a.func == "COUNT":
-                partial.append(AggFuncExpr("COUNT", a.arg, tmp))
-                final.append(AggFuncExpr("SUM", col(tmp), a.output_name))
-            elif a.func == "AVG":
-                partial.append(AggFuncExpr("SUM", a.arg, tmp + "s"))
-                partial.append(AggFuncExpr("COUNT", a.arg, tmp + "c"))
-                final.append(AggFuncExpr("SUM", col(tmp + "s"), tmp + "s"))
-                final.append(AggFuncExpr("SUM", col(tmp + "c"), tmp + "c"))
-                post.append((a.output_name, tmp + "s", tmp + "c"))
-            else:
-                raise NotImplementedError(f"distributed {a.func}")
+        from .execution_engine import decompose_aggs, finish_avgs
+
+        partial, final, post = decompose_aggs(agg_cols)
         local = super().aggregate(df, partition_spec, partial)
         if len(keys) == 0:
             # global aggregate: every rank reduces its partial row; gather the W partial rows everywhere
@@ -318,32 +300,7 @@ class DistributedB200Engine(B200ExecutionEngine):
         else:
             shuffled = self.repartition(local, PartitionSpec(by=keys, num=self._shuffle_partitions()))
         res = super().aggregate(shuffled, partition_spec, final)
-        if post:
-            t: B200Table = res.native
-            names, cols, valid = [], [], []
-            import pyarrow as pa
-
-            fields = []
-            drop = {x for p_ in post for x in p_[1:]}
-            avg_at = {p_[1]: p_ for p_ in post}
-            for name, tp, c, v in zip(t.schema.names, t.schema.types, t.columns, t.valid):
-                if name in avg_at:
-                    out, sname, cname = avg_at[name]
-                    sc, cc = t.column(sname), t.column(cname)
-                    fields.append(pa.field(out, pa.float64()))
-                    cols.append((sc.to(torch.float64) / cc.to(torch.float64)).contiguous())
-                    valid.append((cc > 0).to(torch.uint8))
-                elif name not in drop:
-                    fields.append(pa.field(name, tp))
-                    cols.append(c)
-                    valid.append(v)
-            from .schema import Schema
-
-            res = B200DataFrame(B200Table(Schema(fields), cols, valid, t.dictionaries))
-            want = keys + [a.output_name for a in agg_cols]
-            if res.columns != want:
-                res = res[want]
-        return res
+        return finish_avgs(res, post, keys + [a.output_name for a in agg_cols])
 
     def _allgather_rows(self, df: B200DataFrame) -> B200DataFrame:
         t: B200Table = df.native

@@ -177,6 +177,60 @@ class B200MapEngine:
         return engine.to_df(PandasDataFrame(res, output_schema))
 
 
+def decompose_aggs(agg_cols: List[Any]) -> Any:
+    """Two-level form of plain aggregations: ``partial`` (computed per sub-group), ``final`` (computed
+    over the partials) and ``post`` = [(name, sum column, count column)] for AVG = SUM / COUNT.
+    Used for the multi-GPU group-by (partials per rank) and for COUNT(DISTINCT x) (partials per
+    distinct (keys, x))."""
+    from .column import AggFuncExpr, col
+
+    partial: List[Any] = []
+    final: List[Any] = []
+    post: List[Any] = []
+    for i, a in enumerate(agg_cols):
+        assert_or_throw(isinstance(a, AggFuncExpr) and a.output_name != "",
+                        lambda: ValueError(f"{a} must be a named aggregation"))
+        tmp = f"__p{i}"
+        if a.func in ("SUM", "MIN", "MAX"):
+            partial.append(AggFuncExpr(a.func, a.arg, tmp))
+            final.append(AggFuncExpr(a.func, col(tmp), a.output_name))
+        elif a.func == "COUNT":
+            partial.append(AggFuncExpr("COUNT", a.arg, tmp))
+            final.append(AggFuncExpr("SUM", col(tmp), a.output_name))
+        elif a.func == "AVG":
+            partial.append(AggFuncExpr("SUM", a.arg, tmp + "s"))
+            partial.append(AggFuncExpr("COUNT", a.arg, tmp + "c"))
+            final.append(AggFuncExpr("SUM", col(tmp + "s"), tmp + "s"))
+            final.append(AggFuncExpr("SUM", col(tmp + "c"), tmp + "c"))
+            post.append((a.output_name, tmp + "s", tmp + "c"))
+        else:
+            raise NotImplementedError(f"{a.func} has no partial / final decomposition")
+    return partial, final, post
+
+
+def finish_avgs(res: "B200DataFrame", post: List[Any], want: List[str]) -> "B200DataFrame":
+    """Replace the (sum, count) column pairs of ``decompose_aggs`` by their quotient."""
+    if not post:
+        return res
+    t: B200Table = res.native
+    fields, cols, valid = [], [], []
+    drop = {x for p_ in post for x in p_[1:]}
+    avg_at = {p_[1]: p_ for p_ in post}
+    for name, tp, c, v in zip(t.schema.names, t.schema.types, t.columns, t.valid):
+        if name in avg_at:
+            out, sname, cname = avg_at[name]
+            sc, cc = t.column(sname), t.column(cname)
+            fields.append(pa.field(out, pa.float64()))
+            cols.append((sc.to(torch.float64) / cc.to(torch.float64)).contiguous())
+            valid.append((cc > 0).to(torch.uint8))
+        elif name not in drop:
+            fields.append(pa.field(name, tp))
+            cols.append(c)
+            valid.append(v)
+    res = B200DataFrame(B200Table(Schema(fields), cols, valid, t.dictionaries))
+    return res[want] if res.columns != want else res
+
+
 class B200ExecutionEngine:
     """The engine object ``fa.engine_context`` / ``fa.transform(engine=...)`` see."""
 
@@ -613,17 +667,28 @@ class B200ExecutionEngine:
             X.find_aggs(having, aggs)
         agg_col: Dict[str, str] = {}  # uuid of FUNC(arg) -> its column in the group table
         named_aggs: List[AggFuncExpr] = []
+        distinct_on: Any = None       # ([temporary columns of the DISTINCT argument], is wildcard)
+        distinct_outs: List[str] = []
         for a in aggs:
             bare = a.alias("").cast(None)
             uid = to_uuid(bare)
             if uid in agg_col:
                 continue
-            assert_or_throw(not a.is_distinct, NotImplementedError(f"DISTINCT aggregation {a}"))
             assert_or_throw(a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST", "LAST"),
                             NotImplementedError(f"aggregation {a.func}"))
             assert_or_throw(not is_agg(a.arg), ValueError(f"nested aggregation {a}"))
             out = f"__fb_a{len(agg_col)}"
             agg_col[uid] = out
+            if a.is_distinct:
+                # COUNT(DISTINCT x): group by (keys, x) first, then count the sub-groups per key
+                assert_or_throw(a.func == "COUNT", NotImplementedError(f"DISTINCT aggregation {a}"))
+                dn = [temp(col(n), "d") for n in t.schema.names] if isinstance(a.arg, _WildcardExpr) \
+                    else [temp(a.arg, "d")]
+                assert_or_throw(distinct_on is None or distinct_on[0] == dn, NotImplementedError(
+                    "COUNT(DISTINCT ...) of different arguments in one SELECT"))
+                distinct_on = (dn, isinstance(a.arg, _WildcardExpr))
+                distinct_outs.append(out)
+                continue
             if isinstance(a.arg, _WildcardExpr):
                 named_aggs.append(AggFuncExpr(a.func, col("*"), out))
             elif isinstance(a.arg, _LiteralColumnExpr):
@@ -636,8 +701,18 @@ class B200ExecutionEngine:
         else:
             tmp = X.project(t, pre)
         # (self.aggregate, not the local kernel wrapper: the distributed engine shuffles partials here)
-        g = self.aggregate(B200DataFrame(tmp), PartitionSpec(by=key_names) if key_names else None,
-                           named_aggs).native
+        if distinct_on is None:
+            g = self.aggregate(B200DataFrame(tmp), PartitionSpec(by=key_names) if key_names else None,
+                               named_aggs).native
+        else:
+            dn, wildcard = distinct_on
+            partial, final, post = decompose_aggs(named_aggs)
+            lvl1 = key_names + [d for d in dn if d not in key_names]
+            g1 = self.aggregate(B200DataFrame(tmp), PartitionSpec(by=lvl1),
+                                partial if partial else [AggFuncExpr("COUNT", col("*"), "__fb_n")])
+            final = final + [AggFuncExpr("COUNT", col("*") if wildcard else col(dn[0]), o) for o in distinct_outs]
+            g2 = self.aggregate(g1, PartitionSpec(by=key_names) if key_names else None, final)
+            g = finish_avgs(g2, post, key_names + [a.output_name for a in named_aggs] + distinct_outs).native
 
         def to_group_table(e: Any) -> Any:
             def mapper(node: Any) -> Any:

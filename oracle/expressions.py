@@ -243,12 +243,19 @@ def select(df: pd.DataFrame, cols: SelectColumns, where: Optional[ColumnExpr] = 
         uid = to_uuid(a.alias("").cast(None))
         if uid in aggs:
             continue
-        if a.is_distinct:
-            raise NotImplementedError(str(a))
         if isinstance(a.arg, _WildcardExpr):
             vals = None
         else:
             vals = _as_column(evaluate(a.arg, df), n, df.index, a.arg)
+        if a.is_distinct:  # COUNT(DISTINCT x): NULLs are not counted; COUNT(DISTINCT *): distinct rows
+            assert a.func == "COUNT", str(a)
+            if vals is None:
+                sub = df.assign(__fb_code=codes).drop_duplicates()
+                cnt = sub.groupby("__fb_code").size()
+            else:
+                cnt = vals.groupby(codes).nunique(dropna=True)
+            aggs[uid] = cnt.reindex(range(ngroups), fill_value=0).astype("Int64").reset_index(drop=True)
+            continue
         aggs[uid] = _agg_series(a.func, vals, codes, ngroups, n).reset_index(drop=True)
     gframe = pd.DataFrame(index=range(ngroups))
 

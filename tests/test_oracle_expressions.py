@@ -68,3 +68,11 @@ def test_three_valued_logic():
     assert r["a"].tolist() == [True, False, pd.NA, False, False, False, pd.NA, False, pd.NA]
     assert r["o"].tolist() == [True, True, True, True, False, pd.NA, True, pd.NA, pd.NA]
     assert r["n"].tolist() == [False, False, False, True, True, True, pd.NA, pd.NA, pd.NA]
+
+
+def test_count_distinct():
+    t = pd.DataFrame({"k": [1, 1, 1, 2, 2, None], "x": [5.0, 5.0, np.nan, 7.0, 8.0, 9.0], "y": [1, 2, 3, 4, 5, 6]})
+    r = OX.select(t, SelectColumns(col("k"), ff.count_distinct(col("x")).alias("d"), ff.sum(col("y")).alias("s")))
+    assert rows(r) == expect([[1, 1, 6], [2, 2, 9], [None, 1, 6]])
+    r = OX.select(pd.concat([t, t]), SelectColumns(ff.count_distinct(all_cols()).alias("n")))
+    assert rows(r) == [[6]]

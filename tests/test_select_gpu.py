@@ -301,3 +301,30 @@ def test_full_size_properties_100m_rows(e):
     kept = e.filter(t, (col("a") >= 0) & col("x").not_null()).native
     m = (a >= 0) & xv.bool()
     assert torch.equal(kept.column("a"), a[m]) and torch.equal(kept.column("x"), x[m])   # order preserved
+
+
+def test_count_distinct(e):
+    a = ArrayDataFrame([[1, 5.0, 1], [1, 5.0, 2], [1, None, 3], [2, 7.0, 4], [2, 8.0, 5], [None, 9.0, 6]],
+                       "k:long,x:double,y:long")
+    b = fa.select(a, col("k"), ff.count_distinct(col("x")).alias("d"), ff.sum(col("y")).alias("s"),
+                  ff.avg(col("y")).alias("m"), engine=e)
+    df_eq(b, [[1, 1, 6, 2.0], [2, 2, 9, 4.5], [None, 1, 6, 6.0]], "k:long,d:long,s:long,m:double", throw=True)
+    b = fa.select(fa.union(a, a, distinct=False, engine=e), ff.count_distinct(all_cols()).alias("n"), engine=e)
+    df_eq(b, [[6]], "n:long", throw=True)
+    rng = np.random.default_rng(31)
+    pdf = _random_table(rng, 150_000)
+    edf = e.to_df(pdf)
+    for sel, where in [
+        (SelectColumns(col("g"), ff.count_distinct(col("b")).alias("d"), ff.count(all_cols()).alias("n"),
+                       ff.max(col("y")).alias("mx")), None),
+        (SelectColumns(ff.count_distinct(col("a") + col("b")).alias("d"), ff.avg(col("x")).alias("ax")), col("p")),
+        (SelectColumns(col("b"), (ff.count_distinct(col("g")) * 2).alias("d2")), col("x").not_null()),
+    ]:
+        got = e.select(edf, sel, where=where).as_pandas()
+        want = OX.select(pdf, sel, where=where)
+        _frames_equal(got, want, sort=True)
+    got = fa.raw_sql("SELECT b, COUNT(DISTINCT g) AS d FROM", pdf, "GROUP BY b", engine=e, as_local=True)
+    want = pdf.groupby("b")["g"].nunique().reset_index(name="d")
+    assert np.array_equal(got.sort_values("b")["d"].to_numpy(), want["d"].to_numpy())
+    with raises(NotImplementedError):
+        e.select(edf, SelectColumns(ff.count_distinct(col("a")).alias("x"), ff.count_distinct(col("b")).alias("y")))
