@@ -86,3 +86,72 @@ def test_owner_ranges_cover_everything():
             assert r[0][0] == 0 and r[-1][1] == num
             assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             assert all(b > a for a, b in r)
+
+
+def _dict_worker(rank: int, world: int, port: int, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+
+        import pyarrow as pa
+
+        from fugue_b200.dist import DistributedB200Engine
+        from fugue_b200.schema import Schema
+        from fugue_b200.table import B200Table
+
+        words = [["b", "a", "c"], ["c", "d", "a", "e"]][rank]
+        codes = torch.tensor([[0, 1, 2, 1, 0], [3, 0, 1, 2, 2, 0]][rank], dtype=torch.int32)
+        valid = torch.tensor([[1, 1, 1, 0, 1], [1, 1, 1, 1, 1, 1]][rank], dtype=torch.uint8)
+        t = B200Table(Schema("s:str,v:long"), [codes, torch.arange(len(codes))], [valid, None],
+                      {"s": pa.array(words, type=pa.string())})
+        fake = types.SimpleNamespace(_world=world, _group=None)
+        g = DistributedB200Engine._globalize_dictionaries(fake, t)
+        decoded = [None if m == 0 else g.dictionaries["s"][int(c)].as_py()
+                   for c, m in zip(g.columns[0].tolist(), valid.tolist())]
+        ret[rank] = (g.dictionaries["s"].to_pylist(), decoded)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_string_dictionaries_are_unified_across_ranks():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dict_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0][0] == ret[1][0] == ["b", "a", "c", "d", "e"]          # union, first-appearance order over ranks
+    assert ret[0][1] == ["b", "a", "c", None, "b"]                      # codes re-mapped, NULL kept
+    assert ret[1][1] == ["e", "c", "d", "a", "a", "c"]
+
+
+def test_partial_final_decomposition_of_aggregates():
+    """Host logic shared by the multi-GPU group-by and COUNT(DISTINCT): SUM/COUNT/MIN/MAX/AVG as
+    (partial, final, post) and the AVG finishing step, on CPU tensors."""
+    import pyarrow as pa
+
+    from fugue_b200.column import all_cols, col, functions as ff
+    from fugue_b200.dataframe import B200DataFrame
+    from fugue_b200.execution_engine import decompose_aggs, finish_avgs
+    from fugue_b200.schema import Schema
+    from fugue_b200.table import B200Table
+
+    aggs = [ff.sum(col("v")).alias("s"), ff.count(all_cols()).alias("c"), ff.avg(col("v")).alias("m"),
+            ff.max(col("v")).alias("hi")]
+    partial, final, post = decompose_aggs(aggs)
+    assert [str(a) for a in partial] == ["SUM(v) AS __p0", "COUNT(*) AS __p1", "SUM(v) AS __p2s", "COUNT(v) AS __p2c",
+                                         "MAX(v) AS __p3"]
+    assert [str(a) for a in final] == ["SUM(__p0) AS s", "SUM(__p1) AS c", "SUM(__p2s) AS __p2s",
+                                       "SUM(__p2c) AS __p2c", "MAX(__p3) AS hi"]
+    assert post == [("m", "__p2s", "__p2c")]
+    t = B200Table(Schema("k:long,s:double,c:long,__p2s:double,__p2c:long,hi:double"),
+                  [torch.tensor([1, 2]), torch.tensor([3.0, 4.0], dtype=torch.float64), torch.tensor([2, 0]),
+                   torch.tensor([3.0, 0.0], dtype=torch.float64), torch.tensor([2, 0]),
+                   torch.tensor([2.0, 0.0], dtype=torch.float64)])
+    res = finish_avgs(B200DataFrame(t), post, ["k", "s", "c", "m", "hi"]).native
+    assert res.schema == Schema("k:long,s:double,c:long,m:double,hi:double")
+    i = res.schema.index_of_key("m")
+    assert res.columns[i].tolist()[0] == 1.5 and res.valid[i].tolist() == [1, 0]   # AVG of no rows is NULL
+    with pytest.raises(NotImplementedError):
+        decompose_aggs([ff.first(col("v")).alias("f")])
