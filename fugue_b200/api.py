@@ -452,3 +452,162 @@ def take(df: Any, n: int, presort: Any = None, na_position: str = "last", partit
     return _run_engine_function("take", [df], engine, engine_conf, as_fugue, as_local, n=n, presort=presort,
                                 na_position=na_position,
                                 partition_spec=None if partition is None else PartitionSpec(partition))
+
+
+# ---------------------------------------------------------------------------------------------
+# dataframe / dataset utilities of ``fugue.api`` (fugue/dataframe/api.py, fugue/dataset/api.py):
+# thin functional wrappers over the DataFrame interface, accepting anything ``as_fugue_df`` knows
+# ---------------------------------------------------------------------------------------------
+def _convert_df(input_df: Any, output: DataFrame, as_fugue: bool) -> Any:
+    """Return type rule of fugue/dataframe/api.py ``_convert_df``: a Fugue DataFrame when asked for or
+    when the input was one, otherwise the same kind of native object as the input."""
+    import pandas as pd
+    import pyarrow as pa
+
+    if as_fugue or isinstance(input_df, DataFrame):
+        return output
+    if isinstance(input_df, pd.DataFrame):
+        return output.as_pandas()
+    if isinstance(input_df, pa.Table):
+        return output.as_arrow()
+    return output.native_as_df()
+
+
+def is_df(df: Any) -> bool:
+    import pandas as pd
+    import pyarrow as pa
+
+    from .table import B200Table
+
+    return isinstance(df, (DataFrame, pd.DataFrame, pa.Table, B200Table))
+
+
+def get_native_as_df(df: Any) -> Any:
+    return df.native_as_df() if isinstance(df, DataFrame) else df
+
+
+def get_schema(df: Any) -> Any:
+    return as_fugue_df(df).schema
+
+
+def get_column_names(df: Any) -> List[Any]:
+    return as_fugue_df(df).columns
+
+
+def as_pandas(df: Any) -> Any:
+    return as_fugue_df(df).as_pandas()
+
+
+def as_arrow(df: Any) -> Any:
+    return as_fugue_df(df).as_arrow()
+
+
+def as_array(df: Any, columns: Optional[List[str]] = None, type_safe: bool = False) -> List[Any]:
+    return as_fugue_df(df).as_array(columns, type_safe)
+
+
+def as_array_iterable(df: Any, columns: Optional[List[str]] = None, type_safe: bool = False) -> Iterable[Any]:
+    return as_fugue_df(df).as_array_iterable(columns, type_safe)
+
+
+def as_dicts(df: Any, columns: Optional[List[str]] = None) -> List[Dict[str, Any]]:
+    return as_fugue_df(df).as_dicts(columns)
+
+
+def as_dict_iterable(df: Any, columns: Optional[List[str]] = None) -> Iterable[Dict[str, Any]]:
+    return as_fugue_df(df).as_dict_iterable(columns)
+
+
+def peek_array(df: Any) -> List[Any]:
+    return as_fugue_df(df).peek_array()
+
+
+def peek_dict(df: Any) -> Dict[str, Any]:
+    return as_fugue_df(df).peek_dict()
+
+
+def head(df: Any, n: int, columns: Optional[List[str]] = None, as_fugue: bool = False) -> Any:
+    return _convert_df(df, as_fugue_df(df).head(n, columns), as_fugue)
+
+
+def alter_columns(df: Any, columns: Any, as_fugue: bool = False) -> Any:
+    return _convert_df(df, as_fugue_df(df).alter_columns(columns), as_fugue)
+
+
+def drop_columns(df: Any, columns: List[str], as_fugue: bool = False) -> Any:
+    return _convert_df(df, as_fugue_df(df).drop(columns), as_fugue)
+
+
+def select_columns(df: Any, columns: List[Any], as_fugue: bool = False) -> Any:
+    return _convert_df(df, as_fugue_df(df)[columns], as_fugue)
+
+
+def rename(df: Any, columns: Dict[str, Any], as_fugue: bool = False) -> Any:
+    if len(columns) == 0:
+        return df
+    return _convert_df(df, as_fugue_df(df).rename(columns), as_fugue)
+
+
+def as_local(df: Any) -> Any:
+    return _convert_df(df, as_fugue_df(df).as_local(), False)
+
+
+def as_local_bounded(df: Any) -> Any:
+    return _convert_df(df, as_fugue_df(df).as_local_bounded(), False)
+
+
+def is_local(df: Any) -> bool:
+    return as_fugue_df(df).is_local
+
+
+def is_bounded(df: Any) -> bool:
+    return as_fugue_df(df).is_bounded
+
+
+def is_empty(df: Any) -> bool:
+    return as_fugue_df(df).empty
+
+
+def count(df: Any) -> int:
+    return as_fugue_df(df).count()
+
+
+def get_num_partitions(df: Any) -> int:
+    return as_fugue_df(df).num_partitions
+
+
+def get_current_parallelism(engine: Any = None, engine_conf: Any = None) -> int:
+    """``fa.get_current_parallelism`` (fugue/execution/api.py): number of GPUs behind the engine."""
+    return make_execution_engine(engine, engine_conf).get_current_parallelism()
+
+
+def get_current_conf(engine: Any = None, engine_conf: Any = None) -> Dict[str, Any]:
+    return make_execution_engine(engine, engine_conf).conf
+
+
+def persist(df: Any, lazy: bool = False, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+            as_local: bool = False, **kwargs: Any) -> Any:
+    """``fa.persist``: on this engine = keep the table resident in HBM."""
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    return _finish(e, df, e.persist(e.to_df(df), lazy=lazy, **kwargs), as_fugue, as_local)
+
+
+def broadcast(df: Any, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+              as_local: bool = False) -> Any:
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    return _finish(e, df, e.broadcast(e.to_df(df)), as_fugue, as_local)
+
+
+def run_engine_function(func: Any, engine: Any = None, engine_conf: Any = None, as_fugue: bool = False,
+                        as_local: bool = False, infer_by: Optional[List[Any]] = None) -> Any:
+    """``fa.run_engine_function`` (fugue/execution/api.py:145-179): run ``func(engine)`` in the engine's
+    context and convert a dataframe result the way every ``fa.*`` function does."""
+    e = make_execution_engine(engine, engine_conf, infer_by=infer_by)
+    with engine_context(e):
+        res = func(e)
+    if isinstance(res, DataFrame):
+        res = e.convert_yield_dataframe(res, as_local)
+        if as_fugue or any(isinstance(x, DataFrame) for x in (infer_by or [])):
+            return res
+        return res.as_pandas() if res.is_local else res.native
+    return res

@@ -142,6 +142,33 @@ class DataFrame:
     def rename(self, columns: Dict[str, str]) -> "DataFrame":  # pragma: no cover
         raise NotImplementedError
 
+    def native_as_df(self) -> Any:
+        """The underlying dataframe object (fugue/dataframe/dataframe.py ``native_as_df``)."""
+        return self.native
+
+    def as_dict_iterable(self, columns: Optional[List[str]] = None) -> Iterable[Dict[str, Any]]:
+        return iter(self.as_dicts(columns))
+
+    def _altered_schema(self, columns: Any) -> Optional[Schema]:
+        """Schema after ``alter_columns(columns)``; None when nothing changes
+        (fugue/dataframe/dataframe.py ``alter_columns``: ``columns`` must be a subset of the schema)."""
+        sub = Schema(columns)
+        for f in sub.fields:
+            if f.name not in self._schema:
+                raise FugueDataFrameOperationError(f"{f.name} not in {self._schema}")
+        new = self._schema.alter(sub)
+        return None if new == self._schema else new
+
+    def alter_columns(self, columns: Any) -> "DataFrame":
+        """Change column data types; column order is kept."""
+        new = self._altered_schema(columns)
+        if new is None:
+            return self
+        try:
+            return ArrowDataFrame(self.as_arrow().cast(new.pa_schema, safe=False))
+        except (pa.ArrowInvalid, pa.ArrowNotImplementedError) as e:
+            raise FugueDataFrameOperationError(str(e)) from e
+
     def __copy__(self) -> "DataFrame":
         return self
 
@@ -198,6 +225,10 @@ class ArrowDataFrame(LocalDataFrame):
         elif isinstance(df, pd.DataFrame):
             if schema is None:
                 t = pa.Table.from_pandas(df, preserve_index=False)
+                if any(pa.types.is_large_string(f.type) for f in t.schema):
+                    # pandas 3 string columns arrive as large_string; Fugue's "str" is pa.string()
+                    t = t.cast(pa.schema([pa.field(f.name, pa.string()) if pa.types.is_large_string(f.type) else f
+                                          for f in t.schema]))
                 sch = Schema(t.schema)
             else:
                 sch = Schema(schema)
@@ -311,6 +342,20 @@ class B200DataFrame(DataFrame):
 
     def _select_cols(self, columns: List[Any]) -> DataFrame:
         return B200DataFrame(self._table.select(columns))
+
+    def alter_columns(self, columns: Any) -> DataFrame:
+        """Casts run on the device (one fb_eval_expr program); strings <-> numbers go through the host."""
+        new = self._altered_schema(columns)
+        if new is None:
+            return self
+        from . import expr as X
+        from .column import col
+
+        try:
+            exprs = [col(n) if tp == self._schema[n].type else col(n).cast(tp) for n, tp in zip(new.names, new.types)]
+            return B200DataFrame(X.project(self._table, exprs))
+        except NotImplementedError:
+            return B200DataFrame(super().alter_columns(columns).as_arrow())
 
     def rename(self, columns: Dict[str, str]) -> DataFrame:
         try:
