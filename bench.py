@@ -97,6 +97,12 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path (restated oracle)
 # ------------------------------------------------------------------------------------------
+def _workload(rows_per_gpu: int) -> str:
+    """The workload name both arms report (BASELINE.json config 2)."""
+    return (f"1xB200 config: fa.transform identity map, PartitionSpec(by='key', algo='hash', num={NUM_PARTITIONS}) "
+            f"on {rows_per_gpu}-row int64x4+float64x4 table per GPU")
+
+
 def _host_sample(rows: int, seed: int = 0):
     import numpy as np
     import pandas as pd
@@ -145,9 +151,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64 (byte moves)", "data": "synthetic",
-        "config": {"workload": "fa.transform identity, PartitionSpec(by=key, algo=hash, num=256), "
-                               "int64x4+float64x4", "rows_per_step": REF_SAMPLE_ROWS,
-                   "key_cardinality": KEY_CARDINALITY},
+        "config": {"workload": _workload(ROWS_PER_GPU), "rows_per_gpu": ROWS_PER_GPU,
+                   "key_cardinality": KEY_CARDINALITY, "parallelism": "host cores (1 used: the reference's native "
+                   "engine is single-threaded)", "rows_per_step": REF_SAMPLE_ROWS,
+                   "sample_keys_per_step": REF_SAMPLE_KEYS},
         "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -338,14 +345,13 @@ def run_b200(args):
                 extras = relational_bench.measure(local_rank)
             except Exception as ex:  # pragma: no cover
                 extras = {"error": repr(ex)}
-        launches_per_step = 5 + (1 if n % 4096 else 0)  # hist, 2 scans, 2 x scatter (4 cols each), tail tile
+        # pass 1 (rank kernel), 2 scans, 2 x scatter (4 columns each); + histogram and scatter of the tail tile
+        launches_per_step = 5 + (2 if n % 4096 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64+f64 (byte moves; u64 hash arithmetic)", "data": "synthetic",
-            "config": {"workload": f"1xB200 config: fa.transform identity map, PartitionSpec(by='key', "
-                                   f"algo='hash', num={NUM_PARTITIONS}) on {n}-row int64x4+float64x4 table "
-                                   f"per GPU", "rows_per_gpu": n, "key_cardinality": KEY_CARDINALITY,
+            "config": {"workload": _workload(n), "rows_per_gpu": n, "key_cardinality": KEY_CARDINALITY,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "inputs (6.4 GB/GPU) are larger than L2 (126 MB); no flush needed",
                        "rows_out": nrows_out},
