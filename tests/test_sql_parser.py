@@ -52,3 +52,60 @@ def test_structured_raw_sql_pieces():
     assert st.construct({"a": "tbl"}) == "SELECT * FROM tbl WHERE x>1"
     st = StructuredRawSQL.from_expr("SELECT * FROM <tmpdf:abc> WHERE x<3")
     assert st.construct(lambda n: n.upper()) == "SELECT * FROM ABC WHERE x<3"
+
+
+class _FakeDF:
+    """Stands in for an engine dataframe: records what the SQL engine asks of it."""
+
+    def __init__(self, names):
+        from fugue_b200.schema import Schema
+
+        self.schema = Schema(",".join(f"{n}:long" for n in names))
+        self.columns = list(names)
+        self.picked = None
+
+    def __getitem__(self, cols):
+        out = _FakeDF(cols)
+        out.picked = list(cols)
+        return out
+
+
+class _FakeEngine:
+    is_distributed = False
+
+    def __init__(self):
+        self.calls = []
+
+    def to_df(self, df):
+        return df
+
+    def select(self, df, cols, where=None, having=None):
+        self.calls.append((cols, where, having))
+        return _FakeDF([c.output_name for c in cols.all_cols])
+
+
+def test_sql_engine_hands_select_the_right_trees():
+    from fugue_b200.sql import B200SQLEngine
+
+    eng = _FakeEngine()
+    sql = B200SQLEngine(eng)
+    t = _FakeDF(["key", "v0", "v1"])
+    out = sql.select({"t": t}, "SELECT key, SUM(v0 * 2) AS s FROM t WHERE v1 > 0 GROUP BY key HAVING COUNT(*) > 5")
+    cols, where, having = eng.calls[-1]
+    assert [str(c) for c in cols.all_cols] == ["key", "SUM(*(v0,2)) AS s"] and not cols.is_distinct
+    assert str(where) == ">(v1,0)" and str(having) == ">(COUNT(*),5)"
+    assert out.columns == ["key", "s"]
+    # a GROUP BY key that is not selected rides along as a hidden column and is dropped afterwards
+    out = sql.select({"t": t}, "SELECT MAX(v0) AS m FROM t GROUP BY key, v1 + 1")
+    cols, _, _ = eng.calls[-1]
+    assert [str(c) for c in cols.all_cols] == ["MAX(v0) AS m", "key AS __fb_g0", "+(v1,1) AS __fb_g1"]
+    assert out.picked == ["m"]
+    # select-list keys must all be in GROUP BY; GROUP BY needs an aggregate
+    with raises(ValueError):
+        sql.select({"t": t}, "SELECT key, v1, SUM(v0) AS s FROM t GROUP BY key")
+    with raises(NotImplementedError):
+        sql.select({"t": t}, "SELECT key FROM t GROUP BY key")
+    with raises(KeyError):
+        sql.select({"t": t}, "SELECT key FROM nope")
+    out = sql.select({"t": t}, "SELECT DISTINCT key k, v0 FROM t")
+    assert eng.calls[-1][0].is_distinct and out.columns == ["k", "v0"]
