@@ -2,7 +2,8 @@
 
 This package is a CPU restatement of what the reference (fugue-project/fugue
 @ 91648b2, v0.9.4) computes on the ``fa.transform() -> MapEngine.map_dataframe``
-path and its two neighbours (``ExecutionEngine.join`` / ``aggregate``).
+path and its neighbours (``ExecutionEngine.join`` / ``aggregate`` / ``select`` /
+``filter`` / ``assign``).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import it.  Nothing under
@@ -19,6 +20,12 @@ Parity pinning (see DESIGN.md section "Oracle"):
   ``tests/golden/make_golden.py``.
 * ``native_engine`` is pinned against the literal tables of the reference's
   conformance suite (``fugue_test/execution_suite.py:208-314, 366-543, 177-206``).
+* ``expressions`` (select / filter / assign / expression aggregates, restating the
+  SQL that ``fugue/column/sql.py:275-347`` generates for qpd) is pinned against the
+  literal tables of ``fugue_test/execution_suite.py:85-206`` (test_filter,
+  test_select, test_assign, test_aggregate) in ``tests/test_oracle_expressions.py``;
+  the column DSL it walks is pinned against the expected strings / types of the
+  reference's ``tests/fugue/column/*.py`` in ``tests/test_column_dsl.py``.
 
 The reference package itself cannot be imported here (``triad``/``adagio``
 are absent, no network), so it is not executed; the literals above are the

@@ -18,7 +18,7 @@ which implement exactly the SQL rules the conformance tests pin
 * NaN in a float column of a pandas frame is NULL (Fugue's pandas convention).
 
 The trees are the DSL objects of ``fugue_b200.column`` (API objects, not compute code).
-Parity pinning: ``tests/test_oracle_native.py`` checks this module against the literal input/output
+Parity pinning: ``tests/test_oracle_expressions.py`` checks this module against the literal input/output
 tables of the reference's test_filter / test_select / test_assign / test_aggregate.
 """
 from typing import Any, Dict, List, Optional
