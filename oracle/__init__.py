@@ -25,7 +25,10 @@ Parity pinning (see DESIGN.md section "Oracle"):
   literal tables of ``fugue_test/execution_suite.py:85-206`` (test_filter,
   test_select, test_assign, test_aggregate) in ``tests/test_oracle_expressions.py``;
   the column DSL it walks is pinned against the expected strings / types of the
-  reference's ``tests/fugue/column/*.py`` in ``tests/test_column_dsl.py``.
+  reference's ``tests/fugue/column/*.py`` in ``tests/test_column_dsl.py`` and against
+  golden vectors produced by running the reference's own ``fugue/column`` modules in the
+  build container (``tests/golden/make_column_golden.py`` ->
+  ``tests/golden/column_dsl_vectors.json``, replayed by ``tests/test_column_golden.py``).
 
 The reference package itself cannot be imported here (``triad``/``adagio``
 are absent, no network), so it is not executed; the literals above are the
