@@ -143,6 +143,16 @@ class _Program:
         if cls == "n" or cls == ctx:
             return
         if ctx == "f":
+            # peephole: the accumulator was just loaded from an integer leaf -> convert while loading
+            if self.ins and self.ins[-1][0] == K.X_MOV and self.ins[-1][3] == 0:
+                op, kind, b, _, imm = self.ins[-1]
+                if kind == K.XK_COL:
+                    self.ins[-1] = (op, kind, b, K.XF_B_I2F, imm)
+                    return
+                if kind == K.XK_IMM:
+                    v = imm - (1 << 64) if imm >= (1 << 63) else imm
+                    self.ins[-1] = (op, kind, b, 0, _f64_bits(float(v)))
+                    return
             self.emit(K.X_I2F)
         elif ctx == "b":
             self.emit(K.X_TOBOOL_F if cls == "f" else K.X_TOBOOL_I)

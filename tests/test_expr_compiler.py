@@ -118,6 +118,12 @@ def test_leaf_operands_need_no_temporaries():
     prog = X._Program(t)
     prog.compile(10 - col("a") * 2)
     assert [i[0] for i in prog.ins] == [K.X_MOV, K.X_MUL_I, K.X_RSUB_I]
+    prog = X._Program(t)
+    prog.compile(col("a") / col("b"))       # integer leaves are converted while they are loaded
+    assert [(i[0], i[3]) for i in prog.ins] == [(K.X_MOV, K.XF_B_I2F), (K.X_DIV_F, K.XF_B_I2F)]
+    prog = X._Program(t)
+    prog.compile((col("a") + 1) / 2)        # ... but not after integer arithmetic
+    assert [i[0] for i in prog.ins] == [K.X_MOV, K.X_ADD_I, K.X_I2F, K.X_DIV_F]
 
 
 def test_resource_limits_and_errors():
