@@ -19,7 +19,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ROWS_PER_GPU = 100_000_000  # BASELINE config 2 (1xB200); weak scaling: same rows on every GPU
+ROWS_PER_GPU = 100_000_000     # BASELINE config 2 (1xB200)
+ROWS_PER_GPU_DIST = 125_000_000  # BASELINE config 3: 1 B rows on 8xB200 = 125 M per GPU (used for every N > 1)
 NUM_PARTITIONS = 256
 KEY_CARDINALITY = 1 << 16
 SCHEMA = "key:long,i1:long,i2:long,i3:long,v0:double,v1:double,v2:double,v3:double"
@@ -42,11 +43,19 @@ def _peaks():
 
 
 def _profile_traffic():
-    p = os.path.join(ROOT, "profiles", "r1_summary.json")
-    try:
-        return json.load(open(p)).get("scatter_dram_bytes_per_launch")
-    except Exception:
-        return None
+    """DRAM bytes of the scatter kernel from the committed ncu capture (NOT measured in this run)."""
+    for name in ("r2_summary.json", "r1_summary.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get("scatter_dram_bytes_per_launch")
+            if v is not None:
+                return v, f"profiles/{name} (ncu --set full capture of the same kernel and size; not measured in this run)"
+        except Exception:
+            pass
+    return None, None
+
+
+def rows_for(world: int) -> int:
+    return ROWS_PER_GPU if world == 1 else ROWS_PER_GPU_DIST
 
 
 class ClockSampler(threading.Thread):
@@ -97,10 +106,21 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path (restated oracle)
 # ------------------------------------------------------------------------------------------
-def _workload(rows_per_gpu: int) -> str:
-    """The workload name both arms report (BASELINE.json config 2)."""
-    return (f"1xB200 config: fa.transform identity map, PartitionSpec(by='key', algo='hash', num={NUM_PARTITIONS}) "
-            f"on {rows_per_gpu}-row int64x4+float64x4 table per GPU")
+def _workload(rows_per_gpu: int, world: int = 1) -> str:
+    """The workload name both arms report (BASELINE.json configs 2 / 3)."""
+    which = ("config 2 (1xB200, 100M rows)" if world == 1 and rows_per_gpu == ROWS_PER_GPU else
+             f"config 3 share ({world}xB200, {rows_per_gpu * world} rows = {rows_per_gpu} per GPU"
+             + ("; exactly config 3: 1B rows on 8 GPUs)" if rows_per_gpu * world == 1_000_000_000 else ")"))
+    return (f"{which}: fa.transform identity map, PartitionSpec(by='key', algo='hash', num={NUM_PARTITIONS}) "
+            f"on an int64x4+float64x4 table" + (", shuffle across GPUs over NVLink" if world > 1 else ""))
+
+
+def _config(rows_per_gpu: int, world: int) -> dict:
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": _workload(rows_per_gpu, world), "rows_per_gpu": rows_per_gpu,
+            "rows_total": rows_per_gpu * world, "n_gpus": world, "num_partitions": NUM_PARTITIONS,
+            "key_cardinality": KEY_CARDINALITY, "schema": SCHEMA,
+            "l2": "inputs (>= 6.4 GB/GPU) are larger than L2 (126 MB); no flush needed"}
 
 
 def _host_sample(rows: int, seed: int = 0):
@@ -141,20 +161,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    warmup = max(0, min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    n = args.rows or rows_for(world)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
     rps, dt = _time_reference(REF_SAMPLE_ROWS, steps, warmup)
-    sample = (f"{REF_SAMPLE_ROWS} rows = the logical partitions of {REF_SAMPLE_KEYS} of the {KEY_CARDINALITY} keys "
-              "(same 1526 rows per key as the 100M-row workload), restated "
-              "NativeExecutionEngine.map_dataframe (reference not importable: triad/adagio absent)")
+    sample = (f"each step = {REF_SAMPLE_ROWS} rows = the logical partitions of {REF_SAMPLE_KEYS} of the "
+              f"{KEY_CARDINALITY} keys (same 1526 rows per key as the full workload), restated "
+              "NativeExecutionEngine.map_dataframe (reference not importable: triad/adagio absent); 1 core: the "
+              "reference's native engine is single-threaded (get_current_parallelism() == 1)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64 (byte moves)", "data": "synthetic",
-        "config": {"workload": _workload(ROWS_PER_GPU), "rows_per_gpu": ROWS_PER_GPU,
-                   "key_cardinality": KEY_CARDINALITY, "parallelism": "host cores (1 used: the reference's native "
-                   "engine is single-threaded)", "rows_per_step": REF_SAMPLE_ROWS,
-                   "sample_keys_per_step": REF_SAMPLE_KEYS},
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64 (byte moves; u64 hash arithmetic)",
+        "data": "synthetic", "config": _config(n, world),
         "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,7 +203,7 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.rows
+    n = args.rows or rows_for(world)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
     # synthetic table of the BASELINE shape, generated on the device, seed = rank
@@ -262,10 +281,11 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         pms = e0.elapsed_time(e1) / reps
         achieved = ALG_BYTES_PER_ROW * n / (kms * 1e-3) / 1e9
+        traffic, traffic_src = _profile_traffic()
         roofline = {"bound": "hbm", "kernel": "fb_scatter_ws_kernel (pass 2: TMA ring + placement from rank records + write-combined scatter; "
                                               "2 launches x 4 columns, timed together)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": _profile_traffic(),
+                    "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_ROW * n,
                     "kernel_ms": kms, "pass1_rank_scan_ms": pms,
                     "step_frac": ALG_BYTES_PER_ROW * n / (ms_per_step * 1e-3) / 1e9 / peak}
@@ -324,6 +344,35 @@ def run_b200(args):
                 except Exception:
                     pass
 
+    # ---- multi-GPU parity, outside the timed region: a small shard through the same engine object,
+    #      checked on rank 0 against the oracle / pandas (tests/dist_gpu_check.py; collective)
+    parity = None
+    if world > 1 and not args.no_parity:
+        import contextlib
+
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import dist_gpu_check
+
+        with contextlib.redirect_stdout(sys.stderr):
+            ok, msg = dist_gpu_check.run_checks(engine, rank, world, dev)
+        parity = {"ok": bool(ok), "detail": msg}
+
+    # ---- secondary metrics: BASELINE configs 4 (GROUP BY) and 5 (JOIN) at their per-GPU share,
+    #      through engine.aggregate / engine.join (distributed at N > 1; every rank takes part)
+    extras = None
+    if not args.no_extras:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import relational_bench
+
+            torch.cuda.empty_cache()
+            if world == 1:
+                extras = relational_bench.measure(local_rank)
+            else:
+                extras = relational_bench.measure_dist(engine, rank, world, dev)
+        except Exception as ex:  # pragma: no cover
+            extras = {"error": repr(ex)[:300]}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -334,30 +383,37 @@ def run_b200(args):
                              f"{KEY_CARDINALITY} keys (1526 rows per key as in the full workload), 2 timed passes of the restated "
                              "NativeExecutionEngine.map_dataframe (pandas groupby-iterate + concat); "
                              "the reference is single-threaded (get_current_parallelism() == 1)"}
-        extras = None
-        if world == 1 and not args.no_extras:
-            # secondary metrics: BASELINE configs 4 (GROUP BY) and 5 (JOIN) at their per-GPU sizes
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                import relational_bench
-
-                torch.cuda.empty_cache()
-                extras = relational_bench.measure(local_rank)
-            except Exception as ex:  # pragma: no cover
-                extras = {"error": repr(ex)}
-        # pass 1 (rank kernel), 2 scans, 2 x scatter (4 columns each); + histogram and scatter of the tail tile
-        launches_per_step = 5 + (2 if n % 4096 else 0)
+            if extras is not None and "error" not in extras and not args.no_extras:
+                try:
+                    extras["cpu_baseline"] = relational_bench.cpu_baselines()
+                except Exception as ex:  # pragma: no cover
+                    extras["cpu_baseline"] = {"error": repr(ex)[:200]}
+        # per step: pass 1 (rank kernel), 2 scans, the scatter launches (+ histogram and scatter of the
+        # tail tile); multi-GPU: scatter per column group + barrier kernels, copies are DMA (no kernel)
+        if world == 1:
+            launches_per_step = 5 + (2 if n % 4096 else 0)
+        else:
+            ngroups = (8 + engine._group_cols - 1) // engine._group_cols
+            launches_per_step = 3 + ngroups + (1 + ngroups if n % 4096 else 0)
+        cfg = _config(n, world)
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64+f64 (byte moves; u64 hash arithmetic)", "data": "synthetic",
-            "config": {"workload": _workload(n), "rows_per_gpu": n, "key_cardinality": KEY_CARDINALITY,
-                       "parallelism": f"dp{world}" if world > 1 else "single",
-                       "l2": "inputs (6.4 GB/GPU) are larger than L2 (126 MB); no flush needed",
-                       "rows_out": nrows_out},
+            "config": cfg, "rows_out_rank0": nrows_out,
+            "parallelism": f"dp{world}: rows range-sharded, one exchange over NVLink (copy engines), "
+                           f"{engine._group_cols} columns per scatter/exchange group" if world > 1 else "single GPU",
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,
             "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }
+        if world > 1:
+            line[f"parity_world_{world}"] = None if parity is None else parity["ok"]
+            line["parity_detail"] = None if parity is None else parity["detail"]
+            # NVLink-bound view of the same step: 64 B/row x (G-1)/G leave every GPU
+            out_bytes = 64.0 * n * (world - 1) / world
+            line["nvlink"] = {"bytes_out_per_gpu": out_bytes, "achieved_GBps_per_gpu": out_bytes / (ms_per_step * 1e-3) / 1e9,
+                              "peak_GBps_per_direction": 900.0,
+                              "frac": out_bytes / (ms_per_step * 1e-3) / 1e9 / 900.0}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -369,7 +425,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="rows per GPU (default: BASELINE config)")
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: 100M at N=1 = config 2, "
+                    "125M at N>1 = config 3's share)")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

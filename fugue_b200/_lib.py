@@ -48,6 +48,9 @@ SIGNATURES = {
     "fb_partition_apply": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                      C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _i32p,
                                      _vpp]),
+    "fb_partition_apply_ex": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
+                                        C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _i32p,
+                                        _vpp, C.c_int]),
     "fb_partition_cols": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _i32p,
                                     C.c_int, _vpp, C.c_uint32, _vpp, _vp, _vp, C.c_size_t]),
     "fb_radix_pass": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vpp, _i32p, _vpp, _vp, C.c_size_t,

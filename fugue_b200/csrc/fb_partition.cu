@@ -560,32 +560,8 @@ fb_scatter_kernel(FbKeys keys, FbDiv dv, uint32_t num, ChunkGeom g, int chunk0,
 // Source descriptor: [0, T) row of the staged tile; [T, T + E) old carry entry;
 // 0xFFFF nothing (phantom row at a chunk head / unused carry entry).
 // ---------------------------------------------------------------------------
-constexpr int kTmaThreads = kBlock + 32;   // 16 consumer warps + 1 producer warp
-constexpr int kMaxUnits = FB_MAX_COLS + 1;
 constexpr int kSwcMaxCols = 8;             // payload columns per launch (carry buffers in smem)
 constexpr uint32_t kSwcMaxNum = 256;
-// tile 4096 rows, G = 4 rows (32 B groups); tile 2048 / G = 8 was measured slower (4.59 vs 3.49 ms)
-constexpr int kSwcItemsA = 8, kSwcGA = 4;
-
-struct TmaUnits {
-  const uint64_t* src[kMaxUnits];  // unit 0 is the key column
-  uint64_t* dst[kMaxUnits];        // nullptr: hash-only unit (key is not a payload column)
-  int32_t nunits;
-};
-
-template <int G, int ITEMS>
-__host__ __device__ inline size_t swc_book_bytes(uint32_t num, int ncols) {
-  constexpr size_t kT = (size_t)kBlock * ITEMS;
-  const size_t nbp = nb_padded(num);
-  const size_t E = (size_t)num * (G - 1);
-  size_t b = 2 * 8 * 16;                       // mbarriers (up to 16 stages)
-  b += (size_t)(ncols + 1) * E * 8;            // carry buffers
-  b += (kT + E) * 4;                           // slotinfo
-  b += 6 * nbp * 4 + 64 * 4;                   // per-partition arrays + scanw
-  b += (size_t)kWarps * nbp * 2;               // cnt
-  b += ((E * 2 + 15) / 16) * 16;               // carryinfo
-  return b;
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -625,289 +601,6 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, 
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
-}
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory"); }
-
-template <int kBits, int G, int ITEMS>
-__global__ void __launch_bounds__(kTmaThreads, 1)
-fb_scatter_swc_kernel(TmaUnits units, FbDiv dv, uint32_t num, ChunkGeom g, int nstages, int ncols,
-                      const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
-  constexpr uint32_t T = (uint32_t)kBlock * ITEMS;
-  constexpr uint32_t kStageBytes = T * 8;
-  constexpr uint32_t GM = G - 1;
-  constexpr int kSlotRounds = ((int)T + (int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
-  constexpr int kEntryRounds = ((int)kSwcMaxNum * (G - 1) + kBlock - 1) / kBlock;
-  extern __shared__ __align__(128) uint64_t smem64[];
-  const uint32_t nbp = nb_padded(num);
-  const uint32_t E = num * GM;
-  uint64_t* ring = smem64;
-  uint64_t* bars = ring + (size_t)nstages * T;  // full[0..16), empty[0..16)
-  uint64_t* carry = bars + 32;                  // (ncols + 1) buffers of E entries
-  uint32_t* slotinfo = (uint32_t*)(carry + (size_t)(ncols + 1) * E);
-  uint32_t* wpos = slotinfo + T + E;            // output row of the first pending row of a partition
-  uint32_t* kcnt = wpos + nbp;                  // pending rows | phantom rows << 8
-  uint32_t* binfo = kcnt + nbp;                 // this tile: kold | phold << 4 | w << 8
-  uint32_t* bin_start = binfo + nbp;            // exclusive prefix of the tile histogram
-  uint32_t* wstart = bin_start + nbp;           // exclusive prefix of rows written this tile
-  uint32_t* wdelta = wstart + nbp;              // wpos - wstart: slot j lands at output row wdelta + j
-  uint32_t* scanw = wdelta + nbp;               // [0,16) tile hist totals, [16,32) written totals, [32] W
-  uint16_t* cnt = (uint16_t*)(scanw + 64);
-  uint16_t* carryinfo = cnt + (size_t)kWarps * nbp;
-
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 16);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, kWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == kWarps) {
-    // ===================== producer: one elected lane drives the TMA engine =====================
-    if (lane == 0) {
-      const uint64_t pol = l2_policy_evict_first();
-      const uint32_t ring_s = smem_u32(ring);
-      uint32_t s = 0, ph = 0;
-      for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
-        int64_t r0, r1;
-        chunk_range(g, chunk, r0, r1);
-        for (int64_t t0 = r0; t0 < r1; t0 += T) {
-          for (int u = 0; u < units.nunits; ++u) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * s, kStageBytes);
-            tma_load_1d(ring_s + s * kStageBytes, units.src[u] + t0, kStageBytes, bar_full + 8 * s, pol);
-            if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ================================ consumers (16 warps) ================================
-  const unsigned lt = fb_lanemask_lt();
-  uint16_t* __restrict__ my_cnt = cnt + (size_t)warp * nbp;
-  for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;
-  uint32_t s = 0, ph = 0;
-  const int nbuf = ncols + 1;
-  int rot = 0;  // carry buffer of payload column c is (c + rot) mod nbuf; (rot - 1) mod nbuf is spare
-
-  for (int chunk = (int)blockIdx.x; chunk < g.nchunks_full; chunk += (int)gridDim.x) {
-    int64_t r0, r1;
-    chunk_range(g, chunk, r0, r1);
-    consumer_sync();  // previous chunk's flush is complete
-    for (uint32_t b = threadIdx.x; b < nbp; b += kBlock) {
-      const uint32_t p0 = b < num ? (uint32_t)part_offsets[b] + chunk_base[(size_t)chunk * num + b] : 0u;
-      wpos[b] = p0 & ~GM;
-      kcnt[b] = (p0 & GM) | ((p0 & GM) << 8);  // rows before p0 in its group are phantoms
-    }
-    // (visibility: barrier A below)
-
-    for (int64_t t0 = r0; t0 < r1; t0 += T) {
-      // ---- unit 0: the key tile -> partition ids (warp-striped rows: warp*256 + r*32 + lane)
-      mbar_wait(bar_full + 8 * s, ph);
-      const uint64_t* __restrict__ kst = ring + (size_t)s * T;
-      uint32_t pid[ITEMS];
-#pragma unroll
-      for (int r = 0; r < ITEMS; ++r)
-        pid[r] = fb_fastmod(fb_hash_single_u64(kst[warp * (32 * ITEMS) + r * 32 + lane]), dv);
-
-      // ---- stable rank inside (warp, partition)
-      uint32_t pos[ITEMS];
-#pragma unroll
-      for (int r = 0; r < ITEMS; ++r) {
-        const unsigned m = match_lanes<kBits>(pid[r], 0xFFFFFFFFu);
-        const unsigned before = __popc(m & lt);
-        uint32_t old = 0;
-        if (before == 0) {
-          old = my_cnt[pid[r]];
-          my_cnt[pid[r]] = (uint16_t)(old + __popc(m));
-        }
-        __syncwarp();
-        old = __shfl_sync(0xFFFFFFFFu, old, __ffs(m) - 1);
-        pos[r] = old + before;
-      }
-      consumer_sync();  // A
-
-      // ---- per partition (thread b < num): tile count, rows to write, new pending state;
-      //      block scans of (count, written)
-      {
-        const uint32_t b = threadIdx.x;
-        uint32_t n = 0, w = 0, kold = 0, phold = 0;
-        if (b < num) {
-#pragma unroll
-          for (int wi = 0; wi < kWarps; ++wi) {
-            const uint32_t t = cnt[wi * nbp + b];
-            cnt[wi * nbp + b] = (uint16_t)n;
-            n += t;
-          }
-          const uint32_t kc = kcnt[b];
-          kold = kc & 0xFFu;
-          phold = kc >> 8;
-          const uint32_t wp = wpos[b];
-          const uint32_t end = wp + kold + n;
-          const uint32_t aend = end & ~GM;
-          uint32_t knew = kold + n;
-          if (aend > wp) {
-            w = aend - wp;
-            knew = end - aend;
-            wpos[b] = aend;
-            kcnt[b] = knew;  // phantoms are consumed by the first write
-          } else {
-            kcnt[b] = knew | (phold << 8);
-          }
-          binfo[b] = kold | (phold << 4) | (w << 8);
-        }
-        // two inclusive warp scans
-        uint32_t xn = n, xw = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t yn = __shfl_up_sync(0xFFFFFFFFu, xn, o);
-          const uint32_t yw = __shfl_up_sync(0xFFFFFFFFu, xw, o);
-          if (lane >= (unsigned)o) { xn += yn; xw += yw; }
-        }
-        if (lane == 31) { scanw[warp] = xn; scanw[16 + warp] = xw; }
-        consumer_sync();  // B
-        uint32_t bn = xn - n, bw = xw - w;
-        {
-          const uint32_t tn = lane < kWarps ? scanw[lane] : 0;
-          const uint32_t tw = lane < kWarps ? scanw[16 + lane] : 0;
-#pragma unroll
-          for (int wi = 0; wi < kWarps; ++wi) {
-            const uint32_t vn = __shfl_sync(0xFFFFFFFFu, tn, wi);
-            const uint32_t vw = __shfl_sync(0xFFFFFFFFu, tw, wi);
-            if ((unsigned)wi < warp) { bn += vn; bw += vw; }
-          }
-        }
-        if (b < num) {
-          bin_start[b] = bn;
-          wstart[b] = bw;
-          // the rows written this tile start at the old wpos = (new wpos) - w  when w > 0
-          wdelta[b] = (w ? wpos[b] - w : wpos[b]) - bw;
-        }
-        if (threadIdx.x == kBlock - 1) scanw[32] = bw + w;  // W: slots to store this tile
-      }
-      consumer_sync();  // C
-
-      // ---- every new row and every old carry entry finds its place: an output slot of this
-      //      tile or an entry of the new carry
-#pragma unroll
-      for (int r = 0; r < ITEMS; ++r) {
-        const uint32_t b = pid[r];
-        const uint32_t bi = binfo[b];
-        const uint32_t i = (bi & 0xFu) + pos[r] + my_cnt[b];  // index in the partition's pending list
-        const uint32_t w = bi >> 8;
-        const uint32_t row = warp * (32 * ITEMS) + r * 32 + lane;
-        if (i < w) slotinfo[wstart[b] + i] = (b << 16) | row;
-        else carryinfo[b * GM + (i - w)] = (uint16_t)row;
-      }
-#pragma unroll
-      for (int q = 0; q < kEntryRounds; ++q) {
-        const uint32_t e = q * kBlock + threadIdx.x;
-        if (e < E) {
-          const uint32_t b = e / GM, i = e - b * GM;
-          const uint32_t bi = binfo[b];
-          const uint32_t kold = bi & 0xFu, phold = (bi >> 4) & 0xFu, w = bi >> 8;
-          const uint32_t n = (b + 1 < num ? bin_start[b + 1] : T) - bin_start[b];
-          const uint32_t desc = i < phold ? 0xFFFFu : T + e;
-          if (i < kold) {  // an old carry entry
-            if (i < w) slotinfo[wstart[b] + i] = (b << 16) | desc;
-            else carryinfo[e] = (uint16_t)desc;  // w == 0: stays pending at the same index
-          }
-          // new carry entries nobody else writes: beyond the pending list
-          const uint32_t li = w + i;  // list index that lands in new carry entry i
-          if (li >= kold + n) carryinfo[e] = 0xFFFFu;
-        }
-      }
-      __syncwarp();
-      for (uint32_t i = lane; i < nbp; i += 32) my_cnt[i] = 0;  // my counter row is private again
-      consumer_sync();  // D
-
-      const uint32_t W = scanw[32];
-      uint32_t srcd[kSlotRounds], dst[kSlotRounds];
-#pragma unroll
-      for (int k = 0; k < kSlotRounds; ++k) {
-        const uint32_t j = k * kBlock + threadIdx.x;
-        srcd[k] = 0xFFFFu;
-        dst[k] = 0;
-        if (j < W) {
-          const uint32_t info = slotinfo[j];
-          srcd[k] = info & 0xFFFFu;
-          dst[k] = wdelta[info >> 16] + j;
-        }
-      }
-      uint32_t csrc[kEntryRounds];
-#pragma unroll
-      for (int q = 0; q < kEntryRounds; ++q) {
-        const uint32_t e = q * kBlock + threadIdx.x;
-        csrc[q] = e < E ? (uint32_t)carryinfo[e] : 0xFFFFu;
-      }
-
-      // ---- per column: gather from the staged tile / old carry, store whole sector groups,
-      //      save the new carry
-      int c = 0;  // payload column index (for the carry buffers)
-      for (int u = 0; u < units.nunits; ++u) {
-        if (u > 0) mbar_wait(bar_full + 8 * s, ph);
-        uint64_t* __restrict__ out = units.dst[u];
-        if (out != nullptr) {
-          const uint64_t* __restrict__ st = ring + (size_t)s * T;
-          int bo = c + rot; if (bo >= nbuf) bo -= nbuf;
-          int bn = c + rot - 1; if (bn < 0) bn += nbuf; if (bn >= nbuf) bn -= nbuf;
-          const uint64_t* __restrict__ oldc = carry + (size_t)bo * E;
-          uint64_t* __restrict__ newc = carry + (size_t)bn * E;
-          uint64_t v[kSlotRounds], cv[kEntryRounds];
-#pragma unroll
-          for (int k = 0; k < kSlotRounds; ++k)
-            if (srcd[k] != 0xFFFFu) v[k] = srcd[k] < T ? st[srcd[k]] : oldc[srcd[k] - T];
-#pragma unroll
-          for (int q = 0; q < kEntryRounds; ++q)
-            if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : oldc[csrc[q] - T];
-#pragma unroll
-          for (int k = 0; k < kSlotRounds; ++k)
-            if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
-          consumer_sync();  // every warp has read this column's old carry (= the next spare)
-#pragma unroll
-          for (int q = 0; q < kEntryRounds; ++q) {
-            const uint32_t e = q * kBlock + threadIdx.x;
-            if (csrc[q] != 0xFFFFu) newc[e] = cv[q];
-          }
-          // this column now lives in buffer (c + rot - 1); its old buffer is the next column's spare
-          ++c;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed(bar_empty + 8 * s);  // this warp is done with the stage
-        if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
-      }
-      // after the tile: column c's data is in buffer (c + rot - 1) mod nbuf
-      rot = rot == 0 ? nbuf - 1 : rot - 1;
-    }
-
-    // ---- chunk end: flush the pending rows (partial sector groups)
-    consumer_sync();
-    {
-      int c = 0;
-      for (int u = 0; u < units.nunits; ++u) {
-        uint64_t* __restrict__ out = units.dst[u];
-        if (out == nullptr) continue;
-        int bo = c + rot; if (bo >= nbuf) bo -= nbuf;
-        const uint64_t* __restrict__ oldc = carry + (size_t)bo * E;
-#pragma unroll
-        for (int q = 0; q < kEntryRounds; ++q) {
-          const uint32_t e = q * kBlock + threadIdx.x;
-          if (e < E) {
-            const uint32_t b = e / GM, i = e - b * GM;
-            const uint32_t kc = kcnt[b];
-            if (i < (kc & 0xFFu) && i >= (kc >> 8)) out[wpos[b] + i] = oldc[e];
-          }
-        }
-        ++c;
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1349,8 +1042,6 @@ cudaError_t ensure_smem_optin(int dev) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<4, kSwcGA, kSwcItemsA>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_swc_kernel<8, kSwcGA, kSwcItemsA>, (size_t)smem_max);
   }
   FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
   FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
@@ -1517,7 +1208,7 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
 static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, bool single,
                       uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
                       const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
-                      const int32_t* col_widths, void* const* out_col_ptrs) {
+                      const int32_t* col_widths, void* const* out_col_ptrs, int sm_reserve = 0) {
   FB_CHECK(nrows >= 0 && nrows < ((int64_t)1 << 32), "nrows out of range");
   FB_CHECK(num_partitions >= 1 && num_partitions <= FB_MAX_PARTITIONS,
            "num_partitions=%u out of range [1,%d]", num_partitions, FB_MAX_PARTITIONS);
@@ -1569,15 +1260,9 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
     return 0;
   };
 
-  // ---- split the columns: fast path (TMA ring + write combining) vs generic
-  // v5 (warp-specialised, reads the partition-id plane written by pass 1): any key shape;
-  // v4 (FB_SCATTER=swc, hashes in pass 2): single 8-byte key only.  Both: 8-byte columns, num <= 256.
-  const char* sel = getenv("FB_SCATTER");
-  const bool use_ws = sel == nullptr || strcmp(sel, "ws") == 0;
-  const bool use_swc = sel != nullptr && strcmp(sel, "swc") == 0;
-  const bool fast_ok = num_partitions <= kSwcMaxNum && g.nchunks_full > 0 &&
-                       ((use_ws) || (use_swc && single && ((uintptr_t)k.ptr[0] % 16 == 0))) &&
-                       getenv("FB_DISABLE_TMA") == nullptr;
+  // ---- split the columns: fast path (warp-specialised TMA ring + write combining; reads the rank
+  //      records written by pass 1, so any key shape qualifies) vs generic.  8-byte columns, num <= 256.
+  const bool fast_ok = num_partitions <= kSwcMaxNum && g.nchunks_full > 0;
   int* fast_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
   int* gen_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
   int nfast = 0, ngen = 0;
@@ -1591,75 +1276,37 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
     int smem_max = 0;
     FB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int grid = fb_sm_count(dev) < g.nchunks_full ? fb_sm_count(dev) : g.nchunks_full;
-    if (const char* gs = getenv("FB_WS_GRID")) {  // leave SMs to a concurrent kernel (multi-GPU pull)
-      const int lim = atoi(gs);
-      if (lim >= 1 && lim < grid) grid = lim;
-    }
+    // sm_reserve: SMs left free for kernels that must co-run with this persistent one (the
+    // multi-GPU barrier / pull kernels: a scatter CTA owns the whole register file of its SM)
+    if (sm_reserve > 0 && grid > fb_sm_count(dev) - sm_reserve) grid = fb_sm_count(dev) - sm_reserve;
+    if (grid < 1) grid = 1;
     const uint8_t* pid_plane = (const uint8_t*)scratch + l.pid_offset;  // rank records of pass 1
     // measured (100 M rows x 8 cols, columns per launch): 8 -> 3.45 ms, 4 -> 3.10, 3 -> 3.21, 2 -> 3.33,
     // 1 -> 4.59 (fewer open write streams: half-written lines meet their other half while still in L2;
     // a launch costs ~0.15 ms of ramp + rank-record traffic).  Groups of at most 4, evenly sized.
-    int cols_per_launch = kSwcMaxCols;
-    if (use_ws) {
-      const int ngroups = (nfast + 3) / 4;
-      cols_per_launch = (nfast + ngroups - 1) / ngroups;
-      if (getenv("FB_WS_COLS")) {
-        cols_per_launch = atoi(getenv("FB_WS_COLS"));
-        if (cols_per_launch < 1 || cols_per_launch > kSwcMaxCols) cols_per_launch = kSwcMaxCols;
-      }
-    }
+    const int ngroups = (nfast + 3) / 4;
+    const int cols_per_launch = (nfast + ngroups - 1) / ngroups;
     for (int c0 = 0; c0 < nfast; c0 += cols_per_launch) {
       const int nb = nfast - c0 < cols_per_launch ? nfast - c0 : cols_per_launch;
-      if (use_ws) {
-        WsUnits wu;
-        memset(&wu, 0, sizeof(wu));
-        wu.nunits = nb;
-        for (int c = 0; c < nb; ++c) {
-          wu.src[c] = (const uint64_t*)col_ptrs[fast_idx[c0 + c]];
-          wu.dst[c] = (uint64_t*)out_col_ptrs[fast_idx[c0 + c]];
-        }
-        const size_t book = ws_book_bytes<kWsG, kWsRankItems>(num_partitions, nb);
-        const size_t stage_bytes = (size_t)kWsRankers * kWsRankItems * 8;
-        int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
-        if (nstages > 16) nstages = 16;
-        FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
-        const size_t tsmem = (size_t)nstages * stage_bytes + book;
-        if (bits == 4)
-          fb_scatter_ws_kernel<4, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
-              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
-        else
-          fb_scatter_ws_kernel<8, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
-              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
-        FB_CUDA(cudaGetLastError());
-        continue;
-      }
-      TmaUnits units;
-      memset(&units, 0, sizeof(units));
-      units.src[0] = (const uint64_t*)k.ptr[0];
-      units.dst[0] = nullptr;
-      units.nunits = 1;
+      WsUnits wu;
+      memset(&wu, 0, sizeof(wu));
+      wu.nunits = nb;
       for (int c = 0; c < nb; ++c) {
-        const int ci = fast_idx[c0 + c];
-        if (col_ptrs[ci] == k.ptr[0] && units.dst[0] == nullptr) {
-          units.dst[0] = (uint64_t*)out_col_ptrs[ci];  // the key column is a payload column too
-        } else {
-          units.src[units.nunits] = (const uint64_t*)col_ptrs[ci];
-          units.dst[units.nunits] = (uint64_t*)out_col_ptrs[ci];
-          ++units.nunits;
-        }
+        wu.src[c] = (const uint64_t*)col_ptrs[fast_idx[c0 + c]];
+        wu.dst[c] = (uint64_t*)out_col_ptrs[fast_idx[c0 + c]];
       }
-      const size_t book = swc_book_bytes<kSwcGA, kSwcItemsA>(num_partitions, nb);
-      const size_t stage_bytes = (size_t)kBlock * kSwcItemsA * 8;
+      const size_t book = ws_book_bytes<kWsG, kWsRankItems>(num_partitions, nb);
+      const size_t stage_bytes = (size_t)kWsRankers * kWsRankItems * 8;
       int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
       if (nstages > 16) nstages = 16;
       FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
       const size_t tsmem = (size_t)nstages * stage_bytes + book;
       if (bits == 4)
-        fb_scatter_swc_kernel<4, kSwcGA, kSwcItemsA><<<grid, kTmaThreads, tsmem, st>>>(
-            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
+        fb_scatter_ws_kernel<4, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
+            wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
       else
-        fb_scatter_swc_kernel<8, kSwcGA, kSwcItemsA><<<grid, kTmaThreads, tsmem, st>>>(
-            units, dv, num_partitions, g, nstages, nb, (const uint32_t*)scratch, part_offsets);
+        fb_scatter_ws_kernel<8, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
+            wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
       FB_CUDA(cudaGetLastError());
     }
     // the partial tail tile of the fast columns
@@ -1678,6 +1325,19 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys, const vo
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
                     scratch, scratch_bytes, part_offsets, ncols, col_ptrs, col_widths, out_col_ptrs);
+}
+
+int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                          const int32_t* key_widths, const uint8_t* const* key_valid,
+                          uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
+                          const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
+                          const int32_t* col_widths, void* const* out_col_ptrs, int sm_reserve) {
+  if (nrows == 0 || ncols == 0) return 0;
+  FB_CHECK(sm_reserve >= 0, "sm_reserve < 0");
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
+                    scratch, scratch_bytes, part_offsets, ncols, col_ptrs, col_widths, out_col_ptrs, sm_reserve);
 }
 
 int fb_radix_pass(int dev, void* stream, int64_t nrows, const void* sort_key_u64, int shift, int ncols,

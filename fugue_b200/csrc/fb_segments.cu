@@ -119,8 +119,9 @@ extern "C" int fb_copy_segments(int dev, void* stream, int ncols, const void* co
 
 
 // ---------------------------------------------------------------------------
-// The exchange on the copy engines (see include/fugue_b200.h).  cudaMemcpyBatchAsync (CUDA 12.8+)
-// submits all runs with one driver call; FB_DMA_BATCH=0 falls back to one cudaMemcpyAsync per run.
+// The exchange on the copy engines (see include/fugue_b200.h): a few large runs, one
+// cudaMemcpyAsync each (peer memory mapped through symmetric memory is a plain device pointer
+// here; the driver routes the copy over NVLink).
 // ---------------------------------------------------------------------------
 extern "C" int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void* const* src, void* const* dst,
                                 const size_t* bytes) {
@@ -130,22 +131,6 @@ extern "C" int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
   cudaStream_t st = (cudaStream_t)stream;
-  const char* sel = getenv("FB_DMA_BATCH");
-  const bool batch = sel == nullptr || strcmp(sel, "0") != 0;
-#if CUDART_VERSION >= 12080
-  if (batch) {
-    cudaMemcpyAttributes attr;
-    memset(&attr, 0, sizeof(attr));
-    attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-    attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
-    size_t attr_idx = 0, fail = 0;
-    cudaError_t e = cudaMemcpyBatchAsync((void**)dst, (void**)src, (size_t*)bytes, (size_t)nruns, &attr, &attr_idx, 1,
-                                         &fail, st);
-    if (e == cudaSuccess) return 0;
-    if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue) FB_CUDA(e);
-    (void)cudaGetLastError();  // not available for these pointers / this stream: plain copies below
-  }
-#endif
   for (int64_t i = 0; i < nruns; ++i)
     if (bytes[i] != 0) FB_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDeviceToDevice, st));
   return 0;

@@ -1,11 +1,15 @@
 """Multi-GPU hash repartition: one process per GPU, rows range-sharded.
 
-    local K1-K3 into `num` partitions          (libfugue_b200.so)
- -> all-gather of the per-partition counts     (num x world int64)
- -> ONE all-to-all per column over NCCL/NVLink (partition p is owned by rank p*world//num,
-                                                so every send region is contiguous)
- -> segment copy: received (source, partition) runs -> (partition, source) order, so every
-    owned partition is contiguous and rows keep (source rank, source row) order = stable.
+    pass 1 on the local shard (rank records + per-partition counts)        libfugue_b200.so
+ -> counts to every rank through a symmetric-memory control buffer          (no NCCL, no SM-filling kernel)
+ -> pass 2 (scatter) column group by column group into this rank's slice of a symmetric ARENA
+ -> while group k+1 scatters, the COPY ENGINES pull group k over NVLink 5 / NVSwitch: physical
+    partition p is owned by rank p*world//num, so the partitions one rank owns are contiguous in
+    every source's partitioned table and the exchange is ONE run per (source rank, column)
+ -> the result keeps the received runs in (source rank, partition) order: an owned partition is a
+    list of `world` segments (``B200Table.segment_offsets``), rows inside it ordered by (source
+    rank, source row) = the stable partition of the concatenated table.  ``B200Table.compacted()``
+    makes every partition contiguous with one local segment copy when a consumer needs that.
 
 The reference has no shuffle of its own (Dask: set_index + repartition(divisions),
 fugue_dask/_utils.py:124-130, 166-169; Spark: df.repartition, fugue_spark/_utils/partition.py:23);
@@ -65,6 +69,14 @@ class ExchangePlan:
         part_counts = mine.sum(0)
         self.out_offsets = torch.zeros(hi - lo + 1, dtype=torch.int64)
         self.out_offsets[1:] = torch.cumsum(part_counts, 0)
+        # one-run-per-source exchange: source s's rows for this rank are the contiguous range
+        # [pull_start[s], pull_start[s] + recv_rows[s]) of its partitioned table and land at
+        # recv_base[s]; the received (source, partition) runs are delimited by segment_offsets
+        self.recv_base = recv_base
+        self.pull_start = src_part_off[:, lo]                      # [world]
+        seg = torch.zeros(world, hi - lo + 1, dtype=torch.int64)
+        seg[:, 1:] = torch.cumsum(mine, 1)
+        self.segment_offsets = seg + recv_base[:, None]            # [world, nown + 1]
 
 
 def gather_counts(local_counts: torch.Tensor, group: Any = None) -> torch.Tensor:
@@ -91,6 +103,25 @@ def rearrange_cpu(recv: Sequence[torch.Tensor], plan: ExchangePlan) -> List[torc
     return outs
 
 
+def compact_plan(segment_offsets: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(source, partition) runs -> partition-contiguous order.  Returns (src_off, dst_off, len) of
+    the runs in (partition, source) order and the offsets[nown + 1] of the compacted table."""
+    lens = segment_offsets[:, 1:] - segment_offsets[:, :-1]        # [world, nown]
+    flat = lens.t().contiguous().reshape(-1)
+    dst = torch.cumsum(flat, 0) - flat
+    src = segment_offsets[:, :-1].t().contiguous().reshape(-1)
+    off = torch.zeros(lens.shape[1] + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lens.sum(0), 0)
+    return src, dst, flat, off
+
+
+FUGUE_B200_CONF_DIST_GROUP_COLS = "fugue.b200.dist.group_cols"    # payload columns per scatter/exchange group
+FUGUE_B200_CONF_DIST_EXCHANGE = "fugue.b200.dist.exchange"        # "dma" (copy engines) | "kernel" (SM pull)
+FUGUE_B200_CONF_DIST_SM_RESERVE = "fugue.b200.dist.sm_reserve"    # SMs the persistent scatter leaves free
+_BARRIER_TIMEOUT_MS = 120_000   # a rank that died must not hang the others' GPUs forever
+_CTL_SLOTS = 1024                                                 # counts per rank and parity (K.MAX_PARTITIONS)
+
+
 class DistributedB200Engine(B200ExecutionEngine):
     """``B200ExecutionEngine`` whose ``repartition`` shuffles across the GPUs of the process group."""
 
@@ -101,6 +132,14 @@ class DistributedB200Engine(B200ExecutionEngine):
         self._group = group
         self._world = dist.get_world_size(group)
         self._rank = dist.get_rank(group)
+        self._arena: Optional[torch.Tensor] = None
+        self._ctl: Optional[torch.Tensor] = None
+        self._step = 0
+        self._group_cols = max(1, int(self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, 2)))
+        self._exchange = str(self._conf.get(FUGUE_B200_CONF_DIST_EXCHANGE, "dma"))
+        assert_or_throw(self._exchange in ("dma", "kernel"), ValueError(f"unknown exchange {self._exchange}"))
+        self._sm_reserve = int(self._conf.get(FUGUE_B200_CONF_DIST_SM_RESERVE,
+                                              1 if self._exchange == "dma" else 16))
 
     @property
     def is_distributed(self) -> bool:
@@ -109,16 +148,51 @@ class DistributedB200Engine(B200ExecutionEngine):
     def get_current_parallelism(self) -> int:
         return self._world
 
-    # ---- symmetric arena: this rank's partitioned columns, readable by every peer over NVLink
+    # ---- symmetric memory: the arena (this rank's partitioned columns, readable by every peer over
+    #      NVLink) and a small control buffer for the per-partition counts
     def _ensure_arena(self, nbytes: int) -> None:
-        """All ranks call this with the same ``nbytes`` (derived from the gathered counts)."""
+        """Collective: all ranks call this with the same ``nbytes`` (derived from the gathered counts)."""
         import torch.distributed._symmetric_memory as symm_mem
 
-        if getattr(self, "_arena", None) is not None and self._arena.numel() >= nbytes:
+        if self._arena is not None and self._arena.numel() >= nbytes:
             return
         cap = ((int(nbytes * 1.25) + (1 << 21) - 1) >> 21) << 21
+        self._arena = None  # release the old mapping first
         self._arena = symm_mem.empty(cap, dtype=torch.uint8, device=self._device)
         self._arena_hdl = symm_mem.rendezvous(self._arena, group=self._group or dist.group.WORLD)
+
+    def _ensure_ctl(self) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if self._ctl is not None:
+            return
+        dev = self._device
+        self._ctl = symm_mem.empty(2 * _CTL_SLOTS, dtype=torch.int64, device=dev)
+        self._ctl_hdl = symm_mem.rendezvous(self._ctl, group=self._group or dist.group.WORLD)
+        self._ctl_peers = [[self._ctl_hdl.get_buffer(s, (_CTL_SLOTS,), torch.int64, par * _CTL_SLOTS)
+                            for s in range(self._world)] for par in range(2)]
+        self._counts_dev = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, device=dev)
+        self._counts_host = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, pin_memory=True)
+        self._s_ctl = torch.cuda.Stream(dev)
+        self._s_dma = [torch.cuda.Stream(dev) for _ in range(self._world)]
+
+    def _post_counts(self, local_counts: torch.Tensor) -> torch.cuda.Event:
+        """Stream-ordered all-gather of ``local_counts`` (int64[num], device) over symmetric memory:
+        own slot <- counts; barrier; read every peer's slot; copy the matrix to pinned host memory.
+        Returns the event after which ``self._counts_host[:, :num]`` is valid.  Two slots used
+        alternately: a rank rewrites a slot only after passing the NEXT call's barrier, which every
+        peer reaches after its reads of this call."""
+        self._ensure_ctl()
+        num = int(local_counts.shape[0])
+        par = self._step & 1
+        self._ctl[par * _CTL_SLOTS:par * _CTL_SLOTS + num].copy_(local_counts)
+        self._ctl_hdl.barrier(channel=0, timeout_ms=_BARRIER_TIMEOUT_MS)
+        for s in range(self._world):
+            self._counts_dev[s, :num].copy_(self._ctl_peers[par][s][:num])
+        self._counts_host.copy_(self._counts_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self._device))
+        return ev
 
     @staticmethod
     def _col_offsets(nrows: int, widths: List[int]) -> List[int]:
@@ -130,10 +204,10 @@ class DistributedB200Engine(B200ExecutionEngine):
         return out
 
     def repartition(self, df: Any, partition_spec: PartitionSpec) -> B200DataFrame:
-        """Shuffle = local K1-K3 into a symmetric arena + a pull over NVLink peer memory:
-        pass 1 -> count all-gather -> scatter into the arena -> barrier -> every rank copies the
-        (source rank, partition) runs it owns straight from the peers' arenas into its final,
-        partition-contiguous output (copy engines, or the fb_copy_segments kernel) -> barrier."""
+        """Shuffle (module docstring): pass 1 -> counts over symmetric memory -> per column group:
+        scatter into the arena, then - overlapping the next group's scatter - one copy-engine pull per
+        (source rank, column) over NVLink.  The only host wait is for the count matrix (16 KB), and it
+        happens while the first scatter is already running."""
         from . import kernels as K
 
         keys = partition_spec.partition_by
@@ -144,12 +218,16 @@ class DistributedB200Engine(B200ExecutionEngine):
         for k in keys:
             assert_or_throw(k in t.schema, lambda: KeyError(f"{k} not in {t.schema}"))
         num = self._num_partitions(partition_spec, t.num_rows)
-        assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
-            f"num_partitions={num}: one radix pass handles up to {K.MAX_PARTITIONS} partitions"))
+        assert_or_throw(num <= min(K.MAX_PARTITIONS, _CTL_SLOTS), NotImplementedError(
+            f"num_partitions={num}: the multi-GPU exchange handles up to {K.MAX_PARTITIONS} partitions"))
         assert_or_throw(num >= self._world, ValueError(
             f"num_partitions={num} must be >= the number of GPUs ({self._world})"))
+        if (t.segment_offsets is not None and t.partition_keys == list(keys)
+                and getattr(t, "global_num_partitions", None) == num):
+            return edf  # already shuffled this way
         t = self._globalize_dictionaries(t)  # string columns: one code space on all ranks
         dev = t.device
+        world, rank = self._world, self._rank
         kidx = [t.schema.index_of_key(k) for k in keys]
         kvalid = [t.valid[i] for i in kidx]
         cols = list(t.columns)
@@ -159,118 +237,146 @@ class DistributedB200Engine(B200ExecutionEngine):
                 vpos[i] = len(cols)
                 cols.append(v)
         widths = [c.element_size() for c in cols]
-        # ---- pass 1 on the local shard, counts to everybody
+        s_main = torch.cuda.current_stream(dev)
+        # ---- pass 1 on the local shard; counts to everybody (stream-ordered, host reads them later)
         scratch = self._pool.scratch(dev, K.partition_scratch_bytes(dev, t.num_rows, num))
         plan_local = K.partition_plan([t.columns[i] for i in kidx], num, kvalid, scratch=scratch)
-        counts = gather_counts(plan_local.offsets[1:] - plan_local.offsets[:-1], self._group)
-        plan = ExchangePlan(counts, self._rank)
-        mode = os.environ.get("FB_DIST_EXCHANGE", "pull")
-        if mode == "nccl":
-            return self._repartition_nccl(t, keys, cols, vpos, plan_local, plan)
-        rows = [int(x) for x in plan.rows_per_rank.tolist()]
-        self._ensure_arena(max(self._col_offsets(r, widths)[-1] for r in rows))
-        # ---- pass 2 + exchange in column groups, so that moving group A over NVLink overlaps the
-        #      HBM-bound scatter of group B (peers' reads of the previous call are over: every call
-        #      ends with a barrier).
-        #      "dma" (default): the (source rank, partition) runs are copied by the COPY ENGINES
-        #      (fb_copy_runs_dma): the scatter kernel fills every SM's registers and shared memory, so
-        #      a pull *kernel* cannot co-run with it and the two serialise; DMA needs no SM.
-        #      "pull": one fb_copy_segments kernel with peer pointers (16-byte loads over NVLink).
+        ev_counts = self._post_counts(plan_local.offsets[1:] - plan_local.offsets[:-1])
+        self._step += 1
+        # 8-byte columns first (fast kernel), in groups; narrow columns (validity masks ...) last
+        order = sorted(range(len(cols)), key=lambda i: (widths[i] != 8, i))
+        per = self._group_cols
+        groups = [order[a:a + per] for a in range(0, len(order), per)]
         my_off = self._col_offsets(t.num_rows, widths)
-        parts = [self._arena[my_off[i]:my_off[i] + t.num_rows * w].view(c.dtype)
-                 for i, (c, w) in enumerate(zip(cols, widths))]
-        base = self._arena_hdl.buffer_ptrs
-        peer_off = [self._col_offsets(rows[s], widths) for s in range(self._world)]
-        outs = [torch.empty(plan.total_recv, dtype=c.dtype, device=dev) for c in cols]
-        s_main = torch.cuda.current_stream(dev)
-        if getattr(self, "_pull_stream", None) is None:
-            self._pull_stream = torch.cuda.Stream(dev)
-        s_pull = self._pull_stream
-        per = max(1, int(os.environ.get("FB_DIST_GROUP_COLS", "4")))
-        groups = [list(range(a, min(a + per, len(cols)))) for a in range(0, len(cols), per)]
-        if mode == "dma":
-            import numpy as np
 
-            keep = plan.seg_len.numpy() > 0
-            r_rank = plan.pull_src_rank.numpy()[keep].astype(np.int64)
-            r_src = plan.pull_src_off.numpy()[keep].astype(np.uint64)
-            r_dst = plan.seg_dst_off.numpy()[keep].astype(np.uint64)
-            r_len = plan.seg_len.numpy()[keep].astype(np.uint64)
-            col_base = np.array([[int(base[s]) + peer_off[s][i] for i in range(len(cols))]
-                                 for s in range(self._world)], dtype=np.uint64)   # [rank][column]
-        else:
-            seg_src, seg_dst = plan.pull_src_off.to(dev), plan.seg_dst_off.to(dev)
-            seg_len, seg_rank = plan.seg_len.to(dev), plan.pull_src_rank.to(dev)
+        def scatter_all() -> List[torch.cuda.Event]:
+            parts = [self._arena[my_off[i]:my_off[i] + t.num_rows * w].view(c.dtype)
+                     for i, (c, w) in enumerate(zip(cols, widths))]
+            evs = []
+            for idx in groups:
+                K.partition_apply(plan_local, [cols[i] for i in idx], [parts[i] for i in idx],
+                                  sm_reserve=self._sm_reserve)
+                ev = torch.cuda.Event()
+                ev.record(s_main)
+                evs.append(ev)
+            return evs
+
+        # enqueue the scatters before waiting for the counts if the local shard fits the arena (peers'
+        # reads of the previous call are over: every call ends with a barrier)
+        ev_sc: Optional[List[torch.cuda.Event]] = None
+        if self._arena is not None and self._arena.numel() >= my_off[-1]:
+            ev_sc = scatter_all()
+        ev_counts.synchronize()
+        counts = self._counts_host[:, :num].clone()
+        plan = ExchangePlan(counts, rank)
+        rows = [int(x) for x in plan.rows_per_rank.tolist()]
+        need = max(self._col_offsets(r, widths)[-1] for r in rows)
+        if self._arena is None or self._arena.numel() < need:
+            # first call / growth: every rank takes this branch (same matrix, same capacity everywhere)
+            torch.cuda.synchronize(dev)
+            self._ensure_arena(need)
+            ev_sc = None
+        if ev_sc is None:
+            ev_sc = scatter_all()
+        base = [int(x) for x in self._arena_hdl.buffer_ptrs]
+        peer_off = [self._col_offsets(rows[s], widths) for s in range(world)]
+        outs = [torch.empty(plan.total_recv, dtype=c.dtype, device=dev) for c in cols]
+        recv_rows, recv_base = plan.recv_rows, [int(x) for x in plan.recv_base.tolist()]
+        pull_start = [int(x) for x in plan.pull_start.tolist()]
+        s_ctl = self._s_ctl
+        s_ctl.wait_stream(s_main)  # outs were allocated on the main stream
+        if self._exchange == "kernel":
+            seg_src = plan.pull_start.to(dev)
+            seg_dst = plan.recv_base.to(dev)
+            seg_len = torch.tensor(recv_rows, dtype=torch.int64, device=dev)
+            seg_rank = torch.arange(world, dtype=torch.int32, device=dev)
         for gi, idx in enumerate(groups):
-            K.partition_apply(plan_local, [cols[i] for i in idx], [parts[i] for i in idx])
-            ev = torch.cuda.Event()
-            ev.record(s_main)
-            with torch.cuda.stream(s_pull):
-                s_pull.wait_event(ev)
-                dist.barrier(group=self._group)  # stream-ordered: this group is complete on all ranks
-                if mode == "dma":
-                    src = np.concatenate([col_base[r_rank, i] + r_src * np.uint64(widths[i]) for i in idx])
-                    dst = np.concatenate([np.uint64(outs[i].data_ptr()) + r_dst * np.uint64(widths[i]) for i in idx])
-                    nb = np.concatenate([r_len * np.uint64(widths[i]) for i in idx])
-                    K.copy_runs_dma(dev, src, dst, nb)
-                else:
-                    src_ptrs = [int(base[s]) + peer_off[s][i] for s in range(self._world) for i in idx]
-                    K.copy_segments(None, [outs[i] for i in idx], seg_src, seg_dst, seg_len, max_len=plan.max_seg,
+            # own rows: local copy, needs no barrier
+            with torch.cuda.stream(self._s_dma[0]):
+                self._s_dma[0].wait_event(ev_sc[gi])
+                if self._exchange == "dma" and recv_rows[rank] > 0:
+                    K.copy_runs_dma(dev, [base[rank] + peer_off[rank][i] + pull_start[rank] * widths[i] for i in idx],
+                                    [outs[i].data_ptr() + recv_base[rank] * widths[i] for i in idx],
+                                    [recv_rows[rank] * widths[i] for i in idx])
+            with torch.cuda.stream(s_ctl):
+                s_ctl.wait_event(ev_sc[gi])
+                self._arena_hdl.barrier(channel=1, timeout_ms=_BARRIER_TIMEOUT_MS)  # group gi sits in every rank's arena
+                ev_b = torch.cuda.Event()
+                ev_b.record(s_ctl)
+                if self._exchange == "kernel":
+                    src_ptrs = [base[s] + peer_off[s][i] for s in range(world) for i in idx]
+                    K.copy_segments(None, [outs[i] for i in idx], seg_src, seg_dst, seg_len, max_len=max(recv_rows),
                                     src_table=seg_rank, src_ptrs=src_ptrs)
-        with torch.cuda.stream(s_pull):
-            dist.barrier(group=self._group)  # nobody overwrites an arena that is still being read
-        s_main.wait_stream(s_pull)
+            if self._exchange == "dma":
+                for j in range(1, world):
+                    s = (rank + j) % world
+                    if recv_rows[s] == 0:
+                        continue
+                    with torch.cuda.stream(self._s_dma[j]):
+                        self._s_dma[j].wait_event(ev_b)
+                        K.copy_runs_dma(dev, [base[s] + peer_off[s][i] + pull_start[s] * widths[i] for i in idx],
+                                        [outs[i].data_ptr() + recv_base[s] * widths[i] for i in idx],
+                                        [recv_rows[s] * widths[i] for i in idx])
+        for sd in self._s_dma:
+            s_ctl.wait_stream(sd)
+        with torch.cuda.stream(s_ctl):
+            self._arena_hdl.barrier(channel=1, timeout_ms=_BARRIER_TIMEOUT_MS)  # nobody overwrites an arena that is still being read
+        s_main.wait_stream(s_ctl)
         for o in outs:
-            o.record_stream(s_pull)
+            for sd in self._s_dma:
+                o.record_stream(sd)
+            o.record_stream(s_ctl)
         ncol = len(t.columns)
         valid = [outs[vpos[i]] if i in vpos else None for i in range(ncol)]
-        res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
-        res.global_partition_range = (plan.lo, plan.hi)  # which physical partitions this GPU owns
-        return B200DataFrame(res)
+        res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, None, list(keys))
+        res.segment_offsets = plan.segment_offsets          # [world, nown + 1] (host)
+        res.global_partition_range = (plan.lo, plan.hi)     # which physical partitions this GPU owns
+        res.global_num_partitions = num
+        rdf = B200DataFrame(res)
+        if edf.has_metadata:
+            rdf.reset_metadata(edf.metadata)
+        return rdf
 
     def _globalize_dictionaries(self, t: B200Table) -> B200Table:
-        """String columns are dictionary encoded per rank; before rows travel (and before codes are
-        hashed as partition keys) every rank re-codes them against the union dictionary: the
-        dictionaries are gathered on the host (small), the union is taken in first-appearance order
-        over ranks (identical everywhere), and the codes are remapped on the device."""
-        if len(t.dictionaries) == 0:
-            return t
+        return self._globalize_tables([t])[0]
+
+    def _globalize_tables(self, tables: List[B200Table]) -> List[B200Table]:
+        """String columns are dictionary encoded per rank and per table; before rows travel (and
+        before codes are hashed as partition keys) every rank re-codes them against ONE union
+        dictionary per column name - over all ranks and over all the given tables, so that the two
+        sides of a join hash equal strings to equal codes: the dictionaries are gathered on the
+        host (small), the union is taken in first-appearance order (identical everywhere), and the
+        codes are remapped on the device."""
+        names = sorted({k for t in tables for k in t.dictionaries})
+        if len(names) == 0:
+            return tables
         import pyarrow as pa
         import pyarrow.compute as pc
 
-        names = sorted(t.dictionaries)
-        local = {k: t.dictionaries[k].to_pylist() for k in names}
+        local = {k: [x for t in tables if k in t.dictionaries for x in t.dictionaries[k].to_pylist()]
+                 for k in names}
         gathered: List[Any] = [None] * self._world
         dist.all_gather_object(gathered, local, group=self._group)
-        cols = list(t.columns)
-        dicts: Dict[str, Any] = {}
-        for k in names:
-            union = pc.unique(pa.array([x for g in gathered for x in g[k]], type=pa.string()))
-            pos = pc.index_in(t.dictionaries[k], value_set=union).to_numpy(zero_copy_only=False).astype("int32")
-            i = t.schema.index_of_key(k)
-            if len(pos) > 0:
-                m = torch.from_numpy(pos).to(t.device)
-                cols[i] = m[cols[i].long().clamp_(min=0)].contiguous()
-            dicts[k] = union
-        return B200Table(t.schema, cols, t.valid, dicts, t.offsets, t.partition_keys)
-
-    def _repartition_nccl(self, t: B200Table, keys: List[str], cols: List[torch.Tensor],
-                          vpos: Dict[int, int], plan_local: Any, plan: ExchangePlan) -> B200DataFrame:
-        """Baseline exchange (FB_DIST_EXCHANGE=nccl): one NCCL all-to-all per column + local
-        segment copy.  Kept for comparison; the pull kernel above is the product path."""
-        from . import kernels as K
-
-        dev = t.device
-        parts = K.partition_apply(plan_local, cols)
-        recv = [exchange_column(c, plan, self._group) for c in parts]
-        outs = [torch.empty_like(c) for c in recv]
-        K.copy_segments(recv, outs, plan.seg_src_off.to(dev), plan.seg_dst_off.to(dev), plan.seg_len.to(dev),
-                        max_len=plan.max_seg)
-        ncol = len(t.columns)
-        valid = [outs[vpos[i]] if i in vpos else None for i in range(ncol)]
-        res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, plan.out_offsets.to(dev), list(keys))
-        res.global_partition_range = (plan.lo, plan.hi)
-        return B200DataFrame(res)
+        unions = {k: pc.unique(pa.array([x for g in gathered for x in g.get(k, [])], type=pa.string()))
+                  for k in names}
+        out = []
+        for t in tables:
+            cols = list(t.columns)
+            dicts: Dict[str, Any] = {}
+            for k in t.dictionaries:
+                pos = pc.index_in(t.dictionaries[k], value_set=unions[k]).to_numpy(zero_copy_only=False).astype("int32")
+                i = t.schema.index_of_key(k)
+                if len(pos) > 0:
+                    m = torch.from_numpy(pos).to(t.device)
+                    cols[i] = m[cols[i].long().clamp_(min=0)].contiguous()
+                dicts[k] = unions[k]
+            nt = B200Table(t.schema, cols, t.valid, dicts, t.offsets, t.partition_keys)
+            nt.segment_offsets = t.segment_offsets
+            for a in ("global_partition_range", "global_num_partitions"):
+                if hasattr(t, a):
+                    setattr(nt, a, getattr(t, a))
+            out.append(nt)
+        return out
 
     # ---- distributed relational operators (BASELINE configs 4 and 5) -------------------------
     def _shuffle_partitions(self) -> int:
@@ -329,4 +435,7 @@ class DistributedB200Engine(B200ExecutionEngine):
         key_schema, _ = get_join_schemas(e1, e2, how, on)
         assert_or_throw(how.lower() != "cross", NotImplementedError("distributed cross join"))
         spec = PartitionSpec(by=key_schema.names, num=self._shuffle_partitions())
-        return super().join(self.repartition(e1, spec), self.repartition(e2, spec), how, on)
+        # one code space for string columns of BOTH sides before their codes are hashed
+        g1, g2 = self._globalize_tables([e1.native, e2.native])
+        return super().join(self.repartition(B200DataFrame(g1), spec), self.repartition(B200DataFrame(g2), spec),
+                            how, on)

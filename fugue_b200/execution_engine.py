@@ -115,10 +115,13 @@ class B200MapEngine:
             edf = engine.repartition(edf, partition_spec)  # K1+K2+K3 on the device
         if map_func_format_hint == "b200":
             # device-vectorised map: the function is typed on B200Table and is called once per
-            # device table, the physical partitions delimited by table.offsets
+            # device table, the physical partitions delimited by table.offsets (after a multi-GPU
+            # shuffle: by table.segment_offsets, one segment per source rank and partition)
             if len(presort) > 0 and keyed:
                 from . import sort as S
 
+                if edf.native.segment_offsets is not None:
+                    edf = B200DataFrame(edf.native.compacted())
                 edf.native.logical_offsets = S.logical_offsets(edf.native, partition_spec.partition_by)
             cursor.set(lambda: edf.peek_array(), 0, 0)
             out = map_func(cursor, edf)
@@ -135,6 +138,8 @@ class B200MapEngine:
         engine = self._execution_engine
         presort_keys = list(presort.keys())
         presort_asc = list(presort.values())
+        if keyed and edf.native.segment_offsets is not None:
+            edf = B200DataFrame(edf.native.compacted())  # multi-GPU shuffle result: make partitions contiguous
         pdf = edf.as_pandas()
         outs: List[pd.DataFrame] = []
 

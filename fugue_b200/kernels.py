@@ -94,7 +94,8 @@ def partition_plan(keys: Sequence[torch.Tensor], num: int,
 
 
 def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
-                    out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+                    out: Optional[Sequence[torch.Tensor]] = None, sm_reserve: int = 0) -> List[torch.Tensor]:
+    """Pass 2 for ``cols``; ``sm_reserve`` SMs stay free for kernels that co-run (multi-GPU exchange)."""
     lib = _lib.load()
     dev, n = _check_cols(list(cols) + plan.keys)
     if out is None:
@@ -102,14 +103,14 @@ def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
     else:
         _check_cols(list(out) + plan.keys)
     vp = _valid_ptrs(plan.valid, len(plan.keys))
-    _lib.check(lib.fb_partition_apply(
+    _lib.check(lib.fb_partition_apply_ex(
         dev.index, _stream_ptr(dev), n, len(plan.keys),
         _lib.ptr_array([k.data_ptr() for k in plan.keys]),
         _lib.i32_array([k.element_size() for k in plan.keys]),
         vp, plan.num, plan.scratch.data_ptr(), plan.scratch.numel(), plan.offsets.data_ptr(),
         len(cols), _lib.ptr_array([c.data_ptr() for c in cols]),
         _lib.i32_array([c.element_size() for c in cols]),
-        _lib.ptr_array([o.data_ptr() for o in out])))
+        _lib.ptr_array([o.data_ptr() for o in out]), int(sm_reserve)))
     return list(out)
 
 
@@ -321,11 +322,25 @@ class JoinTable:
         self.num_parts = num_parts if num_parts > 1 else 0
         self.table = torch.empty(int(lib.fb_join_table_bytes(self.capacity)), dtype=torch.uint8, device=dev)
         self.status = torch.zeros(4, dtype=torch.int64, device=dev)
-        _lib.check(lib.fb_join_build_u64(dev.index, _stream_ptr(dev), n, keys.data_ptr(),
-                                         0 if valid is None else valid.data_ptr(), self.capacity,
-                                         self.num_parts, self.table.data_ptr(), self.status.data_ptr(),
-                                         0 if (part_offsets is None or self.num_parts == 0)
-                                         else part_offsets.data_ptr()))
+
+        def build() -> None:
+            _lib.check(lib.fb_join_build_u64(dev.index, _stream_ptr(dev), n, keys.data_ptr(),
+                                             0 if valid is None else valid.data_ptr(), self.capacity,
+                                             self.num_parts, self.table.data_ptr(), self.status.data_ptr(),
+                                             0 if (part_offsets is None or self.num_parts == 0)
+                                             else part_offsets.data_ptr()))
+
+        build()
+        # Region mode gives every partition capacity / num_parts slots: a skewed build side (hot key,
+        # low cardinality) can overflow its region, and the kernel then reports status[0] = 1 instead
+        # of inserting.  Fall back to ONE region over the whole table (load factor <= 0.5: cannot
+        # overflow; the inputs may stay partitioned, the probes just use the same single region).
+        if self.num_parts > 0 and int(self.status[0].item()) != 0:
+            self.num_parts = 0
+            self.status.zero_()
+            build()
+            if int(self.status[0].item()) != 0:  # pragma: no cover - load factor 0.5 always has room
+                raise _lib.FugueB200KernelError("join hash table overflow")
         self.device = dev
 
     def probe_counts(self, keys: torch.Tensor, valid: Optional[torch.Tensor], outer: bool,

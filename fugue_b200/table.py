@@ -64,6 +64,10 @@ class B200Table:
         self.partition_keys = partition_keys  # key column names the offsets refer to
         self.logical_offsets: Optional[torch.Tensor] = None  # set after a device presort: one segment
         #                                                      per distinct key tuple (logical partition)
+        # multi-GPU shuffle result (fugue_b200/dist.py): int64 [world, nown + 1] on the HOST; owned
+        # partition j is the concatenation over source ranks s of rows
+        # [segment_offsets[s, j], segment_offsets[s, j + 1]) - see compacted()
+        self.segment_offsets: Optional[torch.Tensor] = None
         n = self.columns[0].shape[0] if self.columns else 0
         for c in self.columns:
             assert c.dim() == 1 and c.shape[0] == n and c.is_contiguous()
@@ -87,7 +91,32 @@ class B200Table:
 
     @property
     def num_partitions(self) -> int:
+        if self.offsets is None and self.segment_offsets is not None:
+            return int(self.segment_offsets.shape[1]) - 1
         return 1 if self.offsets is None else int(self.offsets.shape[0]) - 1
+
+    def compacted(self) -> "B200Table":
+        """A multi-GPU shuffle leaves every owned partition as one segment per source rank
+        (``segment_offsets``).  This returns the table with every partition contiguous (``offsets``),
+        rows inside a partition in (source rank, source row) order: one local segment copy."""
+        if self.segment_offsets is None or self.offsets is not None:
+            return self
+        from .dist import compact_plan
+
+        src, dst, ln, off = compact_plan(self.segment_offsets)
+        dev = self.device
+        cols = list(self.columns) + [v for v in self.valid if v is not None]
+        outs = [torch.empty_like(c) for c in cols]
+        if self._nrows > 0:
+            K.copy_segments(cols, outs, src.to(dev), dst.to(dev), ln.to(dev), max_len=int(ln.max()))
+        ncol = len(self.columns)
+        it = iter(outs[ncol:])
+        valid = [None if v is None else next(it) for v in self.valid]
+        res = B200Table(self.schema, outs[:ncol], valid, self.dictionaries, off.to(dev), self.partition_keys)
+        for a in ("global_partition_range", "global_num_partitions"):
+            if hasattr(self, a):
+                setattr(res, a, getattr(self, a))
+        return res
 
     def nbytes(self) -> int:
         return sum(c.numel() * c.element_size() for c in self.columns)

@@ -96,6 +96,17 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys,
                        const void* const* col_ptrs, const int32_t* col_widths,
                        void* const* out_col_ptrs);
 
+/* fb_partition_apply with `sm_reserve` SMs left free: the fast scatter kernel is persistent and a
+ * CTA owns its SM's whole register file, so a kernel that must run at the same time (the multi-GPU
+ * barrier / pull kernels of the exchange that overlaps the next column group) needs SMs of its own. */
+int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys,
+                          const void* const* key_ptrs, const int32_t* key_widths,
+                          const uint8_t* const* key_valid, uint32_t num_partitions,
+                          const void* scratch, size_t scratch_bytes,
+                          const int64_t* part_offsets, int ncols,
+                          const void* const* col_ptrs, const int32_t* col_widths,
+                          void* const* out_col_ptrs, int sm_reserve);
+
 int fb_partition_cols(int dev, void* stream, int64_t nrows, int ncols,
                       const void* const* col_ptrs, const int32_t* col_widths,
                       const int32_t* key_col_idx, int nkeys,
@@ -137,10 +148,11 @@ int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_
                      void* const* d_dst_cols, const int32_t* d_widths, int nseg,
                      const int32_t* d_src_table, const int64_t* d_src_off, const int64_t* d_dst_off,
                      const int64_t* d_len, int64_t max_len);
-/* The same exchange on the COPY ENGINES: nruns independent device-to-device copies (local or peer
- * memory mapped into this process), submitted as one batch on `stream`.  Unlike the pull kernel it
- * needs no SM, so it overlaps completely with the scatter kernel of the next column group (which
- * fills every SM's registers and shared memory).  src / dst / bytes are HOST arrays. */
+/* The exchange on the COPY ENGINES: nruns independent device-to-device copies (local or peer
+ * memory mapped into this process) enqueued on `stream`, one cudaMemcpyAsync each.  The multi-GPU
+ * repartition issues ONE run per (source rank, column): the partitions a rank owns are contiguous in
+ * every source's partitioned table.  Copy engines need no SM, so the transfer over NVLink overlaps
+ * the scatter kernel of the next column group.  src / dst / bytes are HOST arrays. */
 int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void* const* src, void* const* dst,
                      const size_t* bytes);
 

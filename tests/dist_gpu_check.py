@@ -21,6 +21,23 @@ from fugue_b200.table import B200Table  # noqa: E402
 from oracle import hash_partition as hp  # noqa: E402
 
 NUM = 256
+_FAILS = []  # rank-0 comparison failures; collected, not raised, so that no rank skips a collective
+
+
+class _guard:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, tp, val, tb):
+        if tp is not None:
+            import traceback
+
+            _FAILS.append(f"{self.name}: " + "".join(traceback.format_exception_only(tp, val)).strip()[:400] +
+                          " @ " + traceback.format_tb(tb)[-1].strip().split("\n")[0][-120:])
+        return True
 
 
 def shard(rank: int, n: int):
@@ -51,23 +68,24 @@ def check_relational(eng, rank, world, dev):
     gathered = [None] * world
     dist.all_gather_object(gathered, (agg.as_pandas(), jn.as_pandas()))
     if rank == 0:
-        facts, dims = zip(*[frames(r) for r in range(world)])
-        F, D = pd.concat(facts, ignore_index=True), pd.concat(dims, ignore_index=True)
-        got = pd.concat([g[0] for g in gathered], ignore_index=True).sort_values("key").reset_index(drop=True)
-        exp = ora.aggregate(F, ["key"], {"s": ("v0", "sum"), "c": ("*", "count"), "a": ("v0", "avg"),
-                                         "m": ("v0", "max")}).sort_values("key").reset_index(drop=True)
-        assert len(got) == len(exp) and got["key"].is_unique
-        assert np.array_equal(got["key"], exp["key"]) and np.array_equal(got["c"], exp["c"])
-        assert np.array_equal(got["m"], exp["m"])
-        assert np.max(np.abs(got["s"] - exp["s"]) / np.maximum(np.abs(exp["s"]), 1e-300)) <= 1e-9
-        assert np.allclose(got["a"], exp["a"], rtol=1e-9)
-        gj = pd.concat([g[1] for g in gathered], ignore_index=True)
-        ej = ora.join(F, D, "inner")
-        cols = list(ej.columns)
-        a = gj.sort_values(cols).reset_index(drop=True)
-        b = ej.sort_values(cols).reset_index(drop=True)
-        pd.testing.assert_frame_equal(a, b, check_exact=True, check_dtype=False)
-        print(f"dist relational ok: {len(got)} groups, {len(gj)} joined rows")
+        with _guard("block 1"):
+            facts, dims = zip(*[frames(r) for r in range(world)])
+            F, D = pd.concat(facts, ignore_index=True), pd.concat(dims, ignore_index=True)
+            got = pd.concat([g[0] for g in gathered], ignore_index=True).sort_values("key").reset_index(drop=True)
+            exp = ora.aggregate(F, ["key"], {"s": ("v0", "sum"), "c": ("*", "count"), "a": ("v0", "avg"),
+                                             "m": ("v0", "max")}).sort_values("key").reset_index(drop=True)
+            assert len(got) == len(exp) and got["key"].is_unique
+            assert np.array_equal(got["key"], exp["key"]) and np.array_equal(got["c"], exp["c"])
+            assert np.array_equal(got["m"], exp["m"])
+            assert np.max(np.abs(got["s"] - exp["s"]) / np.maximum(np.abs(exp["s"]), 1e-300)) <= 1e-9
+            assert np.allclose(got["a"], exp["a"], rtol=1e-9)
+            gj = pd.concat([g[1] for g in gathered], ignore_index=True)
+            ej = ora.join(F, D, "inner")
+            cols = list(ej.columns)
+            a = gj.sort_values(cols).reset_index(drop=True)
+            b = ej.sort_values(cols).reset_index(drop=True)
+            pd.testing.assert_frame_equal(a, b, check_exact=True, check_dtype=False)
+            print(f"dist relational ok: {len(got)} groups, {len(gj)} joined rows")
     # aggregating select with expressions, WHERE and HAVING: row-wise parts local, partials shuffled
     from fugue_b200.column import SelectColumns
     from oracle import expressions as OX
@@ -79,13 +97,14 @@ def check_relational(eng, rank, world, dev):
     gathered = [None] * world
     dist.all_gather_object(gathered, part.as_pandas())
     if rank == 0:
-        got = pd.concat(gathered, ignore_index=True).sort_values("key").reset_index(drop=True)
-        exp = OX.select(F, sel, where=where, having=having).sort_values("key").reset_index(drop=True)
-        assert len(got) == len(exp) and got["key"].is_unique
-        assert np.array_equal(got["key"].to_numpy(), exp["key"].to_numpy(dtype="int64"))
-        assert np.allclose(got["m2"].to_numpy(), exp["m2"].to_numpy(dtype="float64"), rtol=1e-9)
-        assert np.allclose(got["mx"].to_numpy(), exp["mx"].to_numpy(dtype="float64"), rtol=1e-12)
-        print(f"dist select ok: {len(got)} groups")
+        with _guard("block 2"):
+            got = pd.concat(gathered, ignore_index=True).sort_values("key").reset_index(drop=True)
+            exp = OX.select(F, sel, where=where, having=having).sort_values("key").reset_index(drop=True)
+            assert len(got) == len(exp) and got["key"].is_unique
+            assert np.array_equal(got["key"].to_numpy(), exp["key"].to_numpy(dtype="int64"))
+            assert np.allclose(got["m2"].to_numpy(), exp["m2"].to_numpy(dtype="float64"), rtol=1e-9)
+            assert np.allclose(got["mx"].to_numpy(), exp["mx"].to_numpy(dtype="float64"), rtol=1e-12)
+            print(f"dist select ok: {len(got)} groups")
     # string key column: per-rank dictionaries are unified before the shuffle, so equal strings of
     # different ranks land in the same group
     words = [f"w{i:03d}" for i in range(50)]
@@ -96,12 +115,110 @@ def check_relational(eng, rank, world, dev):
     gathered = [None] * world
     dist.all_gather_object(gathered, (sagg.as_pandas(), sdf))
     if rank == 0:
-        got = pd.concat([g[0] for g in gathered], ignore_index=True).sort_values("k").reset_index(drop=True)
-        allrows = pd.concat([g[1] for g in gathered], ignore_index=True)
-        exp = allrows.groupby("k").agg(s=("v", "sum"), c=("v", "size")).reset_index().sort_values("k").reset_index(drop=True)
-        assert got["k"].is_unique and list(got["k"]) == list(exp["k"])
-        assert np.array_equal(got["s"].to_numpy(), exp["s"].to_numpy()) and np.array_equal(got["c"].to_numpy(), exp["c"].to_numpy())
-        print(f"dist string keys ok: {len(got)} groups")
+        with _guard("block 3"):
+            got = pd.concat([g[0] for g in gathered], ignore_index=True).sort_values("k").reset_index(drop=True)
+            allrows = pd.concat([g[1] for g in gathered], ignore_index=True)
+            exp = allrows.groupby("k").agg(s=("v", "sum"), c=("v", "size")).reset_index().sort_values("k").reset_index(drop=True)
+            assert got["k"].is_unique and list(got["k"]) == list(exp["k"])
+            assert np.array_equal(got["s"].to_numpy(), exp["s"].to_numpy()) and np.array_equal(got["c"].to_numpy(), exp["c"].to_numpy())
+            print(f"dist string keys ok: {len(got)} groups")
+
+
+def check_string_join(eng, rank, world):
+    """String join keys: both sides are re-coded against ONE union dictionary (all ranks, both
+    tables) before their codes are hashed, so equal strings meet on one rank."""
+    import pandas as pd
+
+    from oracle import native_engine as ora
+
+    def frames(r):
+        rng = np.random.default_rng(500 + r)
+        words = [f"k{i:04d}" for i in range(400)]
+        # different ranks / sides see different subsets in different orders -> different local codes
+        left = pd.DataFrame({"k": rng.choice(words[r * 20:r * 20 + 300], 5000), "lv": rng.integers(0, 1000, 5000)})
+        right = pd.DataFrame({"k": rng.permutation(words[100:])[:250], "rv": rng.integers(0, 1000, 250)})
+        return left, right
+
+    left, right = frames(rank)
+    out = {}
+    for how in ("inner", "left_outer", "anti"):
+        out[how] = eng.join(eng.to_df(left), eng.to_df(right), how, ["k"]).as_pandas()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        with _guard("block 4"):
+            ls, rs = zip(*[frames(r) for r in range(world)])
+            L, R = pd.concat(ls, ignore_index=True), pd.concat(rs, ignore_index=True)
+            for how in out:
+                got = pd.concat([g[how] for g in gathered], ignore_index=True)
+                exp = ora.join(L, R, how)
+                cols = list(exp.columns)
+                a = got[cols].sort_values(cols).reset_index(drop=True)
+                b = exp.sort_values(cols).reset_index(drop=True)
+                pd.testing.assert_frame_equal(a, b, check_exact=True, check_dtype=False)
+            print(f"dist string-key joins ok: {len(got)} rows in the last")
+
+
+def check_repartition(eng, rank, world, dev):
+    n = 300_000 + 12345 * rank
+    cols = shard(rank, n)
+    t = B200Table(Schema("key:long,v:double,rid:long,b:ubyte"), [torch.from_numpy(c).to(dev) for c in cols])
+    seg_t = eng.repartition(B200DataFrame(t), PartitionSpec(by="key", algo="hash", num=NUM)).native
+    torch.cuda.synchronize()
+    lo, hi = owner_range(NUM, world, rank)
+    assert seg_t.num_partitions == hi - lo and seg_t.global_partition_range == (lo, hi)
+    assert seg_t.offsets is None and tuple(seg_t.segment_offsets.shape) == (world, hi - lo + 1)
+    res = seg_t.compacted()
+    torch.cuda.synchronize()
+    got = [c.cpu().numpy() for c in res.columns]
+    seg_cols = [c.cpu().numpy() for c in seg_t.columns]
+    off = res.offsets.cpu().numpy()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (got, off, lo, hi, n, seg_cols, seg_t.segment_offsets.numpy()))
+    if rank == 0:
+        with _guard("block 5"):
+            shards = [shard(r, 300_000 + 12345 * r) for r in range(world)]
+            glob = [np.concatenate([s[c] for s in shards]) for c in range(4)]
+            exp_cols, exp_off = hp.partition_table(glob, [0], NUM)
+            per_src = [hp.partition_table(s, [0], NUM) for s in shards]
+            total = 0
+            for g_cols, g_off, g_lo, g_hi, _, g_seg_cols, g_seg in gathered:
+                for j, p in enumerate(range(g_lo, g_hi)):
+                    a, b = exp_off[p], exp_off[p + 1]
+                    assert g_off[j + 1] - g_off[j] == b - a, (p, g_off[j + 1] - g_off[j], b - a)
+                    for c in range(4):
+                        assert np.array_equal(g_cols[c][g_off[j]:g_off[j + 1]].view("u1"),
+                                              exp_cols[c][a:b].view("u1")), (p, c)
+                    total += b - a
+                    # the un-compacted result: segment (s, j) = rows of shard s in partition p, source order
+                    for s in range(world):
+                        sc, so = per_src[s]
+                        x, y = g_seg[s, j], g_seg[s, j + 1]
+                        assert y - x == so[p + 1] - so[p], (s, p)
+                        for c in range(4):
+                            assert np.array_equal(g_seg_cols[c][x:y].view("u1"), sc[c][so[p]:so[p + 1]].view("u1")), (s, p, c)
+            assert total == sum(x[4] for x in gathered)
+            print(f"dist_gpu_check ok: world={world}, {total} rows, bit-exact vs oracle (stable order)")
+
+
+def run_checks(eng, rank, world, dev):
+    """All multi-GPU parity checks; collective (every rank calls it).  Returns (ok, message) -
+    meaningful on rank 0, where the comparisons against the oracle run."""
+    del _FAILS[:]
+    ok, msg = True, ""
+    try:
+        check_repartition(eng, rank, world, dev)
+        check_relational(eng, rank, world, dev)
+        check_string_join(eng, rank, world)
+    except Exception as e:  # noqa: BLE001 - reported, not swallowed
+        ok, msg = False, repr(e)[:300]
+    if _FAILS:
+        ok, msg = False, " | ".join(_FAILS)[:600]
+    flags = [None] * world
+    dist.all_gather_object(flags, (ok, msg))
+    bad = [f for f in flags if not f[0]]
+    return (len(bad) == 0, bad[0][1] if bad else f"world={world}: repartition (segments + compacted) bit-exact vs "
+            "oracle; GROUP BY / JOIN / select / string keys vs pandas")
 
 
 def main():
@@ -110,36 +227,15 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
-    n = 300_000 + 12345 * rank
-    cols = shard(rank, n)
     eng = DistributedB200Engine({"fugue.b200.device": local_rank})
-    t = B200Table(Schema("key:long,v:double,rid:long,b:ubyte"), [torch.from_numpy(c).to(dev) for c in cols])
-    res = eng.repartition(B200DataFrame(t), PartitionSpec(by="key", algo="hash", num=NUM)).native
-    torch.cuda.synchronize()
-    lo, hi = owner_range(NUM, world, rank)
-    assert res.num_partitions == hi - lo and res.global_partition_range == (lo, hi)
-    got = [c.cpu().numpy() for c in res.columns]
-    off = res.offsets.cpu().numpy()
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (got, off, lo, hi, n))
+    ok, msg = run_checks(eng, rank, world, dev)
     if rank == 0:
-        shards = [shard(r, 300_000 + 12345 * r) for r in range(world)]
-        glob = [np.concatenate([s[c] for s in shards]) for c in range(4)]
-        exp_cols, exp_off = hp.partition_table(glob, [0], NUM)
-        total = 0
-        for g_cols, g_off, g_lo, g_hi, _ in gathered:
-            for j, p in enumerate(range(g_lo, g_hi)):
-                a, b = exp_off[p], exp_off[p + 1]
-                assert g_off[j + 1] - g_off[j] == b - a, (p, g_off[j + 1] - g_off[j], b - a)
-                for c in range(4):
-                    assert np.array_equal(g_cols[c][g_off[j]:g_off[j + 1]].view("u1"),
-                                          exp_cols[c][a:b].view("u1")), (p, c)
-                total += b - a
-        assert total == sum(x[4] for x in gathered)
-        print(f"dist_gpu_check ok: world={world}, {total} rows, bit-exact vs oracle (stable order)")
-    check_relational(eng, rank, world, dev)
+        with _guard("block 6"):
+            print("PARITY", ok, msg)
     dist.barrier()
     dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

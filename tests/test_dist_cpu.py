@@ -39,6 +39,16 @@ def _worker(rank: int, world: int, port: int, ret):
         recv = [exchange_column(torch.from_numpy(c), plan) for c in part]
         outs = rearrange_cpu(recv, plan)
         lo, hi = owner_range(NUM, world, rank)
+        # the one-run-per-source pull and the (source, partition) segment index describe the same layout
+        from fugue_b200.dist import compact_plan
+
+        src, dst, ln, off = compact_plan(plan.segment_offsets)
+        assert torch.equal(src, plan.seg_src_off) and torch.equal(dst, plan.seg_dst_off)
+        assert torch.equal(ln, plan.seg_len) and torch.equal(off, plan.out_offsets)
+        a, b = int(plan.pull_start[rank]), int(plan.recv_base[rank])
+        for c, r in zip(part, recv):
+            assert np.array_equal(r[b:b + plan.recv_rows[rank]].numpy(), c[a:a + plan.recv_rows[rank]])
+        assert int(plan.segment_offsets[-1, -1]) == plan.total_recv
         ret[rank] = ([o.numpy() for o in outs], plan.out_offsets.numpy(), lo, hi)
     finally:
         dist.destroy_process_group()
@@ -107,10 +117,15 @@ def _dict_worker(rank: int, world: int, port: int, ret):
         t = B200Table(Schema("s:str,v:long"), [codes, torch.arange(len(codes))], [valid, None],
                       {"s": pa.array(words, type=pa.string())})
         fake = types.SimpleNamespace(_world=world, _group=None)
-        g = DistributedB200Engine._globalize_dictionaries(fake, t)
+        # second table (the other side of a join): its own dictionary, other order, one new word
+        words2 = [["e", "b"], ["z", "a"]][rank]
+        t2 = B200Table(Schema("s:str"), [torch.tensor([1, 0, 1], dtype=torch.int32)], None,
+                       {"s": pa.array(words2, type=pa.string())})
+        g, g2 = DistributedB200Engine._globalize_tables(fake, [t, t2])
         decoded = [None if m == 0 else g.dictionaries["s"][int(c)].as_py()
                    for c, m in zip(g.columns[0].tolist(), valid.tolist())]
-        ret[rank] = (g.dictionaries["s"].to_pylist(), decoded)
+        decoded2 = [g2.dictionaries["s"][int(c)].as_py() for c in g2.columns[0].tolist()]
+        ret[rank] = (g.dictionaries["s"].to_pylist(), decoded, g2.dictionaries["s"].to_pylist(), decoded2)
     finally:
         dist.destroy_process_group()
 
@@ -121,9 +136,12 @@ def test_string_dictionaries_are_unified_across_ranks():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_dict_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    assert ret[0][0] == ret[1][0] == ["b", "a", "c", "d", "e"]          # union, first-appearance order over ranks
+    # ONE union per column name over ranks AND tables (both sides of a join share the code space),
+    # first-appearance order: rank 0 (table 1, table 2), then rank 1
+    assert ret[0][0] == ret[1][0] == ret[0][2] == ret[1][2] == ["b", "a", "c", "e", "d", "z"]
     assert ret[0][1] == ["b", "a", "c", None, "b"]                      # codes re-mapped, NULL kept
     assert ret[1][1] == ["e", "c", "d", "a", "a", "c"]
+    assert ret[0][3] == ["b", "e", "b"] and ret[1][3] == ["a", "z", "a"]
 
 
 def test_partial_final_decomposition_of_aggregates():

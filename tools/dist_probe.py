@@ -1,35 +1,98 @@
-import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch, torch.distributed as dist
-from fugue_b200 import kernels as K
-from fugue_b200.dist import ExchangePlan, gather_counts
-rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
-dist.init_process_group("nccl", device_id=dev)
-n, num = 100_000_000, 256
-g = torch.Generator(device=dev).manual_seed(rank)
-cols = [torch.randint(0, 1 << 16, (n,), dtype=torch.int64, device=dev, generator=g)] + [torch.randint(-(2**62), 2**62, (n,), dtype=torch.int64, device=dev, generator=g) for _ in range(7)]
-def T():
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize(); return time.perf_counter()
-plan = K.partition_plan([cols[0]], num)
-parts = K.partition_apply(plan, cols)
-counts = gather_counts(plan.offsets[1:] - plan.offsets[:-1])
-ep = ExchangePlan(counts, rank)
-recv = [torch.empty(ep.total_recv, dtype=torch.int64, device=dev) for _ in cols]
-outs = [torch.empty(ep.total_recv, dtype=torch.int64, device=dev) for _ in cols]
-ss, sd, sl = ep.seg_src_off.to(dev), ep.seg_dst_off.to(dev), ep.seg_len.to(dev)
-for it in range(3):
-    t0 = T(); plan = K.partition_plan([cols[0]], num, scratch=plan.scratch, offsets=plan.offsets)
-    t1 = T(); K.partition_apply(plan, cols, parts)
-    t2 = T()
-    for c in cols: K.partition_apply(plan, [c], [parts[0]])
-    t3 = T(); counts = gather_counts(plan.offsets[1:] - plan.offsets[:-1]); ep = ExchangePlan(counts, rank)
-    t4 = T()
-    for p, r in zip(parts, recv): dist.all_to_all_single(r, p, output_split_sizes=ep.recv_rows, input_split_sizes=ep.send_rows)
-    t5 = T(); K.copy_segments(recv, outs, ss, sd, sl)
-    t6 = T()
-    for r, o in zip(recv, outs): K.copy_segments([r], [o], ss, sd, sl)
-    t7 = T()
-    if rank == 0:
-        print(f"plan {1e3*(t1-t0):.2f} | apply8 {1e3*(t2-t1):.2f} | 8x apply1 {1e3*(t3-t2):.2f} | counts+plan {1e3*(t4-t3):.2f} | a2a x8 {1e3*(t5-t4):.2f} ({8*ep.send_rows[1-rank if world==2 else 0]*8/ (t5-t4)/1e9:.0f} GB/s out to one peer) | segcopy8 {1e3*(t6-t5):.2f} | 8x segcopy1 {1e3*(t7-t6):.2f}", flush=True)
-dist.destroy_process_group()
+"""Multi-GPU exchange probe (torchrun, one rank per GPU): parity check, then the headline transform
+step for a sweep of exchange settings on one engine object.  Prints one line per setting on rank 0.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29544 tools/dist_probe.py [--rows 125000000] [--sweep "dma:2:1,dma:4:1,kernel:4:16"]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=125_000_000)
+    ap.add_argument("--sweep", default="dma:2:1,dma:4:1,dma:1:1,dma:8:1,kernel:4:16,kernel:2:16")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from fugue_b200 import api as fa
+    from fugue_b200.dataframe import B200DataFrame
+    from fugue_b200.dist import DistributedB200Engine
+    from fugue_b200.partition import PartitionSpec
+    from fugue_b200.table import B200Table
+
+    eng = DistributedB200Engine({"fugue.b200.device": local_rank})
+    if not args.no_parity:
+        import dist_gpu_check
+
+        t0 = time.time()
+        ok, msg = dist_gpu_check.run_checks(eng, rank, world, dev)
+        if rank == 0:
+            print(f"PARITY {ok} {msg} ({time.time() - t0:.1f}s)", flush=True)
+    n = args.rows
+    g = torch.Generator(device=dev).manual_seed(rank)
+    cols = [torch.randint(0, 1 << 16, (n,), dtype=torch.int64, device=dev, generator=g)]
+    cols += [torch.randint(-(2**62), 2**62, (n,), dtype=torch.int64, device=dev, generator=g) for _ in range(3)]
+    cols += [torch.randn(n, dtype=torch.float64, device=dev, generator=g) for _ in range(4)]
+    df = B200DataFrame(B200Table("key:long,i1:long,i2:long,i3:long,v0:double,v1:double,v2:double,v3:double", cols))
+    spec = PartitionSpec(by="key", algo="hash", num=256)
+
+    def identity(t: B200Table) -> B200Table:
+        return t
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for item in args.sweep.split(","):
+        mode, gc, res = item.split(":")
+        eng._exchange, eng._group_cols, eng._sm_reserve = mode, int(gc), int(res)
+        try:
+            for _ in range(2):
+                out = fa.transform(df, identity, schema="*", partition=spec, engine=eng)
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                out = fa.transform(df, identity, schema="*", partition=spec, engine=eng)
+            host_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            e1.record()
+            sync()
+            ms = e0.elapsed_time(e1) / args.steps
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rows_out = torch.tensor([out.count()], dtype=torch.int64, device=dev)
+            dist.all_reduce(rows_out)
+            if rank == 0:
+                ms = float(t.item())
+                print(json.dumps({"mode": mode, "group_cols": int(gc), "sm_reserve": int(res), "world": world,
+                                  "rows_per_gpu": n, "ms_per_step": round(ms, 3), "host_enqueue_ms": round(host_ms, 3),
+                                  "G_rows_per_s": round(n * world / ms / 1e6, 2), "rows_out": int(rows_out.item()),
+                                  "nvlink_GBps_out_per_gpu": round(64.0 * n * (world - 1) / world / ms / 1e6, 1)}),
+                      flush=True)
+            del out
+        except Exception as e:  # noqa: BLE001
+            print(f"[rank {rank}] {item}: {e!r}", flush=True)
+            break
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

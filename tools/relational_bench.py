@@ -85,5 +85,101 @@ def measure(device_index: int = 0):
     return out
 
 
+def _dist_time(fn, dev, reps=3):
+    """CUDA-event time of a collective step: barrier + synchronize on both sides, max over ranks, median of reps."""
+    import torch.distributed as dist
+
+    fn(); torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(reps):
+        dist.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t.item()))
+    return sorted(ts)[len(ts) // 2]
+
+
+def measure_dist(engine, rank, world, dev):
+    """BASELINE configs 4 and 5 on `world` GPUs (every rank calls this): per-GPU share of 1 B-row GROUP BY
+    (10 M distinct keys) and of 500 M x 500 M inner join, through DistributedB200Engine.aggregate / .join."""
+    import torch.distributed as dist
+    from fugue_b200.column import all_cols, col, functions as ff
+    from fugue_b200.dataframe import B200DataFrame
+    from fugue_b200.partition import PartitionSpec
+    from fugue_b200.table import B200Table
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    out = {"n_gpus": world}
+    n, nk = 125_000_000, 10_000_000
+    keys = torch.randint(0, nk, (n,), dtype=torch.int64, device=dev, generator=g) * 0x9E3779B97F4A7C15 % (1 << 62)
+    v = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    T = B200DataFrame(B200Table("key:long,v0:double", [keys, v]))
+    spec = PartitionSpec(by=["key"])
+    aggs = [ff.sum(col("v0")).alias("s"), ff.count(all_cols()).alias("c")]
+    res = engine.aggregate(T, spec, aggs)
+    cnt = torch.tensor([res.count(), int(res.native.column("c").sum().item())], dtype=torch.int64, device=dev)
+    dist.all_reduce(cnt)
+    ms = _dist_time(lambda: engine.aggregate(T, spec, aggs), dev)
+    out["groupby_sum_count"] = {"rows": n * world, "rows_per_gpu": n, "distinct_keys": nk, "groups_out": int(cnt[0]),
+                                "count_total_matches_rows": int(cnt[1]) == n * world, "ms": ms,
+                                "rows_per_s": n * world / ms * 1e3, "alg_GBps_per_gpu": 16 * n / ms / 1e6,
+                                "config": "BASELINE config 4 share: SELECT key, SUM(v0), COUNT(*) GROUP BY key"}
+    del keys, v, T, res
+    torch.cuda.empty_cache()
+    n = 62_500_000
+    total = n * world
+    lk = torch.randint(0, total, (n,), dtype=torch.int64, device=dev, generator=g)
+    # unique build side: an affine bijection of [0, total) (a coprime to total), sharded by row range
+    a_mul = 2_654_435_761
+    while total % 2 == 0 and a_mul % 2 == 0:
+        a_mul += 1
+    import math
+    while math.gcd(a_mul, total) != 1:
+        a_mul += 2
+    idx = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int64, device=dev)
+    rk = (idx * a_mul + 12345) % total
+    lv = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    rv = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+    L = B200DataFrame(B200Table("key:long,lv:double", [lk, lv]))
+    R = B200DataFrame(B200Table("key:long,rv:double", [rk, rv]))
+    res = engine.join(L, R, "inner", ["key"])
+    cnt = torch.tensor([res.count()], dtype=torch.int64, device=dev)
+    dist.all_reduce(cnt)
+    del res
+    ms = _dist_time(lambda: engine.join(L, R, "inner", ["key"]), dev)
+    out["inner_join"] = {"left_rows": total, "right_rows": total, "out_rows": int(cnt[0]), "rows_per_gpu": n,
+                         "out_rows_equals_left_rows": int(cnt[0]) == total, "ms": ms,
+                         "out_rows_per_s": total / ms * 1e3, "alg_GBps_per_gpu": 56 * n / ms / 1e6,
+                         "config": "BASELINE config 5 share: inner join on int64 key, unique build side"}
+    return out
+
+
+def cpu_baselines():
+    """pandas (what the reference's native engine runs: qpd -> groupby.agg; triad -> pd.merge) on bounded
+    samples of configs 4 / 5, 1 core."""
+    import numpy as np
+    import pandas as pd
+
+    rng = np.random.default_rng(0)
+    n, nk = 20_000_000, 1_600_000   # same 12.5 rows per key as 125 M rows / 10 M keys
+    df = pd.DataFrame({"key": rng.integers(0, nk, n) * 0x9E3779B97F4A7C15 % (1 << 62), "v0": rng.standard_normal(n)})
+    t0 = time.perf_counter()
+    r = df.groupby("key").agg(s=("v0", "sum"), c=("v0", "size"))
+    t_g = time.perf_counter() - t0
+    m = 10_000_000
+    left = pd.DataFrame({"key": rng.integers(0, m, m), "lv": rng.standard_normal(m)})
+    right = pd.DataFrame({"key": rng.permutation(m), "rv": rng.standard_normal(m)})
+    t0 = time.perf_counter()
+    j = left.merge(right, on="key", how="inner")
+    t_j = time.perf_counter() - t0
+    return {"kind": "port", "cores": 1,
+            "groupby": {"rows": n, "groups": len(r), "s": t_g, "rows_per_s": n / t_g, "sample": "20 M rows, 1.6 M keys "
+                        "(the workload's 12.5 rows per key), pandas groupby.agg(sum, size)"},
+            "inner_join": {"rows": m, "out_rows": len(j), "s": t_j, "out_rows_per_s": len(j) / t_j,
+                           "sample": "10 M x 10 M rows, unique build side, pandas merge"}}
+
+
 if __name__ == "__main__":
     print(json.dumps(measure()))
