@@ -12,6 +12,8 @@ keys uniform over 2**16 values.  Prints ONE JSON line (see the task contract).
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # see fugue_b200/dist.py
 import sys
 import threading
 import time
@@ -393,7 +395,10 @@ def run_b200(args):
         if world == 1:
             launches_per_step = 5 + (2 if n % 4096 else 0)
         else:
-            ngroups = (8 + engine._group_cols - 1) // engine._group_cols
+            ngroups, left, gi = 0, 8, 0
+            while left > 0:
+                left -= engine._group_cols[min(gi, len(engine._group_cols) - 1)]
+                ngroups, gi = ngroups + 1, gi + 1
             launches_per_step = 3 + ngroups + (1 + ngroups if n % 4096 else 0)
         cfg = _config(n, world)
         line = {
@@ -402,7 +407,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "int64+f64 (byte moves; u64 hash arithmetic)", "data": "synthetic",
             "config": cfg, "rows_out_rank0": nrows_out,
             "parallelism": f"dp{world}: rows range-sharded, one exchange over NVLink (copy engines), "
-                           f"{engine._group_cols} columns per scatter/exchange group" if world > 1 else "single GPU",
+                           f"columns per scatter/exchange group: {engine._group_cols}" if world > 1 else "single GPU",
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,
             "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }

@@ -21,8 +21,15 @@ world-size-2 ``gloo`` tests (tests/test_dist_cpu.py) cover this logic without a 
 import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
-import torch
-import torch.distributed as dist
+# The exchange runs ~10 streams at once (scatter, control, one copy-engine stream per peer).  With the
+# default of 8 hardware work queues streams alias each other's queue and pick up false dependencies
+# (measured: the barrier kernel and the copies waited for scatter kernels of OTHER streams).  Must be
+# set before the CUDA context exists; harmless if the application already set it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
 from .dataframe import B200DataFrame
 from .execution_engine import B200ExecutionEngine, assert_or_throw
@@ -116,7 +123,7 @@ def compact_plan(segment_offsets: torch.Tensor) -> Tuple[torch.Tensor, torch.Ten
 
 
 FUGUE_B200_CONF_DIST_GROUP_COLS = "fugue.b200.dist.group_cols"    # payload columns per scatter/exchange group
-FUGUE_B200_CONF_DIST_EXCHANGE = "fugue.b200.dist.exchange"        # "dma" (copy engines) | "kernel" (SM pull)
+FUGUE_B200_CONF_DIST_EXCHANGE = "fugue.b200.dist.exchange"        # "dma" (copy engines) | "tma" | "kernel" (SM pulls)
 FUGUE_B200_CONF_DIST_SM_RESERVE = "fugue.b200.dist.sm_reserve"    # SMs the persistent scatter leaves free
 _BARRIER_TIMEOUT_MS = 120_000   # a rank that died must not hang the others' GPUs forever
 _CTL_SLOTS = 1024                                                 # counts per rank and parity (K.MAX_PARTITIONS)
@@ -135,9 +142,11 @@ class DistributedB200Engine(B200ExecutionEngine):
         self._arena: Optional[torch.Tensor] = None
         self._ctl: Optional[torch.Tensor] = None
         self._step = 0
-        self._group_cols = max(1, int(self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, 2)))
+        self._trace: Optional[List[Any]] = None
+        gc = self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, "1,1,2,4")
+        self._group_cols = [max(1, int(x)) for x in str(gc).split(",")]  # columns per group; last repeats
         self._exchange = str(self._conf.get(FUGUE_B200_CONF_DIST_EXCHANGE, "dma"))
-        assert_or_throw(self._exchange in ("dma", "kernel"), ValueError(f"unknown exchange {self._exchange}"))
+        assert_or_throw(self._exchange in ("dma", "kernel", "tma"), ValueError(f"unknown exchange {self._exchange}"))
         self._sm_reserve = int(self._conf.get(FUGUE_B200_CONF_DIST_SM_RESERVE,
                                               1 if self._exchange == "dma" else 16))
 
@@ -173,7 +182,7 @@ class DistributedB200Engine(B200ExecutionEngine):
                             for s in range(self._world)] for par in range(2)]
         self._counts_dev = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, device=dev)
         self._counts_host = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, pin_memory=True)
-        self._s_ctl = torch.cuda.Stream(dev)
+        self._s_ctl = torch.cuda.Stream(dev, priority=-1)  # barrier kernels must not queue behind the scatter
         self._s_dma = [torch.cuda.Stream(dev) for _ in range(self._world)]
 
     def _post_counts(self, local_counts: torch.Tensor) -> torch.cuda.Event:
@@ -193,6 +202,13 @@ class DistributedB200Engine(B200ExecutionEngine):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self._device))
         return ev
+
+    def _mark(self, label: str, stream: Any = None) -> None:
+        """Timeline probe (tools/dist_probe.py --trace): a timed event on ``stream`` when tracing is on."""
+        if self._trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream(self._device))
+            self._trace.append((label, ev))
 
     @staticmethod
     def _col_offsets(nrows: int, widths: List[int]) -> List[int]:
@@ -240,14 +256,24 @@ class DistributedB200Engine(B200ExecutionEngine):
         s_main = torch.cuda.current_stream(dev)
         # ---- pass 1 on the local shard; counts to everybody (stream-ordered, host reads them later)
         scratch = self._pool.scratch(dev, K.partition_scratch_bytes(dev, t.num_rows, num))
+        self._mark("start")
         plan_local = K.partition_plan([t.columns[i] for i in kidx], num, kvalid, scratch=scratch)
+        self._mark("pass1")
         ev_counts = self._post_counts(plan_local.offsets[1:] - plan_local.offsets[:-1])
+        self._mark("counts")
         self._step += 1
-        # 8-byte columns first (fast kernel), in groups; narrow columns (validity masks ...) last
+        # 8-byte columns first (fast kernel), cut into groups (the first group small: the exchange can
+        # start as soon as it is scattered); narrow columns (validity masks ...) last
         order = sorted(range(len(cols)), key=lambda i: (widths[i] != 8, i))
-        per = self._group_cols
-        groups = [order[a:a + per] for a in range(0, len(order), per)]
+        groups: List[List[int]] = []
+        a0, gi0 = 0, 0
+        while a0 < len(order):
+            per = self._group_cols[min(gi0, len(self._group_cols) - 1)]
+            groups.append(order[a0:a0 + per])
+            a0 += per
+            gi0 += 1
         my_off = self._col_offsets(t.num_rows, widths)
+        s_ctl = self._s_ctl
 
         def scatter_all() -> List[torch.cuda.Event]:
             parts = [self._arena[my_off[i]:my_off[i] + t.num_rows * w].view(c.dtype)
@@ -259,78 +285,122 @@ class DistributedB200Engine(B200ExecutionEngine):
                 ev = torch.cuda.Event()
                 ev.record(s_main)
                 evs.append(ev)
+                self._mark(f"scatter{len(evs) - 1}")
             return evs
 
-        # enqueue the scatters before waiting for the counts if the local shard fits the arena (peers'
-        # reads of the previous call are over: every call ends with a barrier)
+        def barriers(ev_sc: Optional[List[torch.cuda.Event]]) -> List[torch.cuda.Event]:
+            """Per group, on the control stream: after this rank's scatter of the group, a barrier over
+            all ranks ("group k sits in every arena"); the returned events release the pulls."""
+            evs = []
+            with torch.cuda.stream(s_ctl):
+                for gi in range(len(groups)):
+                    if ev_sc is not None:
+                        s_ctl.wait_event(ev_sc[gi])
+                    self._arena_hdl.barrier(channel=1, timeout_ms=_BARRIER_TIMEOUT_MS)
+                    ev = torch.cuda.Event()
+                    ev.record(s_ctl)
+                    evs.append(ev)
+                    self._mark(f"barrier{gi}")
+            return evs
+
+        # Everything that does not need the counts is enqueued BEFORE the host waits for them: the
+        # scatters (if the local shard fits the arena; peers' reads of the previous call are over: every
+        # call ends with a barrier) and the per-group barriers.  Ranks must agree on the number of
+        # barriers: they are issued whenever an arena exists (a collective property), scattered or not.
         ev_sc: Optional[List[torch.cuda.Event]] = None
-        if self._arena is not None and self._arena.numel() >= my_off[-1]:
-            ev_sc = scatter_all()
+        ev_b: Optional[List[torch.cuda.Event]] = None
+        if self._arena is not None:
+            if self._arena.numel() >= my_off[-1]:
+                ev_sc = scatter_all()
+            ev_b = barriers(ev_sc)
         ev_counts.synchronize()
-        counts = self._counts_host[:, :num].clone()
-        plan = ExchangePlan(counts, rank)
-        rows = [int(x) for x in plan.rows_per_rank.tolist()]
-        need = max(self._col_offsets(r, widths)[-1] for r in rows)
+        # ---- host plan from the count matrix (numpy, a few microseconds)
+        c = self._counts_host.numpy()[:, :num]
+        lo, hi = owner_range(num, world, rank)
+        mine = c[:, lo:hi]
+        rows = c.sum(1)
+        recv_rows = mine.sum(1)
+        recv_base = np.cumsum(recv_rows) - recv_rows
+        pull_start = c[:, :lo].sum(1)
+        total_recv = int(recv_rows.sum())
+        seg = np.zeros((world, hi - lo + 1), dtype=np.int64)
+        np.cumsum(mine, axis=1, out=seg[:, 1:])
+        seg += recv_base[:, None]
+        need = max(self._col_offsets(int(r), widths)[-1] for r in rows)
         if self._arena is None or self._arena.numel() < need:
             # first call / growth: every rank takes this branch (same matrix, same capacity everywhere)
             torch.cuda.synchronize(dev)
             self._ensure_arena(need)
-            ev_sc = None
-        if ev_sc is None:
             ev_sc = scatter_all()
+            ev_b = barriers(ev_sc)
         base = [int(x) for x in self._arena_hdl.buffer_ptrs]
-        peer_off = [self._col_offsets(rows[s], widths) for s in range(world)]
-        outs = [torch.empty(plan.total_recv, dtype=c.dtype, device=dev) for c in cols]
-        recv_rows, recv_base = plan.recv_rows, [int(x) for x in plan.recv_base.tolist()]
-        pull_start = [int(x) for x in plan.pull_start.tolist()]
-        s_ctl = self._s_ctl
-        s_ctl.wait_stream(s_main)  # outs were allocated on the main stream
-        if self._exchange == "kernel":
-            seg_src = plan.pull_start.to(dev)
-            seg_dst = plan.recv_base.to(dev)
-            seg_len = torch.tensor(recv_rows, dtype=torch.int64, device=dev)
-            seg_rank = torch.arange(world, dtype=torch.int32, device=dev)
+        peer_off = [self._col_offsets(int(rows[s]), widths) for s in range(world)]
+        outs = [torch.empty(total_recv, dtype=cc.dtype, device=dev) for cc in cols]
+        optr = [o.data_ptr() for o in outs]
+        ev_alloc = torch.cuda.Event()
+        ev_alloc.record(s_main)  # the output buffers were allocated on the main stream
+        streams = self._s_dma
+        sptr = [st.cuda_stream for st in streams]
+        for st in streams:
+            st.wait_event(ev_alloc)
+        if self._exchange != "dma":
+            s_ctl.wait_event(ev_alloc)
         for gi, idx in enumerate(groups):
-            # own rows: local copy, needs no barrier
-            with torch.cuda.stream(self._s_dma[0]):
-                self._s_dma[0].wait_event(ev_sc[gi])
-                if self._exchange == "dma" and recv_rows[rank] > 0:
-                    K.copy_runs_dma(dev, [base[rank] + peer_off[rank][i] + pull_start[rank] * widths[i] for i in idx],
-                                    [outs[i].data_ptr() + recv_base[rank] * widths[i] for i in idx],
-                                    [recv_rows[rank] * widths[i] for i in idx])
-            with torch.cuda.stream(s_ctl):
-                s_ctl.wait_event(ev_sc[gi])
-                self._arena_hdl.barrier(channel=1, timeout_ms=_BARRIER_TIMEOUT_MS)  # group gi sits in every rank's arena
-                ev_b = torch.cuda.Event()
-                ev_b.record(s_ctl)
-                if self._exchange == "kernel":
-                    src_ptrs = [base[s] + peer_off[s][i] for s in range(world) for i in idx]
-                    K.copy_segments(None, [outs[i] for i in idx], seg_src, seg_dst, seg_len, max_len=max(recv_rows),
-                                    src_table=seg_rank, src_ptrs=src_ptrs)
             if self._exchange == "dma":
+                # own rows: local copy on stream 0 as soon as this rank's scatter of the group is done;
+                # peers: stream j pulls from rank + j (every rank starts on a different source)
+                streams[0].wait_event(ev_sc[gi])
                 for j in range(1, world):
-                    s = (rank + j) % world
-                    if recv_rows[s] == 0:
+                    streams[j].wait_event(ev_b[gi])
+                src, dst, nb, stq = [], [], [], []
+                for j in range(world):
+                    sr = (rank + j) % world
+                    if recv_rows[sr] == 0:
                         continue
-                    with torch.cuda.stream(self._s_dma[j]):
-                        self._s_dma[j].wait_event(ev_b)
-                        K.copy_runs_dma(dev, [base[s] + peer_off[s][i] + pull_start[s] * widths[i] for i in idx],
-                                        [outs[i].data_ptr() + recv_base[s] * widths[i] for i in idx],
-                                        [recv_rows[s] * widths[i] for i in idx])
-        for sd in self._s_dma:
-            s_ctl.wait_stream(sd)
+                    for i in idx:
+                        src.append(base[sr] + peer_off[sr][i] + int(pull_start[sr]) * widths[i])
+                        dst.append(optr[i] + int(recv_base[sr]) * widths[i])
+                        nb.append(int(recv_rows[sr]) * widths[i])
+                        stq.append(sptr[j])
+                K.copy_runs_dma_streams(dev, src, dst, nb, stq)
+                continue
+            with torch.cuda.stream(s_ctl):
+                s_ctl.wait_event(ev_b[gi])
+                if self._exchange == "tma":
+                    # persistent TMA pull kernel on the SMs the scatter leaves free; peers first (rotated,
+                    # so that not every rank starts on the same source), own rows last
+                    order_s = [(rank + j) % world for j in range(1, world)] + [rank]
+                    rs = [(base[sr] + peer_off[sr][i] + int(pull_start[sr]) * widths[i],
+                           optr[i] + int(recv_base[sr]) * widths[i], int(recv_rows[sr]) * widths[i])
+                          for i in idx for sr in order_s if recv_rows[sr] > 0]
+                    for a in range(0, len(rs), 64):
+                        K.pull_runs_tma(dev, [r[0] for r in rs[a:a + 64]], [r[1] for r in rs[a:a + 64]],
+                                        [r[2] for r in rs[a:a + 64]], max(1, self._sm_reserve))
+                else:  # "kernel": fb_copy_segments with peer pointers (16-byte loads over NVLink)
+                    src_ptrs = [base[sr] + peer_off[sr][i] for sr in range(world) for i in idx]
+                    K.copy_segments(None, [outs[i] for i in idx], torch.from_numpy(pull_start).to(dev),
+                                    torch.from_numpy(recv_base).to(dev), torch.from_numpy(recv_rows).to(dev),
+                                    max_len=int(recv_rows.max()),
+                                    src_table=torch.arange(world, dtype=torch.int32, device=dev), src_ptrs=src_ptrs)
+        if self._trace is not None:
+            for j, st in enumerate(streams):
+                self._mark(f"dma_done.s{j}", st)
+        for st in streams:
+            s_ctl.wait_stream(st)
         with torch.cuda.stream(s_ctl):
-            self._arena_hdl.barrier(channel=1, timeout_ms=_BARRIER_TIMEOUT_MS)  # nobody overwrites an arena that is still being read
+            # nobody overwrites an arena that is still being read
+            self._arena_hdl.barrier(channel=1, timeout_ms=_BARRIER_TIMEOUT_MS)
         s_main.wait_stream(s_ctl)
+        self._mark("end")
         for o in outs:
-            for sd in self._s_dma:
-                o.record_stream(sd)
+            for st in streams:
+                o.record_stream(st)
             o.record_stream(s_ctl)
         ncol = len(t.columns)
         valid = [outs[vpos[i]] if i in vpos else None for i in range(ncol)]
         res = B200Table(t.schema, outs[:ncol], valid, t.dictionaries, None, list(keys))
-        res.segment_offsets = plan.segment_offsets          # [world, nown + 1] (host)
-        res.global_partition_range = (plan.lo, plan.hi)     # which physical partitions this GPU owns
+        res.segment_offsets = torch.from_numpy(seg)          # [world, nown + 1] (host)
+        res.global_partition_range = (lo, hi)               # which physical partitions this GPU owns
         res.global_num_partitions = num
         rdf = B200DataFrame(res)
         if edf.has_metadata:

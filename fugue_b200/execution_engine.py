@@ -534,7 +534,9 @@ class B200ExecutionEngine:
             assert_or_throw(arg not in t.dictionaries, NotImplementedError(f"{fn} on a string column"))
             is_f = pa.types.is_floating(tp)
             c8 = c if c.element_size() == 8 else c.to(torch.float64 if is_f else torch.int64)
-            nn = add(None, m, K.AGG_COUNT) if m is not None else None  # non-null count -> result validity
+            # non-null count -> result validity.  A global aggregate (no keys) always carries it: over an
+            # empty input (or an empty shard of a multi-GPU aggregate) SUM / MIN / MAX are NULL, not 0
+            nn = add(None, m, K.AGG_COUNT) if (m is not None or len(keys) == 0) else None
             if fn == "SUM":
                 plan.append((a.output_name, "plain", add(c8, m, K.AGG_SUM_F64 if is_f else K.AGG_SUM_I64),
                              pa.float64() if is_f else pa.int64(), nn))

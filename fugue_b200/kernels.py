@@ -202,6 +202,38 @@ def copy_runs_dma(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: An
                                     dst.ctypes.data, nb.ctypes.data))
 
 
+def copy_runs_dma_streams(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: Any, streams: Any) -> None:
+    """:func:`copy_runs_dma` with one CUDA stream per run (raw ``cudaStream_t`` values): the whole
+    exchange of a column group is enqueued by ONE call."""
+    import numpy as np
+
+    lib = _lib.load()
+    src = np.ascontiguousarray(src_ptrs, dtype=np.uint64)
+    dst = np.ascontiguousarray(dst_ptrs, dtype=np.uint64)
+    nb = np.ascontiguousarray(nbytes, dtype=np.uint64)
+    st = np.ascontiguousarray(streams, dtype=np.uint64)
+    assert src.shape == dst.shape == nb.shape == st.shape and src.ndim == 1
+    if src.size == 0:
+        return
+    _lib.check(lib.fb_copy_runs_dma_streams(device.index, int(src.size), src.ctypes.data, dst.ctypes.data,
+                                            nb.ctypes.data, st.ctypes.data))
+
+
+def pull_runs_tma(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: Any, max_ctas: int = 16) -> None:
+    """The same runs as :func:`copy_runs_dma`, moved by the persistent TMA pull kernel on ``max_ctas`` SMs."""
+    import numpy as np
+
+    lib = _lib.load()
+    src = np.ascontiguousarray(src_ptrs, dtype=np.uint64)
+    dst = np.ascontiguousarray(dst_ptrs, dtype=np.uint64)
+    nb = np.ascontiguousarray(nbytes, dtype=np.uint64)
+    assert src.shape == dst.shape == nb.shape and src.ndim == 1
+    if src.size == 0:
+        return
+    _lib.check(lib.fb_pull_runs_tma(device.index, _stream_ptr(device), int(src.size), src.ctypes.data,
+                                    dst.ctypes.data, nb.ctypes.data, int(max_ctas)))
+
+
 AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_MAX_F64 = range(7)
 MAX_AGGS = 16
 

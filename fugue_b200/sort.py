@@ -95,8 +95,12 @@ def argsort_rows(t: B200Table, sorts: "OrderedDict[str, bool]", na_position: str
     idx = torch.arange(n, dtype=torch.int64, device=dev)
     for name, asc in reversed(list(sorts.items())):
         key = _unsigned_order_key(t, name, asc)
-        _, idx = _radix_sort_pairs(key[idx].contiguous(), idx)
         v = t.valid[t.schema.index_of_key(name)]
+        if v is not None:
+            # the value stored under a NULL is undefined (Arrow / parquet leave garbage there): give all
+            # NULL rows one constant key, so that they keep the order set by the less significant columns
+            key = torch.where(v.bool(), key, torch.zeros_like(key))
+        _, idx = _radix_sort_pairs(key[idx].contiguous(), idx)
         if v is not None:
             flag = v.to(torch.int64) if na_position == "first" else (1 - v.to(torch.int64))
             _, idx = _radix_sort_pairs(flag[idx].contiguous(), idx)

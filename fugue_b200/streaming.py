@@ -105,8 +105,11 @@ def streaming_transform(engine: Any, local_df: DataFrame, runner: Any, out_schem
     if res.schema != out_schema:
         raise AssertionError(f"map output {res.schema} mismatches given {out_schema}")
     rt: B200Table = res.native
-    if any(v is not None for v in rt.valid) or len(rt.dictionaries) > 0:
-        return res.as_local()  # rare shapes: plain D2H
+    plain = all(not (pa.types.is_boolean(tp) or pa.types.is_string(tp) or pa.types.is_large_string(tp))
+                and col.element_size() * 8 == tp.bit_width
+                for tp, col in zip(out_schema.types, rt.columns))
+    if any(v is not None for v in rt.valid) or len(rt.dictionaries) > 0 or not plain:
+        return res.as_local()  # rare shapes (NULLs, strings, bool = one byte per row on the device): plain D2H
     ev_f = torch.cuda.Event()
     ev_f.record(s_cmp)
     passthrough = {(t.data_ptr(), t.numel()): c for c, t in outs.items()}
@@ -114,6 +117,8 @@ def streaming_transform(engine: Any, local_df: DataFrame, runner: Any, out_schem
     with torch.cuda.stream(s_out):
         for col in rt.columns:
             src = passthrough.get((col.data_ptr(), col.numel()))
+            # a pass-through column starts its D2H as soon as its scatter is done; tables are immutable
+            # values (fugue/dataframe/dataframe.py:291-295): a map function must not write into its input
             s_out.wait_event(ev_out[src] if src is not None else ev_f)
             h = torch.empty(col.shape, dtype=col.dtype, pin_memory=True)
             h.copy_(col, non_blocking=True)

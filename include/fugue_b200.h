@@ -155,6 +155,16 @@ int fb_copy_segments(int dev, void* stream, int ncols, const void* const* d_src_
  * the scatter kernel of the next column group.  src / dst / bytes are HOST arrays. */
 int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void* const* src, void* const* dst,
                      const size_t* bytes);
+/* fb_copy_runs_dma with a stream per run (`streams` = HOST array of cudaStream_t): one call enqueues a
+ * whole column group of the exchange on the per-peer streams. */
+int fb_copy_runs_dma_streams(int dev, int64_t nruns, const void* const* src, void* const* dst,
+                             const size_t* bytes, void* const* streams);
+/* The same runs pulled by a small persistent TMA kernel (`max_ctas` CTAs, one per SM): one thread per
+ * CTA keeps ~14 x 16 KB bulk loads (cp.async.bulk) in flight against the peers' memory, four warps
+ * drain the stages into the local destination.  nruns <= 64; src / dst / bytes multiples of 8;
+ * src / dst / bytes are HOST arrays. */
+int fb_pull_runs_tma(int dev, void* stream, int nruns, const void* const* src, void* const* dst,
+                     const size_t* bytes, int max_ctas);
 
 /* ---------------------------------------------------------------------------
  * K6  hash group-by with aggregation (single 8-byte key; other key shapes are packed /

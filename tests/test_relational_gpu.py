@@ -182,3 +182,27 @@ def test_presort_and_logical_partitions_for_device_functions(e):
                        engine=e, as_local=True)
     exp = pdf.sort_values("v", ascending=False).groupby("k").head(1)
     assert sorted(map(tuple, got.values.tolist())) == sorted(map(tuple, exp.values.tolist()))
+
+
+@pytest.mark.gpu
+def test_tma_pull_and_dma_runs_copy_any_8_byte_alignment():
+    """The exchange's two run copiers (persistent TMA pull kernel, copy engines) on local memory:
+    runs whose source / destination are only 8-byte aligned, odd lengths, empty and tiny runs."""
+    import torch
+
+    from fugue_b200 import kernels as K
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    src = torch.randint(-(2**62), 2**62, (3_000_000,), dtype=torch.int64, device=dev, generator=g)
+    runs = [(0, 0, 1_000_001), (1_000_001, 1_000_001, 4096), (1_004_097, 1_004_098, 0), (1_004_097, 1_004_099, 1),
+            (1_100_001, 1_100_000, 777_777), (2_000_000, 2_000_003, 2), (2_100_000, 2_100_001, 300_003)]
+    for fn in (lambda s, d, n: K.pull_runs_tma(dev, s, d, n, 7), lambda s, d, n: K.copy_runs_dma(dev, s, d, n)):
+        dst = torch.zeros_like(src)
+        fn([src.data_ptr() + 8 * a for a, _, _ in runs], [dst.data_ptr() + 8 * b for _, b, _ in runs],
+           [8 * n for _, _, n in runs])
+        torch.cuda.synchronize()
+        exp = torch.zeros_like(src)
+        for a, b, n in runs:
+            exp[b:b + n] = src[a:a + n]
+        assert torch.equal(dst, exp)

@@ -1,11 +1,13 @@
 """Multi-GPU exchange probe (torchrun, one rank per GPU): parity check, then the headline transform
 step for a sweep of exchange settings on one engine object.  Prints one line per setting on rank 0.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29544 tools/dist_probe.py [--rows 125000000] [--sweep "dma:2:1,dma:4:1,kernel:4:16"]
+        --master-port 29544 tools/dist_probe.py [--rows 125000000] [--sweep "dma:1-1-2-4:1,dma:2:1,kernel:4:16"]
 """
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # see fugue_b200/dist.py
 import sys
 import time
 
@@ -23,6 +25,7 @@ def main():
     ap.add_argument("--sweep", default="dma:2:1,dma:4:1,dma:1:1,dma:8:1,kernel:4:16,kernel:2:16")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--trace", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -61,7 +64,7 @@ def main():
 
     for item in args.sweep.split(","):
         mode, gc, res = item.split(":")
-        eng._exchange, eng._group_cols, eng._sm_reserve = mode, int(gc), int(res)
+        eng._exchange, eng._group_cols, eng._sm_reserve = mode, [int(x) for x in gc.split('-')], int(res)
         try:
             for _ in range(2):
                 out = fa.transform(df, identity, schema="*", partition=spec, engine=eng)
@@ -81,11 +84,20 @@ def main():
             dist.all_reduce(rows_out)
             if rank == 0:
                 ms = float(t.item())
-                print(json.dumps({"mode": mode, "group_cols": int(gc), "sm_reserve": int(res), "world": world,
+                print(json.dumps({"mode": mode, "group_cols": gc, "sm_reserve": int(res), "world": world,
                                   "rows_per_gpu": n, "ms_per_step": round(ms, 3), "host_enqueue_ms": round(host_ms, 3),
                                   "G_rows_per_s": round(n * world / ms / 1e6, 2), "rows_out": int(rows_out.item()),
                                   "nvlink_GBps_out_per_gpu": round(64.0 * n * (world - 1) / world / ms / 1e6, 1)}),
                       flush=True)
+            if args.trace:
+                eng._trace = []
+                out = fa.transform(df, identity, schema="*", partition=spec, engine=eng)
+                sync()
+                tr, eng._trace = eng._trace, None
+                if rank in (0, world - 1):
+                    t0e = tr[0][1]
+                    print(f"[rank {rank}] trace {item}: " + " ".join(f"{lb}={t0e.elapsed_time(ev):.2f}" for lb, ev in tr[1:]),
+                          flush=True)
             del out
         except Exception as e:  # noqa: BLE001
             print(f"[rank {rank}] {item}: {e!r}", flush=True)
