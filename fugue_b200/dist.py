@@ -124,6 +124,7 @@ def compact_plan(segment_offsets: torch.Tensor) -> Tuple[torch.Tensor, torch.Ten
 
 FUGUE_B200_CONF_DIST_GROUP_COLS = "fugue.b200.dist.group_cols"    # payload columns per scatter/exchange group
 FUGUE_B200_CONF_DIST_EXCHANGE = "fugue.b200.dist.exchange"        # "dma" (copy engines) | "tma" | "kernel" (SM pulls)
+FUGUE_B200_CONF_DIST_DMA_PIECES = "fugue.b200.dist.dma_pieces"    # copy-engine streams per peer
 FUGUE_B200_CONF_DIST_SM_RESERVE = "fugue.b200.dist.sm_reserve"    # SMs the persistent scatter leaves free
 _BARRIER_TIMEOUT_MS = 120_000   # a rank that died must not hang the others' GPUs forever
 _CTL_SLOTS = 1024                                                 # counts per rank and parity (K.MAX_PARTITIONS)
@@ -143,10 +144,13 @@ class DistributedB200Engine(B200ExecutionEngine):
         self._ctl: Optional[torch.Tensor] = None
         self._step = 0
         self._trace: Optional[List[Any]] = None
-        gc = self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, "1,1,2,4")
+        gc = self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, "4")
         self._group_cols = [max(1, int(x)) for x in str(gc).split(",")]  # columns per group; last repeats
         self._exchange = str(self._conf.get(FUGUE_B200_CONF_DIST_EXCHANGE, "dma"))
         assert_or_throw(self._exchange in ("dma", "kernel", "tma"), ValueError(f"unknown exchange {self._exchange}"))
+        # copy-engine streams per peer (pieces every run is cut into): 8 GPUs: 1, 4: 2, 2: 4
+        self._dma_pieces = max(1, min(8, int(self._conf.get(FUGUE_B200_CONF_DIST_DMA_PIECES,
+                                                            max(1, min(4, 6 // max(1, self._world - 1)))))))
         self._sm_reserve = int(self._conf.get(FUGUE_B200_CONF_DIST_SM_RESERVE,
                                               1 if self._exchange == "dma" else 16))
 
@@ -183,7 +187,7 @@ class DistributedB200Engine(B200ExecutionEngine):
         self._counts_dev = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, device=dev)
         self._counts_host = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, pin_memory=True)
         self._s_ctl = torch.cuda.Stream(dev, priority=-1)  # barrier kernels must not queue behind the scatter
-        self._s_dma = [torch.cuda.Stream(dev) for _ in range(self._world)]
+        self._s_dma = [torch.cuda.Stream(dev) for _ in range(1 + (self._world - 1) * 8)]
 
     def _post_counts(self, local_counts: torch.Tensor) -> torch.cuda.Event:
         """Stream-ordered all-gather of ``local_counts`` (int64[num], device) over symmetric memory:
@@ -339,7 +343,8 @@ class DistributedB200Engine(B200ExecutionEngine):
         optr = [o.data_ptr() for o in outs]
         ev_alloc = torch.cuda.Event()
         ev_alloc.record(s_main)  # the output buffers were allocated on the main stream
-        streams = self._s_dma
+        pieces = self._dma_pieces
+        streams = self._s_dma[:1 + (world - 1) * pieces]
         sptr = [st.cuda_stream for st in streams]
         for st in streams:
             st.wait_event(ev_alloc)
@@ -350,18 +355,29 @@ class DistributedB200Engine(B200ExecutionEngine):
                 # own rows: local copy on stream 0 as soon as this rank's scatter of the group is done;
                 # peers: stream j pulls from rank + j (every rank starts on a different source)
                 streams[0].wait_event(ev_sc[gi])
-                for j in range(1, world):
-                    streams[j].wait_event(ev_b[gi])
+                for st in streams[1:]:
+                    st.wait_event(ev_b[gi])
                 src, dst, nb, stq = [], [], [], []
                 for j in range(world):
                     sr = (rank + j) % world
                     if recv_rows[sr] == 0:
                         continue
                     for i in idx:
-                        src.append(base[sr] + peer_off[sr][i] + int(pull_start[sr]) * widths[i])
-                        dst.append(optr[i] + int(recv_base[sr]) * widths[i])
-                        nb.append(int(recv_rows[sr]) * widths[i])
-                        stq.append(sptr[j])
+                        a_src = base[sr] + peer_off[sr][i] + int(pull_start[sr]) * widths[i]
+                        a_dst = optr[i] + int(recv_base[sr]) * widths[i]
+                        total = int(recv_rows[sr]) * widths[i]
+                        if j == 0 or pieces == 1:
+                            src.append(a_src), dst.append(a_dst), nb.append(total), stq.append(sptr[j])
+                            continue
+                        # one copy engine moves ~450 GB/s from one peer: with few peers every run is cut
+                        # into `pieces` parts on different streams so that several engines share it
+                        step = ((total + pieces - 1) // pieces + 255) & ~255
+                        for q in range(pieces):
+                            o = q * step
+                            if o >= total:
+                                break
+                            src.append(a_src + o), dst.append(a_dst + o), nb.append(min(step, total - o))
+                            stq.append(sptr[1 + (j - 1) * pieces + q])
                 K.copy_runs_dma_streams(dev, src, dst, nb, stq)
                 continue
             with torch.cuda.stream(s_ctl):
