@@ -28,6 +28,12 @@ class ExprIns(C.Structure):
                 ("imm", C.c_int64)]
 
 
+class MapUnit(C.Structure):
+    """``fb_map_unit`` of include/fugue_b200.h (K4 fused map epilogue)."""
+    _fields_ = [("src2", C.c_void_p), ("mode", C.c_int32), ("reserved", C.c_int32), ("a", C.c_uint64),
+                ("b", C.c_uint64), ("c", C.c_uint64)]
+
+
 _vp = C.c_void_p
 _i32p = C.POINTER(C.c_int32)
 _vpp = C.POINTER(C.c_void_p)
@@ -51,6 +57,9 @@ SIGNATURES = {
     "fb_partition_apply_ex": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                         C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _i32p,
                                         _vpp, C.c_int]),
+    "fb_partition_map_tail_bytes": (C.c_size_t, [C.c_int]),
+    "fb_partition_apply_map": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
+                                         C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _vpp, _vp, _vp, C.c_int]),
     "fb_partition_cols": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _i32p,
                                     C.c_int, _vpp, C.c_uint32, _vpp, _vp, _vp, C.c_size_t]),
     "fb_radix_pass": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, C.c_int, C.c_int, _vpp, _i32p, _vpp, _vp, C.c_size_t,

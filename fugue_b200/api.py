@@ -214,6 +214,10 @@ class _FuncAsTransformer:
             except tuple(ignore_errors) if ignore_errors else ():  # processors.py:330-338
                 return ArrowDataFrame(None, output_schema)
 
+        from .colmap import ColumnMap
+
+        # a declarative map: the map engine may fuse it into the partition kernels (K4)
+        run.column_map = self._func if isinstance(self._func, ColumnMap) else None  # type: ignore
         return run
 
 
@@ -240,9 +244,14 @@ def transform(
     logical partition on the host after the device partitioned the table).
     """
     assert_or_throw(callback is None, NotImplementedError("callback (RPC) is out of scope"))
-    assert_or_throw(save_path is None and not checkpoint,
-                    NotImplementedError("save_path / checkpoint are out of scope"))
+    # fugue/workflow/api.py:16-31: only parquet paths are accepted for a path input / save_path
+    for what, pth in (("df", df if isinstance(df, str) else None), ("save_path", save_path)):
+        assert_or_throw(pth is None or (isinstance(pth, str) and pth.lower().endswith(".parquet")),
+                        lambda: ValueError(f"fugue transform can only load / save parquet file paths ({what}={pth})"))
     e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    path_input = isinstance(df, str)
+    if path_input:
+        df = e.load_df(df, format_hint="parquet")
     tf = _FuncAsTransformer(using, schema, params)
     spec = PartitionSpec(partition)
     res: Optional[DataFrame] = None
@@ -262,6 +271,23 @@ def transform(
                                          map_func_format_hint=tf.get_format_hint())
     if persist:
         res = e.persist(res)
+    # save_path / checkpoint (fugue/workflow/api.py:100-120, fugue/workflow/_checkpoint.py:38-128): a strong,
+    # non-deterministic file checkpoint = save as parquet, continue from the file
+    if checkpoint or save_path is not None:
+        target = save_path
+        if target is None:
+            import os
+            import uuid
+
+            root = e.conf.get("fugue.workflow.checkpoint.path", "")
+            assert_or_throw(root != "", ValueError(
+                "fugue.workflow.checkpoint.path is not set (needed for checkpoint=True without save_path)"))
+            os.makedirs(root, exist_ok=True)
+            target = os.path.join(root, uuid.uuid4().hex + ".parquet")
+        e.save_df(res, target, format_hint="parquet", mode="overwrite")
+        if not checkpoint:
+            return save_path
+        res = e.load_df(target, format_hint="parquet")
     res = e.convert_yield_dataframe(res, as_local)
     if as_fugue or isinstance(df, DataFrame):
         return res

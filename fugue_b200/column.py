@@ -1,647 +1,429 @@
-"""Fugue's column-expression DSL, as consumed by ``ExecutionEngine.select/filter/assign/aggregate``.
+"""Column expressions of ``ExecutionEngine.select / filter / assign / aggregate``: the engine's own IR.
 
-Same public surface and observable behaviour as the reference (so code written against
-``fugue.column`` runs unchanged), own implementation:
+One immutable node type (:class:`ColumnExpr`) tagged with a :class:`Kind`; everything the engine needs
+from an expression is a function of ``(kind, head, args)``:
 
-* expressions   fugue/column/expressions.py:8-856  (``col, lit, null, all_cols, function``, operators,
-                ``alias / cast / infer_alias / infer_type / is_null / not_null``, ``str()`` format)
-* functions     fugue/column/functions.py:13-370   (``coalesce, min, max, count, count_distinct, avg,
-                sum, first, last, is_agg``)
-* SelectColumns fugue/column/sql.py:38-246         (classification of SELECT columns, group-key inference)
-* SQLExpressionGenerator fugue/column/sql.py:249-497 (the SQL text Fugue itself emits for these trees)
+    NAMED     head = column name                     WILDCARD  ``*``
+    LITERAL   head = python value (None = NULL)      UNARY     head in ``- ~ IS_NULL NOT_NULL``, one arg
+    BINARY    head in ``+ - * / & | < > <= >= == !=``  CALL      head = function name (``COALESCE`` ...)
+    AGG       head in ``SUM COUNT AVG MIN MAX FIRST LAST``, one arg, optional DISTINCT
 
-The B200 engine does not go through SQL text: ``fugue_b200/expr.py`` compiles these trees into programs
-for the device evaluator (``fb_eval_expr``).  The generator is kept because it is part of the reference
-surface (``fugue_plugin`` hands unrecognised statements to the host SQL engine with it).
+plus an optional output alias and an optional cast of the node's result.  ``fugue_b200/expr.py`` compiles
+these trees into programs for the device evaluator (``fb_eval_expr``); nothing goes through SQL text.
+
+The builders keep the names and the observable behaviour (alias / type inference, group-key rules,
+error types, string forms) of the reference's public expression interface, so that code written
+against ``fugue.column`` reads the same here: ``col, lit, null, all_cols, function`` and the operators
+(fugue/column/expressions.py:8-856), ``functions.*`` (fugue/column/functions.py:13-370),
+``SelectColumns`` (fugue/column/sql.py:38-246).  The reference's own trees reach the engine through
+``fugue_b200.fugue_plugin.translate_expr``; tests/test_column_golden.py pins this module to vectors
+produced by the reference's code.
 """
+import enum
 import hashlib
-from typing import Any, Callable, Dict, Iterable, List, Optional, Set, Tuple
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import pyarrow as pa
 
 from .schema import Schema, parse_type, type_to_expr
 
 
+class Kind(enum.IntEnum):
+    NAMED = 0
+    WILDCARD = 1
+    LITERAL = 2
+    UNARY = 3
+    BINARY = 4
+    CALL = 5
+    AGG = 6
+
+
+BOOL_OPS = frozenset(["&", "|", "<", ">", "<=", ">=", "==", "!="])
+ARITH_OPS = frozenset(["+", "-", "*", "/"])
+AGG_KEEPS_ARG_TYPE = frozenset(["MIN", "MAX", "FIRST", "LAST"])
+_LITERAL_TYPES = (int, bool, float, str)
+
+
 def to_pa_datatype(obj: Any) -> pa.DataType:
-    """python type / type expression / pyarrow type -> pyarrow type (triad ``to_pa_datatype`` rules:
-    ``int`` -> int64, ``float`` -> float64, ``str`` -> string, ``bool`` -> bool; strings follow the
-    schema expression syntax, so ``"int"`` -> int32)."""
+    """python type / type expression / pyarrow type -> pyarrow type (``int`` -> int64, ``float`` ->
+    float64, ``str`` -> string, ``bool`` -> bool; strings follow the schema expression syntax, so
+    ``"int"`` -> int32)."""
     import datetime
 
     if isinstance(obj, pa.DataType):
         return obj
-    if obj is int:
-        return pa.int64()
-    if obj is float:
-        return pa.float64()
-    if obj is str:
-        return pa.string()
-    if obj is bool:
-        return pa.bool_()
-    if obj is datetime.datetime:
-        return pa.timestamp("us")
-    if obj is datetime.date:
-        return pa.date32()
     if isinstance(obj, str):
         return parse_type(obj)
+    table = {int: pa.int64(), float: pa.float64(), str: pa.string(), bool: pa.bool_(),
+             datetime.datetime: pa.timestamp("us"), datetime.date: pa.date32()}
+    if obj in table:
+        return table[obj]
     raise TypeError(f"can't convert {obj!r} to a data type")
 
 
-def _quote_name(name: str) -> str:
-    ok = name != "" and (name[0].isalpha() or name[0] == "_") and all(c.isalnum() or c == "_" for c in name)
-    return name if ok else "`" + name.replace("`", "``") + "`"
+def _show_arg(v: Any) -> str:
+    if isinstance(v, bool):
+        return "TRUE" if v else "FALSE"
+    if isinstance(v, str):
+        return f"'{v}'"
+    return str(v)
+
+
+def _show_literal(v: Any) -> str:
+    if v is None:
+        return "NULL"
+    if isinstance(v, bool):
+        return "TRUE" if v else "FALSE"
+    if isinstance(v, str):
+        return "'" + v.replace("\\", "\\\\").replace("'", "\\'") + "'"
+    return str(v)
 
 
 class ColumnExpr:
-    """Base of all column expressions; build them with :func:`col`, :func:`lit`, :func:`null`,
-    :func:`all_cols`, :func:`function` and the operators."""
+    """One node of an expression tree (see the module docstring).  Immutable: ``alias`` / ``cast``
+    return modified copies."""
 
-    def __init__(self) -> None:
-        self._as_name = ""
-        self._as_type: Optional[pa.DataType] = None
+    __slots__ = ("kind", "head", "args", "kwargs", "is_distinct", "as_name", "as_type")
 
+    def __init__(self, kind: Kind, head: Any, args: Sequence[Any] = (), kwargs: Optional[Dict[str, Any]] = None,
+                 distinct: bool = False, as_name: str = "", as_type: Optional[pa.DataType] = None):
+        self.kind = kind
+        self.head = head
+        self.args: Tuple[Any, ...] = tuple(args)
+        self.kwargs: Dict[str, Any] = dict(kwargs or {})
+        self.is_distinct = distinct
+        self.as_name = as_name
+        self.as_type = as_type
+
+    # ---- accessors (one per role of ``head`` / ``args``) ----------------------------------------
     @property
     def name(self) -> str:
-        return ""
+        """Column name of a NAMED node, ``*`` for the wildcard, empty otherwise."""
+        if self.kind == Kind.NAMED:
+            return self.head
+        return "*" if self.kind == Kind.WILDCARD else ""
 
     @property
-    def as_name(self) -> str:
-        return self._as_name
+    def value(self) -> Any:
+        assert self.kind == Kind.LITERAL
+        return self.head
 
     @property
-    def as_type(self) -> Optional[pa.DataType]:
-        return self._as_type
+    def op(self) -> str:
+        assert self.kind in (Kind.UNARY, Kind.BINARY)
+        return self.head
+
+    @property
+    def func(self) -> str:
+        assert self.kind in (Kind.UNARY, Kind.BINARY, Kind.CALL, Kind.AGG)
+        return self.head
+
+    @property
+    def arg(self) -> "ColumnExpr":
+        assert self.kind in (Kind.UNARY, Kind.AGG)
+        return self.args[0]
+
+    col = arg  # operand of a unary operator
+
+    @property
+    def left(self) -> "ColumnExpr":
+        assert self.kind == Kind.BINARY
+        return self.args[0]
+
+    @property
+    def right(self) -> "ColumnExpr":
+        assert self.kind == Kind.BINARY
+        return self.args[1]
+
+    @property
+    def has_args(self) -> bool:
+        return self.kind in (Kind.UNARY, Kind.BINARY, Kind.CALL, Kind.AGG)
 
     @property
     def output_name(self) -> str:
+        if self.kind == Kind.WILDCARD:
+            raise NotImplementedError("wildcard column doesn't have an output name")
         return self.as_name if self.as_name != "" else self.name
 
+    # ---- derived copies ---------------------------------------------------------------------------
+    def _with(self, as_name: str, as_type: Optional[pa.DataType]) -> "ColumnExpr":
+        return ColumnExpr(self.kind, self.head, self.args, self.kwargs, self.is_distinct, as_name, as_type)
+
     def alias(self, as_name: str) -> "ColumnExpr":
-        raise NotImplementedError
+        if self.kind == Kind.WILDCARD:
+            raise NotImplementedError("wildcard column can't have an alias")
+        return self._with(as_name, self.as_type)
 
     def cast(self, data_type: Any) -> "ColumnExpr":
-        raise NotImplementedError
+        if self.kind == Kind.WILDCARD:
+            raise NotImplementedError("wildcard column can't be cast")
+        return self._with(self.as_name, None if data_type is None else to_pa_datatype(data_type))
 
     def infer_alias(self) -> "ColumnExpr":
+        """Give the node the name SQL would give it: a cast column keeps its name, a unary operator or
+        an aggregation of a named column takes the column's name."""
+        if self.kind == Kind.NAMED:
+            return self.alias(self.head) if (self.as_name == "" and self.as_type is not None) else self
+        if self.kind in (Kind.UNARY, Kind.AGG) and self.as_name == "":
+            return self.alias(self.args[0].infer_alias().output_name)
         return self
 
     def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        return self.as_type
+        """The result type where it follows from the tree alone (None: the evaluator decides)."""
+        if self.as_type is not None:
+            return self.as_type
+        k = self.kind
+        if k == Kind.NAMED:
+            return schema[self.head].type if self.head in schema else None
+        if k == Kind.LITERAL:
+            return None if self.head is None else to_pa_datatype(type(self.head))
+        if k == Kind.BINARY:
+            return pa.bool_() if self.head in BOOL_OPS else None
+        if k == Kind.UNARY and self.head in ("-", "~"):
+            tp = self.args[0].infer_type(schema)
+            if tp is None:
+                return None
+            fits = (pa.types.is_signed_integer(tp) or pa.types.is_floating(tp)) if self.head == "-" \
+                else pa.types.is_boolean(tp)
+            return tp if fits else None
+        if k == Kind.AGG and self.head in AGG_KEEPS_ARG_TYPE:
+            return self.args[0].infer_type(schema)
+        return None
 
-    @property
-    def body_str(self) -> str:
-        raise NotImplementedError
+    # ---- text -------------------------------------------------------------------------------------
+    def _body(self) -> str:
+        k = self.kind
+        if k == Kind.NAMED:
+            return self.head
+        if k == Kind.WILDCARD:
+            return "*"
+        if k == Kind.LITERAL:
+            return _show_literal(self.head)
+        parts = [_show_arg(x) for x in self.args] + [n + "=" + _show_arg(v) for n, v in self.kwargs.items()]
+        return f"{self.head}({'DISTINCT ' if self.is_distinct else ''}{','.join(parts)})"
 
     def __str__(self) -> str:
-        res = self.body_str
+        res = self._body()
         if self.as_type is not None:
             res = f"CAST({res} AS {type_to_expr(self.as_type)})"
-        if self.as_name != "":
-            res = res + " AS " + self.as_name
-        return res
+        return res if self.as_name == "" else res + " AS " + self.as_name
 
     __repr__ = __str__
 
+    def fingerprint(self) -> str:
+        """Stable id of the tree (structure, aliases, casts): equal trees get equal temporaries."""
+        return hashlib.sha1(_canon(self).encode()).hexdigest()
+
+    # ---- operators --------------------------------------------------------------------------------
     def is_null(self) -> "ColumnExpr":
-        return _UnaryOpExpr("IS_NULL", self)
+        if self.kind == Kind.LITERAL:
+            return lit(self.head is None)
+        return ColumnExpr(Kind.UNARY, "IS_NULL", [self])
 
     def not_null(self) -> "ColumnExpr":
-        return _UnaryOpExpr("NOT_NULL", self)
+        if self.kind == Kind.LITERAL:
+            return lit(self.head is not None)
+        return ColumnExpr(Kind.UNARY, "NOT_NULL", [self])
 
     def __neg__(self) -> "ColumnExpr":
-        return _InvertOpExpr("-", self)
+        return ColumnExpr(Kind.UNARY, "-", [self])
 
     def __pos__(self) -> "ColumnExpr":
         return self
 
     def __invert__(self) -> "ColumnExpr":
-        return _NotOpExpr("~", self)
-
-    def __add__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("+", self, other)
-
-    def __radd__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("+", other, self)
-
-    def __sub__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("-", self, other)
-
-    def __rsub__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("-", other, self)
-
-    def __mul__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("*", self, other)
-
-    def __rmul__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("*", other, self)
-
-    def __truediv__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("/", self, other)
-
-    def __rtruediv__(self, other: Any) -> "ColumnExpr":
-        return _BinaryOpExpr("/", other, self)
-
-    def __and__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr("&", self, other)
-
-    def __rand__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr("&", other, self)
-
-    def __or__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr("|", self, other)
-
-    def __ror__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr("|", other, self)
-
-    def __lt__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr("<", self, other)
-
-    def __gt__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr(">", self, other)
-
-    def __le__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr("<=", self, other)
-
-    def __ge__(self, other: Any) -> "ColumnExpr":
-        return _BoolBinaryOpExpr(">=", self, other)
-
-    def __eq__(self, other: Any) -> "ColumnExpr":  # type: ignore
-        return _BoolBinaryOpExpr("==", self, other)
-
-    def __ne__(self, other: Any) -> "ColumnExpr":  # type: ignore
-        return _BoolBinaryOpExpr("!=", self, other)
-
-    __hash__ = object.__hash__  # == builds an expression, identity is the only usable hash
+        return ColumnExpr(Kind.UNARY, "~", [self])
 
     def __bool__(self) -> bool:
         raise TypeError("a column expression has no truth value; use & | ~ to combine conditions")
 
-    def _uuid_keys(self) -> List[Any]:
-        raise NotImplementedError
+    __hash__ = object.__hash__
 
-    def __uuid__(self) -> str:
-        return to_uuid(type(self).__name__, self.as_name,
-                       None if self.as_type is None else str(self.as_type), self._uuid_keys())
 
+def _binary_method(op: str, swap: bool) -> Any:
+    def method(self: ColumnExpr, other: Any) -> ColumnExpr:
+        return binary(op, other, self) if swap else binary(op, self, other)
 
-def to_uuid(*args: Any) -> str:
-    """Deterministic id of nested python values / objects exposing ``__uuid__`` (triad ``to_uuid``)."""
-    h = hashlib.md5()
+    return method
 
-    def feed(v: Any) -> None:
-        if hasattr(v, "__uuid__"):
-            h.update(b"u" + v.__uuid__().encode())
-        elif isinstance(v, (list, tuple)):
-            h.update(b"[")
-            for x in v:
-                feed(x)
-            h.update(b"]")
-        elif isinstance(v, dict):
-            h.update(b"{")
-            for k, x in v.items():
-                feed(k)
-                feed(x)
-            h.update(b"}")
-        else:
-            h.update((type(v).__name__ + ":" + repr(v)).encode())
 
-    feed(args)
-    return h.hexdigest()
+for _name, _op in (("add", "+"), ("sub", "-"), ("mul", "*"), ("truediv", "/"), ("and", "&"), ("or", "|")):
+    setattr(ColumnExpr, f"__{_name}__", _binary_method(_op, False))
+    setattr(ColumnExpr, f"__r{_name}__", _binary_method(_op, True))
+for _name, _op in (("lt", "<"), ("gt", ">"), ("le", "<="), ("ge", ">="), ("eq", "=="), ("ne", "!=")):
+    setattr(ColumnExpr, f"__{_name}__", _binary_method(_op, False))
 
 
-class _NamedColumnExpr(ColumnExpr):
-    def __init__(self, name: Any):
-        super().__init__()
-        self._name = name
+def _canon(v: Any) -> str:
+    if isinstance(v, ColumnExpr):
+        inner = ",".join(_canon(a) for a in v.args) + ";" + ",".join(k + "=" + _canon(x) for k, x in v.kwargs.items())
+        return (f"<{int(v.kind)}|{type(v.head).__name__}:{v.head!r}|{inner}|{int(v.is_distinct)}|{v.as_name}|"
+                f"{v.as_type}>")
+    return f"{type(v).__name__}:{v!r}"
 
-    @property
-    def body_str(self) -> str:
-        return self._name
 
-    @property
-    def name(self) -> str:
-        return self._name
-
-    def _derive(self, as_name: str, as_type: Optional[pa.DataType]) -> "ColumnExpr":
-        other = _NamedColumnExpr(self._name)
-        other._as_name, other._as_type = as_name, as_type
-        return other
-
-    def alias(self, as_name: str) -> ColumnExpr:
-        return self._derive(as_name, self.as_type)
-
-    def cast(self, data_type: Any) -> ColumnExpr:
-        return self._derive(self.as_name, None if data_type is None else to_pa_datatype(data_type))
-
-    def infer_alias(self) -> ColumnExpr:
-        if self.as_name == "" and self.as_type is not None:
-            return self.alias(self.output_name)
-        return self
-
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        if self.name not in schema:
-            return self.as_type
-        return self.as_type or schema[self.name].type
-
-    def _uuid_keys(self) -> List[Any]:
-        return [self._name]
-
-
-class _WildcardExpr(ColumnExpr):
-    @property
-    def body_str(self) -> str:
-        return "*"
-
-    @property
-    def name(self) -> str:
-        return "*"
-
-    @property
-    def output_name(self) -> str:
-        raise NotImplementedError("wildcard column doesn't have an output name")
-
-    def alias(self, as_name: str) -> ColumnExpr:
-        raise NotImplementedError("wildcard column can't have an alias")
-
-    def cast(self, data_type: Any) -> ColumnExpr:
-        raise NotImplementedError("wildcard column can't be cast")
-
-    def infer_alias(self) -> ColumnExpr:
-        return self
-
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        return None
-
-    def __uuid__(self) -> str:
-        return to_uuid("*")
-
-
-class _LiteralColumnExpr(ColumnExpr):
-    _VALID_TYPES = (int, bool, float, str)
-
-    def __init__(self, value: Any):
-        super().__init__()
-        if not (value is None or isinstance(value, _LiteralColumnExpr._VALID_TYPES)):
-            raise NotImplementedError(f"{value}, type: {type(value)}")
-        self._value = value
-
-    @property
-    def body_str(self) -> str:
-        v = self._value
-        if v is None:
-            return "NULL"
-        if isinstance(v, str):
-            return "'" + v.replace("\\", "\\\\").replace("'", "\\'") + "'"
-        if isinstance(v, bool):
-            return "TRUE" if v else "FALSE"
-        return str(v)
-
-    @property
-    def value(self) -> Any:
-        return self._value
-
-    def is_null(self) -> ColumnExpr:
-        return _LiteralColumnExpr(self._value is None)
-
-    def not_null(self) -> ColumnExpr:
-        return _LiteralColumnExpr(self._value is not None)
-
-    def _derive(self, as_name: str, as_type: Optional[pa.DataType]) -> ColumnExpr:
-        other = _LiteralColumnExpr(self._value)
-        other._as_name, other._as_type = as_name, as_type
-        return other
-
-    def alias(self, as_name: str) -> ColumnExpr:
-        return self._derive(as_name, self.as_type)
-
-    def cast(self, data_type: Any) -> ColumnExpr:
-        return self._derive(self.as_name, None if data_type is None else to_pa_datatype(data_type))
-
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        if self._value is None:
-            return self.as_type
-        return self.as_type or to_pa_datatype(type(self._value))
-
-    def _uuid_keys(self) -> List[Any]:
-        return [self._value]
-
-
-class _FuncExpr(ColumnExpr):
-    def __init__(self, func: str, *args: Any, arg_distinct: bool = False, **kwargs: Any):
-        super().__init__()
-        self._func = func
-        self._distinct = arg_distinct
-        self._args = list(args)
-        self._kwargs = dict(kwargs)
-
-    @property
-    def body_str(self) -> str:
-        def show(v: Any) -> str:
-            if isinstance(v, bool):
-                return "TRUE" if v else "FALSE"
-            if isinstance(v, str):
-                return f"'{v}'"
-            return str(v)
-
-        parts = [show(x) for x in self._args] + [k + "=" + show(v) for k, v in self._kwargs.items()]
-        return f"{self._func}({'DISTINCT ' if self._distinct else ''}{','.join(parts)})"
-
-    @property
-    def func(self) -> str:
-        return self._func
-
-    @property
-    def is_distinct(self) -> bool:
-        return self._distinct
-
-    @property
-    def args(self) -> List[Any]:
-        return self._args
-
-    @property
-    def kwargs(self) -> Dict[str, Any]:
-        return self._kwargs
-
-    def _copy(self) -> "_FuncExpr":
-        return _FuncExpr(self._func, *self._args, **self._kwargs)
-
-    def _derive(self, as_name: str, as_type: Optional[pa.DataType]) -> ColumnExpr:
-        other = self._copy()
-        other._distinct = self._distinct
-        other._as_name, other._as_type = as_name, as_type
-        return other
-
-    def alias(self, as_name: str) -> ColumnExpr:
-        return self._derive(as_name, self.as_type)
-
-    def cast(self, data_type: Any) -> ColumnExpr:
-        return self._derive(self.as_name, None if data_type is None else to_pa_datatype(data_type))
-
-    def _uuid_keys(self) -> List[Any]:
-        return [self._func, self._distinct, self._args, self._kwargs]
-
-
-class _UnaryOpExpr(_FuncExpr):
-    def __init__(self, op: str, column: ColumnExpr, arg_distinct: bool = False):
-        super().__init__(op, column, arg_distinct=arg_distinct)
-
-    @property
-    def col(self) -> ColumnExpr:
-        return self._args[0]
-
-    @property
-    def op(self) -> str:
-        return self._func
-
-    def infer_alias(self) -> ColumnExpr:
-        return self if self.output_name != "" else self.alias(self.col.infer_alias().output_name)
-
-    def _copy(self) -> _FuncExpr:
-        return type(self)(self._func, self._args[0])
-
-
-class _InvertOpExpr(_UnaryOpExpr):  # arithmetic negation
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        if self.as_type is not None:
-            return self.as_type
-        tp = self.col.infer_type(schema)
-        if tp is not None and (pa.types.is_signed_integer(tp) or pa.types.is_floating(tp)):
-            return tp
-        return None
-
-
-class _NotOpExpr(_UnaryOpExpr):  # logical NOT
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        if self.as_type is not None:
-            return self.as_type
-        tp = self.col.infer_type(schema)
-        if tp is not None and pa.types.is_boolean(tp):
-            return tp
-        return None
-
-
-class _BinaryOpExpr(_FuncExpr):
-    def __init__(self, op: str, left: Any, right: Any, arg_distinct: bool = False):
-        super().__init__(op, _to_col(left), _to_col(right), arg_distinct=arg_distinct)
-
-    @property
-    def left(self) -> ColumnExpr:
-        return self._args[0]
-
-    @property
-    def right(self) -> ColumnExpr:
-        return self._args[1]
-
-    @property
-    def op(self) -> str:
-        return self._func
-
-    def _copy(self) -> _FuncExpr:
-        return type(self)(self._func, self._args[0], self._args[1])
-
-
-class _BoolBinaryOpExpr(_BinaryOpExpr):
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        return self.as_type or pa.bool_()
-
-
-class AggFuncExpr(_FuncExpr):
-    """``FUNC([DISTINCT] arg)`` (reference: ``_UnaryAggFuncExpr``, fugue/column/functions.py:343-356)."""
-
-    def __init__(self, func: str, arg: ColumnExpr, as_name: str = "", arg_distinct: bool = False):
-        super().__init__(func.upper(), arg, arg_distinct=arg_distinct)
-        self._as_name = as_name
-
-    @property
-    def arg(self) -> ColumnExpr:
-        return self._args[0]
-
-    def infer_alias(self) -> ColumnExpr:
-        return self if self.output_name != "" else self.alias(self.arg.infer_alias().output_name)
-
-    def _copy(self) -> _FuncExpr:
-        return type(self)(self._func, self._args[0], arg_distinct=self._distinct)
-
-
-class _SameTypeAggFuncExpr(AggFuncExpr):  # MIN / MAX / FIRST / LAST keep the argument type
-    def infer_type(self, schema: Schema) -> Optional[pa.DataType]:
-        return self.as_type or self.arg.infer_type(schema)
-
-
-_UnaryAggFuncExpr = AggFuncExpr  # the reference's name for it
-
-
+# ---- builders -------------------------------------------------------------------------------------
 def lit(obj: Any, alias: str = "") -> ColumnExpr:
-    res = _LiteralColumnExpr(obj)
-    return res if alias == "" else res.alias(alias)
+    if not (obj is None or isinstance(obj, _LITERAL_TYPES)):
+        raise NotImplementedError(f"{obj}, type: {type(obj)}")
+    return ColumnExpr(Kind.LITERAL, obj, as_name=alias)
 
 
 def null() -> ColumnExpr:
     return lit(None)
 
 
+def all_cols() -> ColumnExpr:
+    return ColumnExpr(Kind.WILDCARD, "*")
+
+
 def col(obj: Any, alias: str = "") -> ColumnExpr:
     if isinstance(obj, ColumnExpr):
         return obj if alias == "" else obj.alias(alias)
     if isinstance(obj, str):
-        if obj == "*":
-            return all_cols()
-        res = _NamedColumnExpr(obj)
-        return res if alias == "" else res.alias(alias)
+        return all_cols() if obj == "*" else ColumnExpr(Kind.NAMED, obj, as_name=alias)
     raise NotImplementedError(obj)
 
 
-def all_cols() -> ColumnExpr:
-    return _WildcardExpr()
-
-
-def function(name: str, *args: Any, arg_distinct: bool = False, **kwargs: Any) -> ColumnExpr:
-    return _FuncExpr(name, *args, arg_distinct=arg_distinct, **kwargs)
-
-
-def _to_col(obj: Any) -> ColumnExpr:
+def _operand(obj: Any) -> ColumnExpr:
     return obj if isinstance(obj, ColumnExpr) else lit(obj)
 
 
-def _get_column_mentions(column: Any) -> Iterable[str]:
-    if isinstance(column, _NamedColumnExpr):
-        yield column.name
-    elif isinstance(column, _FuncExpr):
-        for a in column.args:
-            yield from _get_column_mentions(a)
-        for a in column.kwargs.values():
-            yield from _get_column_mentions(a)
+def binary(op: str, left: Any, right: Any) -> ColumnExpr:
+    return ColumnExpr(Kind.BINARY, op, [_operand(left), _operand(right)])
+
+
+def function(name: str, *args: Any, arg_distinct: bool = False, **kwargs: Any) -> ColumnExpr:
+    return ColumnExpr(Kind.CALL, name, args, kwargs, arg_distinct)
+
+
+def agg(func: str, arg: Any, as_name: str = "", arg_distinct: bool = False) -> ColumnExpr:
+    """``FUNC([DISTINCT] arg)``: SUM / COUNT / AVG / MIN / MAX / FIRST / LAST."""
+    return ColumnExpr(Kind.AGG, func.upper(), [col(arg)], None, arg_distinct, as_name)
 
 
 def is_agg(column: Any) -> bool:
-    """True when the expression contains an aggregation anywhere (functions.py:314-340)."""
-    if isinstance(column, AggFuncExpr):
+    """True when the expression contains an aggregation anywhere."""
+    if not isinstance(column, ColumnExpr):
+        return False
+    if column.kind == Kind.AGG:
         return True
-    if isinstance(column, _FuncExpr):
-        return any(is_agg(x) for x in column.args) or any(is_agg(x) for x in column.kwargs.values())
-    return False
+    return any(is_agg(x) for x in column.args) or any(is_agg(x) for x in column.kwargs.values())
+
+
+def column_mentions(column: Any) -> Iterator[str]:
+    """Names of the columns an expression reads."""
+    if isinstance(column, ColumnExpr):
+        if column.kind == Kind.NAMED:
+            yield column.head
+        for a in column.args:
+            yield from column_mentions(a)
+        for a in column.kwargs.values():
+            yield from column_mentions(a)
 
 
 class functions:
-    """``import fugue_b200.column as fc; f = fc.functions`` == ``import fugue.column.functions as f``."""
+    """``f = fugue_b200.column.functions`` plays the role of ``import fugue.column.functions as f``."""
 
     @staticmethod
     def coalesce(*args: Any) -> ColumnExpr:
-        return function("COALESCE", *[_to_col(x) for x in args])
+        return function("COALESCE", *[_operand(x) for x in args])
 
     @staticmethod
     def min(c: Any) -> ColumnExpr:  # noqa: A003
-        return _SameTypeAggFuncExpr("MIN", col(c))
+        return agg("MIN", c)
 
     @staticmethod
     def max(c: Any) -> ColumnExpr:  # noqa: A003
-        return _SameTypeAggFuncExpr("MAX", col(c))
+        return agg("MAX", c)
 
     @staticmethod
     def first(c: Any) -> ColumnExpr:
-        return _SameTypeAggFuncExpr("FIRST", col(c))
+        return agg("FIRST", c)
 
     @staticmethod
     def last(c: Any) -> ColumnExpr:
-        return _SameTypeAggFuncExpr("LAST", col(c))
+        return agg("LAST", c)
 
     @staticmethod
     def count(c: Any) -> ColumnExpr:
-        return AggFuncExpr("COUNT", col(c))
+        return agg("COUNT", c)
 
     @staticmethod
     def count_distinct(c: Any) -> ColumnExpr:
-        return AggFuncExpr("COUNT", col(c), arg_distinct=True)
+        return agg("COUNT", c, arg_distinct=True)
 
     @staticmethod
     def avg(c: Any) -> ColumnExpr:
-        return AggFuncExpr("AVG", col(c))
+        return agg("AVG", c)
 
     @staticmethod
     def sum(c: Any) -> ColumnExpr:  # noqa: A003
-        return AggFuncExpr("SUM", col(c))
+        return agg("SUM", c)
 
     mean = avg
     is_agg = staticmethod(is_agg)
 
 
-# ---------------------------------------------------------------------------------------------
-# SELECT column collections and the SQL text Fugue emits for them
-# ---------------------------------------------------------------------------------------------
+# ---- one SELECT list ------------------------------------------------------------------------------
 class SelectColumns:
-    """The columns of one ``SELECT`` (fugue/column/sql.py:38-246): literals, plain columns, non-aggregate
-    functions, aggregations; group keys are every non-aggregate, non-literal column when an aggregation
-    is present."""
+    """The output columns of one SELECT, sorted into the roles the engine cares about.  With an
+    aggregation present every other non-literal column is a GROUP BY key (stripped of alias and cast)."""
 
     def __init__(self, *cols: ColumnExpr, arg_distinct: bool = False):
-        self._distinct = arg_distinct
-        self._all: List[ColumnExpr] = []
-        self._literals: List[ColumnExpr] = []
-        self._cols: List[ColumnExpr] = []
-        self._non_agg_funcs: List[ColumnExpr] = []
-        self._agg_funcs: List[ColumnExpr] = []
-        self._group_keys: List[ColumnExpr] = []
-        self._has_wildcard = False
-        keys: List[ColumnExpr] = []
-        for c in cols:
-            c = c.infer_alias()
-            self._all.append(c)
-            if isinstance(c, _LiteralColumnExpr):
-                self._literals.append(c)
-                continue
-            agg = False
-            if isinstance(c, _WildcardExpr):
-                if self._has_wildcard:
-                    raise ValueError("'*' can be used at most once")
-                self._has_wildcard = True
-                self._cols.append(c)
-            elif isinstance(c, _NamedColumnExpr):
-                self._cols.append(c)
-            elif isinstance(c, _FuncExpr):
-                agg = is_agg(c)
-                (self._agg_funcs if agg else self._non_agg_funcs).append(c)
-            if not agg:
-                keys.append(c if isinstance(c, _WildcardExpr) else c.alias("").cast(None))
-        if len(self._agg_funcs) > 0:
-            self._group_keys = keys
-            if self._has_wildcard:
+        self.is_distinct = arg_distinct
+        self.all_cols: List[ColumnExpr] = [c.infer_alias() for c in cols]
+        by_role: Dict[str, List[ColumnExpr]] = {"literal": [], "simple": [], "func": [], "agg": []}
+        for c in self.all_cols:
+            by_role[self._role(c)].append(c)
+        self.literals, self.simple_cols = by_role["literal"], by_role["simple"]
+        self.non_agg_funcs, self.agg_funcs = by_role["func"], by_role["agg"]
+        self._wildcards = sum(1 for c in self.simple_cols if c.kind == Kind.WILDCARD)
+        if self._wildcards > 1:
+            raise ValueError("'*' can be used at most once")
+        self.group_keys: List[ColumnExpr] = []
+        if self.agg_funcs:
+            if self._wildcards:
                 raise ValueError(f"'*' can't be used in aggregation: {self}")
+            self.group_keys = [c.alias("").cast(None) for c in self.all_cols
+                               if self._role(c) in ("simple", "func")]
+
+    @staticmethod
+    def _role(c: ColumnExpr) -> str:
+        if c.kind == Kind.LITERAL:
+            return "literal"
+        if c.kind in (Kind.NAMED, Kind.WILDCARD):
+            return "simple"
+        return "agg" if is_agg(c) else "func"
 
     def __str__(self) -> str:
-        return "[" + ", ".join(str(x) for x in self._all) + "]"
+        return "[" + ", ".join(str(x) for x in self.all_cols) + "]"
 
-    def __uuid__(self) -> str:
-        return to_uuid(self._distinct, self._all)
-
-    @property
-    def is_distinct(self) -> bool:
-        return self._distinct
+    def fingerprint(self) -> str:
+        return hashlib.sha1((str(self.is_distinct) + "|".join(_canon(c) for c in self.all_cols)).encode()).hexdigest()
 
     def replace_wildcard(self, schema: Schema) -> "SelectColumns":
         out: List[ColumnExpr] = []
-        for c in self._all:
-            if isinstance(c, _WildcardExpr):
-                out.extend(col(n) for n in schema.names)
-            else:
-                out.append(c)
-        return SelectColumns(*out, arg_distinct=self._distinct)
+        for c in self.all_cols:
+            out.extend([col(n) for n in schema.names] if c.kind == Kind.WILDCARD else [c])
+        return SelectColumns(*out, arg_distinct=self.is_distinct)
 
     def assert_all_with_names(self) -> "SelectColumns":
-        names: Set[str] = set()
-        for x in self._all:
-            if isinstance(x, _WildcardExpr):
+        seen = set()
+        for x in self.all_cols:
+            if x.kind == Kind.WILDCARD:
                 continue
-            if isinstance(x, _NamedColumnExpr) and self._has_wildcard and x.as_name == "":
+            if x.kind == Kind.NAMED and self._wildcards and x.as_name == "":
                 raise ValueError(f"with '*', all other columns must have an alias: {self}")
             if x.output_name == "":
                 raise ValueError(f"{x} does not have an alias: {self}")
-            if x.output_name in names:
+            if x.output_name in seen:
                 raise ValueError(f"{x} can't be reused in select: {self}")
-            names.add(x.output_name)
+            seen.add(x.output_name)
         return self
 
     def assert_no_wildcard(self) -> "SelectColumns":
-        assert not self._has_wildcard
+        assert self._wildcards == 0
         return self
 
     def assert_no_agg(self) -> "SelectColumns":
@@ -649,142 +431,89 @@ class SelectColumns:
         return self
 
     @property
-    def all_cols(self) -> List[ColumnExpr]:
-        return self._all
-
-    @property
-    def literals(self) -> List[ColumnExpr]:
-        return self._literals
-
-    @property
-    def simple_cols(self) -> List[ColumnExpr]:
-        return self._cols
-
-    @property
-    def non_agg_funcs(self) -> List[ColumnExpr]:
-        return self._non_agg_funcs
-
-    @property
-    def agg_funcs(self) -> List[ColumnExpr]:
-        return self._agg_funcs
-
-    @property
-    def group_keys(self) -> List[ColumnExpr]:
-        return self._group_keys
-
-    @property
     def has_agg(self) -> bool:
-        return len(self._agg_funcs) > 0
+        return len(self.agg_funcs) > 0
 
     @property
     def has_literals(self) -> bool:
-        return len(self._literals) > 0
+        return len(self.literals) > 0
 
     @property
     def simple(self) -> bool:
-        return len(self._cols) == len(self._all)
+        return len(self.simple_cols) == len(self.all_cols)
 
 
-_SQL_OPERATORS: Dict[str, str] = {"+": "+", "-": "-", "*": "*", "/": "/", "&": " AND ", "|": " OR ",
-                                  "<": "<", ">": ">", "<=": "<=", ">=": ">=", "==": "=", "!=": "!="}
+# ---- SQL text of a tree (error messages, INTEGRATION.md examples, the golden test) ------------------
+_SQL_OF_OP = {"&": " AND ", "|": " OR ", "==": "="}
 
 
-class SQLExpressionGenerator:
-    """Expression trees -> the SQL text of fugue/column/sql.py:249-497 (``(is_table, text)`` pieces for
-    whole statements, as ``StructuredRawSQL`` wants them)."""
+def _quote(name: str) -> str:
+    plain = name != "" and (name[0].isalpha() or name[0] == "_") and all(ch.isalnum() or ch == "_" for ch in name)
+    return name if plain else "`" + name.replace("`", "``") + "`"
 
-    def __init__(self, enable_cast: bool = True):
-        self._enable_cast = enable_cast
-        self._func_handler: Dict[str, Callable[[_FuncExpr], Iterable[str]]] = {}
 
-    def add_func_handler(self, name: str, handler: Callable[[_FuncExpr], Iterable[str]]) -> "SQLExpressionGenerator":
-        self._func_handler[name] = handler
-        return self
+def to_sql(expr: ColumnExpr, enable_cast: bool = True, nested: bool = False) -> str:
+    """The expression as SQL text (infix operators, ``CAST(.. AS ..)``, back-quoted odd names)."""
+    k = expr.kind
+    if k == Kind.LITERAL:
+        body = _show_literal(expr.head)
+    elif k == Kind.NAMED:
+        body = _quote(expr.head)
+    elif k == Kind.WILDCARD:
+        body = "*"
+    elif k == Kind.UNARY:
+        inner = to_sql(expr.args[0], enable_cast, True)
+        body = {"-": "-" + inner, "~": "NOT " + inner, "IS_NULL": inner + " IS NULL",
+                "NOT_NULL": inner + " IS NOT NULL"}[expr.head]
+    elif k == Kind.BINARY:
+        if expr.head not in BOOL_OPS and expr.head not in ARITH_OPS:
+            raise NotImplementedError(expr)
+        body = to_sql(expr.args[0], enable_cast, True) + _SQL_OF_OP.get(expr.head, expr.head) + \
+            to_sql(expr.args[1], enable_cast, True)
+        if nested:
+            body = "(" + body + ")"
+    else:
+        parts = [to_sql(_operand(x), enable_cast) for x in expr.args] + \
+            [n + "=" + to_sql(_operand(v), enable_cast) for n, v in expr.kwargs.items()]
+        body = f"{expr.head}({'DISTINCT ' if expr.is_distinct else ''}{','.join(parts)})"
+    if enable_cast and expr.as_type is not None:
+        body = f"CAST({body} AS {type_to_expr(expr.as_type)})"
+    if expr.as_name != "":
+        return body + " AS " + _quote(expr.as_name)
+    if expr.as_type is not None and expr.name != "":
+        return body + " AS " + _quote(expr.name)
+    return body
 
-    def generate(self, expr: ColumnExpr) -> str:
-        return "".join(self._gen(expr, False)).strip()
 
-    def where(self, condition: ColumnExpr, table: str) -> Iterable[Tuple[bool, str]]:
-        if is_agg(condition):
-            raise ValueError(f"{condition} has aggregation functions")
-        yield (False, "SELECT * FROM")
-        yield (True, table)
-        yield (False, "WHERE " + self.generate(condition.alias("")))
-
-    def select(self, columns: SelectColumns, table: str, where: Optional[ColumnExpr] = None,
-               having: Optional[ColumnExpr] = None) -> Iterable[Tuple[bool, str]]:
-        columns.assert_all_with_names()
-        if where is not None and is_agg(where):
-            raise ValueError(f"{where} has aggregation functions")
-        where_sql = "" if where is None else "WHERE " + self.generate(where.alias(""))
-        having_sql = "" if having is None else "HAVING " + self.generate(having.alias(""))
-        distinct = "DISTINCT " if columns.is_distinct else ""
-        if not columns.has_agg:
-            yield (False, f"SELECT {distinct}{', '.join(self.generate(x) for x in columns.all_cols)} FROM")
-            yield (True, table)
-            yield (False, where_sql)
-            return
+def select_sql(columns: SelectColumns, table: str, where: Optional[ColumnExpr] = None,
+               having: Optional[ColumnExpr] = None, enable_cast: bool = True) -> str:
+    """``SELECT .. FROM table [WHERE ..] [GROUP BY ..] [HAVING ..]`` for a SELECT list; literals next to
+    aggregations are attached by an outer SELECT (they are not group keys)."""
+    columns.assert_all_with_names()
+    if where is not None and is_agg(where):
+        raise ValueError(f"{where} has aggregation functions")
+    tail = "" if where is None else " WHERE " + to_sql(where.alias(""), enable_cast)
+    head = "SELECT " + ("DISTINCT " if columns.is_distinct else "")
+    if columns.has_agg and columns.has_literals:
+        inner = SelectColumns(*[x for x in columns.all_cols if x.kind != Kind.LITERAL])
+        names = [to_sql(x, enable_cast) if x.kind == Kind.LITERAL else x.output_name for x in columns.all_cols]
+        return f"SELECT {', '.join(names)} FROM ( {select_sql(inner, table, where, having, enable_cast)} )"
+    text = head + ", ".join(to_sql(x, enable_cast) for x in columns.all_cols) + " FROM " + table + tail
+    if columns.has_agg:
         columns.assert_no_wildcard()
-        if columns.has_literals:  # literals are attached around the aggregation
-            inner = [x for x in columns.all_cols if not isinstance(x, _LiteralColumnExpr)]
-            names = [self.generate(x) if isinstance(x, _LiteralColumnExpr) else x.output_name
-                     for x in columns.all_cols]
-            yield (False, f"SELECT {', '.join(names)} FROM (")
-            yield from self.select(SelectColumns(*inner), table, where=where, having=having)
-            yield (False, ")")
-            return
-        yield (False, f"SELECT {distinct}{', '.join(self.generate(x) for x in columns.all_cols)} FROM")
-        yield (True, table)
-        yield (False, where_sql)
-        if len(columns.group_keys) > 0:
-            yield (False, "GROUP BY " + ", ".join(self.generate(x) for x in columns.group_keys))
-        yield (False, having_sql)
+        if columns.group_keys:
+            text += " GROUP BY " + ", ".join(to_sql(x, enable_cast) for x in columns.group_keys)
+        if having is not None:
+            text += " HAVING " + to_sql(having.alias(""), enable_cast)
+    return text
 
-    def correct_select_schema(self, input_schema: Schema, select: SelectColumns,
-                              output_schema: Schema) -> Optional[Schema]:
-        cols = select.replace_wildcard(input_schema).assert_all_with_names()
-        fields = []
-        for c in cols.all_cols:
-            tp = c.infer_type(input_schema)
-            if tp is not None and tp != output_schema[c.output_name].type:
-                fields.append(pa.field(c.output_name, tp))
-        return Schema(fields) if fields else None
 
-    def type_to_expr(self, data_type: pa.DataType) -> str:
-        return type_to_expr(data_type)
-
-    def _gen(self, expr: ColumnExpr, bracket: bool) -> Iterable[str]:
-        casting = self._enable_cast and expr.as_type is not None
-        if casting:
-            yield "CAST("
-        if isinstance(expr, _LiteralColumnExpr):
-            yield expr.body_str
-        elif isinstance(expr, _NamedColumnExpr):
-            yield _quote_name(expr.name)
-        elif isinstance(expr, _WildcardExpr):
-            yield "*"
-        elif isinstance(expr, _FuncExpr):
-            if expr.func in self._func_handler:
-                yield from self._func_handler[expr.func](expr)
-            elif isinstance(expr, _UnaryOpExpr):
-                inner = "".join(self._gen(expr.col, True))
-                yield {"-": "-" + inner, "~": "NOT " + inner, "IS_NULL": inner + " IS NULL",
-                       "NOT_NULL": inner + " IS NOT NULL"}[expr.op]
-            elif isinstance(expr, _BinaryOpExpr):
-                if expr.op not in _SQL_OPERATORS:
-                    raise NotImplementedError(expr)
-                body = "".join(self._gen(expr.left, True)) + _SQL_OPERATORS[expr.op] + \
-                    "".join(self._gen(expr.right, True))
-                yield "(" + body + ")" if bracket else body
-            else:
-                def piece(v: Any) -> str:
-                    return "".join(self._gen(v if isinstance(v, ColumnExpr) else lit(v), False))
-
-                parts = [piece(x) for x in expr.args] + [k + "=" + piece(v) for k, v in expr.kwargs.items()]
-                yield f"{expr.func}({'DISTINCT ' if expr.is_distinct else ''}{','.join(parts)})"
-        if casting:
-            yield " AS " + self.type_to_expr(expr.as_type) + ")"
-        if expr.as_name != "":
-            yield " AS " + _quote_name(expr.as_name)
-        elif expr.as_type is not None and expr.name != "":
-            yield " AS " + _quote_name(expr.name)
+def correct_select_schema(input_schema: Schema, select: SelectColumns, output_schema: Schema) -> Optional[Schema]:
+    """Fields whose inferred type differs from what an evaluator produced (None: nothing to fix)."""
+    cols = select.replace_wildcard(input_schema).assert_all_with_names()
+    fields = []
+    for c in cols.all_cols:
+        tp = c.infer_type(input_schema)
+        if tp is not None and tp != output_schema[c.output_name].type:
+            fields.append(pa.field(c.output_name, tp))
+    return Schema(fields) if fields else None

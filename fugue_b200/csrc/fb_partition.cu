@@ -637,6 +637,29 @@ struct WsUnits {
   int32_t nunits;
 };
 
+// K4, the fused map epilogue: output unit u is not a copy of src[u] but an affine function of one or
+// two staged input tiles, computed by the movers right after the gather and before the store:
+//   mode 1 (float64): (a * x + b * y) + c, every operation rounded on its own (no FMA contraction), i.e.
+//                     exactly what the expression evaluator (K8) gives for `x * a + y * b + c`
+//   mode 2 (int64)  : a * x + b * y + c  (wrapping)
+// src2 == nullptr: y does not exist (b ignored).  A two-operand unit occupies two ring stages.
+struct WsMap {
+  const uint64_t* src2[kSwcMaxCols];
+  uint64_t a[kSwcMaxCols], b[kSwcMaxCols], c[kSwcMaxCols];
+  int32_t mode[kSwcMaxCols];
+};
+
+__device__ __forceinline__ uint64_t ws_apply_map(int mode, bool two, uint64_t x, uint64_t y, uint64_t a, uint64_t b,
+                                                 uint64_t c) {
+  if (mode == 1) {
+    double r = __dmul_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)x));
+    if (two) r = __dadd_rn(r, __dmul_rn(__longlong_as_double((long long)b), __longlong_as_double((long long)y)));
+    return (uint64_t)__double_as_longlong(__dadd_rn(r, __longlong_as_double((long long)c)));
+  }
+  if (mode == 2) return a * x + (two ? b * y : 0ULL) + c;
+  return x;
+}
+
 template <int G, int RI>
 __host__ __device__ inline size_t ws_book_bytes(uint32_t num, int ncols) {
   constexpr size_t kT = (size_t)kWsRankers * RI;
@@ -657,11 +680,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {  // release.cta: pub
 __device__ __forceinline__ void mover_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWsMovers) : "memory"); }
 __device__ __forceinline__ void ranker_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kWsRankers) : "memory"); }
 
-template <int kBits, int G, int kWsRankItems>
+template <int kBits, int G, int kWsRankItems, bool kMap>
 __global__ void __launch_bounds__(kWsThreads, 1)
 fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
                      const uint8_t* __restrict__ meta,
-                     const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets) {
+                     const uint32_t* __restrict__ chunk_base, const int64_t* __restrict__ part_offsets,
+                     const __grid_constant__ WsMap map) {
   constexpr uint32_t T = (uint32_t)kWsRankers * kWsRankItems;  // rows per tile
   static_assert(T == (uint32_t)kTile, "pass 1 ranks tiles of kTile rows");
   constexpr uint32_t GM = G - 1;
@@ -750,6 +774,14 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
           mbar_expect_tx(bar_full + 8 * s, kStageBytes);
           tma_load_1d(ring_s + s * kStageBytes, units.src[u] + t0, kStageBytes, bar_full + 8 * s, pol);
           if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+          if constexpr (kMap) {
+            if (map.src2[u] != nullptr) {  // second operand of a fused map: the next stage
+              mbar_wait(bar_empty + 8 * s, ph ^ 1);
+              mbar_expect_tx(bar_full + 8 * s, kStageBytes);
+              tma_load_1d(ring_s + s * kStageBytes, map.src2[u] + t0, kStageBytes, bar_full + 8 * s, pol);
+              if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+            }
+          }
         }
         chunk = nchunk; r0 = nr0; r1 = nr1; t0 = nt0; have = nhave;
         ++seq;
@@ -905,12 +937,36 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
         uint64_t* __restrict__ out = units.dst[u];
         const uint64_t* __restrict__ cbuf = carry + (size_t)u * E;
         uint64_t v[kSlotRounds], cv[kEntryRoundsM];
+        uint32_t s2 = s;
+        bool two = false;
+        if constexpr (kMap) {
+          // fused map (K4): rows taken from the staged tile(s) are mapped here; carry entries already are
+          // output values
+          const int mode = map.mode[u];
+          two = map.src2[u] != nullptr;
+          const uint64_t* __restrict__ st2 = st;
+          if (two) {
+            s2 = s + 1 == (uint32_t)nstages ? 0 : s + 1;
+            mbar_wait(bar_full + 8 * s2, s2 == 0 ? ph ^ 1 : ph);
+            st2 = ring + (size_t)s2 * T;
+          }
+          const uint64_t ma = map.a[u], mb = map.b[u], mc = map.c[u];
 #pragma unroll
-        for (int k = 0; k < kSlotRounds; ++k)
-          if (srcd[k] != 0xFFFFu) v[k] = srcd[k] < T ? st[srcd[k]] : cbuf[srcd[k] - T];
+          for (int k = 0; k < kSlotRounds; ++k)
+            if (srcd[k] != 0xFFFFu)
+              v[k] = srcd[k] < T ? ws_apply_map(mode, two, st[srcd[k]], st2[srcd[k]], ma, mb, mc) : cbuf[srcd[k] - T];
 #pragma unroll
-        for (int q = 0; q < kEntryRoundsM; ++q)
-          if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : cbuf[csrc[q] - T];
+          for (int q = 0; q < kEntryRoundsM; ++q)
+            if (csrc[q] != 0xFFFFu)
+              cv[q] = csrc[q] < T ? ws_apply_map(mode, two, st[csrc[q]], st2[csrc[q]], ma, mb, mc) : cbuf[csrc[q] - T];
+        } else {
+#pragma unroll
+          for (int k = 0; k < kSlotRounds; ++k)
+            if (srcd[k] != 0xFFFFu) v[k] = srcd[k] < T ? st[srcd[k]] : cbuf[srcd[k] - T];
+#pragma unroll
+          for (int q = 0; q < kEntryRoundsM; ++q)
+            if (csrc[q] != 0xFFFFu) cv[q] = csrc[q] < T ? st[csrc[q]] : cbuf[csrc[q] - T];
+        }
 #pragma unroll
         for (int k = 0; k < kSlotRounds; ++k)
           if (srcd[k] != 0xFFFFu) out[dst[k]] = v[k];
@@ -919,10 +975,14 @@ fb_scatter_ws_kernel(WsUnits units, uint32_t num, ChunkGeom g, int nstages,
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_relaxed(bar_empty + 8 * s);
+          if (kMap && two) mbar_arrive_relaxed(bar_empty + 8 * s2);
           mbar_arrive_relaxed(bar_carry_read + 8 * (astep & 1));
         }
         ++astep;
         if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+        if (kMap && two) {
+          if (++s == (uint32_t)nstages) { s = 0; ph ^= 1; }
+        }
         if (u > 0) {  // write the previous column's new carry
           mbar_wait(bar_carry_read + 8 * (wstep & 1), (wstep >> 1) & 1);
           ++wstep;
@@ -1040,8 +1100,10 @@ cudaError_t ensure_smem_optin(int dev) {
   {
     int smem_max = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems, false>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems, false>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems, true>, (size_t)smem_max);
+    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems, true>, (size_t)smem_max);
   }
   FB_OPTIN(true, 4); FB_OPTIN(true, 8); FB_OPTIN(true, 10);
   FB_OPTIN(false, 4); FB_OPTIN(false, 8); FB_OPTIN(false, 10);
@@ -1205,10 +1267,26 @@ int fb_partition_plan(int dev, void* stream, int64_t nrows, int nkeys, const voi
                    scratch, scratch_bytes, out_part_offsets);
 }
 
+// Rows of the partial tail tile of the mapped units, evaluated into tail_tmp[c][0 .. nrows - full_rows): the
+// generic scatter kernel then moves them like any column.
+__global__ void fb_map_tail_kernel(int ncols, const void* const* __restrict__ x_ptrs, const fb_map_unit* __restrict__ maps,
+                                   int64_t row0, int64_t nrows, uint64_t* __restrict__ tmp) {
+  const int64_t n = nrows - row0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * ncols; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / n);
+    const int64_t r = row0 + i % n;
+    const fb_map_unit m = maps[c];
+    const uint64_t x = ((const uint64_t*)x_ptrs[c])[r];
+    const uint64_t y = m.src2 != nullptr ? ((const uint64_t*)m.src2)[r] : 0;
+    tmp[(size_t)c * kTile + (size_t)(i % n)] = ws_apply_map(m.mode, m.src2 != nullptr, x, y, m.a, m.b, m.c);
+  }
+}
+
 static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, bool single,
                       uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
                       const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
-                      const int32_t* col_widths, void* const* out_col_ptrs, int sm_reserve = 0) {
+                      const int32_t* col_widths, void* const* out_col_ptrs, int sm_reserve = 0,
+                      const fb_map_unit* maps = nullptr, void* tail_tmp = nullptr) {
   FB_CHECK(nrows >= 0 && nrows < ((int64_t)1 << 32), "nrows out of range");
   FB_CHECK(num_partitions >= 1 && num_partitions <= FB_MAX_PARTITIONS,
            "num_partitions=%u out of range [1,%d]", num_partitions, FB_MAX_PARTITIONS);
@@ -1232,6 +1310,7 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
   }
 
   // generic kernel over chunks [chunk0, chunk0 + nch) for the columns listed in idx[0..n)
+  const void* const* gen_src = col_ptrs;
   auto launch_generic = [&](const int* idx, int n, int chunk0, int nch) -> int {
     for (int c0 = 0; c0 < n && nch > 0; c0 += FB_MAX_COLS) {
       FbCols cols;
@@ -1239,7 +1318,7 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
       cols.ncols = n - c0 < FB_MAX_COLS ? n - c0 : FB_MAX_COLS;
       bool all8 = true;
       for (int c = 0; c < cols.ncols; ++c) {
-        cols.src[c] = col_ptrs[idx[c0 + c]];
+        cols.src[c] = gen_src[idx[c0 + c]];
         cols.dst[c] = out_col_ptrs[idx[c0 + c]];
         cols.width[c] = col_widths[idx[c0 + c]];
         all8 = all8 && cols.width[c] == 8;
@@ -1263,6 +1342,16 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
   // ---- split the columns: fast path (warp-specialised TMA ring + write combining; reads the rank
   //      records written by pass 1, so any key shape qualifies) vs generic.  8-byte columns, num <= 256.
   const bool fast_ok = num_partitions <= kSwcMaxNum && g.nchunks_full > 0;
+  if (maps != nullptr) {  // fused map epilogue (K4): every unit must qualify for the fast kernel
+    FB_CHECK(num_partitions <= kSwcMaxNum, "fused map needs num_partitions <= %u", kSwcMaxNum);
+    FB_CHECK(tail_tmp != nullptr || g.full_rows == nrows, "fused map: tail_tmp is NULL");
+    for (int c = 0; c < ncols; ++c) {
+      FB_CHECK(col_widths[c] == 8 && (uintptr_t)col_ptrs[c] % 16 == 0, "fused map: column %d is not an aligned 8-byte column", c);
+      FB_CHECK(maps[c].mode >= 0 && maps[c].mode <= 2, "fused map: column %d has mode %d", c, maps[c].mode);
+      FB_CHECK(maps[c].src2 == nullptr || (maps[c].mode != 0 && (uintptr_t)maps[c].src2 % 16 == 0),
+               "fused map: bad second operand of column %d", c);
+    }
+  }
   int* fast_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
   int* gen_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
   int nfast = 0, ngen = 0;
@@ -1301,16 +1390,56 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
       if (nstages > 16) nstages = 16;
       FB_CHECK(nstages >= 2, "not enough shared memory for the TMA ring (%d stages)", nstages);
       const size_t tsmem = (size_t)nstages * stage_bytes + book;
-      if (bits == 4)
-        fb_scatter_ws_kernel<4, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
-            wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
-      else
-        fb_scatter_ws_kernel<8, kWsG, kWsRankItems><<<grid, kWsThreads, tsmem, st>>>(
-            wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets);
+      WsMap wm;
+      memset(&wm, 0, sizeof(wm));
+      if (maps != nullptr) {
+        for (int c = 0; c < nb; ++c) {
+          const fb_map_unit& m = maps[fast_idx[c0 + c]];
+          wm.src2[c] = (const uint64_t*)m.src2;
+          wm.a[c] = m.a; wm.b[c] = m.b; wm.c[c] = m.c;
+          wm.mode[c] = m.mode;
+        }
+        if (bits == 4)
+          fb_scatter_ws_kernel<4, kWsG, kWsRankItems, true><<<grid, kWsThreads, tsmem, st>>>(
+              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
+        else
+          fb_scatter_ws_kernel<8, kWsG, kWsRankItems, true><<<grid, kWsThreads, tsmem, st>>>(
+              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
+      } else if (bits == 4) {
+        fb_scatter_ws_kernel<4, kWsG, kWsRankItems, false><<<grid, kWsThreads, tsmem, st>>>(
+            wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
+      } else {
+        fb_scatter_ws_kernel<8, kWsG, kWsRankItems, false><<<grid, kWsThreads, tsmem, st>>>(
+            wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
+      }
       FB_CUDA(cudaGetLastError());
     }
     // the partial tail tile of the fast columns
-    if (int rc = launch_generic(fast_idx, nfast, g.nchunks_full, g.nchunks - g.nchunks_full)) return rc;
+    if (maps == nullptr)
+      if (int rc = launch_generic(fast_idx, nfast, g.nchunks_full, g.nchunks - g.nchunks_full)) return rc;
+  }
+  if (maps != nullptr && g.full_rows < nrows) {
+    // fused map: the tail rows are mapped into tail_tmp (device arrays of pointers / descriptors live in
+    // its first bytes) and the generic kernel reads them through shifted column bases
+    FB_CHECK(ncols <= kSwcMaxCols * 8, "fused map: too many columns (%d)", ncols);
+    uint8_t* base = (uint8_t*)tail_tmp;
+    const size_t hdr = (((size_t)ncols * (sizeof(void*) + sizeof(fb_map_unit))) + 255) & ~(size_t)255;
+    FB_CUDA(cudaMemcpyAsync(base, col_ptrs, sizeof(void*) * (size_t)ncols, cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemcpyAsync(base + sizeof(void*) * (size_t)ncols, maps, sizeof(fb_map_unit) * (size_t)ncols,
+                            cudaMemcpyHostToDevice, st));
+    uint64_t* vals = (uint64_t*)(base + hdr);
+    fb_map_tail_kernel<<<32, 256, 0, st>>>(ncols, (const void* const*)base,
+                                           (const fb_map_unit*)(base + sizeof(void*) * (size_t)ncols), g.full_rows,
+                                           nrows, vals);
+    FB_CUDA(cudaGetLastError());
+    const void** shifted = (const void**)alloca(sizeof(void*) * (size_t)ncols);
+    int* all_idx = (int*)alloca(sizeof(int) * (size_t)ncols);
+    for (int c = 0; c < ncols; ++c) {
+      shifted[c] = (const uint8_t*)(vals + (size_t)c * kTile) - (size_t)g.full_rows * 8;
+      all_idx[c] = c;
+    }
+    gen_src = shifted;
+    if (int rc = launch_generic(all_idx, ncols, g.nchunks_full, g.nchunks - g.nchunks_full)) return rc;
   }
   return 0;
 }
@@ -1338,6 +1467,28 @@ int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys, const
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
                     scratch, scratch_bytes, part_offsets, ncols, col_ptrs, col_widths, out_col_ptrs, sm_reserve);
+}
+
+size_t fb_partition_map_tail_bytes(int ncols) {
+  if (ncols < 0) return 0;
+  return ((((size_t)ncols * (sizeof(void*) + sizeof(fb_map_unit))) + 255) & ~(size_t)255) + (size_t)ncols * kTile * 8;
+}
+
+int fb_partition_apply_map(int dev, void* stream, int64_t nrows, int nkeys, const void* const* key_ptrs,
+                           const int32_t* key_widths, const uint8_t* const* key_valid,
+                           uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
+                           const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
+                           void* const* out_col_ptrs, const fb_map_unit* maps, void* tail_tmp, int sm_reserve) {
+  if (nrows == 0 || ncols == 0) return 0;
+  FB_CHECK(maps != nullptr, "maps is NULL");
+  FB_CHECK(ncols <= FB_MAX_COLS, "ncols=%d > %d", ncols, FB_MAX_COLS);
+  FbKeys k;
+  if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
+  int32_t widths[FB_MAX_COLS];
+  for (int c = 0; c < ncols; ++c) widths[c] = 8;
+  return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
+                    scratch, scratch_bytes, part_offsets, ncols, col_ptrs, widths, out_col_ptrs, sm_reserve, maps,
+                    tail_tmp);
 }
 
 int fb_radix_pass(int dev, void* stream, int64_t nrows, const void* sort_key_u64, int shift, int ncols,

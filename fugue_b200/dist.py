@@ -475,7 +475,6 @@ class DistributedB200Engine(B200ExecutionEngine):
         """GROUP BY across GPUs: local partial aggregation (K6) -> shuffle of the partials by key
         (pull exchange) -> final aggregation of the partials.  Every group ends up on exactly one
         rank; the result stays sharded.  SUM/COUNT/MIN/MAX decompose directly, AVG as SUM + COUNT."""
-        from .column import AggFuncExpr, col
 
         keys = [] if partition_spec is None else list(partition_spec.partition_by)
         if self._world == 1 or not self._plain_aggs(agg_cols):

@@ -111,6 +111,11 @@ class B200MapEngine:
             for k, v in presort.items():
                 order[k] = v
             edf = B200DataFrame(S.sort_table(edf.native, order))
+        cmap = getattr(map_func, "column_map", None)
+        if keyed and cmap is not None and map_func_format_hint == "b200" and len(presort) == 0:
+            fused = engine._repartition_fused_map(edf, partition_spec, cmap, output_schema)  # K4
+            if fused is not None:
+                return fused
         if keyed:
             edf = engine.repartition(edf, partition_spec)  # K1+K2+K3 on the device
         if map_func_format_hint == "b200":
@@ -187,26 +192,26 @@ def decompose_aggs(agg_cols: List[Any]) -> Any:
     over the partials) and ``post`` = [(name, sum column, count column)] for AVG = SUM / COUNT.
     Used for the multi-GPU group-by (partials per rank) and for COUNT(DISTINCT x) (partials per
     distinct (keys, x))."""
-    from .column import AggFuncExpr, col
+    from .column import Kind, agg as _agg, col
 
     partial: List[Any] = []
     final: List[Any] = []
     post: List[Any] = []
     for i, a in enumerate(agg_cols):
-        assert_or_throw(isinstance(a, AggFuncExpr) and a.output_name != "",
+        assert_or_throw(a.kind == Kind.AGG and a.output_name != "",
                         lambda: ValueError(f"{a} must be a named aggregation"))
         tmp = f"__p{i}"
         if a.func in ("SUM", "MIN", "MAX"):
-            partial.append(AggFuncExpr(a.func, a.arg, tmp))
-            final.append(AggFuncExpr(a.func, col(tmp), a.output_name))
+            partial.append(_agg(a.func, a.arg, tmp))
+            final.append(_agg(a.func, col(tmp), a.output_name))
         elif a.func == "COUNT":
-            partial.append(AggFuncExpr("COUNT", a.arg, tmp))
-            final.append(AggFuncExpr("SUM", col(tmp), a.output_name))
+            partial.append(_agg("COUNT", a.arg, tmp))
+            final.append(_agg("SUM", col(tmp), a.output_name))
         elif a.func == "AVG":
-            partial.append(AggFuncExpr("SUM", a.arg, tmp + "s"))
-            partial.append(AggFuncExpr("COUNT", a.arg, tmp + "c"))
-            final.append(AggFuncExpr("SUM", col(tmp + "s"), tmp + "s"))
-            final.append(AggFuncExpr("SUM", col(tmp + "c"), tmp + "c"))
+            partial.append(_agg("SUM", a.arg, tmp + "s"))
+            partial.append(_agg("COUNT", a.arg, tmp + "c"))
+            final.append(_agg("SUM", col(tmp + "s"), tmp + "s"))
+            final.append(_agg("SUM", col(tmp + "c"), tmp + "c"))
             post.append((a.output_name, tmp + "s", tmp + "c"))
         else:
             raise NotImplementedError(f"{a.func} has no partial / final decomposition")
@@ -350,10 +355,10 @@ class B200ExecutionEngine:
         if len(keys) == 0:
             return edf
         num = self._num_partitions(partition_spec, t.num_rows)
-        assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
-            f"num_partitions={num}: one radix pass handles up to {K.MAX_PARTITIONS} partitions"))
         if t.offsets is not None and t.partition_keys == keys and t.num_partitions == num:
             return edf  # already partitioned this way
+        if num > K.MAX_PARTITIONS:
+            return self._repartition_wide(edf, keys, num)
         kidx = [t.schema.index_of_key(k) for k in keys]
         kvalid = [t.valid[i] for i in kidx]
         # validity masks travel as extra 1-byte columns
@@ -368,6 +373,67 @@ class B200ExecutionEngine:
         ncol = len(t.columns)
         valid = [out[vpos[i]] if i in vpos else None for i in range(ncol)]
         res = B200Table(t.schema, out[:ncol], valid, t.dictionaries, offsets, list(keys))
+        rdf = B200DataFrame(res)
+        if edf.has_metadata:
+            rdf.reset_metadata(edf.metadata)
+        return rdf
+
+    def _repartition_fused_map(self, edf: B200DataFrame, spec: PartitionSpec, cmap: Any,
+                               output_schema: Schema) -> Optional[B200DataFrame]:
+        """Hash partition + per-row map in ONE pass over the table (K4): pass 1 as usual, pass 2 with the
+        map evaluated in the scatter kernel's epilogue (``fb_partition_apply_map``).  Returns None when
+        the map (or the table) does not qualify - the caller then partitions and evaluates the map with
+        the expression evaluator, still on the device."""
+        t: B200Table = edf.native
+        keys = list(spec.partition_by)
+        if self.is_distributed or spec.algo in ("even", "rand") or t.num_rows == 0:
+            return None
+        for k in keys:
+            if k not in t.schema:
+                return None
+        num = self._num_partitions(spec, t.num_rows)
+        if num > 256 or (t.offsets is not None and t.partition_keys == keys and t.num_partitions == num):
+            return None
+        units = cmap.fusion_units(t)
+        if units is None:
+            return None
+        names = [c.output_name for c in cmap.select(t).all_cols]
+        got = Schema([pa.field(n, u[6]) for n, u in zip(names, units)])
+        assert_or_throw(got == output_schema, lambda: f"map output {got} mismatches given {output_schema}")
+        kidx = [t.schema.index_of_key(k) for k in keys]
+        scratch = self._pool.scratch(t.device, K.partition_scratch_bytes(t.device, t.num_rows, num))
+        plan = K.partition_plan([t.columns[i] for i in kidx], num, [t.valid[i] for i in kidx], scratch=scratch)
+        outs = K.partition_apply_map(plan, [u[:6] for u in units])
+        outs = [o.view(torch.float64) if u[6] == pa.float64() else
+                (o.view(torch.int64) if o.dtype != torch.int64 and u[2] != K.MAP_COPY else o)
+                for o, u in zip(outs, units)]
+        plain = {n: u for n, u in zip(names, units) if u[2] == K.MAP_COPY}
+        keep = all(k in plain and plain[k][0].data_ptr() == t.column(k).data_ptr() for k in keys)
+        res = B200Table(output_schema, outs, None, {}, plan.offsets if keep else None, keys if keep else None)
+        return B200DataFrame(res)
+
+    def _repartition_wide(self, edf: B200DataFrame, keys: List[str], num: int) -> B200DataFrame:
+        """More physical partitions than one radix pass separates (``num=65536``, ``PartitionSpec("per_row")``
+        = ROWCOUNT partitions, fugue/collections/partition.py:95,115,186-207): the partition id
+        ``hash % num`` of every row (K1) is sorted with stable byte-wise radix passes - the same
+        partition kernels in digit mode, one pass per varying byte of the id - carrying the row number,
+        and the table is gathered once.  Stable like the single-pass path, so the result is the same
+        partition-contiguous table the oracle produces; ``offsets`` has ``num + 1`` entries."""
+        from . import sort as S
+
+        t: B200Table = edf.native
+        dev, n = t.device, t.num_rows
+        assert_or_throw(num < (1 << 32), NotImplementedError(f"num_partitions={num} >= 2^32"))
+        kidx = [t.schema.index_of_key(k) for k in keys]
+        if n == 0:
+            res = B200Table(t.schema, t.columns, t.valid, t.dictionaries,
+                            torch.zeros(num + 1, dtype=torch.int64, device=dev), list(keys))
+            return B200DataFrame(res)
+        pid = K.partition_ids([t.columns[i] for i in kidx], num, [t.valid[i] for i in kidx]).to(torch.int64)
+        spid, idx = S._radix_sort_pairs(pid.contiguous(), torch.arange(n, dtype=torch.int64, device=dev))
+        moved = S.take_rows(t, idx)
+        offsets = torch.searchsorted(spid.contiguous(), torch.arange(num + 1, dtype=torch.int64, device=dev))
+        res = B200Table(t.schema, moved.columns, moved.valid, t.dictionaries, offsets, list(keys))
         rdf = B200DataFrame(res)
         if edf.has_metadata:
             rdf.reset_metadata(edf.metadata)
@@ -398,7 +464,6 @@ class B200ExecutionEngine:
             if num <= 1 or n == 0:
                 return edf if not rand or n == 0 else B200DataFrame(
                     S.take_rows(t, torch.randperm(n, device=dev, generator=gen)))
-            assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(f"num_partitions={num}"))
             src = S.take_rows(t, torch.randperm(n, device=dev, generator=gen)) if rand else t
             res = B200Table(src.schema, src.columns, src.valid, src.dictionaries, even_offsets(n, num), [])
         else:
@@ -409,8 +474,6 @@ class B200ExecutionEngine:
             ngroups = int(gid[-1].item()) + 1
             if num <= 0:
                 num = ngroups
-            assert_or_throw(num <= K.MAX_PARTITIONS, NotImplementedError(
-                f"num_partitions={num}: at most {K.MAX_PARTITIONS} physical partitions"))
             if rand:
                 gid = torch.randperm(ngroups, device=dev, generator=gen)[gid]
             pid = (gid * num) // ngroups
@@ -448,12 +511,12 @@ class B200ExecutionEngine:
     def _plain_aggs(agg_cols: List[Any]) -> bool:
         """``SUM/COUNT/MIN/MAX/AVG`` of a named column (or ``*``) without casts: what the group-by
         kernel takes directly (and what the distributed engine decomposes into partial / final)."""
-        from .column import AggFuncExpr, _NamedColumnExpr, _WildcardExpr
+        from .column import ColumnExpr, Kind
 
-        return all(isinstance(a, AggFuncExpr) and a.as_type is None and not a.is_distinct
+        return all(isinstance(a, ColumnExpr) and a.kind == Kind.AGG and a.as_type is None and not a.is_distinct
                    and a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST", "LAST")
-                   and isinstance(a.arg, (_NamedColumnExpr, _WildcardExpr)) and a.arg.as_type is None
-                   and not (a.func in ("FIRST", "LAST") and isinstance(a.arg, _WildcardExpr))
+                   and a.arg.kind in (Kind.NAMED, Kind.WILDCARD) and a.arg.as_type is None
+                   and not (a.func in ("FIRST", "LAST") and a.arg.kind == Kind.WILDCARD)
                    for a in agg_cols)
 
     def _aggregate_named(self, df: Any, partition_spec: Optional[PartitionSpec],
@@ -630,8 +693,7 @@ class B200ExecutionEngine:
         SQL text.  Pins: fugue_test/execution_suite.py:98-155."""
         from . import expr as X
         from . import relational as R
-        from .column import (AggFuncExpr, SelectColumns, _LiteralColumnExpr, _NamedColumnExpr,
-                             _WildcardExpr, col, is_agg, to_uuid)
+        from .column import ColumnExpr, Kind, SelectColumns, agg as _agg, col, is_agg
 
         edf = self.to_df(df)
         t: B200Table = edf.native
@@ -650,12 +712,12 @@ class B200ExecutionEngine:
 
         def temp(e: Any, prefix: str) -> str:
             """Name of the temporary column holding ``e`` (plain columns keep their name)."""
-            if isinstance(e, _NamedColumnExpr) and e.as_type is None:
+            if e.kind == Kind.NAMED and e.as_type is None:
                 if e.name not in pre_names:
                     pre_names[e.name] = e.name
                     pre.append(col(e.name))
                 return e.name
-            uid = to_uuid(e)
+            uid = e.fingerprint()
             if uid not in pre_names:
                 pre_names[uid] = f"__fb_{prefix}{len(pre_names)}"
                 pre.append(e.alias(pre_names[uid]))
@@ -664,21 +726,21 @@ class B200ExecutionEngine:
         key_of: Dict[str, str] = {}  # uuid of a group-key expression -> its column in the group table
         for k in sel.group_keys:
             nm = temp(k, "k")
-            key_of[to_uuid(k)] = nm
+            key_of[k.fingerprint()] = nm
             if nm not in key_names:
                 key_names.append(nm)
-        aggs: List[AggFuncExpr] = []
+        aggs: List[ColumnExpr] = []
         for c in sel.all_cols:
             X.find_aggs(c, aggs)
         if having is not None:
             X.find_aggs(having, aggs)
         agg_col: Dict[str, str] = {}  # uuid of FUNC(arg) -> its column in the group table
-        named_aggs: List[AggFuncExpr] = []
+        named_aggs: List[ColumnExpr] = []
         distinct_on: Any = None       # ([temporary columns of the DISTINCT argument], is wildcard)
         distinct_outs: List[str] = []
         for a in aggs:
             bare = a.alias("").cast(None)
-            uid = to_uuid(bare)
+            uid = bare.fingerprint()
             if uid in agg_col:
                 continue
             assert_or_throw(a.func in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST", "LAST"),
@@ -689,20 +751,20 @@ class B200ExecutionEngine:
             if a.is_distinct:
                 # COUNT(DISTINCT x): group by (keys, x) first, then count the sub-groups per key
                 assert_or_throw(a.func == "COUNT", NotImplementedError(f"DISTINCT aggregation {a}"))
-                dn = [temp(col(n), "d") for n in t.schema.names] if isinstance(a.arg, _WildcardExpr) \
+                dn = [temp(col(n), "d") for n in t.schema.names] if a.arg.kind == Kind.WILDCARD \
                     else [temp(a.arg, "d")]
                 assert_or_throw(distinct_on is None or distinct_on[0] == dn, NotImplementedError(
                     "COUNT(DISTINCT ...) of different arguments in one SELECT"))
-                distinct_on = (dn, isinstance(a.arg, _WildcardExpr))
+                distinct_on = (dn, a.arg.kind == Kind.WILDCARD)
                 distinct_outs.append(out)
                 continue
-            if isinstance(a.arg, _WildcardExpr):
-                named_aggs.append(AggFuncExpr(a.func, col("*"), out))
-            elif isinstance(a.arg, _LiteralColumnExpr):
+            if a.arg.kind == Kind.WILDCARD:
+                named_aggs.append(_agg(a.func, col("*"), out))
+            elif a.arg.kind == Kind.LITERAL:
                 nm = temp(a.arg.alias("").cast(a.arg.as_type), "l")
-                named_aggs.append(AggFuncExpr(a.func, col(nm), out))
+                named_aggs.append(_agg(a.func, col(nm), out))
             else:
-                named_aggs.append(AggFuncExpr(a.func, col(temp(a.arg, "v")), out))
+                named_aggs.append(_agg(a.func, col(temp(a.arg, "v")), out))
         if len(pre) == 0:  # e.g. SELECT COUNT(*) FROM t
             tmp = t
         else:
@@ -716,18 +778,18 @@ class B200ExecutionEngine:
             partial, final, post = decompose_aggs(named_aggs)
             lvl1 = key_names + [d for d in dn if d not in key_names]
             g1 = self.aggregate(B200DataFrame(tmp), PartitionSpec(by=lvl1),
-                                partial if partial else [AggFuncExpr("COUNT", col("*"), "__fb_n")])
-            final = final + [AggFuncExpr("COUNT", col("*") if wildcard else col(dn[0]), o) for o in distinct_outs]
+                                partial if partial else [_agg("COUNT", col("*"), "__fb_n")])
+            final = final + [_agg("COUNT", col("*") if wildcard else col(dn[0]), o) for o in distinct_outs]
             g2 = self.aggregate(g1, PartitionSpec(by=key_names) if key_names else None, final)
             g = finish_avgs(g2, post, key_names + [a.output_name for a in named_aggs] + distinct_outs).native
 
         def to_group_table(e: Any) -> Any:
             def mapper(node: Any) -> Any:
-                if isinstance(node, AggFuncExpr):
-                    return col(agg_col[to_uuid(node.alias("").cast(None))])
-                if isinstance(node, _LiteralColumnExpr):
+                if node.kind == Kind.AGG:
+                    return col(agg_col[node.alias("").cast(None).fingerprint()])
+                if node.kind == Kind.LITERAL:
                     return None
-                uid = to_uuid(node.alias("").cast(None))
+                uid = node.alias("").cast(None).fingerprint()
                 if uid in key_of:
                     return col(key_of[uid])
                 return None

@@ -18,8 +18,7 @@ import pyarrow as pa
 import torch
 
 from . import kernels as K
-from .column import (AggFuncExpr, ColumnExpr, _BinaryOpExpr, _FuncExpr, _LiteralColumnExpr, _NamedColumnExpr,
-                     _UnaryOpExpr, _WildcardExpr)
+from .column import ColumnExpr, Kind, lit as _lit
 from .schema import Schema
 from .table import B200Table, _storage_dtype
 
@@ -107,14 +106,14 @@ class _Program:
     def _leaf(self, e: Any) -> Optional[Tuple[int, int, int, str, bool]]:
         if e.as_type is not None:
             return None
-        if isinstance(e, _NamedColumnExpr):
+        if e.kind == Kind.NAMED:
             t = self.t
             if e.name not in t.schema:
                 raise KeyError(f"column {e.name} is not in {t.schema}")
             ci = t.schema.index_of_key(e.name)
             cls = _cls_of(t.schema.types[ci])
             return (K.XK_COL, ci, 0, cls, t.valid[ci] is not None)  # b = table column, slot assigned on use
-        if isinstance(e, _LiteralColumnExpr):
+        if e.kind == Kind.LITERAL:
             v = e.value
             if v is None:
                 return (K.XK_NULL, 0, 0, "n", True)
@@ -175,19 +174,19 @@ class _Program:
         return cls, nullable
 
     def _node(self, e: ColumnExpr) -> Tuple[str, bool]:  # noqa: C901
-        if isinstance(e, _WildcardExpr):
+        if e.kind == Kind.WILDCARD:
             raise ValueError("'*' can't be evaluated as a value")
-        if isinstance(e, AggFuncExpr):
+        if e.kind == Kind.AGG:
             raise ValueError(f"aggregation {e} in a row-wise expression")
-        if isinstance(e, (_NamedColumnExpr, _LiteralColumnExpr)):
-            if isinstance(e, _LiteralColumnExpr) and isinstance(e.value, str):
+        if e.kind in (Kind.NAMED, Kind.LITERAL):
+            if e.kind == Kind.LITERAL and isinstance(e.value, str):
                 raise NotImplementedError(f"string literal {e} outside a comparison with a string column")
             bare = e.cast(None) if e.as_type is not None else e
             leaf = self._leaf(bare)
             assert leaf is not None
             self._emit_with(K.X_MOV, leaf, leaf[3])
             return leaf[3], leaf[4]
-        if isinstance(e, _UnaryOpExpr):
+        if e.kind == Kind.UNARY:
             cls, nullable = self.compile(e.col)
             if e.op in ("IS_NULL", "NOT_NULL"):  # string columns are fine here: only validity is read
                 self.emit(K.X_IS_NULL if e.op == "IS_NULL" else K.X_NOT_NULL)
@@ -204,15 +203,15 @@ class _Program:
                 self.emit(K.X_NOT)
                 return "b", nullable
             raise NotImplementedError(f"unary operator {e.op}")
-        if isinstance(e, _BinaryOpExpr):
+        if e.kind == Kind.BINARY:
             return self._binary(e)
-        if isinstance(e, _FuncExpr):
+        if e.kind == Kind.CALL:
             if e.func.upper() == "COALESCE":
                 return self._coalesce(e)
             raise NotImplementedError(f"function {e.func} has no device implementation")
         raise NotImplementedError(f"can't evaluate {e!r}")
 
-    def _binary(self, e: _BinaryOpExpr) -> Tuple[str, bool]:
+    def _binary(self, e: ColumnExpr) -> Tuple[str, bool]:
         op = e.op
         if op not in self._REVERSE:
             raise NotImplementedError(f"operator {op}")
@@ -256,13 +255,13 @@ class _Program:
         self.release(tmp)
         return res, na or nb
 
-    def _string_compare(self, e: _BinaryOpExpr) -> Optional[Tuple[str, bool]]:
+    def _string_compare(self, e: ColumnExpr) -> Optional[Tuple[str, bool]]:
         """``strcol == 'lit'`` / ``!=``: compare dictionary codes."""
         t = self.t
         sides = [e.left, e.right]
-        named = [isinstance(s, _NamedColumnExpr) and s.as_type is None and s.name in t.schema
+        named = [s.kind == Kind.NAMED and s.as_type is None and s.name in t.schema
                  and _is_str(t.schema[s.name].type) for s in sides]
-        lits = [isinstance(s, _LiteralColumnExpr) and isinstance(s.value, str) for s in sides]
+        lits = [s.kind == Kind.LITERAL and isinstance(s.value, str) for s in sides]
         if not (any(named) or any(lits)):
             return None
         if e.op not in ("==", "!="):
@@ -281,8 +280,8 @@ class _Program:
                   (code if code is not None else -1) & ((1 << 64) - 1))
         return "b", t.valid[ci] is not None
 
-    def _coalesce(self, e: _FuncExpr) -> Tuple[str, bool]:
-        args = [a if isinstance(a, ColumnExpr) else _LiteralColumnExpr(a) for a in e.args]
+    def _coalesce(self, e: ColumnExpr) -> Tuple[str, bool]:
+        args = [a if isinstance(a, ColumnExpr) else _lit(a) for a in e.args]
         if len(args) == 0:
             raise ValueError("COALESCE needs arguments")
         probe = [self._static_cls(a) for a in args]
@@ -310,26 +309,26 @@ class _Program:
         """Class an expression will evaluate to (without emitting code)."""
         if e.as_type is not None:
             return _cls_of(e.as_type)
-        if isinstance(e, _NamedColumnExpr):
+        if e.kind == Kind.NAMED:
             if e.name not in self.t.schema:
                 raise KeyError(f"column {e.name} is not in {self.t.schema}")
             return _cls_of(self.t.schema[e.name].type)
-        if isinstance(e, _LiteralColumnExpr):
+        if e.kind == Kind.LITERAL:
             v = e.value
             return "n" if v is None else "b" if isinstance(v, bool) else "i" if isinstance(v, int) else \
                 "f" if isinstance(v, float) else "s"
-        if isinstance(e, _UnaryOpExpr):
+        if e.kind == Kind.UNARY:
             if e.op in ("IS_NULL", "NOT_NULL", "~"):
                 return "b"
             c = self._static_cls(e.col)
             return "i" if c == "b" else c
-        if isinstance(e, _BinaryOpExpr):
+        if e.kind == Kind.BINARY:
             if e.op in ("+", "-", "*", "/"):
                 cs = (self._static_cls(e.left), self._static_cls(e.right))
                 return "f" if (e.op == "/" or "f" in cs) else "i"
             return "b"
-        if isinstance(e, _FuncExpr) and e.func.upper() == "COALESCE":
-            cs = [self._static_cls(a if isinstance(a, ColumnExpr) else _LiteralColumnExpr(a)) for a in e.args]
+        if e.kind == Kind.CALL and e.func.upper() == "COALESCE":
+            cs = [self._static_cls(a if isinstance(a, ColumnExpr) else _lit(a)) for a in e.args]
             return "f" if "f" in cs else ("b" if "b" in cs and all(c in ("b", "n") for c in cs) else "i")
         return "i"
 
@@ -374,7 +373,7 @@ def project(t: B200Table, exprs: Sequence[ColumnExpr]) -> B200Table:
     dicts: Dict[str, pa.Array] = {}
     pending: List[Tuple[int, ColumnExpr]] = []
     for i, e in enumerate(exprs):
-        if isinstance(e, _NamedColumnExpr):
+        if e.kind == Kind.NAMED:
             if e.name not in t.schema:
                 raise KeyError(f"column {e.name} is not in {t.schema}")
             ci = t.schema.index_of_key(e.name)
@@ -386,7 +385,7 @@ def project(t: B200Table, exprs: Sequence[ColumnExpr]) -> B200Table:
                 continue
             if _is_str(tp):
                 raise NotImplementedError(f"cast of string column {e.name} to {e.as_type}")
-        if isinstance(e, _LiteralColumnExpr) and (isinstance(e.value, str) or e.value is None):
+        if e.kind == Kind.LITERAL and (isinstance(e.value, str) or e.value is None):
             tp = e.as_type or (pa.string() if isinstance(e.value, str) else None)
             if tp is None:
                 raise NotImplementedError(f"NULL literal {e} needs a cast to know its type")
@@ -477,27 +476,19 @@ def rewrite(e: Any, mapper: Any) -> Any:
         if e.as_type is not None:
             rep = rep.cast(e.as_type)
         return rep.alias(e.as_name) if e.as_name != "" else rep
-    if isinstance(e, _FuncExpr):
+    if e.has_args:
         args = [rewrite(a, mapper) for a in e.args]
         kwargs = {k: rewrite(v, mapper) for k, v in e.kwargs.items()}
-        if isinstance(e, AggFuncExpr):
-            res: ColumnExpr = type(e)(e.func, args[0], arg_distinct=e.is_distinct)
-        elif isinstance(e, _UnaryOpExpr):
-            res = type(e)(e.op, args[0])
-        elif isinstance(e, _BinaryOpExpr):
-            res = type(e)(e.op, args[0], args[1])
-        else:
-            res = _FuncExpr(e.func, *args, arg_distinct=e.is_distinct, **kwargs)
-        if e.as_type is not None:
-            res = res.cast(e.as_type)
-        return res.alias(e.as_name) if e.as_name != "" else res
+        return ColumnExpr(e.kind, e.head, args, kwargs, e.is_distinct, e.as_name, e.as_type)
     return e
 
 
-def find_aggs(e: Any, out: List[AggFuncExpr]) -> None:
-    if isinstance(e, AggFuncExpr):
+def find_aggs(e: Any, out: List[ColumnExpr]) -> None:
+    if not isinstance(e, ColumnExpr):
+        return
+    if e.kind == Kind.AGG:
         out.append(e)
-    elif isinstance(e, _FuncExpr):
+    elif e.has_args:
         for a in e.args:
             find_aggs(a, out)
         for a in e.kwargs.values():

@@ -9,10 +9,13 @@ entry-point group ``fugue.plugins`` (fugue/constants.py:7, setup.py:99-107).
 Design: subclass ``NativeExecutionEngine`` for everything outside the hot path (exactly how
 ``fugue_duckdb`` reuses ``PandasMapEngine``, fugue_duckdb/execution_engine.py:200-201) and
 override the facets SURVEY.md section 8 puts on the path: ``map_engine`` (map_dataframe),
-``repartition``, ``join``, ``aggregate`` and ``select`` (hence ``filter`` / ``assign``), translating the
-reference's column expressions node by node into ``fugue_b200.column``.
+``repartition``, ``join``, ``aggregate``, ``select`` (hence ``filter`` / ``assign``) and the SQL facet
+(``create_default_sql_engine`` / ``register_sql_engine("b200")``, so FugueSQL SELECTs reach the device),
+translating the reference's column expressions node by node into the engine's IR (``translate_expr``).
+None of these falls back to the host engine.
 """
-from typing import Any, Callable, Dict, List, Optional
+from contextlib import contextmanager
+from typing import Any, Callable, Dict, Iterator, List, Optional
 
 import pyarrow as pa
 
@@ -20,18 +23,21 @@ import fugue  # noqa: F401  (ImportError here means: no Fugue, no adapter)
 from fugue import (ArrowDataFrame as FArrowDataFrame, DataFrame as FDataFrame,
                    LocalDataFrame as FLocalDataFrame, MapEngine as FMapEngine,
                    NativeExecutionEngine, PartitionCursor as FPartitionCursor,
-                   PartitionSpec as FPartitionSpec)
+                   PartitionSpec as FPartitionSpec, SQLEngine as FSQLEngine)
 from fugue.dataframe.dataframe import LocalBoundedDataFrame as FLocalBoundedDataFrame
 from fugue.dev import LocalDataFrameParam, fugue_annotated_param
-from fugue.execution.factory import register_execution_engine
-from fugue.plugins import as_fugue_dataset, infer_execution_engine
+from fugue.execution.factory import register_execution_engine, register_sql_engine
+from fugue.plugins import (as_fugue_dataset, count, get_column_names, get_num_partitions, get_schema,
+                           infer_execution_engine, is_bounded, is_df, is_empty, is_local)
 from triad import Schema as TSchema
 
-from . import api as _api
+from . import api as _api  # noqa: F401
+from . import column as _ir
 from .dataframe import ArrowDataFrame as _ArrowDF, B200DataFrame as _B200DF, DataFrame as _DF
 from .execution_engine import B200ExecutionEngine as _Engine
 from .partition import PartitionSpec as _Spec
 from .schema import Schema as _Schema
+from .sql import B200SQLEngine as _SQLEngine, StructuredRawSQL as _RawSQL
 from .table import B200Table
 
 
@@ -187,73 +193,100 @@ class FugueB200ExecutionEngine(NativeExecutionEngine):
     def persist(self, df: FDataFrame, lazy: bool = False, **kwargs: Any) -> FDataFrame:
         return self.to_df(df)
 
+    def create_default_sql_engine(self) -> FSQLEngine:
+        """FugueSQL ``SELECT`` statements (``RunSQLSelect`` -> ``SQLEngine.select``,
+        fugue/extensions/_builtins/processors.py:148-154) run on the device too."""
+        return FugueB200SQLEngine(self)
+
+    # The operators SURVEY.md section 8 puts on the path never fall back to the host engine: what the
+    # device path can't do raises NotImplementedError (north_star: no CPU fallback on join / aggregate).
     def join(self, df1: FDataFrame, df2: FDataFrame, how: str, on: Optional[List[str]] = None) -> FDataFrame:
-        try:  # every join type runs on the device (fugue_b200/join.py); exotic column types fall back
-            res = self._b200.join(self._to_device(df1), self._to_device(df2), how, on)
-            return FugueB200DataFrame(res.native)
-        except NotImplementedError:
-            return super().join(self.to_df(df1).as_local(), self.to_df(df2).as_local(), how, on)
+        res = self._b200.join(self._to_device(df1), self._to_device(df2), how, on)
+        return FugueB200DataFrame(res.native)
 
     # ``filter`` and ``assign`` of the base class are written in terms of ``select``
     # (fugue/execution/execution_engine.py:808-887), so these two overrides put all four on the device
     def select(self, df: FDataFrame, cols: Any, where: Any = None, having: Any = None) -> FDataFrame:
-        from .column import SelectColumns as _SelectColumns
-
-        try:
-            mine = _SelectColumns(*[_translate_expr(c) for c in cols.all_cols], arg_distinct=cols.is_distinct)
-            res = self._b200.select(self._to_device(df), mine,
-                                    where=None if where is None else _translate_expr(where),
-                                    having=None if having is None else _translate_expr(having))
-            return FugueB200DataFrame(res.native)
-        except NotImplementedError:
-            return super().select(self.to_df(df).as_local(), cols, where=where, having=having)
+        mine = _ir.SelectColumns(*[translate_expr(c) for c in cols.all_cols], arg_distinct=cols.is_distinct)
+        res = self._b200.select(self._to_device(df), mine,
+                                where=None if where is None else translate_expr(where),
+                                having=None if having is None else translate_expr(having))
+        return FugueB200DataFrame(res.native)
 
     def aggregate(self, df: FDataFrame, partition_spec: Optional[FPartitionSpec], agg_cols: List[Any]) -> FDataFrame:
-        try:
-            res = self._b200.aggregate(self._to_device(df),
-                                       None if partition_spec is None else _to_spec(partition_spec),
-                                       [_translate_expr(c) for c in agg_cols])
-            return FugueB200DataFrame(res.native)
-        except NotImplementedError:
-            return super().aggregate(self.to_df(df).as_local(), partition_spec, agg_cols)
+        res = self._b200.aggregate(self._to_device(df),
+                                   None if partition_spec is None else _to_spec(partition_spec),
+                                   [translate_expr(c) for c in agg_cols])
+        return FugueB200DataFrame(res.native)
 
 
-def _translate_expr(e: Any) -> Any:
-    """``fugue.column`` expression tree -> the same tree in ``fugue_b200.column`` (the two DSLs have the
-    same node kinds: named / wildcard / literal / function / unary / binary / aggregation)."""
+class FugueB200SQLEngine(FSQLEngine):
+    """``SQLEngine.select`` (fugue/execution/execution_engine.py:209-238) for the B200 engine: the
+    statement's table references are bound to device tables and the text goes to the engine's own
+    SELECT parser (fugue_b200/sql.py: single-table SELECT / WHERE / GROUP BY / HAVING / ORDER BY /
+    LIMIT and two-table equi-joins -> device select / group-by / join kernels).  Statements outside
+    that grammar raise NotImplementedError; there is no host SQL engine behind it."""
+
+    @property
+    def execution_engine_constraint(self):
+        return FugueB200ExecutionEngine
+
+    @property
+    def is_distributed(self) -> bool:
+        return False
+
+    @property
+    def dialect(self) -> Optional[str]:
+        return None  # no sqlglot transpile (fugue/collections/sql.py:99-103)
+
+    def select(self, dfs: Any, statement: Any) -> FDataFrame:
+        eng: "FugueB200ExecutionEngine" = self.execution_engine  # type: ignore
+        named, text = self.encode(dfs, statement)
+        tables = {k: eng._to_device(v) for k, v in named.items()}
+        res = _SQLEngine(eng.b200).select(tables, _RawSQL([(False, text)]))
+        return FugueB200DataFrame(res.native if isinstance(res, _B200DF) else eng._to_device(
+            FArrowDataFrame(res.as_arrow())).native)
+
+
+# ---- the reference's expression trees -> the engine's IR ---------------------------------------------
+_UNARY_BUILDERS = {"-": lambda x: -x, "~": lambda x: ~x, "IS_NULL": lambda x: x.is_null(),
+                   "NOT_NULL": lambda x: x.not_null()}
+
+
+def translate_expr(e: Any) -> Any:
+    """``fugue.column`` expression tree (fugue/column/expressions.py, functions.py) -> ``fugue_b200.column``
+    IR, node by node.  The reference encodes the node kind in its class; here it becomes ``Kind``."""
     from fugue.column import expressions as fe
     from fugue.column import functions as ff
 
-    from . import column as bc
-
     if not isinstance(e, fe.ColumnExpr):
-        return e
+        return e  # plain python value used as a function argument
     if isinstance(e, fe._WildcardExpr):
-        return bc.all_cols()
+        return _ir.all_cols()
     if isinstance(e, fe._NamedColumnExpr):
-        res: Any = bc.col(e.name)
+        out: Any = _ir.col(e.name)
     elif isinstance(e, fe._LiteralColumnExpr):
-        res = bc.lit(e.value)
+        out = _ir.lit(e.value)
     elif isinstance(e, ff._UnaryAggFuncExpr):
-        same = isinstance(e, ff._SameTypeUnaryAggFuncExpr)
-        cls = bc._SameTypeAggFuncExpr if same else bc.AggFuncExpr
-        res = cls(e.func, _translate_expr(e.args[0]), arg_distinct=e.is_distinct)
+        out = _ir.agg(e.func, translate_expr(e.args[0]), arg_distinct=e.is_distinct)
     elif isinstance(e, fe._UnaryOpExpr):
-        arg = _translate_expr(e.col)
-        res = {"-": lambda: -arg, "~": lambda: ~arg, "IS_NULL": arg.is_null, "NOT_NULL": arg.not_null}[e.op]()
+        if e.op not in _UNARY_BUILDERS:
+            raise NotImplementedError(f"unary operator {e.op}")
+        out = _UNARY_BUILDERS[e.op](translate_expr(e.col))
     elif isinstance(e, fe._BinaryOpExpr):
-        kind = bc._BoolBinaryOpExpr if isinstance(e, fe._BoolBinaryOpExpr) else bc._BinaryOpExpr
-        res = kind(e.op, _translate_expr(e.left), _translate_expr(e.right))
+        out = _ir.binary(e.op, translate_expr(e.left), translate_expr(e.right))
     elif isinstance(e, fe._FuncExpr):
-        res = bc.function(e.func, *[_translate_expr(a) for a in e.args], arg_distinct=e.is_distinct,
-                          **{k: _translate_expr(v) for k, v in e.kwargs.items()})
+        out = _ir.function(e.func, *[translate_expr(x) for x in e.args], arg_distinct=e.is_distinct,
+                           **{k: translate_expr(v) for k, v in e.kwargs.items()})
     else:
         raise NotImplementedError(f"can't translate {type(e).__name__}")
     if e.as_type is not None:
-        res = res.cast(e.as_type)
-    return res.alias(e.as_name) if e.as_name != "" else res
+        out = out.cast(e.as_type)
+    return out.alias(e.as_name) if e.as_name != "" else out
 
 
+# ---- registration (patterns: fugue_duckdb/registry.py:30-75, fugue_dask/registry.py:25-70,
+#      fugue/dataframe/arrow_dataframe.py:263-331) --------------------------------------------------------
 @infer_execution_engine.candidate(
     lambda objs: any(isinstance(o, (B200Table, FugueB200DataFrame)) for o in objs))
 def _infer_b200(objs: Any) -> Any:
@@ -284,9 +317,77 @@ class _B200TableParam(LocalDataFrameParam):
         return "b200"
 
 
+def _is_table(df: Any, *args: Any, **kwargs: Any) -> bool:
+    return isinstance(df, B200Table)
+
+
+@is_df.candidate(_is_table)
+def _b200_is_df(df: B200Table) -> bool:
+    return True
+
+
+@count.candidate(_is_table)
+def _b200_count(df: B200Table) -> int:
+    return df.num_rows
+
+
+@is_bounded.candidate(_is_table)
+def _b200_is_bounded(df: B200Table) -> bool:
+    return True
+
+
+@is_empty.candidate(_is_table)
+def _b200_is_empty(df: B200Table) -> bool:
+    return df.num_rows == 0
+
+
+@is_local.candidate(_is_table)
+def _b200_is_local(df: B200Table) -> bool:
+    return False  # lives in HBM
+
+
+@get_num_partitions.candidate(_is_table)
+def _b200_num_partitions(df: B200Table) -> int:
+    return df.num_partitions
+
+
+@get_column_names.candidate(_is_table)
+def _b200_column_names(df: B200Table) -> List[Any]:
+    return list(df.schema.names)
+
+
+@get_schema.candidate(_is_table)
+def _b200_schema(df: B200Table) -> TSchema:
+    return TSchema(df.schema.pa_schema)
+
+
+def _make_test_backend() -> Any:
+    """``@ft.fugue_test_backend`` class (fugue/test/plugins.py:99-136, 226-312): lets the reference's own
+    conformance suites (``fugue_test/execution_suite.py``, ``builtin_suite.py``) run against this engine with
+    ``@ft.fugue_test_suite("b200", mark_test=True)``.  ``fugue.test`` needs pytest; skipped where absent."""
+    try:
+        import fugue.test as ft
+    except Exception:  # pragma: no cover
+        return None
+
+    @ft.fugue_test_backend
+    class B200TestBackend(ft.FugueTestBackend):
+        name = "b200"
+        default_fugue_conf: Dict[str, Any] = {"fugue.b200.default.partitions": 16}
+
+        @classmethod
+        @contextmanager
+        def session_context(cls, session_conf: Dict[str, Any]) -> Iterator[Any]:
+            yield "b200"  # the engine name is the session object: make_execution_engine("b200", conf)
+
+    return B200TestBackend
+
+
 def register() -> None:
     register_execution_engine("b200", lambda conf, **kwargs: FugueB200ExecutionEngine(conf, **kwargs),
                               on_dup="ignore")
+    register_sql_engine("b200", lambda engine: FugueB200SQLEngine(engine), on_dup="ignore")
 
 
 register()
+B200TestBackend = _make_test_backend()

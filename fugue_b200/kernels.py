@@ -114,6 +114,38 @@ def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
     return list(out)
 
 
+MAP_COPY, MAP_AFFINE_F64, MAP_AFFINE_I64 = 0, 1, 2
+
+
+def partition_apply_map(plan: PartitionPlan, units: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], int, int, int, int]],
+                        out: Optional[Sequence[torch.Tensor]] = None, sm_reserve: int = 0) -> List[torch.Tensor]:
+    """K4: pass 2 with a fused map epilogue.  ``units`` = one ``(x, y or None, mode, a, b, c)`` per output
+    column (8-byte columns; a / b / c are 64-bit patterns): ``MAP_COPY`` x, ``MAP_AFFINE_F64``
+    (a*x + b*y) + c in float64, ``MAP_AFFINE_I64`` a*x + b*y + c in wrapping int64."""
+    lib = _lib.load()
+    xs = [u[0] for u in units]
+    dev, n = _check_cols(xs + [u[1] for u in units if u[1] is not None] + plan.keys)
+    assert all(c.element_size() == 8 for c in xs) and plan.num <= 256
+    if out is None:
+        out = [torch.empty_like(x) for x in xs]
+    maps = (_lib.MapUnit * len(units))()
+    for i, (x, y, mode, a, b, c) in enumerate(units):
+        maps[i].src2 = 0 if y is None else y.data_ptr()
+        maps[i].mode = mode
+        maps[i].a, maps[i].b, maps[i].c = a & ((1 << 64) - 1), b & ((1 << 64) - 1), c & ((1 << 64) - 1)
+    tail = torch.empty(int(lib.fb_partition_map_tail_bytes(len(units))), dtype=torch.uint8, device=dev)
+    vp = _valid_ptrs(plan.valid, len(plan.keys))
+    _lib.check(lib.fb_partition_apply_map(
+        dev.index, _stream_ptr(dev), n, len(plan.keys),
+        _lib.ptr_array([k.data_ptr() for k in plan.keys]),
+        _lib.i32_array([k.element_size() for k in plan.keys]),
+        vp, plan.num, plan.scratch.data_ptr(), plan.scratch.numel(), plan.offsets.data_ptr(),
+        len(units), _lib.ptr_array([x.data_ptr() for x in xs]), _lib.ptr_array([o.data_ptr() for o in out]),
+        maps, tail.data_ptr(), int(sm_reserve)))
+    tail.record_stream(torch.cuda.current_stream(dev))
+    return list(out)
+
+
 def partition_columns(cols: Sequence[torch.Tensor], key_idx: Sequence[int], num: int,
                       key_valid: Optional[Sequence[Optional[torch.Tensor]]] = None,
                       out: Optional[Sequence[torch.Tensor]] = None,

@@ -16,7 +16,7 @@ import pyarrow.compute as pc
 import torch
 
 from . import kernels as K
-from .column import AggFuncExpr, col
+from .column import agg as _agg, col
 from .dataframe import ArrowDataFrame, B200DataFrame
 from .partition import PartitionSpec
 from .schema import Schema
@@ -62,7 +62,7 @@ def distinct(engine: Any, df: B200DataFrame) -> B200DataFrame:
     t: B200Table = df.native
     if t.num_rows == 0:
         return df
-    res = engine.aggregate(df, PartitionSpec(by=t.schema.names), [AggFuncExpr("COUNT", col("*"), "__fb_n")])
+    res = engine.aggregate(df, PartitionSpec(by=t.schema.names), [_agg("COUNT", col("*"), "__fb_n")])
     return res[t.schema.names]
 
 
@@ -84,7 +84,7 @@ def _tagged_groups(engine: Any, df1: B200DataFrame, df2: B200DataFrame) -> B200D
 
     both = B200DataFrame(concat_tables(tag(t1, 1), tag(t2, 2)))
     return engine.aggregate(both, PartitionSpec(by=t1.schema.names),
-                            [AggFuncExpr("MIN", col(_TAG), "__fb_lo"), AggFuncExpr("MAX", col(_TAG), "__fb_hi")])
+                            [_agg("MIN", col(_TAG), "__fb_lo"), _agg("MAX", col(_TAG), "__fb_hi")])
 
 
 def _keep_groups(groups: B200DataFrame, names: List[str], lo: int, hi: int) -> B200DataFrame:

@@ -21,7 +21,7 @@ Anything else raises NotImplementedError (there is no host SQL fallback in this 
 import re
 from typing import Any, Dict, List, Tuple
 
-from .column import ColumnExpr, SelectColumns, all_cols, col, function, functions, is_agg, lit, null, to_uuid
+from .column import ColumnExpr, Kind, SelectColumns, all_cols, col, function, functions, is_agg, lit, null
 from .dataframe import DataFrame
 
 _AGG = r"(SUM|COUNT|MIN|MAX|AVG|MEAN)\s*\(\s*(\*|[A-Za-z_][\w]*)\s*\)"
@@ -97,17 +97,17 @@ class B200SQLEngine:
             probe = SelectColumns(*cols)
             if not probe.has_agg:
                 raise NotImplementedError(f"GROUP BY without aggregates: {sql}")
-            inferred = {to_uuid(k) for k in probe.group_keys}
+            inferred = {k.fingerprint() for k in probe.group_keys}
             listed = set()
             for g in st.group_by:
-                uid = to_uuid(g.alias("").cast(None))
+                uid = g.alias("").cast(None).fingerprint()
                 listed.add(uid)
                 if uid not in inferred:
                     name = f"__fb_g{len(hidden)}"
                     hidden.append(name)
                     cols.append(g.alias(name))
             for k in probe.group_keys:
-                if to_uuid(k) not in listed:
+                if k.fingerprint() not in listed:
                     raise ValueError(f"{k} is neither aggregated nor in GROUP BY: {sql}")
         res = self._engine.select(df, SelectColumns(*cols, arg_distinct=st.distinct), where=st.where,
                                   having=st.having)
@@ -442,11 +442,9 @@ def _number(text: str) -> Any:
 
 def _default_alias(e: ColumnExpr) -> ColumnExpr:
     """Name an unnamed select item the way the SQL engines do for the common cases."""
-    from .column import AggFuncExpr, _WildcardExpr
-
-    if isinstance(e, _WildcardExpr) or e.output_name != "":
+    if e.kind == Kind.WILDCARD or e.output_name != "":
         return e
-    if isinstance(e, AggFuncExpr) and isinstance(e.arg, _WildcardExpr):
+    if e.kind == Kind.AGG and e.arg.kind == Kind.WILDCARD:
         return e.alias(e.func.lower())          # COUNT(*) -> "count"
     named = e.infer_alias()
     return named

@@ -107,6 +107,30 @@ int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys,
                           const void* const* col_ptrs, const int32_t* col_widths,
                           void* const* out_col_ptrs, int sm_reserve);
 
+/* K4  fused map epilogue: fb_partition_apply whose output column c is not a copy of col_ptrs[c] but
+ *   mode 1 (float64): (a * x + b * y) + c    mode 2 (int64): a * x + b * y + c (wrapping)    mode 0: x
+ * with x = col_ptrs[c][row], y = maps[c].src2[row] (src2 NULL: no y), evaluated by the movers of the
+ * scatter kernel between the gather from the staged tile and the store - the per-partition map of
+ * PandasMapEngine.map_dataframe (fugue/execution/native_execution_engine.py:156-164) for maps that
+ * are column expressions, with no second pass over the table.  float64 operations are rounded one by
+ * one (same result as the expression evaluator K8).  All columns 8 bytes wide and 16-byte aligned,
+ * num_partitions <= 256.  a / b / c are the constants' bit patterns.  tail_tmp: device scratch of
+ * fb_partition_map_tail_bytes(ncols) bytes (the partial last tile is mapped there first). */
+typedef struct {
+  const void* src2;
+  int32_t mode;
+  int32_t reserved;
+  uint64_t a, b, c;
+} fb_map_unit;
+size_t fb_partition_map_tail_bytes(int ncols);
+int fb_partition_apply_map(int dev, void* stream, int64_t nrows, int nkeys,
+                           const void* const* key_ptrs, const int32_t* key_widths,
+                           const uint8_t* const* key_valid, uint32_t num_partitions,
+                           const void* scratch, size_t scratch_bytes,
+                           const int64_t* part_offsets, int ncols,
+                           const void* const* col_ptrs, void* const* out_col_ptrs,
+                           const fb_map_unit* maps, void* tail_tmp, int sm_reserve);
+
 int fb_partition_cols(int dev, void* stream, int64_t nrows, int ncols,
                       const void* const* col_ptrs, const int32_t* col_widths,
                       const int32_t* key_col_idx, int nkeys,

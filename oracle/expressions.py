@@ -27,9 +27,7 @@ import numpy as np
 import pandas as pd
 import pyarrow as pa
 
-from fugue_b200.column import (AggFuncExpr, ColumnExpr, SelectColumns, _BinaryOpExpr, _FuncExpr,
-                               _LiteralColumnExpr, _NamedColumnExpr, _UnaryOpExpr, _WildcardExpr, col,
-                               is_agg, to_uuid)
+from fugue_b200.column import ColumnExpr, Kind, SelectColumns, col, is_agg
 
 
 def _nullable(s: pd.Series) -> pd.Series:
@@ -80,16 +78,16 @@ def evaluate(e: Any, df: pd.DataFrame, aggs: Optional[Dict[str, pd.Series]] = No
     if not isinstance(e, ColumnExpr):
         return e
     n = len(df)
-    if isinstance(e, AggFuncExpr):
+    if e.kind == Kind.AGG:
         assert aggs is not None, f"aggregation {e} outside an aggregating select"
-        res: Any = aggs[to_uuid(e.alias("").cast(None))]
-    elif isinstance(e, _NamedColumnExpr):
+        res: Any = aggs[e.alias("").cast(None).fingerprint()]
+    elif e.kind == Kind.NAMED:
         res = _nullable(df[e.name])
-    elif isinstance(e, _LiteralColumnExpr):
+    elif e.kind == Kind.LITERAL:
         res = pd.NA if e.value is None else e.value
-    elif isinstance(e, _WildcardExpr):
+    elif e.kind == Kind.WILDCARD:
         raise ValueError("'*' has no value")
-    elif isinstance(e, _UnaryOpExpr):
+    elif e.kind == Kind.UNARY:
         v = evaluate(e.col, df, aggs)
         if e.op == "IS_NULL":
             res = v.isna().astype("boolean") if isinstance(v, pd.Series) else (v is pd.NA)
@@ -101,7 +99,7 @@ def evaluate(e: Any, df: pd.DataFrame, aggs: Optional[Dict[str, pd.Series]] = No
             res = ~(v.astype("boolean") if isinstance(v, pd.Series) else v)
         else:
             raise NotImplementedError(e.op)
-    elif isinstance(e, _BinaryOpExpr):
+    elif e.kind == Kind.BINARY:
         a, b = evaluate(e.left, df, aggs), evaluate(e.right, df, aggs)
         if not isinstance(a, pd.Series) and not isinstance(b, pd.Series):
             a = pd.Series(pd.array([a] * n), index=df.index)
@@ -134,7 +132,7 @@ def evaluate(e: Any, df: pd.DataFrame, aggs: Optional[Dict[str, pd.Series]] = No
             res = a != b
         else:
             raise NotImplementedError(op)
-    elif isinstance(e, _FuncExpr) and e.func.upper() == "COALESCE":
+    elif e.kind == Kind.CALL and e.func.upper() == "COALESCE":
         vals = [evaluate(a, df, aggs) for a in e.args]
         series = [v for v in vals if isinstance(v, pd.Series)]
         is_f = any(pd.api.types.is_float_dtype(s.dtype) for s in series) or \
@@ -172,10 +170,12 @@ def _predicate(e: ColumnExpr, df: pd.DataFrame, aggs: Optional[Dict[str, pd.Seri
     return v.astype("boolean").fillna(False).to_numpy(dtype=bool)
 
 
-def _find_aggs(e: Any, out: List[AggFuncExpr]) -> None:
-    if isinstance(e, AggFuncExpr):
+def _find_aggs(e: Any, out: List[ColumnExpr]) -> None:
+    if not isinstance(e, ColumnExpr):
+        return
+    if e.kind == Kind.AGG:
         out.append(e)
-    elif isinstance(e, _FuncExpr):
+    elif e.has_args:
         for a in list(e.args) + list(e.kwargs.values()):
             _find_aggs(a, out)
 
@@ -207,7 +207,7 @@ def select(df: pd.DataFrame, cols: SelectColumns, where: Optional[ColumnExpr] = 
     names = list(df.columns)
     out_cols: List[ColumnExpr] = []
     for c in cols.all_cols:
-        if isinstance(c, _WildcardExpr):
+        if c.kind == Kind.WILDCARD:
             out_cols.extend(col(n) for n in names)
         else:
             out_cols.append(c)
@@ -232,18 +232,18 @@ def select(df: pd.DataFrame, cols: SelectColumns, where: Optional[ColumnExpr] = 
         codes = np.zeros(n, dtype=np.int64)
         ngroups = 1  # a global aggregate always yields one row
         gkeys = pd.DataFrame(index=range(1))
-    key_uuid = {to_uuid(k): gkeys[f"k{i}"] for i, k in enumerate(sel.group_keys)}
-    found: List[AggFuncExpr] = []
+    key_uuid = {k.fingerprint(): gkeys[f"k{i}"] for i, k in enumerate(sel.group_keys)}
+    found: List[ColumnExpr] = []
     for c in sel.all_cols:
         _find_aggs(c, found)
     if having is not None:
         _find_aggs(having, found)
     aggs: Dict[str, pd.Series] = {}
     for a in found:
-        uid = to_uuid(a.alias("").cast(None))
+        uid = a.alias("").cast(None).fingerprint()
         if uid in aggs:
             continue
-        if isinstance(a.arg, _WildcardExpr):
+        if a.arg.kind == Kind.WILDCARD:
             vals = None
         else:
             vals = _as_column(evaluate(a.arg, df), n, df.index, a.arg)
@@ -261,7 +261,7 @@ def select(df: pd.DataFrame, cols: SelectColumns, where: Optional[ColumnExpr] = 
 
     def group_value(e: ColumnExpr) -> Any:
         """Evaluate a select column on the group table: group keys come from ``gkeys``."""
-        uid = to_uuid(e.alias("").cast(None))
+        uid = e.alias("").cast(None).fingerprint()
         if uid in key_uuid and not is_agg(e):
             v: Any = key_uuid[uid]
             return _cast(v, e.as_type, ngroups, gframe.index) if e.as_type is not None else v
@@ -270,22 +270,22 @@ def select(df: pd.DataFrame, cols: SelectColumns, where: Optional[ColumnExpr] = 
     def _eval_on_groups(e: Any) -> Any:
         if not isinstance(e, ColumnExpr):
             return e
-        uid = to_uuid(e.alias("").cast(None))
+        uid = e.alias("").cast(None).fingerprint()
         if uid in key_uuid and not is_agg(e):
             v = key_uuid[uid]
-        elif isinstance(e, AggFuncExpr):
+        elif e.kind == Kind.AGG:
             v = aggs[uid]
-        elif isinstance(e, _LiteralColumnExpr):
+        elif e.kind == Kind.LITERAL:
             v = pd.NA if e.value is None else e.value
-        elif isinstance(e, _UnaryOpExpr):
+        elif e.kind == Kind.UNARY:
             sub = _eval_on_groups(e.col)
             tmp = pd.DataFrame({"x": _as_column(sub, ngroups, gframe.index, e.col)})
-            v = evaluate(type(e)(e.op, col("x")), tmp)
-        elif isinstance(e, _BinaryOpExpr):
+            v = evaluate(ColumnExpr(Kind.UNARY, e.op, [col("x")]), tmp)
+        elif e.kind == Kind.BINARY:
             a, b = _eval_on_groups(e.left), _eval_on_groups(e.right)
             tmp = pd.DataFrame({"a": _as_column(a, ngroups, gframe.index, e.left),
                                 "b": _as_column(b, ngroups, gframe.index, e.right)})
-            v = evaluate(type(e)(e.op, col("a"), col("b")), tmp)
+            v = evaluate(ColumnExpr(Kind.BINARY, e.op, [col("a"), col("b")]), tmp)
         else:
             raise NotImplementedError(str(e))
         if e.as_type is not None:

@@ -30,7 +30,21 @@ def _load_reference_column():
 
     triad = types.ModuleType("triad")
     triad.Schema = msch.Schema
-    triad.to_uuid = mine.to_uuid
+    def _to_uuid(*args):  # stand-in for triad.to_uuid: any deterministic id of nested values will do
+        import hashlib
+
+        def feed(v):
+            if hasattr(v, "__uuid__"):
+                return "u" + v.__uuid__()
+            if isinstance(v, (list, tuple)):
+                return "[" + ",".join(feed(x) for x in v) + "]"
+            if isinstance(v, dict):
+                return "{" + ",".join(feed(k) + ":" + feed(x) for k, x in v.items()) + "}"
+            return type(v).__name__ + ":" + repr(v)
+
+        return hashlib.md5(feed(args).encode()).hexdigest()
+
+    triad.to_uuid = _to_uuid
 
     def assert_or_throw(cond, exc=None):
         if not cond:
@@ -43,7 +57,7 @@ def _load_reference_column():
     tpa._type_to_expression = msch.type_to_expr
     tpa.to_pa_datatype = mine.to_pa_datatype
     tsc = types.ModuleType("triad.utils.schema")
-    tsc.quote_name = mine._quote_name
+    tsc.quote_name = mine._quote
     fugue = types.ModuleType("fugue")
     fugue.__path__ = []
     fcol = types.ModuleType("fugue.column")

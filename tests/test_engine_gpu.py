@@ -294,3 +294,126 @@ def test_even_and_rand_partition_algos():
                        engine=e, as_local=True)
     exp = pdf.groupby("k").size().reset_index(name="c")
     assert np.array_equal(out.sort_values("k")["c"].to_numpy(), exp["c"].to_numpy())
+
+
+@pytest.mark.parametrize("spec_kw,nparts", [({"by": "key", "algo": "hash", "num": 65536}, 65536),
+                                           ({"by": ["key", "b"], "num": 5000}, 5000)])
+def test_repartition_beyond_one_radix_pass(engine, spec_kw, nparts):
+    """num_partitions > 1024 (SURVEY.md 7.1: num=65536): byte-wise stable radix passes on the partition id;
+    bit-exact with the oracle's stable partition (same rows, same order, same offsets)."""
+    from oracle import hash_partition as hp
+
+    rng = np.random.default_rng(11)
+    n = 200_003
+    cols = [rng.integers(-(2**40), 2**40, n).astype("int64"), rng.integers(0, 7, n).astype("int32"),
+            rng.standard_normal(n), np.arange(n, dtype="int64")]
+    t = B200Table("key:long,b:int,v:double,rid:long", [torch.from_numpy(c).cuda() for c in cols])
+    res = engine.repartition(B200DataFrame(t), PartitionSpec(**spec_kw)).native
+    assert res.num_partitions == nparts
+    kidx = [0] if spec_kw["by"] == "key" else [0, 1]
+    exp_cols, exp_off = hp.partition_table(cols, kidx, nparts)
+    assert np.array_equal(res.offsets.cpu().numpy(), exp_off)
+    for g, e in zip(res.columns, exp_cols):
+        assert np.array_equal(g.cpu().numpy().view("u1"), e.view("u1"))
+
+
+def test_repartition_per_row(engine):
+    """``PartitionSpec("per_row")`` = algo even, num = ROWCOUNT (fugue/collections/partition.py:95,115,186-207):
+    every row its own physical partition; and a hash spec whose num is the ROWCOUNT expression."""
+    from oracle import hash_partition as hp
+
+    rng = np.random.default_rng(12)
+    n = 3000
+    cols = [rng.integers(0, 10**9, n).astype("int64"), rng.standard_normal(n)]
+    t = B200Table("key:long,v:double", [torch.from_numpy(c).cuda() for c in cols])
+    spec = PartitionSpec("per_row")
+    assert spec.num_partitions == "ROWCOUNT" and spec.algo == "even"
+    res = engine.repartition(B200DataFrame(t), spec).native
+    assert res.num_partitions == n and np.array_equal(res.offsets.cpu().numpy(), np.arange(n + 1))
+    assert np.array_equal(res.columns[0].cpu().numpy(), cols[0])
+    hspec = PartitionSpec(by="key", algo="hash", num="ROWCOUNT")
+    res = engine.repartition(B200DataFrame(t), hspec).native
+    exp_cols, exp_off = hp.partition_table(cols, [0], n)
+    assert res.num_partitions == n and np.array_equal(res.offsets.cpu().numpy(), exp_off)
+    assert np.array_equal(res.columns[0].cpu().numpy(), exp_cols[0])
+    out = engine.map_engine.map_dataframe(B200DataFrame(t), lambda c, d: d, t.schema, hspec,
+                                          map_func_format_hint="b200")
+    assert out.count() == n
+
+
+def test_transform_save_path_and_checkpoint(engine, tmp_path):
+    """fugue/workflow/api.py:100-120: save_path -> the path is returned; + checkpoint -> the dataframe
+    loaded back from it; checkpoint alone -> a file under fugue.workflow.checkpoint.path; a parquet
+    path as input."""
+    pdf = pd.DataFrame({"key": [3, 1, 2, 1, 3, 3], "v": [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]})
+
+    def ident(t: B200Table) -> B200Table:
+        return t
+
+    spec = PartitionSpec(by="key", algo="hash", num=4)
+    p1 = str(tmp_path / "out.parquet")
+    assert fa.transform(pdf, ident, schema="*", partition=spec, engine=engine, save_path=p1) == p1
+    back = pd.read_parquet(p1).sort_values(["key", "v"]).reset_index(drop=True)
+    pd.testing.assert_frame_equal(back, pdf.sort_values(["key", "v"]).reset_index(drop=True))
+    p2 = str(tmp_path / "out2.parquet")
+    res = fa.transform(pdf, ident, schema="*", partition=spec, engine=engine, save_path=p2, checkpoint=True,
+                       as_local=True, as_fugue=True)
+    assert res.count() == 6 and len(pd.read_parquet(p2)) == 6
+    with pytest.raises(ValueError):
+        fa.transform(pdf, ident, schema="*", engine=engine, checkpoint=True)        # no checkpoint path configured
+    with pytest.raises(ValueError):
+        fa.transform(pdf, ident, schema="*", engine=engine, save_path=str(tmp_path / "x.csv"))
+    eng2 = fa.make_execution_engine("b200", {"fugue.workflow.checkpoint.path": str(tmp_path / "ckpt")})
+    res = fa.transform(p1, ident, schema="*", partition=spec, engine=eng2, checkpoint=True, as_fugue=True)
+    assert res.count() == 6
+    import os
+
+    assert len(os.listdir(tmp_path / "ckpt")) == 1
+
+
+@pytest.mark.parametrize("n", [100_003, 4096 * 300, 1000])
+def test_fused_column_map_matches_the_evaluator_bit_for_bit(engine, n):
+    """K4: a ColumnMap of affine expressions is evaluated inside the scatter kernel of the hash partition
+    (fb_partition_apply_map).  Same bits as partition -> expression evaluator (K8), and as numpy."""
+    from fugue_b200.colmap import ColumnMap
+    from fugue_b200.column import col
+
+    rng = np.random.default_rng(21)
+    key = rng.integers(0, 1 << 16, n).astype("int64")
+    i1 = rng.integers(-(2**62), 2**62, n).astype("int64")
+    v0, v1 = rng.standard_normal(n), rng.standard_normal(n)
+    v0[:5] = [0.0, -0.0, np.inf, np.nan, 1e308]
+    t = B200Table("key:long,i1:long,v0:double,v1:double", [torch.from_numpy(c).cuda() for c in (key, i1, v0, v1)])
+    cmap = ColumnMap("key", col("v0").alias("z"), (col("v0") * 2 + col("v1")).alias("w"), (col("key") * 3 - 7).alias("k3"),
+                     (col("v1") - col("v0") * 0.5 + 1.25).alias("u"), (-col("i1") + col("key")).alias("m"),
+                     (col("v0") * -1.5).alias("s"))
+    schema = "key:long,z:double,w:double,k3:long,u:double,m:long,s:double"
+    spec = PartitionSpec(by="key", algo="hash", num=256)
+    assert cmap.fusion_units(t) is not None
+    fused = fa.transform(B200DataFrame(t), cmap, schema=schema, partition=spec, engine=engine, as_fugue=True).native
+    assert fused.offsets is not None and fused.num_partitions == 256
+    part = engine.repartition(B200DataFrame(t), spec).native
+    plain = cmap(part)                                      # unfused: evaluator over the partitioned table
+    for name in fused.schema.names:
+        a, b = fused.column(name), plain.column(name)
+        assert a.dtype == b.dtype and torch.equal(a.view(torch.int64), b.view(torch.int64)), name
+    assert torch.equal(fused.offsets, part.offsets)
+    k, a0, a1 = part.column("key").cpu().numpy(), part.column("v0").cpu().numpy(), part.column("v1").cpu().numpy()
+    with np.errstate(all="ignore"):
+        assert np.array_equal(fused.column("w").cpu().numpy().view("i8"), (a0 * 2 + a1).view("i8"))
+        assert np.array_equal(fused.column("u").cpu().numpy().view("i8"), ((a1 - a0 * 0.5) + 1.25).view("i8"))
+    assert np.array_equal(fused.column("k3").cpu().numpy(), k * 3 - 7)
+
+
+def test_column_map_that_cannot_be_fused_still_runs_on_the_device(engine):
+    from fugue_b200.colmap import ColumnMap
+    from fugue_b200.column import col
+
+    pdf = pd.DataFrame({"key": [1, 2, 1, 3], "a": [1.0, 2.0, 3.0, 4.0], "b": [2.0, 4.0, 8.0, 16.0]})
+    cmap = ColumnMap("key", (col("a") / col("b")).alias("q"), ((col("a") + 1) * col("b")).alias("p"))
+    assert cmap.fusion_units(engine.to_df(pdf).native) is None
+    res = fa.transform(pdf, cmap, schema="key:long,q:double,p:double", partition=PartitionSpec(by="key", num=4),
+                       engine=engine)
+    exp = pdf.assign(q=pdf.a / pdf.b, p=(pdf.a + 1) * pdf.b)[["key", "q", "p"]]
+    pd.testing.assert_frame_equal(res.sort_values(["key", "q"]).reset_index(drop=True),
+                                  exp.sort_values(["key", "q"]).reset_index(drop=True))

@@ -80,6 +80,27 @@ def measure(device_index: int = 0):
     sizes = (off[1:] - off[:-1])
     pid = K.partition_ids([outs[0]], 256).long()
     ok = bool((pid == torch.repeat_interleave(torch.arange(256, device=dev), sizes)).all()) and int(off[-1]) == n
+    # K4: the fused map epilogue - hash partition + map (w = v0*2 + v1 replaces v1) in one pass, beside identity
+    from fugue_b200.colmap import ColumnMap
+    from fugue_b200.partition import PartitionSpec
+    from fugue_b200.column import col as _c
+    g2 = torch.Generator(device=dev).manual_seed(3)
+    ucols = [torch.randint(0, 1 << 16, (n,), dtype=torch.int64, device=dev, generator=g2)] \
+        + [torch.randint(-(2**62), 2**62, (n,), dtype=torch.int64, device=dev, generator=g2) for _ in range(3)] \
+        + [torch.randn(n, dtype=torch.float64, device=dev, generator=g2) for _ in range(4)]
+    names = ["key", "i1", "i2", "i3", "v0", "v1", "v2", "v3"]
+    U = B200DataFrame(B200Table("key:long,i1:long,i2:long,i3:long,v0:double,v1:double,v2:double,v3:double", ucols))
+    spec = PartitionSpec(by="key", algo="hash", num=256)
+    cm_id = ColumnMap(*names)
+    cm = ColumnMap("key", "i1", "i2", "i3", "v0", (_c("v0") * 2 + _c("v1")).alias("w"), "v2", "v3")
+    sch_map = "key:long,i1:long,i2:long,i3:long,v0:double,w:double,v2:double,v3:double"
+    ms_id = timeit(lambda: fa.transform(U, cm_id, schema="*", partition=spec, engine=e), reps=5)
+    ms_map = timeit(lambda: fa.transform(U, cm, schema=sch_map, partition=spec, engine=e), reps=5)
+    ms_unfused = timeit(lambda: cm(e.repartition(U, spec).native), reps=3)
+    out["transform_fused_map"] = {"rows": n, "map": "w = v0 * 2 + v1 (7 columns copied)", "identity_ms": ms_id,
+                                  "fused_map_ms": ms_map, "partition_then_evaluator_ms": ms_unfused,
+                                  "rows_per_s": n / ms_map * 1e3, "alg_GBps": (64 + 64) * n / ms_map / 1e6}
+    del ucols, U
     out["transform_zipf_s1"] = {"rows": n, "ms": ms, "rows_per_s": n / ms * 1e3, "largest_partition_share":
                                 float(sizes.max()) / n, "every_row_in_its_partition": ok}
     return out
