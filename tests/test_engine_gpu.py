@@ -413,7 +413,7 @@ def test_column_map_that_cannot_be_fused_still_runs_on_the_device(engine):
     cmap = ColumnMap("key", (col("a") / col("b")).alias("q"), ((col("a") + 1) * col("b")).alias("p"))
     assert cmap.fusion_units(engine.to_df(pdf).native) is None
     res = fa.transform(pdf, cmap, schema="key:long,q:double,p:double", partition=PartitionSpec(by="key", num=4),
-                       engine=engine)
+                       engine=engine, as_local=True)
     exp = pdf.assign(q=pdf.a / pdf.b, p=(pdf.a + 1) * pdf.b)[["key", "q", "p"]]
     pd.testing.assert_frame_equal(res.sort_values(["key", "q"]).reset_index(drop=True),
                                   exp.sort_values(["key", "q"]).reset_index(drop=True))
