@@ -56,7 +56,7 @@ SIGNATURES = {
                                      _vpp]),
     "fb_partition_apply_ex": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                         C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _i32p,
-                                        _vpp, C.c_int]),
+                                        _vpp, C.c_int, C.c_int, C.c_int]),
     "fb_partition_map_tail_bytes": (C.c_size_t, [C.c_int]),
     "fb_partition_apply_map": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                          C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _vpp, _vp, _vp, C.c_int]),

@@ -94,8 +94,10 @@ def partition_plan(keys: Sequence[torch.Tensor], num: int,
 
 
 def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
-                    out: Optional[Sequence[torch.Tensor]] = None, sm_reserve: int = 0) -> List[torch.Tensor]:
-    """Pass 2 for ``cols``; ``sm_reserve`` SMs stay free for kernels that co-run (multi-GPU exchange)."""
+                    out: Optional[Sequence[torch.Tensor]] = None, sm_reserve: int = 0, cols_per_launch: int = 0,
+                    write_group: int = 0) -> List[torch.Tensor]:
+    """Pass 2 for ``cols``; ``sm_reserve`` SMs stay free for kernels that co-run (multi-GPU exchange);
+    ``cols_per_launch`` / ``write_group`` are tuning arguments of the fast kernel (0 = default)."""
     lib = _lib.load()
     dev, n = _check_cols(list(cols) + plan.keys)
     if out is None:
@@ -110,7 +112,7 @@ def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
         vp, plan.num, plan.scratch.data_ptr(), plan.scratch.numel(), plan.offsets.data_ptr(),
         len(cols), _lib.ptr_array([c.data_ptr() for c in cols]),
         _lib.i32_array([c.element_size() for c in cols]),
-        _lib.ptr_array([o.data_ptr() for o in out]), int(sm_reserve)))
+        _lib.ptr_array([o.data_ptr() for o in out]), int(sm_reserve), int(cols_per_launch), int(write_group)))
     return list(out)
 
 

@@ -96,7 +96,7 @@ int fb_partition_apply(int dev, void* stream, int64_t nrows, int nkeys,
                        const void* const* col_ptrs, const int32_t* col_widths,
                        void* const* out_col_ptrs);
 
-/* fb_partition_apply with `sm_reserve` SMs left free: the fast scatter kernel is persistent and a
+/* fb_partition_apply with tuning arguments (0 = default for each).  `sm_reserve` SMs left free: the fast scatter kernel is persistent and a
  * CTA owns its SM's whole register file, so a kernel that must run at the same time (the multi-GPU
  * barrier / pull kernels of the exchange that overlaps the next column group) needs SMs of its own. */
 int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys,
@@ -105,7 +105,9 @@ int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys,
                           const void* scratch, size_t scratch_bytes,
                           const int64_t* part_offsets, int ncols,
                           const void* const* col_ptrs, const int32_t* col_widths,
-                          void* const* out_col_ptrs, int sm_reserve);
+                          void* const* out_col_ptrs, int sm_reserve,
+                          int cols_per_launch /* 8-byte columns per launch of the fast kernel, 1..8 */,
+                          int write_group /* rows per write-combined group: 4 (32 B, default) or 8 (64 B) */);
 
 /* K4  fused map epilogue: fb_partition_apply whose output column c is not a copy of col_ptrs[c] but
  *   mode 1 (float64): (a * x + b * y) + c    mode 2 (int64): a * x + b * y + c (wrapping)    mode 0: x
