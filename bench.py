@@ -70,6 +70,7 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self._stop_evt = threading.Event()
+        self.ready = threading.Event()  # NVML is initialised and the first sample is in
 
     def run(self):
         try:
@@ -86,6 +87,7 @@ class ClockSampler(threading.Thread):
             }
             while not self._stop_evt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.ready.set()
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
@@ -96,6 +98,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.004)  # the default timed region is ~40 ms: take several samples inside it
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def stop(self):
         self._stop_evt.set()
@@ -241,6 +244,7 @@ def run_b200(args):
     sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(timeout=10)  # importing / initialising NVML takes longer than the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()

@@ -56,7 +56,7 @@ SIGNATURES = {
                                      _vpp]),
     "fb_partition_apply_ex": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                         C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _i32p,
-                                        _vpp, C.c_int, C.c_int, C.c_int]),
+                                        _vpp, C.c_int, C.c_int]),
     "fb_partition_map_tail_bytes": (C.c_size_t, [C.c_int]),
     "fb_partition_apply_map": (C.c_int, [C.c_int, _vp, C.c_int64, C.c_int, _vpp, _i32p, _vpp,
                                          C.c_uint32, _vp, C.c_size_t, _vp, C.c_int, _vpp, _vpp, _vp, _vp, C.c_int]),
@@ -77,6 +77,15 @@ SIGNATURES = {
     "fb_join_probe_write_u64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp,
                                           C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "fb_join_mark_matched": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, _vp]),
+    "fb_join2_table_bytes": (C.c_size_t, [C.c_int64]),
+    "fb_join2_build": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp, _vp, _vp]),
+    "fb_join2_tiles_bytes": (C.c_size_t, [C.c_int64]),
+    "fb_join2_probe": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_uint32, _vp, C.c_int,
+                                 _vp, _vp, _vp, _vp, _vp]),
+    "fb_join2_build_probe": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64,
+                                       C.c_uint32, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "fb_join2_emit": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint32, _vp, _vp, _vp, _vp,
+                                C.c_int, _vpp, _vpp, _i32p, C.c_int, _vpp, _vpp, _i32p, _vpp, _vpp]),
     "fb_exclusive_scan_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "fb_exclusive_scan_i64": (C.c_int, [C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_size_t]),
     "fb_compact_scratch_bytes": (C.c_size_t, [C.c_int64]),

@@ -189,6 +189,120 @@ fb_groupby_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lean variant of fb_groupby_kernel for hash-partitioned input and at most four aggregates (the shape of
+// SELECT key, SUM(v), COUNT(*) ... GROUP BY key): ONE hash per row (the partitioner's; region = partition
+// id, slot from its upper bits), the aggregate descriptors in registers, the loop over aggregates
+// unrolled.  The generic kernel spends ~660 thread instructions per row and is issue-bound (ncu: 70 %
+// issue-active, profiles/r2_groupby_notes.md); this one leaves the L2 atomic units as the limit.
+// ---------------------------------------------------------------------------------------------------
+template <int NAGG>
+struct LeanAggs {
+  const uint64_t* val[NAGG];
+  const uint8_t* valid[NAGG];
+  int32_t op[NAGG];
+};
+
+template <int NAGG>
+__global__ void __launch_bounds__(256)
+fb_groupby_lean_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ key_valid, int64_t nrows,
+                       uint64_t* __restrict__ table, int64_t capacity, const LeanAggs<NAGG> aggs,
+                       int64_t* __restrict__ status, uint32_t parts_mask, int region_shift) {
+  constexpr int words = (1 + NAGG + 3) & ~3;
+  const uint32_t mask = (1u << region_shift) - 1u;
+  const unsigned lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = (nrows + stride - 1) / stride;
+  for (int64_t it = 0; it < nround; ++it) {
+    const int64_t row = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = row < nrows;
+    uint64_t key = ok ? keys[row] : 0;
+    int64_t s = -2;
+    bool special = false;
+    if (ok) {
+      if (key_valid != nullptr && key_valid[row] == 0) { s = capacity + 1; special = true; }  // NULL group
+      else if (key == kEmpty) { s = capacity; special = true; }                             // EMPTY-valued key
+    }
+    const uint64_t h = fb_hash_single_u64(key);
+    // warp pre-merge on 6 hash bits (verified on the key): one prober per distinct key per warp, so that a hot
+    // key costs one probe + 32 updates instead of 32 serialised probes
+    const bool need = ok && !special;
+    const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need);
+    unsigned peers = need_mask;
+    if (need) {
+      const uint32_t hb = (uint32_t)(h >> 40);
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const bool bit = (hb >> b) & 1u;
+        const unsigned bal = __ballot_sync(need_mask, bit);
+        peers &= bit ? bal : ~bal;
+      }
+    }
+    const int leader = need ? (__ffs(peers) - 1) : (int)lane;
+    const uint64_t lkey = __shfl_sync(0xFFFFFFFFu, key, leader);
+    const bool follow = need && leader != (int)lane && lkey == key;
+    if (need && !follow) {
+      const int64_t base = (int64_t)((uint32_t)h & parts_mask) << region_shift;
+      uint32_t o = (uint32_t)(h >> 10) & mask;
+      s = -1;
+#pragma unroll 1
+      for (int probe = 0; probe < kMaxProbe; ++probe) {
+        uint64_t* slot = table + (base + o) * words;
+        uint64_t cur = *(volatile uint64_t*)slot;
+        if (cur == kEmpty) {
+          cur = atomicCAS((unsigned long long*)slot, (unsigned long long)kEmpty, (unsigned long long)key);
+          if (cur == kEmpty) cur = key;
+        }
+        if (cur == key) { s = base + o; break; }
+        o = (o + 1) & mask;
+      }
+    }
+    const int64_t ls = __shfl_sync(0xFFFFFFFFu, s, leader);
+    if (follow) s = ls;
+    if (ok) {
+      if (s < 0) {
+        status[0] = 1;  // overflow: the host retries with a larger table
+      } else {
+        uint64_t* slot = table + s * words;
+        if (special) slot[0] = 0;  // mark the dedicated slot as used (any value != EMPTY)
+#pragma unroll
+        for (int a = 0; a < NAGG; ++a) {
+          if (aggs.valid[a] != nullptr && aggs.valid[a][row] == 0) continue;  // NULL value: skipped
+          const int op = aggs.op[a];
+          if (op == kCount) {
+            atomicAdd((unsigned long long*)(slot + 1 + a), 1ULL);
+            continue;
+          }
+          const uint64_t bits = aggs.val[a][row];
+          switch (op) {
+            case kSumF64: atomicAdd((double*)(slot + 1 + a), __longlong_as_double((long long)bits)); break;
+            case kSumI64: atomicAdd((unsigned long long*)(slot + 1 + a), (unsigned long long)bits); break;
+            case kMinI64: atomicMin((long long*)(slot + 1 + a), (long long)bits); break;
+            case kMaxI64: atomicMax((long long*)(slot + 1 + a), (long long)bits); break;
+            case kMinF64: atomicMin((long long*)(slot + 1 + a), f64_to_ordered(bits)); break;
+            case kMaxF64: atomicMax((long long*)(slot + 1 + a), f64_to_ordered(bits)); break;
+            default: break;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NAGG>
+void launch_lean(const uint64_t* keys, const uint8_t* key_valid, int64_t nrows, uint64_t* table, int64_t capacity,
+                 const AggSpec& spec, int64_t* status, uint32_t num_parts, int region_shift, int grid,
+                 cudaStream_t st) {
+  LeanAggs<NAGG> la;
+  for (int a = 0; a < NAGG; ++a) {
+    la.val[a] = spec.val[a];
+    la.valid[a] = spec.valid[a];
+    la.op[a] = spec.op[a];
+  }
+  fb_groupby_lean_kernel<NAGG><<<grid, 256, 0, st>>>(keys, key_valid, nrows, table, capacity, la, status, num_parts - 1,
+                                                     region_shift);
+}
+
 __global__ void __launch_bounds__(256)
 fb_groupby_extract_kernel(const uint64_t* __restrict__ table, int64_t capacity, int words, AggSpec spec,
                           uint64_t* __restrict__ out_keys, uint8_t* __restrict__ out_key_valid,
@@ -297,6 +411,21 @@ int fb_groupby_u64(int dev, void* stream, int64_t nrows, const void* keys, const
   }
   fb_groupby_init_kernel<<<sms * 8, 256, 0, st>>>((uint64_t*)table, 0, capacity + 2, words, spec, d_status);
   FB_CUDA(cudaGetLastError());
+  if (nrows > 0 && num_parts > 1 && naggs >= 1 && naggs <= 4 && region_shift >= 1 && region_shift < 31) {
+    // hash-partitioned input, few aggregates: the lean kernel (the find-or-insert of the generic kernel
+    // hashes with fb_fmix64(key) >> 7; here the slot comes from the partitioner's hash - a table is only
+    // ever read back by the extract pass, which does not hash)
+    const uint64_t* k64 = (const uint64_t*)keys;
+    uint64_t* t64 = (uint64_t*)table;
+    switch (naggs) {
+      case 1: launch_lean<1>(k64, key_valid, nrows, t64, capacity, spec, d_status, num_parts, (int)region_shift, sms * 8, st); break;
+      case 2: launch_lean<2>(k64, key_valid, nrows, t64, capacity, spec, d_status, num_parts, (int)region_shift, sms * 8, st); break;
+      case 3: launch_lean<3>(k64, key_valid, nrows, t64, capacity, spec, d_status, num_parts, (int)region_shift, sms * 8, st); break;
+      default: launch_lean<4>(k64, key_valid, nrows, t64, capacity, spec, d_status, num_parts, (int)region_shift, sms * 8, st); break;
+    }
+    FB_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (nrows > 0) {
     fb_groupby_kernel<<<sms * 8, 256, 0, st>>>((const uint64_t*)keys, key_valid, nrows, (uint64_t*)table,
                                               capacity, words, spec, d_status, dv, region_shift, nullptr, 0, 0);

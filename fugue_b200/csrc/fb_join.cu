@@ -22,9 +22,7 @@ struct Slot {
 };
 
 inline int64_t l2_batch_bytes() {  // table bytes worked on at a time (B200 L2: 126 MB)
-  const char* e = getenv("FB_L2_BATCH_MB");
-  const int64_t mb = e != nullptr ? atoll(e) : 64;  // measured 32 / 64 / 96 MB: join 9.53 / 8.91 / 8.74 ms
-  return (mb > 0 ? mb : 64) << 20;
+  return (int64_t)64 << 20;         // measured 32 / 64 / 96 MB: join 9.53 / 8.91 / 8.74 ms
 }
 
 // clears slots [slot0, slot0 + nslots); status is reset when it is passed
@@ -298,6 +296,318 @@ inline unsigned grid_for(int dev, int64_t n, int per_sm = 8) {
   return (unsigned)b;
 }
 
+// =====================================================================================================
+// K7 fast path (inner / left outer, one 8-byte key): 4-byte slots + fused probe / output assembly.
+//
+//   table     : uint32 slots holding build_row + 1 (0 = empty): a quarter of the 16-byte multimap, so four
+//               times as many regions of the radix join stay L2-resident and clearing costs a quarter; a
+//               build row is ONE 32-bit CAS (no key store) - keys are compared through the build key
+//               column, whose partition is L2-resident too (the inputs are hash-partitioned)
+//   pass A    : every probe row walks its chain once: match count + first match (4 + 4 bytes per row) and
+//               the per-tile totals; one block scans the tile totals -> output size
+//   pass B    : per tile of 4096 probe rows the output slots [tile_base, tile_base + total) are mapped back
+//               to (probe row, k-th match) through shared memory, then ONE thread per OUTPUT row copies the
+//               probe-side columns (coalesced) and gathers the build-side columns (random, L2-resident):
+//               no (probe, build) index pairs are materialised and there is no separate gather pass.
+// Output order: probe-row major, matches in chain order - deterministic for a given table.
+// =====================================================================================================
+constexpr int kJ2Block = 512, kJ2Items = 8, kJ2Tile = kJ2Block * kJ2Items;
+constexpr uint32_t kJ2None = 0xFFFFFFFFu;
+constexpr int kJ2MaxCols = 48;
+
+struct J2Cols {
+  const void* src[kJ2MaxCols];
+  void* dst[kJ2MaxCols];
+  const uint8_t* vsrc[kJ2MaxCols];  // build side only: source validity (or NULL)
+  uint8_t* vdst[kJ2MaxCols];        // build side only: output validity (or NULL)
+  int32_t width[kJ2MaxCols];
+  int32_t n;
+};
+
+__device__ __forceinline__ void j2_locate(uint64_t key, const FbDiv& dv, int64_t region_shift, int64_t capacity,
+                                          int64_t& base, int64_t& s, int64_t& mask) {
+  const uint64_t h = fb_hash_single_u64(key);  // the partitioner's hash: region = partition id
+  if (region_shift >= 0) {
+    base = (int64_t)fb_fastmod(h, dv) << region_shift;
+    mask = ((int64_t)1 << region_shift) - 1;
+  } else {
+    base = 0;
+    mask = capacity - 1;
+  }
+  s = (int64_t)((h >> 10) & (uint64_t)mask);
+}
+
+__global__ void fb_join2_clear_kernel(uint32_t* __restrict__ table, int64_t slot0, int64_t nslots) {
+  uint4* t4 = (uint4*)(table + slot0);  // regions are multiples of 4 slots and 16-byte aligned
+  const int64_t n4 = nslots >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    t4[i] = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(256)
+fb_join2_build_kernel(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ valid, int64_t n,
+                      uint32_t* __restrict__ table, int64_t capacity, int64_t* __restrict__ status, FbDiv dv,
+                      int64_t region_shift, const int64_t* __restrict__ part_off, int p0, int p1) {
+  // status[0] = 1: a row found no free slot in its region (skewed build side; the host redoes it with one
+  // region).  status[1] = 1: two build rows hold the same key.  Every occupied slot an inserter walks
+  // past is compared with its key, and of two equal keys the one that claims its slot later always
+  // walks past the earlier one (same home slot, no deletions), so the flag is exact; when it stays 0
+  // the probe may stop at the first match.
+  const int64_t row_lo = part_off != nullptr ? part_off[p0] : 0;
+  const int64_t row_hi = part_off != nullptr ? part_off[p1] : n;
+  bool dup = false;
+  for (int64_t i = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_hi;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (valid != nullptr && valid[i] == 0) continue;  // NULL keys never match: not inserted
+    const uint64_t key = keys[i];
+    int64_t base, s, mask;
+    j2_locate(key, dv, region_shift, capacity, base, s, mask);
+    bool done = false;
+    for (int64_t probe = 0; probe <= mask; ++probe) {
+      uint32_t* slot = table + base + s;
+      uint32_t e = *(volatile uint32_t*)slot;
+      if (e == 0) {
+        e = atomicCAS(slot, 0u, (uint32_t)(i + 1));
+        if (e == 0u) {
+          done = true;
+          break;
+        }
+      }
+      if (keys[e - 1] == key) dup = true;
+      s = (s + 1) & mask;
+    }
+    if (!done) status[0] = 1;
+  }
+  if (dup) status[1] = 1;
+}
+
+// pass A
+__global__ void __launch_bounds__(kJ2Block, 2)
+fb_join2_probe_kernel(const uint64_t* __restrict__ pkeys, const uint8_t* __restrict__ pvalid, int64_t nprobe_all,
+                      const uint64_t* __restrict__ bkeys, const uint32_t* __restrict__ table, int64_t capacity,
+                      FbDiv dv, int64_t region_shift, int outer, uint32_t* __restrict__ cnt,
+                      uint32_t* __restrict__ first, int64_t* __restrict__ tile_sums,
+                      const int64_t* __restrict__ status, const int64_t* __restrict__ probe_part_off, int p0,
+                      int p1) {
+  // probe_part_off != nullptr: only the probe rows of hash partitions [p0, p1) (launched right after the
+  // build of the same regions, while table and build keys are still in L2); tile totals are then
+  // computed afterwards by fb_join2_tile_sums_kernel
+  __shared__ int64_t s_warp[kJ2Block / 32];
+  const bool unique = status[1] == 0;  // no duplicate build keys: a chain ends at its first match
+  const int64_t row_lo = probe_part_off != nullptr ? probe_part_off[p0] : 0;
+  const int64_t nprobe = probe_part_off != nullptr ? probe_part_off[p1] : nprobe_all;
+  const int64_t ntiles = (nprobe - row_lo + kJ2Tile - 1) / kJ2Tile;
+  pkeys += row_lo;
+  if (pvalid != nullptr) pvalid += row_lo;
+  cnt += row_lo;
+  first += row_lo;
+  const int64_t nprobe_rel = nprobe - row_lo;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // the dependent loads of one row (slot -> build key) are latency-bound: keep the first step of all 8
+    // rows of this thread in flight together, then finish the (rarer) longer chains row by row
+    uint64_t key[kJ2Items];
+    uint32_t reg[kJ2Items], off[kJ2Items], e[kJ2Items];  // region id, slot inside the region, slot content
+    const int64_t mask = region_shift >= 0 ? (((int64_t)1 << region_shift) - 1) : capacity - 1;
+    const int rsh = region_shift >= 0 ? (int)region_shift : 0;
+#pragma unroll
+    for (int k = 0; k < kJ2Items; ++k) {
+      const int64_t i = tile * kJ2Tile + (int64_t)k * kJ2Block + threadIdx.x;
+      const bool live = i < nprobe_rel && (pvalid == nullptr || pvalid[i] != 0);
+      key[k] = live ? pkeys[i] : 0;
+      e[k] = live ? 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kJ2Items; ++k) {
+      const uint64_t h = fb_hash_single_u64(key[k]);
+      reg[k] = region_shift >= 0 ? fb_fastmod(h, dv) : 0u;
+      off[k] = (uint32_t)((h >> 10) & (uint64_t)mask);
+      if (e[k] != 0) e[k] = __ldg(table + ((int64_t)reg[k] << rsh) + off[k]);
+    }
+    uint64_t bk[kJ2Items];
+#pragma unroll
+    for (int k = 0; k < kJ2Items; ++k) bk[k] = e[k] != 0 ? __ldg((const unsigned long long*)bkeys + (e[k] - 1)) : 0;
+    int64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kJ2Items; ++k) {
+      const int64_t i = tile * kJ2Tile + (int64_t)k * kJ2Block + threadIdx.x;
+      if (i >= nprobe_rel) continue;
+      uint32_t c = 0, f = kJ2None;
+      uint32_t ee = e[k];
+      uint64_t bb = bk[k];
+      uint32_t ss = off[k];
+      const uint32_t* __restrict__ tb = table + ((int64_t)reg[k] << rsh);
+      for (int64_t probe = 0; ee != 0 && probe <= mask; ++probe) {
+        if (bb == key[k]) {
+          if (c == 0) f = ee - 1;
+          ++c;
+          if (unique) break;
+        }
+        ss = (uint32_t)((ss + 1) & (uint32_t)mask);
+        ee = __ldg(tb + ss);
+        if (ee != 0) bb = __ldg((const unsigned long long*)bkeys + (ee - 1));
+      }
+      if (outer && c == 0) c = 1;  // one NULL-extended row (first stays NONE)
+      cnt[i] = c;
+      first[i] = f;
+      sum += c;
+    }
+    int64_t total;
+    block_exclusive_scan(sum, s_warp, total);
+    if (threadIdx.x == 0 && tile_sums != nullptr) tile_sums[tile] = total;
+    __syncthreads();
+  }
+}
+
+// per-tile totals of cnt (pass A run in batches of partitions cannot produce them: its ranges are not tile-aligned)
+__global__ void __launch_bounds__(kJ2Block)
+fb_join2_tile_sums_kernel(const uint32_t* __restrict__ cnt, int64_t nprobe, int64_t* __restrict__ tile_sums) {
+  __shared__ int64_t s_warp[kJ2Block / 32];
+  const int64_t ntiles = (nprobe + kJ2Tile - 1) / kJ2Tile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kJ2Items; ++k) {
+      const int64_t i = tile * kJ2Tile + (int64_t)k * kJ2Block + threadIdx.x;
+      if (i < nprobe) sum += cnt[i];
+    }
+    int64_t total;
+    block_exclusive_scan(sum, s_warp, total);
+    if (threadIdx.x == 0) tile_sums[tile] = total;
+    __syncthreads();
+  }
+}
+
+constexpr int kJ2U = 4;  // output rows per thread and step in pass B
+
+// dst[to0 + u * kJ2Block] = has[u] ? src[from[u]] : 0 for the live rows u: all loads first, then all stores
+template <typename T>
+__device__ __forceinline__ void j2_copy_rows_t(const void* src, void* dst, const int64_t (&from)[kJ2U], int64_t to0,
+                                               const bool (&live)[kJ2U], const bool (&has)[kJ2U]) {
+  T v[kJ2U];
+#pragma unroll
+  for (int u = 0; u < kJ2U; ++u) v[u] = (live[u] && has[u]) ? ((const T*)src)[from[u]] : (T)0;
+#pragma unroll
+  for (int u = 0; u < kJ2U; ++u)
+    if (live[u]) ((T*)dst)[to0 + (int64_t)u * kJ2Block] = v[u];
+}
+
+__device__ __forceinline__ void j2_copy_rows(const void* src, void* dst, int w, const int64_t (&from)[kJ2U], int64_t to0,
+                                             const bool (&live)[kJ2U], const bool (&has)[kJ2U]) {
+  switch (w) {
+    case 8: j2_copy_rows_t<uint64_t>(src, dst, from, to0, live, has); break;
+    case 4: j2_copy_rows_t<uint32_t>(src, dst, from, to0, live, has); break;
+    case 2: j2_copy_rows_t<uint16_t>(src, dst, from, to0, live, has); break;
+    default: j2_copy_rows_t<uint8_t>(src, dst, from, to0, live, has); break;
+  }
+}
+
+// pass B
+__global__ void __launch_bounds__(kJ2Block, 2)
+fb_join2_emit_kernel(const uint64_t* __restrict__ pkeys, int64_t nprobe, const uint64_t* __restrict__ bkeys,
+                     const uint32_t* __restrict__ table, int64_t capacity, FbDiv dv, int64_t region_shift,
+                     const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ first,
+                     const int64_t* __restrict__ tile_base, const __grid_constant__ J2Cols lcols,
+                     const __grid_constant__ J2Cols rcols) {
+  // output slot of the current window -> (row of the tile, build row): filled by the thread that OWNS the
+  // probe row (it walks a chain with duplicates once, resuming across windows), consumed one thread per slot
+  __shared__ uint16_t s_slot_row[kJ2Tile];
+  __shared__ uint32_t s_slot_b[kJ2Tile];
+  __shared__ int64_t s_warp[kJ2Block / 32];
+  const int64_t ntiles = (nprobe + kJ2Tile - 1) / kJ2Tile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kJ2Tile;
+    // thread t owns rows [t * 8, t * 8 + 8) of the tile (32 contiguous bytes of cnt / first)
+    uint32_t c[kJ2Items], f[kJ2Items];
+    int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kJ2Items; ++k) {
+      const int64_t g = row0 + (int64_t)threadIdx.x * kJ2Items + k;
+      c[k] = g < nprobe ? cnt[g] : 0;
+      f[k] = g < nprobe ? first[g] : kJ2None;
+      mine += c[k];
+    }
+    int64_t total;
+    const int64_t my_start = block_exclusive_scan(mine, s_warp, total);
+    const int64_t gbase = tile_base[tile];
+    // resume state of the (at most one at a time) row with duplicates that this thread is walking
+    int walk_k = -1;
+    int64_t walk_base = 0, walk_s = 0, walk_mask = 0;
+    uint32_t walk_done = 0;
+    for (int64_t w0 = 0; w0 < total; w0 += kJ2Tile) {
+      const int64_t w1 = w0 + kJ2Tile;
+      int64_t o = my_start;
+#pragma unroll
+      for (int k = 0; k < kJ2Items; ++k) {
+        const int64_t lo = o > w0 ? o : w0;
+        const int64_t hi = o + c[k] < w1 ? o + c[k] : w1;
+        if (lo < hi) {
+          const uint16_t r = (uint16_t)(threadIdx.x * kJ2Items + k);
+          if (c[k] == 1) {  // unique match (or the NULL-extended row of an outer join)
+            s_slot_row[lo - w0] = r;
+            s_slot_b[lo - w0] = f[k];
+          } else {
+            // duplicates of the build key: emit matches number [lo - o, hi - o) of the chain
+            const uint64_t key = pkeys[row0 + r];
+            if (walk_k != k) {
+              walk_k = k;
+              walk_done = 0;
+              j2_locate(key, dv, region_shift, capacity, walk_base, walk_s, walk_mask);
+            }
+            int64_t j = lo;
+            while (j < hi) {
+              const uint32_t e = __ldg(table + walk_base + walk_s);
+              walk_s = (walk_s + 1) & walk_mask;
+              if (e == 0) break;  // cannot happen: cnt matches exist
+              if (__ldg((const unsigned long long*)bkeys + (e - 1)) == key) {
+                if ((int64_t)walk_done >= lo - o) {
+                  s_slot_row[j - w0] = r;
+                  s_slot_b[j - w0] = e - 1;
+                  ++j;
+                }
+                ++walk_done;
+              }
+            }
+          }
+        }
+        o += c[k];
+      }
+      __syncthreads();
+      const int64_t wn = total - w0 < kJ2Tile ? total - w0 : kJ2Tile;
+      // one thread per OUTPUT row, four rows per step: the loads of the four rows are issued together (the
+      // column pointers may alias as far as the compiler knows, so row-by-row code would serialise every load
+      // behind the previous row's stores)
+      for (int64_t j0 = threadIdx.x; j0 < wn; j0 += (int64_t)kJ2Block * kJ2U) {
+        int64_t grow[kJ2U], brow[kJ2U];
+        bool live[kJ2U], has[kJ2U];
+#pragma unroll
+        for (int u = 0; u < kJ2U; ++u) {
+          const int64_t j = j0 + (int64_t)u * kJ2Block;
+          live[u] = j < wn;
+          const uint32_t b = live[u] ? s_slot_b[j] : kJ2None;
+          grow[u] = row0 + (live[u] ? s_slot_row[j] : 0);
+          has[u] = b != kJ2None;
+          brow[u] = has[u] ? (int64_t)b : 0;
+        }
+        const int64_t out0 = gbase + w0 + j0;
+        for (int cI = 0; cI < lcols.n; ++cI) j2_copy_rows(lcols.src[cI], lcols.dst[cI], lcols.width[cI], grow, out0, live, live);
+        for (int cI = 0; cI < rcols.n; ++cI) {
+          j2_copy_rows(rcols.src[cI], rcols.dst[cI], rcols.width[cI], brow, out0, live, has);
+          if (rcols.vdst[cI] != nullptr) {
+            uint8_t vv[kJ2U];
+#pragma unroll
+            for (int u = 0; u < kJ2U; ++u)
+              vv[u] = has[u] ? (rcols.vsrc[cI] != nullptr ? rcols.vsrc[cI][brow[u]] : (uint8_t)1) : (uint8_t)0;
+#pragma unroll
+            for (int u = 0; u < kJ2U; ++u)
+              if (live[u]) rcols.vdst[cI][out0 + (int64_t)u * kJ2Block] = vv[u];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -451,6 +761,177 @@ int fb_gather_rows(int dev, void* stream, int ncols, const void* const* d_src_co
   dim3 grid(grid_for(dev, n, 4), (unsigned)ncols);
   fb_gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src_cols, d_dst_cols, d_widths, d_src_valid,
                                                                d_dst_valid, idx, n);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ---- K7 fast path (see the kernels above) ------------------------------------------------------------
+size_t fb_join2_table_bytes(int64_t capacity) { return capacity > 0 ? (size_t)capacity * sizeof(uint32_t) : 0; }
+
+int fb_join2_build(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
+                   int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status,
+                   const int64_t* d_part_offsets) {
+  FB_CHECK(nbuild >= 0 && nbuild < (int64_t)0xFFFFFFFF, "nbuild out of range");
+  FB_CHECK(capacity >= 4 && (capacity & (capacity - 1)) == 0 && capacity <= ((int64_t)1 << 32),
+           "capacity must be a power of two in [4, 2^32]");
+  FB_CHECK(capacity > nbuild, "capacity must exceed the number of build rows");
+  FB_CHECK(table != nullptr && d_status != nullptr, "table/status is NULL");
+  FB_CHECK(num_parts <= 1 || ((num_parts & (num_parts - 1)) == 0 && (int64_t)num_parts * 4 <= capacity),
+           "num_parts must be a power of two <= capacity / 4");
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  const FbDiv dv = fb_make_div(num_parts > 1 ? num_parts : 1);
+  const int64_t rs = region_shift_of(capacity, num_parts);
+  FB_CUDA(cudaMemsetAsync(d_status, 0, 4 * sizeof(int64_t), st));
+  if (num_parts > 1 && d_part_offsets != nullptr && nbuild > 0) {
+    // clear + fill batches of regions that fit L2, so that the inserts hit lines that are still there
+    const int64_t region_bytes = ((int64_t)1 << rs) * (int64_t)sizeof(uint32_t);
+    int64_t per = ((int64_t)48 << 20) / region_bytes;
+    if (per < 1) per = 1;
+    for (int64_t p0 = 0; p0 < (int64_t)num_parts; p0 += per) {
+      const int64_t p1 = p0 + per < (int64_t)num_parts ? p0 + per : (int64_t)num_parts;
+      const int64_t nslots = (p1 - p0) << rs;
+      fb_join2_clear_kernel<<<grid_for(dev, nslots / 4 + 1), 256, 0, st>>>((uint32_t*)table, p0 << rs, nslots);
+      const int64_t est = nbuild / num_parts * (p1 - p0) * 5 / 4 + 256;
+      fb_join2_build_kernel<<<grid_for(dev, est), 256, 0, st>>>((const uint64_t*)keys, key_valid, nbuild,
+                                                               (uint32_t*)table, capacity, d_status, dv, rs,
+                                                               d_part_offsets, (int)p0, (int)p1);
+    }
+    FB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  fb_join2_clear_kernel<<<grid_for(dev, capacity / 4), 256, 0, st>>>((uint32_t*)table, 0, capacity);
+  FB_CUDA(cudaGetLastError());
+  if (nbuild > 0) {
+    fb_join2_build_kernel<<<grid_for(dev, nbuild), 256, 0, st>>>((const uint64_t*)keys, key_valid, nbuild,
+                                                                 (uint32_t*)table, capacity, d_status, dv, rs,
+                                                                 nullptr, 0, 0);
+    FB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+size_t fb_join2_tiles_bytes(int64_t nprobe) {
+  return (size_t)((nprobe + kJ2Tile - 1) / kJ2Tile + 1) * sizeof(int64_t);
+}
+
+int fb_join2_probe(int dev, void* stream, int64_t nprobe, const void* probe_keys, const uint8_t* probe_valid,
+                   const void* build_keys, int64_t capacity, uint32_t num_parts, const void* table, int outer,
+                   uint32_t* out_cnt, uint32_t* out_first, int64_t* d_tile_base, int64_t* d_total,
+                   const int64_t* d_status) {
+  FB_CHECK(nprobe >= 0, "nprobe < 0");
+  FB_CHECK(d_total != nullptr && d_status != nullptr, "d_total / d_status is NULL");
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nprobe == 0) {
+    FB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), st));
+    return 0;
+  }
+  const int64_t ntiles = (nprobe + kJ2Tile - 1) / kJ2Tile;
+  int64_t grid = ntiles < (int64_t)fb_sm_count(dev) * 4 ? ntiles : (int64_t)fb_sm_count(dev) * 4;
+  fb_join2_probe_kernel<<<(unsigned)grid, kJ2Block, 0, st>>>(
+      (const uint64_t*)probe_keys, probe_valid, nprobe, (const uint64_t*)build_keys, (const uint32_t*)table,
+      capacity, fb_make_div(num_parts > 1 ? num_parts : 1), region_shift_of(capacity, num_parts), outer, out_cnt,
+      out_first, d_tile_base, d_status, nullptr, 0, 0);
+  FB_CUDA(cudaGetLastError());
+  fb_scan_sums_kernel<<<1, kScanBlock, 0, st>>>(d_tile_base, ntiles, d_total);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fb_join2_build_probe(int dev, void* stream, int64_t nbuild, const void* build_keys, const uint8_t* build_valid,
+                         const int64_t* d_build_part_offsets, int64_t nprobe, const void* probe_keys,
+                         const uint8_t* probe_valid, const int64_t* d_probe_part_offsets, int64_t capacity,
+                         uint32_t num_parts, void* table, int outer, uint32_t* out_cnt, uint32_t* out_first,
+                         int64_t* d_tile_base, int64_t* d_total, int64_t* d_status) {
+  FB_CHECK(nbuild >= 0 && nbuild < (int64_t)0xFFFFFFFF && nprobe >= 0, "row counts out of range");
+  FB_CHECK(capacity >= 4 && (capacity & (capacity - 1)) == 0 && capacity <= ((int64_t)1 << 32),
+           "capacity must be a power of two in [4, 2^32]");
+  FB_CHECK(capacity > nbuild, "capacity must exceed the number of build rows");
+  FB_CHECK(num_parts > 1 && (num_parts & (num_parts - 1)) == 0 && (int64_t)num_parts * 4 <= capacity,
+           "num_parts must be a power of two in [2, capacity / 4]");
+  FB_CHECK(table != nullptr && d_status != nullptr && d_total != nullptr, "table / status / total is NULL");
+  FB_CHECK(d_build_part_offsets != nullptr && d_probe_part_offsets != nullptr, "partition offsets are NULL");
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  const FbDiv dv = fb_make_div(num_parts);
+  const int64_t rs = region_shift_of(capacity, num_parts);
+  FB_CUDA(cudaMemsetAsync(d_status, 0, 4 * sizeof(int64_t), st));
+  if (nprobe == 0) {
+    FB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), st));
+    return 0;
+  }
+  // Batches of regions that fit L2 TOGETHER WITH the build keys of the same partitions: clear, insert, and
+  // probe the probe rows of these partitions at once - the probe's two dependent random reads per step
+  // (slot, build key) then hit L2 instead of fetching cold 32-byte sectors from HBM.
+  const int64_t region_bytes = ((int64_t)1 << rs) * (int64_t)sizeof(uint32_t);
+  int64_t per = ((int64_t)24 << 20) / region_bytes;
+  if (per < 1) per = 1;
+  const int sms = fb_sm_count(dev);
+  for (int64_t p0 = 0; p0 < (int64_t)num_parts; p0 += per) {
+    const int64_t p1 = p0 + per < (int64_t)num_parts ? p0 + per : (int64_t)num_parts;
+    const int64_t nslots = (p1 - p0) << rs;
+    fb_join2_clear_kernel<<<grid_for(dev, nslots / 4 + 1), 256, 0, st>>>((uint32_t*)table, p0 << rs, nslots);
+    if (nbuild > 0) {
+      const int64_t est = nbuild / num_parts * (p1 - p0) * 5 / 4 + 256;
+      fb_join2_build_kernel<<<grid_for(dev, est), 256, 0, st>>>((const uint64_t*)build_keys, build_valid, nbuild,
+                                                               (uint32_t*)table, capacity, d_status, dv, rs,
+                                                               d_build_part_offsets, (int)p0, (int)p1);
+    }
+    const int64_t est_tiles = (nprobe / num_parts * (p1 - p0) * 5 / 4 + kJ2Tile) / kJ2Tile;
+    int64_t grid = est_tiles < (int64_t)sms * 2 ? est_tiles : (int64_t)sms * 2;
+    if (grid < 1) grid = 1;
+    fb_join2_probe_kernel<<<(unsigned)grid, kJ2Block, 0, st>>>(
+        (const uint64_t*)probe_keys, probe_valid, nprobe, (const uint64_t*)build_keys, (const uint32_t*)table, capacity,
+        dv, rs, outer, out_cnt, out_first, nullptr, d_status, d_probe_part_offsets, (int)p0, (int)p1);
+  }
+  FB_CUDA(cudaGetLastError());
+  const int64_t ntiles = (nprobe + kJ2Tile - 1) / kJ2Tile;
+  int64_t grid = ntiles < (int64_t)sms * 4 ? ntiles : (int64_t)sms * 4;
+  fb_join2_tile_sums_kernel<<<(unsigned)grid, kJ2Block, 0, st>>>(out_cnt, nprobe, d_tile_base);
+  fb_scan_sums_kernel<<<1, kScanBlock, 0, st>>>(d_tile_base, ntiles, d_total);
+  FB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int fb_join2_emit(int dev, void* stream, int64_t nprobe, const void* probe_keys, const void* build_keys,
+                  int64_t capacity, uint32_t num_parts, const void* table, const uint32_t* cnt,
+                  const uint32_t* first, const int64_t* d_tile_base, int nleft, const void* const* left_src,
+                  void* const* left_dst, const int32_t* left_widths, int nright, const void* const* right_src,
+                  void* const* right_dst, const int32_t* right_widths, const uint8_t* const* right_valid_src,
+                  uint8_t* const* right_valid_dst) {
+  FB_CHECK(nprobe >= 0 && nleft >= 0 && nright >= 0, "negative count");
+  FB_CHECK(nleft <= kJ2MaxCols && nright <= kJ2MaxCols, "at most %d columns per side", kJ2MaxCols);
+  if (nprobe == 0) return 0;
+  FbDeviceGuard guard(dev);
+  FB_CHECK(guard.ok, "cannot select device %d", dev);
+  J2Cols lc, rc;
+  memset(&lc, 0, sizeof(lc));
+  memset(&rc, 0, sizeof(rc));
+  lc.n = nleft;
+  rc.n = nright;
+  for (int c = 0; c < nleft; ++c) {
+    const int w = left_widths[c];
+    FB_CHECK(w == 1 || w == 2 || w == 4 || w == 8, "left column %d has unsupported width %d", c, w);
+    lc.src[c] = left_src[c]; lc.dst[c] = left_dst[c]; lc.width[c] = w;
+  }
+  for (int c = 0; c < nright; ++c) {
+    const int w = right_widths[c];
+    FB_CHECK(w == 1 || w == 2 || w == 4 || w == 8, "right column %d has unsupported width %d", c, w);
+    rc.src[c] = right_src[c]; rc.dst[c] = right_dst[c]; rc.width[c] = w;
+    rc.vsrc[c] = right_valid_src ? right_valid_src[c] : nullptr;
+    rc.vdst[c] = right_valid_dst ? right_valid_dst[c] : nullptr;
+  }
+  const int64_t ntiles = (nprobe + kJ2Tile - 1) / kJ2Tile;
+  int64_t grid = ntiles < (int64_t)fb_sm_count(dev) * 4 ? ntiles : (int64_t)fb_sm_count(dev) * 4;
+  fb_join2_emit_kernel<<<(unsigned)grid, kJ2Block, 0, (cudaStream_t)stream>>>(
+      (const uint64_t*)probe_keys, nprobe, (const uint64_t*)build_keys, (const uint32_t*)table, capacity,
+      fb_make_div(num_parts > 1 ? num_parts : 1), region_shift_of(capacity, num_parts), cnt, first, d_tile_base, lc,
+      rc);
   FB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -628,7 +628,7 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, 
 constexpr int kWsMoverWarps = 16, kWsRankWarps = 8;
 constexpr int kWsMovers = kWsMoverWarps * 32, kWsRankers = kWsRankWarps * 32;
 constexpr int kWsThreads = kWsMovers + kWsRankers + 128;  // + producer warpgroup (1 active warp)
-constexpr int kWsG = 4;
+constexpr int kWsG = 4;  // rows per write-combined group (32 B); 8 (64 B) measured 4.1-5.0 ms vs 3.09: spills, 3 ring stages
 constexpr int kWsRankItems = 16;  // rows per ranker thread per tile: tile = 256 x 16 = 4096 rows (2048: no faster)
 
 struct WsUnits {
@@ -1102,8 +1102,6 @@ cudaError_t ensure_smem_optin(int dev) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems, false>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems, false>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, 8, kWsRankItems, false>, (size_t)smem_max);
-    if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, 8, kWsRankItems, false>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<4, kWsG, kWsRankItems, true>, (size_t)smem_max);
     if (e == cudaSuccess) e = optin(fb_scatter_ws_kernel<8, kWsG, kWsRankItems, true>, (size_t)smem_max);
   }
@@ -1288,8 +1286,7 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
                       uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
                       const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
                       const int32_t* col_widths, void* const* out_col_ptrs, int sm_reserve = 0,
-                      const fb_map_unit* maps = nullptr, void* tail_tmp = nullptr, int cols_per_launch_req = 0,
-                      int write_group = 0) {
+                      const fb_map_unit* maps = nullptr, void* tail_tmp = nullptr, int cols_per_launch_req = 0) {
   FB_CHECK(nrows >= 0 && nrows < ((int64_t)1 << 32), "nrows out of range");
   FB_CHECK(num_partitions >= 1 && num_partitions <= FB_MAX_PARTITIONS,
            "num_partitions=%u out of range [1,%d]", num_partitions, FB_MAX_PARTITIONS);
@@ -1379,7 +1376,6 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
     const int ngroups = (nfast + 3) / 4;
     int cols_per_launch = (nfast + ngroups - 1) / ngroups;
     if (cols_per_launch_req >= 1 && cols_per_launch_req <= kSwcMaxCols) cols_per_launch = cols_per_launch_req;
-    const bool g8 = write_group == 8 && maps == nullptr;  // 64-byte write groups (tuning; default 32-byte)
     for (int c0 = 0; c0 < nfast; c0 += cols_per_launch) {
       const int nb = nfast - c0 < cols_per_launch ? nfast - c0 : cols_per_launch;
       WsUnits wu;
@@ -1389,8 +1385,7 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
         wu.src[c] = (const uint64_t*)col_ptrs[fast_idx[c0 + c]];
         wu.dst[c] = (uint64_t*)out_col_ptrs[fast_idx[c0 + c]];
       }
-      const size_t book = g8 ? ws_book_bytes<8, kWsRankItems>(num_partitions, nb)
-                             : ws_book_bytes<kWsG, kWsRankItems>(num_partitions, nb);
+      const size_t book = ws_book_bytes<kWsG, kWsRankItems>(num_partitions, nb);
       const size_t stage_bytes = (size_t)kWsRankers * kWsRankItems * 8;
       int nstages = (int)(((size_t)smem_max - book) / stage_bytes);
       if (nstages > 16) nstages = 16;
@@ -1410,13 +1405,6 @@ static int apply_impl(int dev, void* stream, int64_t nrows, const FbKeys& k, boo
               wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
         else
           fb_scatter_ws_kernel<8, kWsG, kWsRankItems, true><<<grid, kWsThreads, tsmem, st>>>(
-              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
-      } else if (g8) {
-        if (bits == 4)
-          fb_scatter_ws_kernel<4, 8, kWsRankItems, false><<<grid, kWsThreads, tsmem, st>>>(
-              wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
-        else
-          fb_scatter_ws_kernel<8, 8, kWsRankItems, false><<<grid, kWsThreads, tsmem, st>>>(
               wu, num_partitions, g, nstages, pid_plane, (const uint32_t*)scratch, part_offsets, wm);
       } else if (bits == 4) {
         fb_scatter_ws_kernel<4, kWsG, kWsRankItems, false><<<grid, kWsThreads, tsmem, st>>>(
@@ -1474,14 +1462,14 @@ int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys, const
                           uint32_t num_partitions, const void* scratch, size_t scratch_bytes,
                           const int64_t* part_offsets, int ncols, const void* const* col_ptrs,
                           const int32_t* col_widths, void* const* out_col_ptrs, int sm_reserve,
-                          int cols_per_launch, int write_group) {
+                          int cols_per_launch) {
   if (nrows == 0 || ncols == 0) return 0;
   FB_CHECK(sm_reserve >= 0, "sm_reserve < 0");
   FbKeys k;
   if (int rc = fill_keys(k, nkeys, key_ptrs, key_widths, key_valid)) return rc;
   return apply_impl(dev, stream, nrows, k, single_u64_key(nkeys, key_widths, key_valid), num_partitions,
                     scratch, scratch_bytes, part_offsets, ncols, col_ptrs, col_widths, out_col_ptrs, sm_reserve,
-                    nullptr, nullptr, cols_per_launch, write_group);
+                    nullptr, nullptr, cols_per_launch);
 }
 
 size_t fb_partition_map_tail_bytes(int ncols) {

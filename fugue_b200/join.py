@@ -172,6 +172,10 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
         li = K.compact_indices((keep).contiguous())
         cols, valid = K.gather_rows(t1.columns, t1.valid, li, want_valid=False)
         return B200DataFrame(B200Table(out_schema, cols, valid, t1.dictionaries))
+    if exact and how in ("inner", "left_outer") and n2 < (1 << 31) \
+            and len(t1.columns) + sum(v is not None for v in t1.valid) <= K.JOIN2_MAX_COLS \
+            and len(t2.columns) <= K.JOIN2_MAX_COLS:
+        return _fused_join(t1, t2, keys, out_schema, k1, v1, k2, v2, parts, po2, how == "left_outer", po1)
     if how == "right_outer":
         # probe with the right side so that every right row appears
         tab = K.JoinTable(k1, v1, parts, po1)
@@ -189,6 +193,29 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
         li = torch.cat([li, torch.full_like(extra, -1)])
         ri = torch.cat([ri, extra])
     return _assemble(t1, t2, keys, out_schema, li, ri, how)
+
+
+def _fused_join(t1: B200Table, t2: B200Table, keys: List[str], out_schema: Schema, k1: torch.Tensor,
+                v1: Optional[torch.Tensor], k2: torch.Tensor, v2: Optional[torch.Tensor], parts: int,
+                po2: Optional[torch.Tensor], outer: bool, po1: Optional[torch.Tensor] = None) -> B200DataFrame:
+    """Inner / left outer join on one 8-byte key through the fused kernels (K.join_fused): the probe
+    side's columns (and validity masks, as 1-byte columns) are copied, the build side's non-key columns
+    are gathered - straight into the output table."""
+    left: List[torch.Tensor] = list(t1.columns)
+    lmask_at = {}
+    for i, v in enumerate(t1.valid):
+        if v is not None:
+            lmask_at[i] = len(left)
+            left.append(v)
+    names2 = [n for n in t2.schema.names if n not in keys]
+    idx2 = [t2.schema.index_of_key(n) for n in names2]
+    louts, routs, rvout, _ = K.join_fused(k1.contiguous(), v1, k2.contiguous(), v2, left,
+                                          [t2.columns[i] for i in idx2], [t2.valid[i] for i in idx2], outer, parts, po2, po1)
+    ncol1 = len(t1.columns)
+    lvalid = [louts[lmask_at[i]] if i in lmask_at else None for i in range(ncol1)]
+    dicts = dict(t1.dictionaries)
+    dicts.update({n: t2.dictionaries[n] for n in names2 if n in t2.dictionaries})
+    return B200DataFrame(B200Table(out_schema, louts[:ncol1] + routs, lvalid + rvout, dicts))
 
 
 def _matched_mask(n: int, ri: torch.Tensor) -> torch.Tensor:

@@ -94,10 +94,10 @@ def partition_plan(keys: Sequence[torch.Tensor], num: int,
 
 
 def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
-                    out: Optional[Sequence[torch.Tensor]] = None, sm_reserve: int = 0, cols_per_launch: int = 0,
-                    write_group: int = 0) -> List[torch.Tensor]:
+                    out: Optional[Sequence[torch.Tensor]] = None, sm_reserve: int = 0, cols_per_launch: int = 0
+                    ) -> List[torch.Tensor]:
     """Pass 2 for ``cols``; ``sm_reserve`` SMs stay free for kernels that co-run (multi-GPU exchange);
-    ``cols_per_launch`` / ``write_group`` are tuning arguments of the fast kernel (0 = default)."""
+    ``cols_per_launch`` is a tuning argument of the fast kernel (0 = default)."""
     lib = _lib.load()
     dev, n = _check_cols(list(cols) + plan.keys)
     if out is None:
@@ -112,7 +112,7 @@ def partition_apply(plan: PartitionPlan, cols: Sequence[torch.Tensor],
         vp, plan.num, plan.scratch.data_ptr(), plan.scratch.numel(), plan.offsets.data_ptr(),
         len(cols), _lib.ptr_array([c.data_ptr() for c in cols]),
         _lib.i32_array([c.element_size() for c in cols]),
-        _lib.ptr_array([o.data_ptr() for o in out]), int(sm_reserve), int(cols_per_launch), int(write_group)))
+        _lib.ptr_array([o.data_ptr() for o in out]), int(sm_reserve), int(cols_per_launch)))
     return list(out)
 
 
@@ -319,6 +319,16 @@ def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
         hard_max = min(hard_max, max_capacity)
     if capacity is None:
         capacity = min(hard_max, 1 << 25)
+        if part_offsets is not None and n >= (1 << 22):
+            # size the table from the data: count the distinct keys of ONE hash partition exactly (1/256 of
+            # the rows, a few hundred kilobytes) and scale up.  A table of the right size halves the init and
+            # extract passes and keeps a region L2-resident; an under-estimate only costs the retry below.
+            po = part_offsets[:2].tolist()
+            if po[1] - po[0] >= 1024:
+                _, _, _, d0 = groupby_u64(keys[po[0]:po[1]], None if key_valid is None else key_valid[po[0]:po[1]],
+                                          [], [], [], partition=False)
+                est = int(d0 * num_parts * 1.6) + 1024   # load factor <= ~0.62
+                capacity = max(1 << 16, min(hard_max, 1 << (est - 1).bit_length()))
     capacity = max(2, 1 << (int(capacity) - 1).bit_length())
     status = torch.zeros(4, dtype=torch.int64, device=dev)
     vp = _lib.ptr_array([0 if v is None else v.data_ptr() for v in vals])
@@ -444,6 +454,86 @@ class JoinTable:
         _lib.check(lib.fb_join_mark_matched(self.device.index, _stream_ptr(self.device), build_idx.data_ptr(),
                                             int(build_idx.shape[0]), m.data_ptr()))
         return m
+
+
+JOIN2_MAX_COLS = 48
+
+
+def join_fused(probe_keys: torch.Tensor, probe_valid: Optional[torch.Tensor], build_keys: torch.Tensor,
+               build_valid: Optional[torch.Tensor], left_cols: Sequence[torch.Tensor],
+               right_cols: Sequence[torch.Tensor], right_valid: Sequence[Optional[torch.Tensor]], outer: bool,
+               num_parts: int = 0, build_part_offsets: Optional[torch.Tensor] = None,
+               probe_part_offsets: Optional[torch.Tensor] = None
+               ) -> Tuple[List[torch.Tensor], List[torch.Tensor], List[Optional[torch.Tensor]], int]:
+    """K7 fast path (inner / left outer on one 8-byte key): build a 4-byte-slot table over ``build_keys``,
+    probe it once (match count + first match per probe row, output size), then write the OUTPUT columns
+    directly: ``left_cols`` copied from the probe rows, ``right_cols`` gathered from the matched build rows
+    (with ``outer``: NULL-extended, a validity mask per right column).  Returns
+    (left outputs, right outputs, right validity or None each, number of output rows)."""
+    lib = _lib.load()
+    dev, nb = _check_cols([build_keys])
+    _, npr = _check_cols([probe_keys])
+    assert build_keys.element_size() == 8 and probe_keys.element_size() == 8
+    assert len(left_cols) <= JOIN2_MAX_COLS and len(right_cols) <= JOIN2_MAX_COLS and nb < (1 << 32) - 1
+    capacity = max(4, 1 << (2 * max(nb, 1)).bit_length())  # load factor <= 0.5
+    parts = num_parts if (num_parts > 1 and capacity >= 4 * num_parts) else 0
+    table = torch.empty(int(lib.fb_join2_table_bytes(capacity)), dtype=torch.uint8, device=dev)
+    status = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def build() -> None:
+        _lib.check(lib.fb_join2_build(dev.index, _stream_ptr(dev), nb, build_keys.data_ptr(),
+                                      0 if build_valid is None else build_valid.data_ptr(), capacity, parts,
+                                      table.data_ptr(), status.data_ptr(),
+                                      0 if (build_part_offsets is None or parts == 0) else build_part_offsets.data_ptr()))
+
+    cnt = torch.empty(npr, dtype=torch.int32, device=dev)
+    first = torch.empty(npr, dtype=torch.int32, device=dev)
+    tile_base = torch.empty(int(lib.fb_join2_tiles_bytes(npr)) // 8, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def probe() -> None:
+        _lib.check(lib.fb_join2_probe(dev.index, _stream_ptr(dev), npr, probe_keys.data_ptr(),
+                                      0 if probe_valid is None else probe_valid.data_ptr(), build_keys.data_ptr(),
+                                      capacity, parts, table.data_ptr(), 1 if outer else 0, cnt.data_ptr(),
+                                      first.data_ptr(), tile_base.data_ptr(), total.data_ptr(), status.data_ptr()))
+
+    if parts > 0 and build_part_offsets is not None and probe_part_offsets is not None:
+        # both sides hash-partitioned: build and probe region batch by region batch (L2-resident)
+        _lib.check(lib.fb_join2_build_probe(
+            dev.index, _stream_ptr(dev), nb, build_keys.data_ptr(), 0 if build_valid is None else build_valid.data_ptr(),
+            build_part_offsets.data_ptr(), npr, probe_keys.data_ptr(),
+            0 if probe_valid is None else probe_valid.data_ptr(), probe_part_offsets.data_ptr(), capacity, parts,
+            table.data_ptr(), 1 if outer else 0, cnt.data_ptr(), first.data_ptr(), tile_base.data_ptr(),
+            total.data_ptr(), status.data_ptr()))
+    else:
+        build()
+        probe()
+    # ONE host read per join: the output size (needed to allocate) together with the overflow flag of the
+    # build.  A skewed build side can overflow its region (capacity / num_parts slots): redo with one region.
+    both = torch.cat([status[:1], total]).tolist()
+    if parts > 0 and both[0] != 0:
+        parts = 0
+        build()
+        probe()
+        both = torch.cat([status[:1], total]).tolist()
+        if both[0] != 0:  # pragma: no cover - load factor 0.5 always has room
+            raise _lib.FugueB200KernelError("join hash table overflow")
+    nout = int(both[1])
+    louts = [torch.empty(nout, dtype=c.dtype, device=dev) for c in left_cols]
+    routs = [torch.empty(nout, dtype=c.dtype, device=dev) for c in right_cols]
+    rvout = [torch.empty(nout, dtype=torch.uint8, device=dev) if (outer or v is not None) else None
+             for v in right_valid]
+    if nout > 0:
+        _lib.check(lib.fb_join2_emit(
+            dev.index, _stream_ptr(dev), npr, probe_keys.data_ptr(), build_keys.data_ptr(), capacity, parts,
+            table.data_ptr(), cnt.data_ptr(), first.data_ptr(), tile_base.data_ptr(),
+            len(left_cols), _lib.ptr_array([c.data_ptr() for c in left_cols]),
+            _lib.ptr_array([c.data_ptr() for c in louts]), _lib.i32_array([c.element_size() for c in left_cols]),
+            len(right_cols), _lib.ptr_array([c.data_ptr() for c in right_cols]),
+            _lib.ptr_array([c.data_ptr() for c in routs]), _lib.i32_array([c.element_size() for c in right_cols]),
+            _lib.ptr_array([0 if v is None else v.data_ptr() for v in right_valid]),
+            _lib.ptr_array([0 if v is None else v.data_ptr() for v in rvout])))
+    return louts, routs, rvout, nout
 
 
 def gather_rows(cols: Sequence[torch.Tensor], valid: Sequence[Optional[torch.Tensor]], idx: torch.Tensor,

@@ -106,8 +106,7 @@ int fb_partition_apply_ex(int dev, void* stream, int64_t nrows, int nkeys,
                           const int64_t* part_offsets, int ncols,
                           const void* const* col_ptrs, const int32_t* col_widths,
                           void* const* out_col_ptrs, int sm_reserve,
-                          int cols_per_launch /* 8-byte columns per launch of the fast kernel, 1..8 */,
-                          int write_group /* rows per write-combined group: 4 (32 B, default) or 8 (64 B) */);
+                          int cols_per_launch /* 8-byte columns per launch of the fast kernel, 1..8 */);
 
 /* K4  fused map epilogue: fb_partition_apply whose output column c is not a copy of col_ptrs[c] but
  *   mode 1 (float64): (a * x + b * y) + c    mode 2 (int64): a * x + b * y + c (wrapping)    mode 0: x
@@ -284,6 +283,45 @@ int fb_compact_indices(int dev, void* stream, const uint8_t* mask, int64_t n, in
 int fb_gather_rows(int dev, void* stream, int ncols, const void* const* d_src_cols, void* const* d_dst_cols,
                    const int32_t* d_widths, const uint8_t* const* d_src_valid, uint8_t* const* d_dst_valid,
                    const int64_t* idx, int64_t n);
+
+/* K7 fast path: inner / left-outer join on one 8-byte key with 4-byte slots (build row + 1; keys are
+ * compared through the build key column) and a fused probe -> output assembly.
+ *   fb_join2_build  : clear + insert (one 32-bit CAS per build row); d_status[0] = 1 on region overflow,
+ *                     d_status[1] = 1 when two build rows share a key (exact)
+ *   fb_join2_probe  : pass A - per probe row the match count and the first match (uint32 each), per tile
+ *                     of 4096 rows the exclusive output offset (d_tile_base, fb_join2_tiles_bytes() bytes)
+ *                     and the output size (*d_total)
+ *   fb_join2_emit   : pass B - writes the OUTPUT COLUMNS directly: left columns copied from the probe row,
+ *                     right columns gathered from the matched build row (NULL-extended with `outer`; then
+ *                     right_valid_dst[c] receives the validity of every right column).  No (probe, build)
+ *                     index pairs are materialised, no separate gather pass.
+ * Replaces the same reference code as the K7 entry points above (native_execution_engine.py:230-241).
+ * left_* / right_* are HOST arrays of device pointers / widths (<= 48 columns per side). */
+size_t fb_join2_table_bytes(int64_t capacity);
+int fb_join2_build(int dev, void* stream, int64_t nbuild, const void* keys, const uint8_t* key_valid,
+                   int64_t capacity, uint32_t num_parts, void* table, int64_t* d_status,
+                   const int64_t* d_part_offsets);
+size_t fb_join2_tiles_bytes(int64_t nprobe);
+int fb_join2_probe(int dev, void* stream, int64_t nprobe, const void* probe_keys, const uint8_t* probe_valid,
+                   const void* build_keys, int64_t capacity, uint32_t num_parts, const void* table, int outer,
+                   uint32_t* out_cnt, uint32_t* out_first, int64_t* d_tile_base, int64_t* d_total,
+                   const int64_t* d_status /* of fb_join2_build: [1] == 0 (no duplicate build keys) lets a
+                                              chain end at its first match */);
+/* fb_join2_build + fb_join2_probe for hash-partitioned inputs (both sides partitioned on the key into
+ * num_parts partitions, offsets on the device): per batch of table regions that fits L2 - clear, insert,
+ * probe the probe rows of the same partitions - so that the probe reads a table and build keys that are
+ * still L2-resident. */
+int fb_join2_build_probe(int dev, void* stream, int64_t nbuild, const void* build_keys, const uint8_t* build_valid,
+                         const int64_t* d_build_part_offsets, int64_t nprobe, const void* probe_keys,
+                         const uint8_t* probe_valid, const int64_t* d_probe_part_offsets, int64_t capacity,
+                         uint32_t num_parts, void* table, int outer, uint32_t* out_cnt, uint32_t* out_first,
+                         int64_t* d_tile_base, int64_t* d_total, int64_t* d_status);
+int fb_join2_emit(int dev, void* stream, int64_t nprobe, const void* probe_keys, const void* build_keys,
+                  int64_t capacity, uint32_t num_parts, const void* table, const uint32_t* cnt,
+                  const uint32_t* first, const int64_t* d_tile_base, int nleft, const void* const* left_src,
+                  void* const* left_dst, const int32_t* left_widths, int nright, const void* const* right_src,
+                  void* const* right_dst, const int32_t* right_widths, const uint8_t* const* right_valid_src,
+                  uint8_t* const* right_valid_dst);
 
 /* ---------------------------------------------------------------------------
  * K8  column-expression evaluator (SELECT list / WHERE predicate / assign)

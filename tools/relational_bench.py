@@ -185,7 +185,8 @@ def cpu_baselines():
 
     rng = np.random.default_rng(0)
     n, nk = 20_000_000, 1_600_000   # same 12.5 rows per key as 125 M rows / 10 M keys
-    df = pd.DataFrame({"key": rng.integers(0, nk, n) * 0x9E3779B97F4A7C15 % (1 << 62), "v0": rng.standard_normal(n)})
+    kk = (rng.integers(0, nk, n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) % np.uint64(1 << 62)
+    df = pd.DataFrame({"key": kk.astype(np.int64), "v0": rng.standard_normal(n)})
     t0 = time.perf_counter()
     r = df.groupby("key").agg(s=("v0", "sum"), c=("v0", "size"))
     t_g = time.perf_counter() - t0

@@ -15,14 +15,14 @@ def main():
     plan = K.partition_plan([cols[0]], 256)
     ref = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for wg in (4, 8):
+    for wg in (4,):
         for cpl in (4, 3, 2, 8):
             for _ in range(2):
-                K.partition_apply(plan, cols, outs, cols_per_launch=cpl, write_group=wg)
+                K.partition_apply(plan, cols, outs, cols_per_launch=cpl)
             torch.cuda.synchronize()
             e0.record()
             for _ in range(5):
-                K.partition_apply(plan, cols, outs, cols_per_launch=cpl, write_group=wg)
+                K.partition_apply(plan, cols, outs, cols_per_launch=cpl)
             e1.record(); torch.cuda.synchronize()
             chk = [int(o.view(torch.int64).sum().item()) for o in outs] + [int(outs[1][12345].item()), int(outs[5].view(torch.int64)[n - 7].item())]
             if ref is None:
