@@ -255,14 +255,15 @@ def transform(
     tf = _FuncAsTransformer(using, schema, params)
     spec = PartitionSpec(partition)
     res: Optional[DataFrame] = None
-    if (as_local and tf.get_format_hint() == "b200" and not isinstance(df, (B200DataFrame, B200Table))
-            and not e.is_distributed):
-        # host input, host output, device function: overlap H2D / partition / D2H column by column
+    if as_local and tf.get_format_hint() == "b200" and not isinstance(df, (B200DataFrame, B200Table)):
+        # host input, host output, device function: overlap H2D / partition (/ exchange) / D2H column by column
         from .streaming import streaming_transform
 
         ldf = as_fugue_df(df)
         out_schema = tf.get_output_schema(ldf)
-        res = streaming_transform(e, ldf, tf.make_runner(out_schema, list(ignore_errors or [])), out_schema, spec)
+        run = tf.make_runner(out_schema, list(ignore_errors or []))
+        res = e.streaming_transform(ldf, run, out_schema, spec) if e.is_distributed \
+            else streaming_transform(e, ldf, run, out_schema, spec)
     if res is None:
         edf = e.to_df(df)
         out_schema = tf.get_output_schema(edf)

@@ -246,6 +246,22 @@ class DistributedB200Engine(B200ExecutionEngine):
                 and getattr(t, "global_num_partitions", None) == num):
             return edf  # already shuffled this way
         t = self._globalize_dictionaries(t)  # string columns: one code space on all ranks
+        res, _ = self._shuffle_table(t, list(keys), num)
+        rdf = B200DataFrame(res)
+        if edf.has_metadata:
+            rdf.reset_metadata(edf.metadata)
+        return rdf
+
+    def _shuffle_table(self, t: B200Table, keys: List[str], num: int,
+                       col_events: Optional[List[Optional[torch.cuda.Event]]] = None
+                       ) -> Tuple[B200Table, List[List[torch.cuda.Event]]]:
+        """The exchange itself.  ``col_events[i]`` (optional): event after which column i of ``t`` is on
+        the device (host -> device copies still in flight: the pipelined host-to-host transform); pass 1
+        waits for the key columns, the scatter of a group for its columns.  Returns the shuffled table and,
+        per output column, the events after which that column is complete (its group's pulls), so that a
+        device -> host copy of an early column can overlap the exchange of the later ones."""
+        from . import kernels as K
+
         dev = t.device
         world, rank = self._world, self._rank
         kidx = [t.schema.index_of_key(k) for k in keys]
@@ -258,6 +274,11 @@ class DistributedB200Engine(B200ExecutionEngine):
                 cols.append(v)
         widths = [c.element_size() for c in cols]
         s_main = torch.cuda.current_stream(dev)
+        if col_events is not None:
+            col_events = list(col_events) + [None] * (len(cols) - len(col_events))
+            for i in kidx:
+                if col_events[i] is not None:
+                    s_main.wait_event(col_events[i])
         # ---- pass 1 on the local shard; counts to everybody (stream-ordered, host reads them later)
         scratch = self._pool.scratch(dev, K.partition_scratch_bytes(dev, t.num_rows, num))
         self._mark("start")
@@ -284,6 +305,10 @@ class DistributedB200Engine(B200ExecutionEngine):
                      for i, (c, w) in enumerate(zip(cols, widths))]
             evs = []
             for idx in groups:
+                if col_events is not None:
+                    for i in idx:
+                        if col_events[i] is not None:
+                            s_main.wait_event(col_events[i])
                 K.partition_apply(plan_local, [cols[i] for i in idx], [parts[i] for i in idx],
                                   sm_reserve=self._sm_reserve)
                 ev = torch.cuda.Event()
@@ -350,6 +375,7 @@ class DistributedB200Engine(B200ExecutionEngine):
             st.wait_event(ev_alloc)
         if self._exchange != "dma":
             s_ctl.wait_event(ev_alloc)
+        col_done: List[List[torch.cuda.Event]] = [[] for _ in cols]
         for gi, idx in enumerate(groups):
             if self._exchange == "dma":
                 # own rows: local copy on stream 0 as soon as this rank's scatter of the group is done;
@@ -379,6 +405,13 @@ class DistributedB200Engine(B200ExecutionEngine):
                             src.append(a_src + o), dst.append(a_dst + o), nb.append(min(step, total - o))
                             stq.append(sptr[1 + (j - 1) * pieces + q])
                 K.copy_runs_dma_streams(dev, src, dst, nb, stq)
+                evs = []
+                for st in streams:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    evs.append(ev)
+                for i in idx:
+                    col_done[i] = evs
                 continue
             with torch.cuda.stream(s_ctl):
                 s_ctl.wait_event(ev_b[gi])
@@ -398,6 +431,10 @@ class DistributedB200Engine(B200ExecutionEngine):
                                     torch.from_numpy(recv_base).to(dev), torch.from_numpy(recv_rows).to(dev),
                                     max_len=int(recv_rows.max()),
                                     src_table=torch.arange(world, dtype=torch.int32, device=dev), src_ptrs=src_ptrs)
+                ev = torch.cuda.Event()
+                ev.record(s_ctl)
+                for i in idx:
+                    col_done[i] = [ev]
         if self._trace is not None:
             for j, st in enumerate(streams):
                 self._mark(f"dma_done.s{j}", st)
@@ -418,10 +455,97 @@ class DistributedB200Engine(B200ExecutionEngine):
         res.segment_offsets = torch.from_numpy(seg)          # [world, nown + 1] (host)
         res.global_partition_range = (lo, hi)               # which physical partitions this GPU owns
         res.global_num_partitions = num
-        rdf = B200DataFrame(res)
-        if edf.has_metadata:
-            rdf.reset_metadata(edf.metadata)
-        return rdf
+        return res, col_done
+
+    # ---- host table in, host table out: H2D / shuffle / D2H overlapped column by column -----------
+    def streaming_transform(self, local_df: Any, runner: Any, out_schema: Any, spec: PartitionSpec) -> Any:
+        """``fa.transform(host_table, device_function, hash spec, as_local=True)`` across GPUs with the three
+        stages overlapped (the single-GPU counterpart is fugue_b200/streaming.py): every column is copied
+        to the device on its own, scattered and exchanged as soon as it has arrived (one column per
+        group), and copied back to pinned host memory as soon as its pulls are done - PCIe runs full
+        duplex while the GPUs shuffle.  Returns None when the input does not qualify (NULLs, strings,
+        presort ...): the caller then takes the step-by-step path."""
+        import numpy as np  # noqa: F811
+        import pyarrow as pa
+
+        from .dataframe import ArrowDataFrame
+        from .streaming import _eligible
+        from .table import _from_readonly, _np_storage, _storage_dtype
+
+        table = local_df.as_arrow()
+        schema = local_df.schema
+        keys = list(spec.partition_by)
+        if not _eligible(table, schema, spec) or any(k not in schema for k in keys) or spec.algo in ("even", "rand"):
+            return None
+        n = table.num_rows
+        num = self._num_partitions(spec, n)
+        if num > 1024 or num < self._world:
+            return None
+        dev = self._device
+        s_cmp = torch.cuda.current_stream(dev)
+        if getattr(self, "_s_h2d", None) is None:
+            self._s_h2d, self._s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_in, s_out = self._s_h2d, self._s_d2h
+        names = schema.names
+        order = keys + [c for c in names if c not in keys]
+        dcols = {c: torch.empty(n, dtype=_storage_dtype(schema[c].type), device=dev) for c in names}
+        ev_in: Dict[str, torch.cuda.Event] = {}
+        s_in.wait_stream(s_cmp)
+        with torch.cuda.stream(s_in):
+            for c in order:
+                pos = 0
+                st = _np_storage(schema[c].type)
+                for arr in table.column(c).chunks:
+                    m = len(arr)
+                    if m == 0:
+                        continue
+                    host = np.frombuffer(arr.buffers()[1], dtype=st, count=m + arr.offset)[arr.offset:]
+                    dcols[c][pos:pos + m].copy_(_from_readonly(host), non_blocking=True)
+                    pos += m
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                ev_in[c] = ev
+        t = B200Table(schema, [dcols[c] for c in names])
+        saved = self._group_cols
+        self._group_cols = [1]  # ship every column as soon as it is there
+        try:
+            shuffled, col_done = self._shuffle_table(t, keys, num, [ev_in[c] for c in names])
+        finally:
+            self._group_cols = saved
+        cursor = spec.get_cursor(schema, 0)
+        pdf = B200DataFrame(shuffled)
+        cursor.set(lambda: pdf.peek_array(), 0, 0)
+        res = self.to_df(runner(cursor, pdf))
+        if res.schema != out_schema:
+            raise AssertionError(f"map output {res.schema} mismatches given {out_schema}")
+        rt: B200Table = res.native
+        plain = all(not (pa.types.is_boolean(tp) or pa.types.is_string(tp) or pa.types.is_large_string(tp))
+                    and col.element_size() * 8 == tp.bit_width for tp, col in zip(out_schema.types, rt.columns))
+        if any(v is not None for v in rt.valid) or len(rt.dictionaries) > 0 or not plain:
+            return res.as_local()
+        ev_f = torch.cuda.Event()
+        ev_f.record(s_cmp)
+        passthrough = {(c.data_ptr(), c.numel()): i for i, c in enumerate(shuffled.columns)}
+        hosts: List[torch.Tensor] = []
+        with torch.cuda.stream(s_out):
+            for col in rt.columns:
+                src = passthrough.get((col.data_ptr(), col.numel()))
+                if src is not None and col_done[src]:
+                    for ev in col_done[src]:   # this column's pulls are done; later columns still travel
+                        s_out.wait_event(ev)
+                else:
+                    s_out.wait_event(ev_f)
+                h = torch.empty(col.shape, dtype=col.dtype, pin_memory=True)
+                h.copy_(col, non_blocking=True)
+                hosts.append(h)
+            done = torch.cuda.Event()
+            done.record(s_out)
+        done.synchronize()
+        s_cmp.wait_stream(s_out)
+        nout = rt.num_rows
+        arrays = [pa.Array.from_buffers(tp, nout, [None, pa.py_buffer(h.numpy())])
+                  for h, tp in zip(hosts, out_schema.types)]
+        return ArrowDataFrame(pa.Table.from_arrays(arrays, schema=out_schema.pa_schema))
 
     def _globalize_dictionaries(self, t: B200Table) -> B200Table:
         return self._globalize_tables([t])[0]

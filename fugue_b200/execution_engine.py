@@ -615,7 +615,12 @@ class B200ExecutionEngine:
                 raise NotImplementedError(f"aggregation {fn}")
         assert_or_throw(len(ops) <= K.MAX_AGGS, NotImplementedError(
             f"{len(ops)} accumulators needed, one kernel call handles {K.MAX_AGGS}"))
+        shuffled = getattr(t, "global_num_partitions", None) is not None and len(keys) > 0
+        if shuffled:  # see kernels.scramble64: local partitions must not reuse the shuffle's hash
+            key64 = K.scramble64(key64)
         gkeys, gvalid, gaggs, ng = K.groupby_u64(key64, kvalid, vals, vvalid, ops)
+        if shuffled:
+            gkeys = K.unscramble64(gkeys)
         if len(keys) == 0 and ng == 0:  # SQL: a global aggregate of an empty table is one row
             gaggs = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in ops]
             ng = 1

@@ -153,6 +153,8 @@ def device_join(engine: Any, df1: B200DataFrame, df2: B200DataFrame, how: str,
         li, ri = (o // max(n2, 1)), (o % max(n2, 1))
         return _assemble(t1, t2, keys, out_schema, li, ri, how)
     k1, v1, k2, v2, exact = _key64(t1, t2, keys)
+    if getattr(t1, "global_num_partitions", None) or getattr(t2, "global_num_partitions", None):
+        k1, k2 = K.scramble64(k1), K.scramble64(k2)  # shuffled input: see kernels.scramble64
     parts = 0
     po1 = po2 = None
     if min(n1, n2) >= RADIX_JOIN_MIN_ROWS:

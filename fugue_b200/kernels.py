@@ -268,6 +268,23 @@ def pull_runs_tma(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: An
                                     dst.ctypes.data, nb.ctypes.data, int(max_ctas)))
 
 
+# A table that went through the multi-GPU shuffle holds, on every rank, only keys whose partitioner hash % N
+# falls into the rank's range.  Local radix partitions of the same keys by the same hash would then fill only
+# a fraction of their partitions (and overflow the hash-table regions sized for an even spread).  Local
+# operators therefore hash a bijective re-coding of such keys: k * odd constant (mod 2^64) - equal keys stay
+# equal, the partition ids become independent of the shuffle's.
+_SCRAMBLE = 0x9E3779B97F4A7C15 - (1 << 64)
+_UNSCRAMBLE = pow(0x9E3779B97F4A7C15, -1, 1 << 64) - (1 << 64)
+
+
+def scramble64(k: torch.Tensor) -> torch.Tensor:
+    return k * _SCRAMBLE
+
+
+def unscramble64(k: torch.Tensor) -> torch.Tensor:
+    return k * _UNSCRAMBLE
+
+
 AGG_SUM_F64, AGG_SUM_I64, AGG_COUNT, AGG_MIN_I64, AGG_MAX_I64, AGG_MIN_F64, AGG_MAX_F64 = range(7)
 MAX_AGGS = 16
 

@@ -201,6 +201,39 @@ def check_repartition(eng, rank, world, dev):
             print(f"dist_gpu_check ok: world={world}, {total} rows, bit-exact vs oracle (stable order)")
 
 
+def check_streaming(eng, rank, world):
+    """Host table in, host table out through fa.transform(..., as_local=True) on the distributed engine: the
+    pipelined H2D / shuffle / D2H path.  Union over ranks == the input rows; every key lives on one rank."""
+    import pyarrow as pa
+
+    from fugue_b200 import api as fa
+
+    n = 200_000 + 777 * rank
+    cols = shard(rank, n)[:3]
+    tbl = pa.table({"key": cols[0], "v": cols[1], "rid": cols[2]})
+
+    def ident(t: B200Table) -> B200Table:
+        return t
+
+    out = fa.transform(tbl, ident, schema="*", partition=PartitionSpec(by="key", algo="hash", num=NUM), engine=eng,
+                       as_local=True, as_fugue=True).as_arrow()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (out.column("key").to_numpy(), out.column("v").to_numpy(), out.column("rid").to_numpy()))
+    if rank == 0:
+        with _guard("streaming"):
+            shards = [shard(r, 200_000 + 777 * r)[:3] for r in range(world)]
+            exp = np.stack([np.concatenate([s_[c] for s_ in shards]).view("i8") for c in range(3)], 1)
+            got = np.stack([np.concatenate([g[c] for g in gathered]).view("i8") for c in range(3)], 1)
+            assert got.shape == exp.shape
+            order_e, order_g = np.lexsort(exp.T[::-1]), np.lexsort(got.T[::-1])
+            assert np.array_equal(exp[order_e], got[order_g])
+            owner = {}
+            for r, g in enumerate(gathered):
+                for k in np.unique(g[0]).tolist():
+                    assert owner.setdefault(k, r) == r, f"key {k} on ranks {owner[k]} and {r}"
+            print(f"dist streaming transform ok: {len(got)} rows")
+
+
 def run_checks(eng, rank, world, dev):
     """All multi-GPU parity checks; collective (every rank calls it).  Returns (ok, message) -
     meaningful on rank 0, where the comparisons against the oracle run."""
@@ -210,6 +243,7 @@ def run_checks(eng, rank, world, dev):
         check_repartition(eng, rank, world, dev)
         check_relational(eng, rank, world, dev)
         check_string_join(eng, rank, world)
+        check_streaming(eng, rank, world)
     except Exception as e:  # noqa: BLE001 - reported, not swallowed
         ok, msg = False, repr(e)[:300]
     if _FAILS:
@@ -218,7 +252,7 @@ def run_checks(eng, rank, world, dev):
     dist.all_gather_object(flags, (ok, msg))
     bad = [f for f in flags if not f[0]]
     return (len(bad) == 0, bad[0][1] if bad else f"world={world}: repartition (segments + compacted) bit-exact vs "
-            "oracle; GROUP BY / JOIN / select / string keys vs pandas")
+            "oracle; GROUP BY / JOIN / select / string keys vs pandas; pipelined host-to-host transform")
 
 
 def main():
