@@ -867,12 +867,21 @@ int fb_join2_build_probe(int dev, void* stream, int64_t nbuild, const void* buil
   }
   // Batches of regions that fit L2 TOGETHER WITH the build keys of the same partitions: clear, insert, and
   // probe the probe rows of these partitions at once - the probe's two dependent random reads per step
-  // (slot, build key) then hit L2 instead of fetching cold 32-byte sectors from HBM.
+  // (slot, build key) then hit L2 instead of fetching cold 32-byte sectors from HBM.  Both kernels are
+  // chains of dependent L2 accesses (ncu: 22 % / 32 % issue-active, long-scoreboard bound), so the probe of
+  // batch b runs on a second stream next to the build of batch b + 1 (disjoint regions): two latency-bound
+  // kernels fill the machine better than one.
   const int64_t region_bytes = ((int64_t)1 << rs) * (int64_t)sizeof(uint32_t);
   int64_t per = ((int64_t)24 << 20) / region_bytes;
   if (per < 1) per = 1;
   const int sms = fb_sm_count(dev);
-  for (int64_t p0 = 0; p0 < (int64_t)num_parts; p0 += per) {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done = nullptr;
+  FB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) FB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  FB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+  int b = 0;
+  for (int64_t p0 = 0; p0 < (int64_t)num_parts; p0 += per, ++b) {
     const int64_t p1 = p0 + per < (int64_t)num_parts ? p0 + per : (int64_t)num_parts;
     const int64_t nslots = (p1 - p0) << rs;
     fb_join2_clear_kernel<<<grid_for(dev, nslots / 4 + 1), 256, 0, st>>>((uint32_t*)table, p0 << rs, nslots);
@@ -882,14 +891,23 @@ int fb_join2_build_probe(int dev, void* stream, int64_t nbuild, const void* buil
                                                                (uint32_t*)table, capacity, d_status, dv, rs,
                                                                d_build_part_offsets, (int)p0, (int)p1);
     }
+    cudaEventRecord(ev[b & 1], st);
+    cudaStreamWaitEvent(s2, ev[b & 1], 0);
     const int64_t est_tiles = (nprobe / num_parts * (p1 - p0) * 5 / 4 + kJ2Tile) / kJ2Tile;
     int64_t grid = est_tiles < (int64_t)sms * 2 ? est_tiles : (int64_t)sms * 2;
     if (grid < 1) grid = 1;
-    fb_join2_probe_kernel<<<(unsigned)grid, kJ2Block, 0, st>>>(
+    fb_join2_probe_kernel<<<(unsigned)grid, kJ2Block, 0, s2>>>(
         (const uint64_t*)probe_keys, probe_valid, nprobe, (const uint64_t*)build_keys, (const uint32_t*)table, capacity,
         dv, rs, outer, out_cnt, out_first, nullptr, d_status, d_probe_part_offsets, (int)p0, (int)p1);
   }
-  FB_CUDA(cudaGetLastError());
+  cudaEventRecord(ev_done, s2);
+  cudaStreamWaitEvent(st, ev_done, 0);
+  const cudaError_t launch_err = cudaGetLastError();
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  cudaEventDestroy(ev_done);
+  cudaStreamDestroy(s2);  // released once its work has completed
+  FB_CUDA(launch_err);
   const int64_t ntiles = (nprobe + kJ2Tile - 1) / kJ2Tile;
   int64_t grid = ntiles < (int64_t)sms * 4 ? ntiles : (int64_t)sms * 4;
   fb_join2_tile_sums_kernel<<<(unsigned)grid, kJ2Block, 0, st>>>(out_cnt, nprobe, d_tile_base);

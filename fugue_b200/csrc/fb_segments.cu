@@ -282,14 +282,31 @@ extern "C" int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void
 }
 
 extern "C" int fb_copy_runs_dma_streams(int dev, int64_t nruns, const void* const* src, void* const* dst,
-                                        const size_t* bytes, void* const* streams) {
+                                        const size_t* bytes, void* const* streams, int prefer_overlap) {
   FB_CHECK(nruns >= 0, "nruns < 0");
   if (nruns == 0) return 0;
   FB_CHECK(src != nullptr && dst != nullptr && bytes != nullptr && streams != nullptr, "NULL argument");
   FbDeviceGuard guard(dev);
   FB_CHECK(guard.ok, "cannot select device %d", dev);
-  for (int64_t i = 0; i < nruns; ++i)
-    if (bytes[i] != 0)
-      FB_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDeviceToDevice, (cudaStream_t)streams[i]));
+  for (int64_t i = 0; i < nruns; ++i) {
+    if (bytes[i] == 0) continue;
+#if CUDART_VERSION >= 12080
+    if (prefer_overlap) {
+      // cudaMemcpyFlagPreferOverlapWithCompute: "try and overlap the copy with compute work on the SMs" - without
+      // it the copies made no progress next to the persistent scatter kernel (profiles/r2_exchange_notes.md)
+      cudaMemcpyAttributes attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+      attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+      void* d = dst[i];
+      void* s_ = (void*)src[i];
+      size_t n = bytes[i], idx = 0, fail = 0;
+      cudaError_t e = cudaMemcpyBatchAsync(&d, &s_, &n, 1, &attr, &idx, 1, &fail, (cudaStream_t)streams[i]);
+      if (e == cudaSuccess) continue;
+      (void)cudaGetLastError();  // not supported for these pointers: plain copy below
+    }
+#endif
+    FB_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDeviceToDevice, (cudaStream_t)streams[i]));
+  }
   return 0;
 }

@@ -151,6 +151,7 @@ class DistributedB200Engine(B200ExecutionEngine):
         # copy-engine streams per peer (pieces every run is cut into): 8 GPUs: 1, 4: 2, 2: 4
         self._dma_pieces = max(1, min(8, int(self._conf.get(FUGUE_B200_CONF_DIST_DMA_PIECES,
                                                             max(1, min(4, 6 // max(1, self._world - 1)))))))
+        self._dma_overlap_flag = bool(int(self._conf.get("fugue.b200.dist.dma_overlap_flag", 1)))
         self._sm_reserve = int(self._conf.get(FUGUE_B200_CONF_DIST_SM_RESERVE,
                                               1 if self._exchange == "dma" else 16))
 
@@ -404,7 +405,7 @@ class DistributedB200Engine(B200ExecutionEngine):
                                 break
                             src.append(a_src + o), dst.append(a_dst + o), nb.append(min(step, total - o))
                             stq.append(sptr[1 + (j - 1) * pieces + q])
-                K.copy_runs_dma_streams(dev, src, dst, nb, stq)
+                K.copy_runs_dma_streams(dev, src, dst, nb, stq, self._dma_overlap_flag)
                 evs = []
                 for st in streams:
                     ev = torch.cuda.Event()

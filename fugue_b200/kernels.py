@@ -236,7 +236,8 @@ def copy_runs_dma(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: An
                                     dst.ctypes.data, nb.ctypes.data))
 
 
-def copy_runs_dma_streams(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: Any, streams: Any) -> None:
+def copy_runs_dma_streams(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: Any, streams: Any,
+                          prefer_overlap: bool = True) -> None:
     """:func:`copy_runs_dma` with one CUDA stream per run (raw ``cudaStream_t`` values): the whole
     exchange of a column group is enqueued by ONE call."""
     import numpy as np
@@ -250,7 +251,7 @@ def copy_runs_dma_streams(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nb
     if src.size == 0:
         return
     _lib.check(lib.fb_copy_runs_dma_streams(device.index, int(src.size), src.ctypes.data, dst.ctypes.data,
-                                            nb.ctypes.data, st.ctypes.data))
+                                            nb.ctypes.data, st.ctypes.data, 1 if prefer_overlap else 0))
 
 
 def pull_runs_tma(device: torch.device, src_ptrs: Any, dst_ptrs: Any, nbytes: Any, max_ctas: int = 16) -> None:

@@ -183,7 +183,8 @@ int fb_copy_runs_dma(int dev, void* stream, int64_t nruns, const void* const* sr
 /* fb_copy_runs_dma with a stream per run (`streams` = HOST array of cudaStream_t): one call enqueues a
  * whole column group of the exchange on the per-peer streams. */
 int fb_copy_runs_dma_streams(int dev, int64_t nruns, const void* const* src, void* const* dst,
-                             const size_t* bytes, void* const* streams);
+                             const size_t* bytes, void* const* streams,
+                             int prefer_overlap /* 1: cudaMemcpyBatchAsync + cudaMemcpyFlagPreferOverlapWithCompute */);
 /* The same runs pulled by a small persistent TMA kernel (`max_ctas` CTAs, one per SM): one thread per
  * CTA keeps ~14 x 16 KB bulk loads (cp.async.bulk) in flight against the peers' memory, four warps
  * drain the stages into the local destination.  nruns <= 64; src / dst / bytes multiples of 8;

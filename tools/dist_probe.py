@@ -66,6 +66,8 @@ def main():
         mode, gc, res = item.split(":")[:3]
         if len(item.split(":")) > 3:
             eng._dma_pieces = int(item.split(":")[3])
+        if len(item.split(":")) > 4:
+            eng._dma_overlap_flag = bool(int(item.split(":")[4]))
         eng._exchange, eng._group_cols, eng._sm_reserve = mode, [int(x) for x in gc.split('-')], int(res)
         try:
             for _ in range(2):
@@ -86,7 +88,7 @@ def main():
             dist.all_reduce(rows_out)
             if rank == 0:
                 ms = float(t.item())
-                print(json.dumps({"mode": mode, "group_cols": gc, "sm_reserve": int(res), "dma_pieces": eng._dma_pieces, "world": world,
+                print(json.dumps({"mode": mode, "group_cols": gc, "sm_reserve": int(res), "dma_pieces": eng._dma_pieces, "overlap_flag": eng._dma_overlap_flag, "world": world,
                                   "rows_per_gpu": n, "ms_per_step": round(ms, 3), "host_enqueue_ms": round(host_ms, 3),
                                   "G_rows_per_s": round(n * world / ms / 1e6, 2), "rows_out": int(rows_out.item()),
                                   "nvlink_GBps_out_per_gpu": round(64.0 * n * (world - 1) / world / ms / 1e6, 1)}),
