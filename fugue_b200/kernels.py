@@ -361,25 +361,23 @@ def groupby_u64(keys: torch.Tensor, key_valid: Optional[torch.Tensor],
                                       table.data_ptr(), status.data_ptr(),
                                       part_offsets.data_ptr() if (part_offsets is not None and GROUPBY_BATCHED)
                                       else 0))
-        if int(status[0].item()) == 0:
+        # extract right away and read overflow flag + group count with ONE host sync (an overflowing attempt
+        # wastes its extract; that is the rare path)
+        bound = min(n, capacity) + 2  # upper bound on the number of groups
+        out_keys = torch.empty(bound, dtype=torch.int64, device=dev)
+        out_valid = torch.empty(bound, dtype=torch.uint8, device=dev) if key_valid is not None else None
+        out_aggs = [torch.empty(bound, dtype=torch.int64, device=dev) for _ in range(naggs)]
+        d_ptrs = torch.tensor([a.data_ptr() for a in out_aggs] or [0], dtype=torch.int64, device=dev)
+        _lib.check(lib.fb_groupby_extract(dev.index, _stream_ptr(dev), capacity, naggs, opa, table.data_ptr(),
+                                          out_keys.data_ptr(), 0 if out_valid is None else out_valid.data_ptr(),
+                                          d_ptrs.data_ptr(), status.data_ptr()))
+        overflow, ngroups = (int(x) for x in status[:2].tolist())
+        if overflow == 0:
             break
         if capacity >= hard_max:
             raise _lib.FugueB200KernelError("group-by hash table overflow at the maximum capacity")
-        del table
+        del table, out_keys, out_valid, out_aggs
         capacity *= 4
-    # compact: first learn the group count, then allocate exactly
-    out_cap = capacity + 2
-    # upper bound on groups is min(n + 2, capacity + 2); allocate that
-    bound = min(n, capacity) + 2
-    out_keys = torch.empty(bound, dtype=torch.int64, device=dev)
-    out_valid = torch.empty(bound, dtype=torch.uint8, device=dev) if key_valid is not None else None
-    out_aggs = [torch.empty(bound, dtype=torch.int64, device=dev) for _ in range(naggs)]
-    d_ptrs = torch.tensor([a.data_ptr() for a in out_aggs] or [0], dtype=torch.int64, device=dev)
-    _lib.check(lib.fb_groupby_extract(dev.index, _stream_ptr(dev), capacity, naggs, opa, table.data_ptr(),
-                                      out_keys.data_ptr(), 0 if out_valid is None else out_valid.data_ptr(),
-                                      d_ptrs.data_ptr(), status.data_ptr()))
-    ngroups = int(status[1].item())
-    del out_cap
     return (out_keys[:ngroups], None if out_valid is None else out_valid[:ngroups],
             [a[:ngroups] for a in out_aggs], ngroups)
 
