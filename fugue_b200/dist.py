@@ -144,7 +144,10 @@ class DistributedB200Engine(B200ExecutionEngine):
         self._ctl: Optional[torch.Tensor] = None
         self._step = 0
         self._trace: Optional[List[Any]] = None
-        gc = self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, "4")
+        # measured (profiles/r2_exchange_notes.md): at 2 GPUs scatter and exchange take about as long and
+        # groups of 2 interleave best (8.5 ms vs 9.6); from 4 GPUs on the exchange dominates and the copy
+        # engines lose more to a running scatter than an earlier start wins: groups of 4 (14.1 vs 15.8)
+        gc = self._conf.get(FUGUE_B200_CONF_DIST_GROUP_COLS, "2" if self._world == 2 else "4")
         self._group_cols = [max(1, int(x)) for x in str(gc).split(",")]  # columns per group; last repeats
         self._exchange = str(self._conf.get(FUGUE_B200_CONF_DIST_EXCHANGE, "dma"))
         assert_or_throw(self._exchange in ("dma", "kernel", "tma"), ValueError(f"unknown exchange {self._exchange}"))
@@ -189,6 +192,7 @@ class DistributedB200Engine(B200ExecutionEngine):
         self._counts_host = torch.empty(self._world, _CTL_SLOTS, dtype=torch.int64, pin_memory=True)
         self._s_ctl = torch.cuda.Stream(dev, priority=-1)  # barrier kernels must not queue behind the scatter
         self._s_dma = [torch.cuda.Stream(dev) for _ in range(1 + (self._world - 1) * 8)]
+        self._s_alloc = torch.cuda.Stream(dev)  # allocation-only stream (see _shuffle_table)
 
     def _post_counts(self, local_counts: torch.Tensor) -> torch.cuda.Event:
         """Stream-ordered all-gather of ``local_counts`` (int64[num], device) over symmetric memory:
@@ -365,17 +369,17 @@ class DistributedB200Engine(B200ExecutionEngine):
             ev_b = barriers(ev_sc)
         base = [int(x) for x in self._arena_hdl.buffer_ptrs]
         peer_off = [self._col_offsets(int(rows[s]), widths) for s in range(world)]
-        outs = [torch.empty(total_recv, dtype=cc.dtype, device=dev) for cc in cols]
+        # The receive buffers come from the pool of a stream that never runs work: a block in that pool
+        # is idle on the device (the allocator returns it only after the events of every stream recorded
+        # below have passed), so the pulls may write it at once.  Allocated on the main stream they would
+        # have to wait for an event BEHIND the scatters enqueued above - the exchange of group 0 would
+        # start when the last scatter is over (measured: 10.9 -> 8.5 ms per step at 2 GPUs).
+        with torch.cuda.stream(self._s_alloc):
+            outs = [torch.empty(total_recv, dtype=cc.dtype, device=dev) for cc in cols]
         optr = [o.data_ptr() for o in outs]
-        ev_alloc = torch.cuda.Event()
-        ev_alloc.record(s_main)  # the output buffers were allocated on the main stream
         pieces = self._dma_pieces
         streams = self._s_dma[:1 + (world - 1) * pieces]
         sptr = [st.cuda_stream for st in streams]
-        for st in streams:
-            st.wait_event(ev_alloc)
-        if self._exchange != "dma":
-            s_ctl.wait_event(ev_alloc)
         col_done: List[List[torch.cuda.Event]] = [[] for _ in cols]
         for gi, idx in enumerate(groups):
             if self._exchange == "dma":
@@ -405,7 +409,11 @@ class DistributedB200Engine(B200ExecutionEngine):
                                 break
                             src.append(a_src + o), dst.append(a_dst + o), nb.append(min(step, total - o))
                             stq.append(sptr[1 + (j - 1) * pieces + q])
+                if self._trace is not None:
+                    self._mark(f"dmaB{gi}.s1", streams[1])
                 K.copy_runs_dma_streams(dev, src, dst, nb, stq, self._dma_overlap_flag)
+                if self._trace is not None:
+                    self._mark(f"dma{gi}.s1", streams[1])
                 evs = []
                 for st in streams:
                     ev = torch.cuda.Event()
@@ -447,6 +455,7 @@ class DistributedB200Engine(B200ExecutionEngine):
         s_main.wait_stream(s_ctl)
         self._mark("end")
         for o in outs:
+            o.record_stream(s_main)
             for st in streams:
                 o.record_stream(st)
             o.record_stream(s_ctl)
