@@ -219,6 +219,15 @@ class PartitionSpec:
                     partition_by=self._partition_by, presort=self.presort_expr,
                     size_limit=self._size_limit, row_limit=self._row_limit)
 
+    def __uuid__(self) -> str:
+        """Deterministic id of the spec (fugue/collections/partition.py:259-261: the id of ``jsondict``):
+        equal for specs that mean the same (``num=0`` and no argument, ``num=2`` and ``num="2"``), different
+        when the key ORDER differs.  A name-based UUID over the canonical JSON text of ``jsondict``."""
+        import json
+        import uuid
+
+        return str(uuid.uuid5(uuid.NAMESPACE_OID, json.dumps(self.jsondict, sort_keys=True)))
+
     def get_sorts(self, schema: Schema, with_partition_keys: bool = True) -> "OrderedDict[str, bool]":
         d: "OrderedDict[str, bool]" = OrderedDict()
         if with_partition_keys:

@@ -103,6 +103,18 @@ def test_partition_spec():
         p.get_sorts(Schema("x:int"))
 
 
+def test_partition_spec_determinism():
+    """The id properties tests/fugue/collections/test_partition.py:242-253 asserts (there through
+    triad's ``to_uuid``, which calls ``__uuid__``)."""
+    uid = lambda spec: spec.__uuid__()  # noqa: E731
+    assert uid(PartitionSpec(num=0)) == uid(PartitionSpec())
+    assert uid(PartitionSpec(by=["a"], num=2)) == uid(PartitionSpec(num="2", by=["a"]))
+    assert uid(PartitionSpec(by=["a", "b"])) != uid(PartitionSpec(by=["b", "a"]))
+    assert uid(PartitionSpec(by=["a"], presort="b")) != uid(PartitionSpec(by=["a"], presort="b desc"))
+    assert uid(PartitionSpec(by=["a"], algo="hash")) != uid(PartitionSpec(by=["a"], algo="even"))
+    assert uid(PartitionSpec(PartitionSpec(by=["a"], num=3))) == uid(PartitionSpec(by=["a"], num=3))
+
+
 def test_partition_cursor():
     # tests/fugue/collections/test_partition.py (test_partition_cursor)
     p = PartitionSpec(dict(partition_by=["b", "a"]))
