@@ -10,11 +10,12 @@ Mirrors
 The reference builds a two-task DAG (adagio) around one ``map_dataframe`` call; that
 driver-side plumbing is O(1) and is collapsed into a direct call here.
 """
+import collections.abc
 import contextvars
 import inspect
 import re
 from contextlib import contextmanager
-from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, get_type_hints
+from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, get_args, get_origin, get_type_hints
 
 import pandas as pd
 import pyarrow as pa
@@ -133,17 +134,20 @@ class _FuncAsTransformer:
 
     @staticmethod
     def _schema_from_comment(func: Callable) -> Optional[str]:
-        # fugue/_utils/interfaceless.py:9-73 (parse_comment_annotation)
+        """The ``# schema: ...`` hint in the comment block directly above the function
+        (fugue/_utils/interfaceless.py:9-66): the LOWEST matching line wins, anything after a second
+        ``#`` on that line is a remark, an empty hint is a SyntaxError."""
         try:
-            src = inspect.getsource(func)
+            block = inspect.getcomments(func) or ""
         except Exception:
             return None
-        for line in src.splitlines():
-            m = re.match(r"^\s*#\s*schema\s*:\s*(.+)$", line)
-            if m:
-                return m.group(1).strip()
-            if line.strip().startswith("def "):
-                break
+        hint = re.compile(r"^\s*#\s*schema\s*:([^#]*)")
+        for line in reversed(block.splitlines()):
+            m = hint.match(line)
+            if m is not None:
+                text = m.group(1).strip()
+                assert_or_throw(text != "", SyntaxError("incorrect schema annotation"))
+                return text
         return None
 
     @staticmethod
@@ -158,10 +162,18 @@ class _FuncAsTransformer:
             return "pyarrow"
         if inspect.isclass(tp) and issubclass(tp, DataFrame):
             return "fugue"
+        # generic annotations (function_wrapper.py:330-516: _ListListParam, _IterableListParam, _ListDictParam,
+        # _IterableDictParam, _IterablePandasParam, _IterableArrowParam): outer container, then the element
+        origin, args = get_origin(tp), get_args(tp)
+        lazy = origin in (collections.abc.Iterable, collections.abc.Iterator, collections.abc.Generator)
+        if lazy and args and args[0] is pd.DataFrame:
+            return "pandas_iter"
+        if lazy and args and args[0] is pa.Table:
+            return "pyarrow_iter"
         s = str(tp)
         if "Dict" in s or "dict" in s:
             return "dicts"
-        if "List" in s or "list" in s or "Iterable" in s:
+        if "List" in s or "list" in s or "Iterable" in s or "Iterator" in s:
             return "array"
         return None
 
@@ -183,6 +195,10 @@ class _FuncAsTransformer:
             return df.as_pandas()
         if k == "pyarrow":
             return df.as_arrow()
+        if k == "pandas_iter":   # one chunk: a logical partition is materialised as a whole here
+            return iter([df.as_pandas()])
+        if k == "pyarrow_iter":
+            return iter([df.as_arrow()])
         if k == "array":
             return df.as_array(type_safe=True)
         if k == "dicts":
@@ -199,6 +215,12 @@ class _FuncAsTransformer:
         if out is None:
             return ArrowDataFrame(None, schema)
         out = list(out)
+        if out and all(isinstance(x, pd.DataFrame) for x in out):   # Iterable[pd.DataFrame]: chunks of the result
+            frames = [x for x in out if x.shape[0] > 0]
+            return ArrowDataFrame(pd.concat(frames, ignore_index=True) if frames else None, schema)
+        if out and all(isinstance(x, pa.Table) for x in out):
+            tables = [x for x in out if x.num_rows > 0]
+            return ArrowDataFrame(pa.concat_tables(tables) if tables else None, schema)
         if out and isinstance(out[0], dict):
             out = [[r.get(n) for n in schema.names] for r in out]
         return ArrayDataFrame(out, schema)

@@ -1,0 +1,149 @@
+"""Host logic of the function -> transformer adapter (``fugue_b200.api._FuncAsTransformer``), CPU only.
+
+What the reference's adapter does for the north-star path (``_FuncAsTransformer.transform``
+fugue/extensions/transformer/convert.py:343-348, ``DataFrameFunctionWrapper.run``
+fugue/dataframe/function_wrapper.py:68-148 with the annotated-parameter classes :330-516): the first
+parameter's annotation decides how a logical partition is handed to the user function, the return value is
+turned back into a local dataframe of the declared schema, extra parameters come from ``params``, a
+``PartitionCursor``-typed parameter receives the cursor, ``ignore_errors`` turns listed exceptions into an
+empty partition.  The runner is exercised here on host dataframes - no engine, no GPU.
+"""
+from typing import Any, Dict, Iterable, Iterator, List
+
+import pandas as pd
+import pyarrow as pa
+import pytest
+
+from fugue_b200.api import _FuncAsTransformer
+from fugue_b200.dataframe import ArrayDataFrame, ArrowDataFrame
+from fugue_b200.partition import PartitionCursor, PartitionSpec
+from fugue_b200.schema import Schema
+
+ROWS = [[0, 1.5], [0, 2.5], [1, 4.0]]
+SCHEMA = "k:long,v:double"
+
+
+def _run(func: Any, schema: Any = "*", params: Any = None, ignore: Any = None, rows: Any = ROWS) -> Any:
+    df = ArrowDataFrame(ArrayDataFrame(rows, SCHEMA).as_arrow(), SCHEMA)
+    tf = _FuncAsTransformer(func, schema, params)
+    out_schema = tf.get_output_schema(df)
+    spec = PartitionSpec(by=["k"])
+    cursor = spec.get_cursor(df.schema, 0)
+    cursor.set(lambda: df.peek_array(), 3, 0)
+    res = tf.make_runner(out_schema, ignore or [])(cursor, df)
+    assert res.schema == out_schema
+    return tf, res.as_array(type_safe=True)
+
+
+def test_pandas_in_out():
+    def f(df: pd.DataFrame) -> pd.DataFrame:
+        return df.assign(v=df.v * 2)
+
+    tf, out = _run(f)
+    assert tf.get_format_hint() == "pandas" and out == [[0, 3.0], [0, 5.0], [1, 8.0]]
+
+
+def test_arrow_in_out():
+    def f(df: pa.Table) -> pa.Table:
+        return df.slice(1)
+
+    tf, out = _run(f)
+    assert tf.get_format_hint() == "pyarrow" and out == ROWS[1:]
+
+
+def test_rows_and_dicts():
+    def rows(df: List[List[Any]]) -> Iterable[List[Any]]:
+        for r in df:
+            yield [r[0], r[1] + 1]
+
+    def lazy_rows(df: Iterable[List[Any]]) -> List[List[Any]]:
+        return [[r[0], -r[1]] for r in df]
+
+    def dicts(df: List[Dict[str, Any]]) -> Iterable[Dict[str, Any]]:
+        for r in df:
+            yield dict(v=r["v"], k=r["k"] + 10)  # key order of the dict does not matter, the schema does
+
+    tf, out = _run(rows)
+    assert tf.get_format_hint() is None and out == [[0, 2.5], [0, 3.5], [1, 5.0]]
+    assert _run(lazy_rows)[1] == [[0, -1.5], [0, -2.5], [1, -4.0]]
+    assert _run(dicts)[1] == [[10, 1.5], [10, 2.5], [11, 4.0]]
+
+
+def test_iterables_of_frames():
+    def chunks(df: Iterable[pd.DataFrame]) -> Iterable[pd.DataFrame]:
+        for part in df:
+            yield part.iloc[:1]
+            yield part.iloc[:0]  # empty chunks are dropped
+            yield part.iloc[1:]
+
+    def tables(df: Iterator[pa.Table]) -> Iterable[pa.Table]:
+        for part in df:
+            yield part.slice(2)
+            yield part.slice(0, 2)
+
+    def nothing(df: Iterable[pd.DataFrame]) -> Iterable[pd.DataFrame]:
+        for part in df:
+            yield part.iloc[:0]
+
+    assert _run(chunks)[1] == ROWS
+    assert _run(tables)[1] == [ROWS[2], ROWS[0], ROWS[1]]
+    assert _run(nothing)[1] == []
+
+
+def test_schema_sources():
+    # schema: *,w:double
+    def commented(df: pd.DataFrame) -> pd.DataFrame:
+        return df.assign(w=df.v + 1)
+
+    def bare(df: pd.DataFrame) -> pd.DataFrame:
+        return df
+
+    # schema: k:long
+    # a remark in between
+    #schema:*,w:double # the lowest hint wins, the remark after the second '#' is dropped
+    # another remark
+    def lowest(df: pd.DataFrame) -> pd.DataFrame:
+        return df.assign(w=df.v + 1)
+
+    # schema:
+    def empty_hint(df: pd.DataFrame) -> pd.DataFrame:
+        return df
+
+    assert _run(commented, schema=None)[1] == [[0, 1.5, 2.5], [0, 2.5, 3.5], [1, 4.0, 5.0]]
+    assert _run(lowest, schema=None)[1] == [[0, 1.5, 2.5], [0, 2.5, 3.5], [1, 4.0, 5.0]]
+    with pytest.raises(SyntaxError):
+        _FuncAsTransformer(empty_hint, None, None)
+    assert _run(commented, schema=Schema("k:long,v:double,w:double"))[1][2] == [1, 4.0, 5.0]
+    with pytest.raises(ValueError):
+        _FuncAsTransformer(bare, None, None)         # no schema argument, no '# schema:' comment
+    with pytest.raises(TypeError):
+        _FuncAsTransformer(lambda df: df, "*", None)  # un-annotated dataframe parameter
+    with pytest.raises(TypeError):
+        _FuncAsTransformer(123, "*", None)
+
+
+def test_params_cursor_and_ignored_errors():
+    def f(df: pd.DataFrame, c: PartitionCursor, add: float, scale: float = 1.0) -> pd.DataFrame:
+        assert c.partition_no == 3 and c.key_value_array == [0] and c.row == [0, 1.5]
+        return df.assign(v=(df.v + add) * scale)
+
+    assert _run(f, params=dict(add=0.5, scale=2.0))[1] == [[0, 4.0], [0, 6.0], [1, 9.0]]
+
+    def boom(df: pd.DataFrame) -> pd.DataFrame:
+        raise NotImplementedError("nope")
+
+    assert _run(boom, ignore=[NotImplementedError])[1] == []   # processors.py:330-338
+    with pytest.raises(NotImplementedError):
+        _run(boom, ignore=[ValueError])
+    with pytest.raises(NotImplementedError):
+        _run(boom)
+
+
+def test_none_and_empty_outputs():
+    def none(df: pd.DataFrame) -> None:
+        return None
+
+    def empty_rows(df: List[List[Any]]) -> List[List[Any]]:
+        return []
+
+    assert _run(none)[1] == [] and _run(empty_rows)[1] == []
