@@ -531,6 +531,11 @@ def is_df(df: Any) -> bool:
     return isinstance(df, (DataFrame, pd.DataFrame, pa.Table, B200Table))
 
 
+def show(df: Any, n: int = 10, with_count: bool = False, title: Optional[str] = None) -> None:
+    """``fa.show`` (fugue/dataset/api.py:18-35)."""
+    as_fugue_df(df).show(n=n, with_count=with_count, title=title)
+
+
 def get_native_as_df(df: Any) -> Any:
     return df.native_as_df() if isinstance(df, DataFrame) else df
 
@@ -598,10 +603,13 @@ def rename(df: Any, columns: Dict[str, Any], as_fugue: bool = False) -> Any:
 
 
 def as_local(df: Any) -> Any:
+    assert_or_throw(is_df(df), lambda: NotImplementedError(f"{type(df)} can't be converted to a local dataset"))
     return _convert_df(df, as_fugue_df(df).as_local(), False)
 
 
 def as_local_bounded(df: Any) -> Any:
+    assert_or_throw(is_df(df), lambda: NotImplementedError(
+        f"{type(df)} can't be converted to a local bounded dataset"))  # fugue/dataset/api.py:47-55
     return _convert_df(df, as_fugue_df(df).as_local_bounded(), False)
 
 

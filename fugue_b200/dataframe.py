@@ -165,9 +165,28 @@ class DataFrame:
         if new is None:
             return self
         try:
-            return ArrowDataFrame(self.as_arrow().cast(new.pa_schema, safe=False))
+            return ArrowDataFrame(_cast_table(self.as_arrow(), new))
         except (pa.ArrowInvalid, pa.ArrowNotImplementedError) as e:
             raise FugueDataFrameOperationError(str(e)) from e
+
+    def show(self, n: int = 10, with_count: bool = False, title: Optional[str] = None) -> None:
+        """Print the first ``n`` rows (fugue/dataset/dataset.py:86-102, display of
+        fugue/dataframe/dataframe_iterable_dataframe / DataFrameDisplay): title, schema line, rows,
+        optionally the total count, then the metadata if there is any."""
+        lines: List[str] = []
+        if title:
+            lines.append(str(title))
+        lines.append(f"{type(self).__name__}")
+        lines.append(str(self.schema))
+        head = self.head(n).as_array()
+        lines.extend(str(r) for r in head)
+        if len(head) == 0:
+            lines.append("(empty)")
+        if with_count:
+            lines.append(f"Total count: {self.count()}")
+        if self.has_metadata:
+            lines.append(f"Metadata: {self.metadata}")
+        print("\n".join(lines))
 
     def __copy__(self) -> "DataFrame":
         return self
@@ -185,6 +204,29 @@ class LocalDataFrame(DataFrame):
         return self
 
 
+def _clean_cell(v: Any, tp: pa.DataType) -> Any:
+    """One row value -> what ``pa.array`` takes for ``tp``: pandas' missing markers (NaT, NA) and float NaN
+    in a numeric / temporal column are NULL (fugue_test/dataframe_suite.py:179-196), ISO strings and pandas
+    Timestamps become datetimes / dates."""
+    if v is None or v is pd.NaT or v is pd.NA:
+        return None
+    if pa.types.is_timestamp(tp) or pa.types.is_date(tp):
+        if isinstance(v, str):
+            v = pd.Timestamp(v)
+        if isinstance(v, pd.Timestamp):
+            v = v.to_pydatetime()
+        if pa.types.is_date(tp) and hasattr(v, "date") and callable(v.date):
+            v = v.date()
+        return v
+    if (pa.types.is_floating(tp) or pa.types.is_integer(tp)) and isinstance(v, float) and v != v:
+        return None
+    if (pa.types.is_list(tp) or pa.types.is_large_list(tp)) and isinstance(v, (list, tuple)):
+        return [_clean_cell(x, tp.value_type) for x in v]
+    if pa.types.is_struct(tp) and isinstance(v, dict):   # keys the type does not name are dropped
+        return {tp.field(i).name: _clean_cell(v.get(tp.field(i).name), tp.field(i).type) for i in range(tp.num_fields)}
+    return v
+
+
 def _rows_to_arrow(rows: Any, schema: Schema) -> pa.Table:
     rows = list(rows) if rows is not None else []
     ncol = len(schema)
@@ -194,16 +236,28 @@ def _rows_to_arrow(rows: Any, schema: Schema) -> pa.Table:
         assert len(r) == ncol, f"row {r} doesn't match schema {schema}"
         for i in range(ncol):
             cols[i].append(r[i])
-    arrays = []
-    for vals, tp in zip(cols, schema.types):
-        if pa.types.is_timestamp(tp) or pa.types.is_date(tp):
-            vals = [pd.Timestamp(v).to_pydatetime() if isinstance(v, str) else v for v in vals]
-            if pa.types.is_date(tp):
-                vals = [v.date() if hasattr(v, "date") and callable(v.date) and v is not None else v for v in vals]
-        if pa.types.is_floating(tp) or pa.types.is_integer(tp):
-            vals = [None if (isinstance(v, float) and v != v) else v for v in vals]
-        arrays.append(pa.array(vals, type=tp))
+    arrays = [pa.array([_clean_cell(v, tp) for v in vals], type=tp) for vals, tp in zip(cols, schema.types)]
     return pa.Table.from_arrays(arrays, schema=schema.pa_schema)
+
+
+def _cast_table(t: pa.Table, new: Schema) -> pa.Table:
+    """``alter_columns`` on a host table, column by column, with the string forms the reference's suites pin
+    (fugue_test/dataframe_suite.py:296-420): a datetime becomes ``YYYY-MM-DD HH:MM:SS`` (fractional seconds
+    only when there are any), everything else is the Arrow cast (unsafe: double -> int truncates)."""
+    import pyarrow.compute as pc
+
+    cols = []
+    for name, tp in zip(new.names, new.types):
+        c = t.column(name)
+        if c.type != tp and pa.types.is_timestamp(c.type) and (pa.types.is_string(tp) or pa.types.is_large_string(tp)):
+            whole = c.cast(pa.timestamp("s", c.type.tz), safe=False)
+            if whole.cast(c.type).equals(c):
+                c = whole
+            c = pc.strftime(c, format="%Y-%m-%d %H:%M:%S").cast(tp)
+        elif c.type != tp:
+            c = c.cast(tp, safe=False)
+        cols.append(c)
+    return pa.Table.from_arrays(cols, schema=new.pa_schema)
 
 
 class ArrowDataFrame(LocalDataFrame):

@@ -41,12 +41,33 @@ class SchemaError(Exception):
 
 
 def parse_type(expr: str) -> pa.DataType:
-    e = expr.strip().lower()
+    """One type expression -> pyarrow type.  Flat names (``int``, ``long``, ``str``, ``datetime`` ...),
+    ``timestamp(unit[,tz])``, ``decimal(p[,s])``, ``null`` and the nested forms ``[T]`` (list),
+    ``{name:T,...}`` (struct) and ``<K,V>`` (map), recursively.  Nested columns live in host frames only
+    (``B200Table.from_arrow`` refuses them)."""
+    raw = expr.strip()
+    e = raw.lower()
     if e in _TYPE_ALIASES:
         return _TYPE_ALIASES[e]
+    if e == "null":
+        return pa.null()
     if e.startswith("timestamp(") and e.endswith(")"):
-        args = [x.strip() for x in e[10:-1].split(",")]
-        return pa.timestamp(args[0], args[1] if len(args) > 1 else None)
+        args = [x.strip() for x in raw[10:-1].split(",")]
+        return pa.timestamp(args[0].lower(), args[1] if len(args) > 1 else None)
+    if e.startswith("decimal(") and e.endswith(")"):
+        args = [int(x) for x in e[8:-1].split(",")]
+        return pa.decimal128(args[0], args[1] if len(args) > 1 else 0)
+    if len(raw) >= 2:
+        inner = raw[1:-1]
+        if raw[0] == "[" and raw[-1] == "]":
+            return pa.list_(parse_type(inner))
+        if raw[0] == "{" and raw[-1] == "}":
+            return pa.struct(Schema(inner).fields)
+        if raw[0] == "<" and raw[-1] == ">":
+            kv = _split_top_level(inner)
+            if len(kv) != 2:
+                raise SchemaError(f"a map type needs a key and a value type: {expr!r}")
+            return pa.map_(parse_type(kv[0]), parse_type(kv[1]))
     raise SchemaError(f"unsupported type expression {expr!r}")
 
 
@@ -60,6 +81,17 @@ def type_to_expr(tp: pa.DataType) -> str:
         return f"timestamp({tp.unit},{tp.tz})" if tp.tz else f"timestamp({tp.unit})"
     if pa.types.is_large_string(tp):
         return "str"
+    if pa.types.is_null(tp):
+        return "null"
+    if pa.types.is_decimal(tp):
+        return f"decimal({tp.precision},{tp.scale})"
+    if pa.types.is_map(tp):
+        return f"<{type_to_expr(tp.key_type)},{type_to_expr(tp.item_type)}>"
+    if pa.types.is_list(tp) or pa.types.is_large_list(tp):
+        return f"[{type_to_expr(tp.value_type)}]"
+    if pa.types.is_struct(tp):
+        return "{" + ",".join(f"{tp.field(i).name}:{type_to_expr(tp.field(i).type)}"
+                              for i in range(tp.num_fields)) + "}"
     raise SchemaError(f"unsupported arrow type {tp}")
 
 
