@@ -195,7 +195,13 @@ class PartitionSpec:
         for k, fn in expr_map_funcs.items():
             if k in expr:
                 expr = expr.replace(k, str(fn()))
-        return int(eval(expr, {"__builtins__": {}}, {}))  # arithmetic expression only
+        # the reference evaluates the text with a bare eval (partition.py:203-207); here only arithmetic and
+        # a few pure functions are visible ("min(ROWCOUNT,CONCURRENCY)" is one of its test cases)
+        import math
+
+        allowed = dict(min=min, max=max, abs=abs, round=round, int=int, float=float, pow=pow,
+                       ceil=math.ceil, floor=math.floor, sqrt=math.sqrt, log2=math.log2)
+        return int(eval(expr, {"__builtins__": {}}, allowed))
 
     @property
     def algo(self) -> str:

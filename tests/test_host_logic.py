@@ -115,6 +115,43 @@ def test_partition_spec_determinism():
     assert uid(PartitionSpec(PartitionSpec(by=["a"], num=3))) == uid(PartitionSpec(by=["a"], num=3))
 
 
+def test_presort_forms_and_spec_equality():
+    """Presort given as text, pairs, bare names or a mix; quoted names; specs compare by meaning
+    (tests/fugue/collections/test_partition.py:20-56, 170-212)."""
+    od = OrderedDict
+    assert parse_presort_exp("DESC DESC, ASC ASC") == od([("DESC", False), ("ASC", True)])
+    assert parse_presort_exp("`` desc, `a b` asc, ````, `中国`") == od([("", False), ("a b", True), ("`", True),
+                                                                      ("中国", True)])
+    assert parse_presort_exp([("", False), ("a b", True), "中国"]) == od([("", False), ("a b", True), ("中国", True)])
+    same = [PartitionSpec(by=["a"], presort=p) for p in
+            ("b DESC, c", [("b", False), ("c", True)], [("b", False), "c"], od([("b", False), ("c", True)]))]
+    assert all(x.presort == same[0].presort and x == same[0] for x in same)
+    other = PartitionSpec(by=["a"], presort="c,b DESC")
+    assert other.presort != same[0].presort and other != same[0]
+    assert PartitionSpec(other, presort=same[0].presort) == same[0]          # override while copying
+    assert len(PartitionSpec(other, presort=[]).presort) == 0
+    assert PartitionSpec(by=["a"], presort=["b", "c"]) == dict(presort="b asc, c", by=["a"])
+    assert PartitionSpec(num=10, by=["a"], presort=["b", "c"]) != PartitionSpec(num=10, by=["a"], presort=["c", "b"])
+    for bad in ("a b asc,a desc", [("a",), ("b")], ["a", ["b", True]]):
+        with raises(SyntaxError):
+            PartitionSpec(presort=bad)
+
+
+def test_num_partitions_expressions():
+    """tests/fugue/collections/test_partition.py:228-241."""
+    by = dict(partition_by=["b", "a"])
+    assert PartitionSpec(by).get_num_partitions() == 0
+    assert PartitionSpec(dict(by, num=123)).get_num_partitions() == 123
+    p = PartitionSpec(dict(by, num="(x + Y) * 2"))
+    assert p.get_num_partitions(x=lambda: 1, Y=lambda: 2) == 6
+    with raises(Exception):
+        p.get_num_partitions(x=lambda: 1)
+    p = PartitionSpec(dict(by, num="min(ROWCOUNT,CONCURRENCY)"))
+    assert p.get_num_partitions(**{KEYWORD_ROWCOUNT: lambda: 100, "CONCURRENCY": lambda: 90}) == 90
+    with raises(Exception):
+        PartitionSpec(num="__import__('os').getpid()").get_num_partitions()   # no builtins in the expression
+
+
 def test_partition_cursor():
     # tests/fugue/collections/test_partition.py (test_partition_cursor)
     p = PartitionSpec(dict(partition_by=["b", "a"]))
