@@ -183,3 +183,25 @@ def test_local_dataframes():
     assert not df_eq(df, [[None, 3.5], [1, 2.1]], "a:long,b:double")
     assert not df_eq(df, [[None, 3.5], [1, 2.0]], "a:long,c:double")
     assert df_eq(df, [[None, 3.5], [1, 2.0 + 1e-10]], "a:long,b:double", throw=True)
+
+
+def test_join_schemas():
+    """Key schema / output schema rule of every join type (fugue/dataframe/utils.py:152-226; cases of
+    tests/fugue/dataframe/test_utils.py:55-88)."""
+    from fugue_b200.join import get_join_schemas
+
+    a, b, c = (ArrayDataFrame([], s) for s in ("a:int,b:int", "c:int", "d:str,a:int"))
+    assert get_join_schemas(a, b, how="cross", on=[]) == ("", "a:int,b:int,c:int")
+    for how, on in (("inner", ["a"]), ("inner", []), ("Left_Outer", None)):          # keys given or inferred
+        assert get_join_schemas(a, c, how=how, on=on) == ("a:int", "a:int,b:int,d:str")
+    for how in ("SEMI", "LEFT_Semi", "Anti", "left_Anti"):                             # left columns only
+        assert get_join_schemas(c, a, how=how, on=["a"]) == ("a:int", "d:str,a:int")
+    wide1, wide2 = ArrayDataFrame([], "a:int,b:int,c:int"), ArrayDataFrame([], "c:int,b:int,x:int")
+    assert get_join_schemas(wide1, wide2, how="inner", on=["c", "b"]) == ("b:int,c:int", "a:int,b:int,c:int,x:int")
+    for exc, l, r, how, on in [
+        (Exception, a, b, None, []), (ValueError, a, b, "x", []), (ValueError, a, c, "outer", ["a"]),
+        (SchemaError, a, b, "CROSS", ["a"]), (SchemaError, a, c, "CROSS", ["a"]), (SchemaError, a, c, "CROSS", []),
+        (SchemaError, a, b, "inner", ["a"]), (SchemaError, wide1, wide2, "inner", ["a"]),
+    ]:
+        with raises(exc):
+            get_join_schemas(l, r, how=how, on=on)
