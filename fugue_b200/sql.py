@@ -28,28 +28,74 @@ _AGG = r"(SUM|COUNT|MIN|MAX|AVG|MEAN)\s*\(\s*(\*|[A-Za-z_][\w]*)\s*\)"
 _IDENT = r"[A-Za-z_][\w]*"
 
 
-class StructuredRawSQL:
-    """(is_table_ref, text) pieces - fugue/collections/sql.py:48-151."""
+_TEMP_TABLE_EXPR_PREFIX, _TEMP_TABLE_EXPR_SUFFIX = "<tmpdf:", ">"
 
-    def __init__(self, statements: Any):
-        self._pieces: List[Tuple[bool, str]] = [(bool(a), str(b)) for a, b in statements]
+
+class TempTableName:
+    """A random table name that prints as ``<tmpdf:_XXXXX>`` - the placeholder ``from_expr`` recognises
+    (fugue/collections/sql.py:14-21)."""
+
+    def __init__(self) -> None:
+        import uuid
+
+        self.key = "_" + uuid.uuid4().hex[:5].upper()
+
+    def __repr__(self) -> str:
+        return _TEMP_TABLE_EXPR_PREFIX + self.key + _TEMP_TABLE_EXPR_SUFFIX
+
+
+class StructuredRawSQL:
+    """SQL text as ``(is_table_ref, text)`` pieces plus the dialect it is written in
+    (fugue/collections/sql.py:48-151).  ``construct`` joins the pieces with single spaces, table references
+    mapped through ``name_map`` (a function, or a dict - names it does not hold stay as they are).  A change
+    of dialect needs sqlglot (``transpile_sql``, :24-45), which this image does not have: asking for one
+    raises; the engine's own dialect is None, which never transpiles (:99-103)."""
+
+    def __init__(self, statements: Any, dialect: Any = None):
+        self._statements: List[Tuple[bool, str]] = [(bool(a), str(b)) for a, b in statements]
+        self._dialect = dialect
+
+    @property
+    def dialect(self) -> Any:
+        return self._dialect
+
+    def __uuid__(self) -> str:
+        import json
+        import uuid
+
+        return str(uuid.uuid5(uuid.NAMESPACE_OID, json.dumps([self._statements, self._dialect])))
 
     @staticmethod
-    def from_expr(sql: str, prefix: str = "<tmpdf:", suffix: str = ">") -> "StructuredRawSQL":
+    def from_expr(sql: str, prefix: str = _TEMP_TABLE_EXPR_PREFIX, suffix: str = _TEMP_TABLE_EXPR_SUFFIX,
+                  dialect: Any = None) -> "StructuredRawSQL":
         pieces: List[Tuple[bool, str]] = []
         pos = 0
-        for m in re.finditer(re.escape(prefix) + r"([^>]+)" + re.escape(suffix), sql):
-            if m.start() > pos:
-                pieces.append((False, sql[pos:m.start()]))
-            pieces.append((True, m.group(1)))
-            pos = m.end()
-        if pos < len(sql):
-            pieces.append((False, sql[pos:]))
-        return StructuredRawSQL(pieces)
+        while pos < len(sql):
+            start = sql.find(prefix, pos)
+            if start < 0:
+                pieces.append((False, sql[pos:]))
+                break
+            if start > pos:
+                pieces.append((False, sql[pos:start]))
+            end = sql.find(suffix, start + len(prefix))
+            if end < 0:
+                raise SyntaxError(f"unterminated table reference in {sql!r}")
+            pieces.append((True, sql[start + len(prefix):end]))
+            pos = end + len(suffix)
+        return StructuredRawSQL(pieces, dialect=dialect)
 
-    def construct(self, name_map: Any = None) -> str:
-        f = (lambda x: x) if name_map is None else (name_map if callable(name_map) else (lambda x: name_map[x]))
-        return " ".join(f(t) if is_t else t.strip() for is_t, t in self._pieces).strip()
+    def construct(self, name_map: Any = None, dialect: Any = None, log: Any = None) -> str:
+        if name_map is None:
+            rename = lambda x: x  # noqa: E731
+        elif isinstance(name_map, dict):
+            rename = lambda x: name_map.get(x, x)  # noqa: E731
+        else:
+            rename = name_map
+        text = " ".join(rename(t) if is_ref else t for is_ref, t in self._statements)
+        if self._dialect is not None and dialect is not None and self._dialect != dialect:
+            raise NotImplementedError(
+                f"SQL transpilation {self._dialect} -> {dialect} needs sqlglot, which is not installed")
+        return text
 
 
 class B200SQLEngine:

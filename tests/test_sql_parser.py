@@ -47,11 +47,34 @@ def test_rejections():
 
 
 def test_structured_raw_sql_pieces():
-    st = StructuredRawSQL([(False, "SELECT * FROM"), (True, "a"), (False, " WHERE x>1 ")])
-    assert st.construct() == "SELECT * FROM a WHERE x>1"
-    assert st.construct({"a": "tbl"}) == "SELECT * FROM tbl WHERE x>1"
-    st = StructuredRawSQL.from_expr("SELECT * FROM <tmpdf:abc> WHERE x<3")
-    assert st.construct(lambda n: n.upper()) == "SELECT * FROM ABC WHERE x<3"
+    """tests/fugue/collections/test_sql.py:34-88 (without the sqlglot transpile cases)."""
+    from fugue_b200.sql import TempTableName
+
+    def marked(sql):
+        return "".join(t if not ref else "!" + t + "!" for ref, t in StructuredRawSQL.from_expr(sql)._statements)
+
+    t1, t2 = TempTableName(), TempTableName()
+    assert t1.key != t2.key and str(t1) == f"<tmpdf:{t1.key}>"
+    assert marked("") == "" and marked(f"{t1}") == f"!{t1.key}!" and marked(f" {t1} ") == f" !{t1.key}! "
+    assert marked(f"SELECT {t1}.* FROM {t1} NATURAL JOIN {t2} WHERE {t2}.x<1") == \
+        f"SELECT !{t1.key}!.* FROM !{t1.key}! NATURAL JOIN !{t2.key}! WHERE !{t2.key}!.x<1"
+    assert StructuredRawSQL.from_expr("SELECT * FROM abc", dialect="y").dialect == "y"
+    with raises(SyntaxError):
+        StructuredRawSQL.from_expr("SELECT * FROM <tmpdf:abc")
+
+    pieces = [(False, "SELECT * FROM"), (True, "tb1"), (False, "NATURAL JOIN"), (True, "tb2")]
+    q = StructuredRawSQL(pieces, dialect="x")
+    assert q.dialect == "x" and q.construct() == "SELECT * FROM tb1 NATURAL JOIN tb2"
+    assert q.construct({"tb1": "tt"}) == "SELECT * FROM tt NATURAL JOIN tb2"       # unknown names stay
+    assert q.construct(lambda n: n + "_", dialect="x") == "SELECT * FROM tb1_ NATURAL JOIN tb2_"
+    with raises(NotImplementedError):
+        q.construct(dialect="y")                                                    # would need sqlglot
+    assert StructuredRawSQL(pieces).construct(dialect="y") == q.construct()         # no source dialect: as is
+
+    uid = lambda *a, **k: StructuredRawSQL(*a, **k).__uuid__()  # noqa: E731
+    same = [(False, "SELECT * FROM"), (True, "tb1")]
+    assert uid(same) == uid(list(same)) and uid(same) != uid(same, dialect="x")
+    assert uid(same) != uid([(False, "SELECT * from"), (True, "tb1")])
 
 
 class _FakeDF:
