@@ -17,7 +17,7 @@ import torch
 
 from . import kernels as K
 from .column import agg as _agg, col
-from .dataframe import ArrowDataFrame, B200DataFrame
+from .dataframe import B200DataFrame
 from .partition import PartitionSpec
 from .schema import Schema
 from .table import B200Table
@@ -177,73 +177,17 @@ def sample(df: B200DataFrame, n: Optional[int] = None, frac: Optional[float] = N
     return B200DataFrame(_take_rows(t, idx))
 
 
-def _format_of(path: str, format_hint: Any) -> str:
-    if format_hint:
-        return str(format_hint).lower().lstrip(".")
-    ext = os.path.splitext(path.rstrip("/"))[1].lower().lstrip(".")
-    if ext not in ("parquet", "csv", "json"):
-        raise NotImplementedError(f"can't infer the file format of {path}")
-    return ext
-
-
 def load_df(engine: Any, path: Any, format_hint: Any = None, columns: Any = None, **kwargs: Any) -> B200DataFrame:
-    """Host IO through pyarrow, then one H2D per column (fugue/_utils/io.py:107-147)."""
-    import pyarrow.csv as pcsv
-    import pyarrow.json as pjson
-    import pyarrow.parquet as pq
+    """Host IO through pyarrow (fugue_b200/io.py: files, folders, patterns; parquet / csv / json), then one H2D
+    per column (``ExecutionEngine.load_df`` execution_engine.py:1127-1146, fugue/_utils/io.py:107-147)."""
+    from . import io as IO
 
-    paths = [path] if isinstance(path, str) else list(path)
-    tables = []
-    for p in paths:
-        fmt = _format_of(p, format_hint)
-        names = None if columns is None or isinstance(columns, str) else list(columns)
-        if fmt == "parquet":
-            tables.append(pq.read_table(p, columns=names))
-        elif fmt == "csv":
-            header = kwargs.get("header", False)
-            ro = pcsv.ReadOptions(autogenerate_column_names=not header)
-            tb = pcsv.read_csv(p, read_options=ro)
-            tables.append(tb.select(names) if names and header else tb)
-        elif fmt == "json":
-            tb = pjson.read_json(p)
-            tables.append(tb.select(names) if names else tb)
-        else:
-            raise NotImplementedError(fmt)
-    table = pa.concat_tables(tables)
-    schema = Schema(columns) if isinstance(columns, str) else None
-    if schema is not None:
-        if len(schema) == table.num_columns and table.schema.names != schema.names:
-            table = table.rename_columns(schema.names)
-        table = table.select(schema.names).cast(schema.pa_schema)
-    return engine.to_df(ArrowDataFrame(table))
+    return engine.to_df(IO.load_df(path, format_hint, columns, **kwargs))
 
 
 def save_df(engine: Any, df: Any, path: str, format_hint: Any = None, mode: str = "overwrite",
             **kwargs: Any) -> None:
-    import pyarrow.csv as pcsv
-    import pyarrow.parquet as pq
+    """One D2H (``as_local_bounded``), then the host writer (execution_engine.py:1148-1174)."""
+    from . import io as IO
 
-    if mode not in ("overwrite", "error"):
-        raise NotImplementedError(f"{mode} is not supported")
-    if os.path.exists(path):
-        if mode == "error":
-            raise FileExistsError(path)
-        if os.path.isdir(path):
-            import shutil
-
-            shutil.rmtree(path)
-        else:
-            os.remove(path)
-    d = os.path.dirname(path)
-    if d:
-        os.makedirs(d, exist_ok=True)
-    table = engine.to_df(df).as_arrow()
-    fmt = _format_of(path, format_hint)
-    if fmt == "parquet":
-        pq.write_table(table, path)
-    elif fmt == "csv":
-        pcsv.write_csv(table, path, pcsv.WriteOptions(include_header=bool(kwargs.get("header", False))))
-    elif fmt == "json":
-        table.to_pandas().to_json(path, orient="records", lines=True)
-    else:
-        raise NotImplementedError(fmt)
+    IO.save_df(engine.to_df(df).as_local_bounded(), path, format_hint, mode, **kwargs)

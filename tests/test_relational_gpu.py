@@ -115,7 +115,11 @@ def test_save_and_load_parquet_csv_json(e, tmp_path):
         fa.save(c, path, mode="error", engine=e)
     p2 = os.path.join(tmp_path, "x.csv")
     fa.save(ArrayDataFrame([[1, 2], [3, 4]], "a:long,b:long"), p2, header=True, engine=e)
-    df_eq(fa.load(p2, header=True, engine=e, as_fugue=True), [[1, 2], [3, 4]], "a:long,b:long", throw=True)
+    df_eq(fa.load(p2, header=True, infer_schema=True, engine=e, as_fugue=True), [[1, 2], [3, 4]], "a:long,b:long",
+          throw=True)
+    df_eq(fa.load(p2, header=True, engine=e, as_fugue=True), [["1", "2"], ["3", "4"]], "a:str,b:str", throw=True)
+    df_eq(fa.load(p2, header=True, columns="b:long,a:double", engine=e, as_fugue=True), [[2, 1.0], [4, 3.0]],
+          "b:long,a:double", throw=True)
     p3 = os.path.join(tmp_path, "x.json")
     fa.save(ArrayDataFrame([[1, 2], [3, 4]], "a:long,b:long"), p3, engine=e)
     df_eq(fa.load(p3, engine=e, as_fugue=True), [[1, 2], [3, 4]], "a:long,b:long", throw=True)
