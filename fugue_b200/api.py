@@ -11,10 +11,8 @@ The reference builds a two-task DAG (adagio) around one ``map_dataframe`` call; 
 driver-side plumbing is O(1) and is collapsed into a direct call here.
 """
 import collections.abc
-import contextvars
 import inspect
 import re
-from contextlib import contextmanager
 from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, get_args, get_origin, get_type_hints
 
 import pandas as pd
@@ -23,71 +21,112 @@ import pyarrow as pa
 from .dataframe import (ArrayDataFrame, ArrowDataFrame, B200DataFrame, DataFrame, LocalDataFrame,
                         PandasDataFrame, as_fugue_df)
 from .execution_engine import B200ExecutionEngine, assert_or_throw
+from .lifecycle import (EngineLifecycle, FugueInvalidOperation, clear_global_engine, register_global_conf,  # noqa: F401
+                        try_get_context_engine)
+from .lifecycle import get_current_conf as _context_conf
 from .partition import PartitionCursor, PartitionSpec
 from .schema import Schema
 from .table import B200Table
 
-_CONTEXT_ENGINE: "contextvars.ContextVar[Optional[B200ExecutionEngine]]" = contextvars.ContextVar(
-    "fugue_b200_engine", default=None)
-_GLOBAL_ENGINE: List[Optional[B200ExecutionEngine]] = [None]
-_ENGINE_FACTORIES: Dict[str, Callable[..., B200ExecutionEngine]] = {}
+_ENGINE_FACTORIES: Dict[str, Callable[..., Any]] = {}
+_SQL_ENGINE_FACTORIES: Dict[str, Callable[..., Any]] = {}
 
 
-def register_execution_engine(name: str, func: Callable[..., B200ExecutionEngine],
-                              on_dup: str = "overwrite") -> None:
-    """fugue/execution/factory.py:18-88 (name registration only)."""
-    if name in _ENGINE_FACTORIES and on_dup == "ignore":
+def _register(table: Dict[str, Callable[..., Any]], name: str, func: Callable[..., Any], on_dup: str) -> None:
+    if name in table and on_dup == "ignore":
         return
-    if name in _ENGINE_FACTORIES and on_dup == "throw":
+    if name in table and on_dup == "throw":
         raise KeyError(f"{name} is already registered")
-    _ENGINE_FACTORIES[name] = func
+    table[name] = func
+
+
+def register_execution_engine(name: str, func: Callable[..., Any], on_dup: str = "overwrite") -> None:
+    """fugue/execution/factory.py:18-88 (name registration only): ``func(conf, **kwargs) -> engine``."""
+    _register(_ENGINE_FACTORIES, name, func, on_dup)
+
+
+def register_sql_engine(name: str, func: Callable[..., Any], on_dup: str = "overwrite") -> None:
+    """fugue/execution/factory.py:132-170: ``func(execution_engine, **kwargs) -> sql engine``."""
+    _register(_SQL_ENGINE_FACTORIES, name, func, on_dup)
 
 
 register_execution_engine("b200", lambda conf, **kw: B200ExecutionEngine(conf, **kw))
+register_sql_engine("b200", lambda engine, **kw: engine.create_default_sql_engine())
+
+
+def infer_execution_engine(objs: Optional[List[Any]]) -> Any:
+    """Which engine the inputs ask for (fugue/execution/factory.py:401-447): device tables / frames -> "b200"."""
+    for o in objs or []:
+        if isinstance(o, (B200Table, B200DataFrame)):
+            return "b200"
+    return None
+
+
+def make_sql_engine(engine: Any, execution_engine: Any, **kwargs: Any) -> Any:
+    """fugue/execution/factory.py:342-398: None -> the engine's default, a registered name, a type (called with
+    the execution engine) or a ready instance."""
+    if engine is None or engine == "":
+        return execution_engine.create_default_sql_engine()
+    if isinstance(engine, str):
+        assert_or_throw(engine in _SQL_ENGINE_FACTORIES, lambda: ValueError(
+            f"{engine!r} is not a registered SQL engine (this package provides 'b200')"))
+        return _SQL_ENGINE_FACTORIES[engine](execution_engine, **kwargs)
+    if isinstance(engine, type):
+        return engine(execution_engine, **kwargs)
+    return engine
 
 
 def make_execution_engine(engine: Any = None, conf: Any = None, infer_by: Optional[List[Any]] = None,
-                          **kwargs: Any) -> B200ExecutionEngine:
-    """None -> context engine -> global engine -> a new "b200" engine."""
-    if isinstance(engine, B200ExecutionEngine):
-        if conf:
-            engine.conf.update(dict(conf))
-        return engine
-    if engine is None:
-        cur = _CONTEXT_ENGINE.get() or _GLOBAL_ENGINE[0]
-        if cur is not None:
-            return cur
-        engine = "b200"
-    if isinstance(engine, str):
+                          **kwargs: Any) -> Any:
+    """Engine resolution of fugue/execution/factory.py:237-339.  ``engine`` None: the context engine, else the
+    global engine, else what ``infer_by`` asks for, else a new "b200" engine.  Otherwise a registered name, an
+    engine type, an engine instance, or a pair ``(engine, sql_engine)``.  ``conf`` and ``kwargs`` end up in the
+    engine's conf in every case."""
+    if engine is None or engine == "":
+        engine = try_get_context_engine()
+        if engine is None:
+            engine = infer_execution_engine(infer_by)
+        if engine is None:
+            engine = "b200"
+    if isinstance(engine, tuple):
+        assert_or_throw(len(engine) == 2, lambda: ValueError(f"(engine, sql_engine) expected, got {engine}"))
+        result = make_execution_engine(engine[0], conf, **kwargs)
+        result._sql_engine = make_sql_engine(engine[1], result)
+        return result
+    if isinstance(engine, EngineLifecycle):
+        result = engine
+    elif isinstance(engine, str):
         assert_or_throw(engine in _ENGINE_FACTORIES, lambda: ValueError(
             f"{engine!r} is not a registered execution engine (this package provides 'b200')"))
-        return _ENGINE_FACTORIES[engine](conf, **kwargs)
-    raise TypeError(f"{engine} can't be converted to an execution engine")
+        result = _ENGINE_FACTORIES[engine](conf, **kwargs)
+    elif isinstance(engine, type) and issubclass(engine, EngineLifecycle):
+        result = engine(conf, **kwargs)
+    else:
+        raise TypeError(f"{engine} can't be converted to an execution engine")
+    if conf:
+        result.conf.update(dict(conf))
+    if kwargs:
+        result.conf.update(kwargs)
+    return result
 
 
-@contextmanager
-def engine_context(engine: Any = None, engine_conf: Any = None, infer_by: Any = None
-                   ) -> Iterator[B200ExecutionEngine]:
-    e = make_execution_engine(engine, engine_conf, infer_by=infer_by)
-    token = _CONTEXT_ENGINE.set(e)
-    try:
-        yield e
-    finally:
-        _CONTEXT_ENGINE.reset(token)
+def engine_context(engine: Any = None, engine_conf: Any = None, infer_by: Any = None) -> Any:
+    """``with fa.engine_context(...) as e`` (fugue/execution/api.py:21-50): the engine becomes the context
+    engine; leaving its last context stops it."""
+    return make_execution_engine(engine, engine_conf, infer_by=infer_by).as_context()
 
 
-def set_global_engine(engine: Any, engine_conf: Any = None) -> B200ExecutionEngine:
-    e = make_execution_engine(engine, engine_conf)
-    _GLOBAL_ENGINE[0] = e
-    return e
+def set_global_engine(engine: Any, engine_conf: Any = None) -> Any:
+    assert_or_throw(engine is not None, ValueError("engine must be specified"))
+    return make_execution_engine(engine, engine_conf).set_global()
 
 
-def clear_global_engine() -> None:
-    _GLOBAL_ENGINE[0] = None
-
-
-def get_context_engine() -> B200ExecutionEngine:
-    return make_execution_engine(None)
+def get_context_engine() -> Any:
+    """The context (else global) engine; an error when there is none (fugue/execution/api.py:95-102)."""
+    engine = try_get_context_engine()
+    if engine is None:
+        raise FugueInvalidOperation("No global/context engine is set")
+    return engine
 
 
 def as_fugue_engine_df(engine: B200ExecutionEngine, df: Any, schema: Any = None) -> DataFrame:
@@ -639,6 +678,10 @@ def get_current_parallelism(engine: Any = None, engine_conf: Any = None) -> int:
 
 
 def get_current_conf(engine: Any = None, engine_conf: Any = None) -> Dict[str, Any]:
+    """Conf of the context / global engine, else the registered global conf (fugue/execution/api.py:104-111);
+    with an explicit ``engine``: that engine's conf."""
+    if engine is None and engine_conf is None:
+        return _context_conf()
     return make_execution_engine(engine, engine_conf).conf
 
 

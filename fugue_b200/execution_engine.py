@@ -19,6 +19,7 @@ import torch
 from . import kernels as K
 from .dataframe import (ArrowDataFrame, B200DataFrame, DataFrame, LocalDataFrame, PandasDataFrame,
                         as_fugue_df)
+from .lifecycle import FUGUE_GLOBAL_CONF, EngineLifecycle
 from .partition import KEYWORD_PARALLELISM, KEYWORD_ROWCOUNT, PartitionCursor, PartitionSpec
 from .schema import Schema
 from .table import B200Table
@@ -241,11 +242,12 @@ def finish_avgs(res: "B200DataFrame", post: List[Any], want: List[str]) -> "B200
     return res[want] if res.columns != want else res
 
 
-class B200ExecutionEngine:
-    """The engine object ``fa.engine_context`` / ``fa.transform(engine=...)`` see."""
+class B200ExecutionEngine(EngineLifecycle):
+    """The engine object ``fa.engine_context`` / ``fa.transform(engine=...)`` see.  Context / global / stop
+    protocol: ``EngineLifecycle`` (fugue_b200/lifecycle.py)."""
 
     def __init__(self, conf: Any = None, **kwargs: Any):
-        self._conf: Dict[str, Any] = dict(conf or {})
+        self._conf: Dict[str, Any] = {**FUGUE_GLOBAL_CONF, **dict(conf or {})}  # execution_engine.py:351-354
         self._conf.update(kwargs)
         self._log = logging.getLogger("fugue_b200")
         if not torch.cuda.is_available():
@@ -302,7 +304,9 @@ class B200ExecutionEngine:
     def get_current_parallelism(self) -> int:
         return 1
 
-    def stop(self) -> None:
+    def stop_engine(self) -> None:
+        """Called once, when the engine leaves its last context (or by ``stop()``): drops the cached scratch
+        buffers.  The engine object stays usable; scratch is re-allocated on demand."""
         self._pool = _ScratchPool()
 
     # ---- ingest -----------------------------------------------------------------------
