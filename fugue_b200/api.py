@@ -217,7 +217,15 @@ class _FuncAsTransformer:
         return None
 
     def get_format_hint(self) -> Optional[str]:
-        return {"b200": "b200", "pandas": "pandas", "pyarrow": "pyarrow"}.get(self._in_kind)
+        """Preferred hand-off format: the input annotation's, else the return annotation's
+        (function_wrapper.py:150-160).  Only an INPUT typed ``B200Table`` makes the map engine hand over whole
+        device partitions, so "b200" is never derived from the return type."""
+        hints = {"b200": "b200", "pandas": "pandas", "pandas_iter": "pandas", "pyarrow": "pyarrow",
+                 "pyarrow_iter": "pyarrow"}
+        if self._in_kind in hints:
+            return hints[self._in_kind]
+        out = hints.get(self._out_kind or "")
+        return None if out == "b200" else out
 
     def get_output_schema(self, df: DataFrame) -> Schema:
         if isinstance(self._schema_expr, Schema):

@@ -147,3 +147,24 @@ def test_none_and_empty_outputs():
         return []
 
     assert _run(none)[1] == [] and _run(empty_rows)[1] == []
+
+
+def test_format_hints():
+    """Input annotation first, then the return annotation (tests/fugue/dataframe/test_function_wrapper.py:93-107)."""
+    from fugue_b200.table import B200Table
+
+    def arrow_in(df: pa.Table) -> None: ...
+    def pandas_in(df: pd.DataFrame) -> pa.Table: ...
+    def frames_in(df: Iterable[pd.DataFrame]) -> pa.Table: ...
+    def tables_in(df: Iterator[pa.Table]) -> List[List[Any]]: ...
+    def frames_out(df: List[List[Any]]) -> Iterator[pd.DataFrame]: ...
+    def table_out(df: Iterable[Dict[str, Any]]) -> pa.Table: ...
+    def rows(df: List[List[Any]]) -> List[List[Any]]: ...
+    def device_in(df: B200Table) -> B200Table: ...
+    def device_out(df: pd.DataFrame) -> B200Table: ...
+    def device_out_rows(df: List[List[Any]]) -> B200Table: ...
+
+    hint = lambda f: _FuncAsTransformer(f, "*", None).get_format_hint()  # noqa: E731
+    assert [hint(f) for f in (arrow_in, pandas_in, frames_in, tables_in, frames_out, table_out, rows)] == \
+        ["pyarrow", "pandas", "pandas", "pyarrow", "pandas", "pyarrow", None]
+    assert hint(device_in) == "b200" and hint(device_out) == "pandas" and hint(device_out_rows) is None
