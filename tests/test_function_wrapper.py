@@ -109,10 +109,16 @@ def test_schema_sources():
     def empty_hint(df: pd.DataFrame) -> pd.DataFrame:
         return df
 
+    # schema : *, w : double # trailing remark
+    # # # schema : k:long    (commented out twice: not a hint)
+    def nested_hash(df: pd.DataFrame) -> pd.DataFrame:
+        return df.assign(w=df.v + 1)
+
     assert _run(commented, schema=None)[1] == [[0, 1.5, 2.5], [0, 2.5, 3.5], [1, 4.0, 5.0]]
     assert _run(lowest, schema=None)[1] == [[0, 1.5, 2.5], [0, 2.5, 3.5], [1, 4.0, 5.0]]
     with pytest.raises(SyntaxError):
         _FuncAsTransformer(empty_hint, None, None)
+    assert _run(nested_hash, schema=None)[1][0] == [0, 1.5, 2.5]
     assert _run(commented, schema=Schema("k:long,v:double,w:double"))[1][2] == [1, 4.0, 5.0]
     with pytest.raises(ValueError):
         _FuncAsTransformer(bare, None, None)         # no schema argument, no '# schema:' comment
