@@ -204,10 +204,22 @@ class LocalDataFrame(DataFrame):
         return self
 
 
+_TRUE_WORDS, _FALSE_WORDS = ("true", "t", "yes", "1"), ("false", "f", "no", "0")
+
+
 def _clean_cell(v: Any, tp: pa.DataType) -> Any:
-    """One row value -> what ``pa.array`` takes for ``tp``: pandas' missing markers (NaT, NA) and float NaN
-    in a numeric / temporal column are NULL (fugue_test/dataframe_suite.py:179-196), ISO strings and pandas
-    Timestamps become datetimes / dates."""
+    """One row value -> what ``pa.array`` takes for ``tp``.  Rows are untyped Python data in the reference
+    (``ArrayDataFrame`` keeps them as given and converts on ``as_array(type_safe=True)``,
+    fugue/dataframe/array_dataframe.py + triad's type-safe converters); this frame is typed at construction,
+    so the same conversions run here:
+
+    * pandas' missing markers (NaT, NA) and float NaN in a numeric / temporal column are NULL
+      (fugue_test/dataframe_suite.py:179-196);
+    * text into a numeric / boolean / temporal column is parsed, numbers into a text column are written with
+      ``str``, a float into an integer column is truncated (tests/fugue/dataframe/test_array_dataframe.py:25-60,
+      106-140);
+    * nested values may come as JSON text; struct keys the type does not name are dropped, missing ones are
+      NULL, members are converted recursively (:86-96)."""
     if v is None or v is pd.NaT or v is pd.NA:
         return None
     if pa.types.is_timestamp(tp) or pa.types.is_date(tp):
@@ -218,12 +230,37 @@ def _clean_cell(v: Any, tp: pa.DataType) -> Any:
         if pa.types.is_date(tp) and hasattr(v, "date") and callable(v.date):
             v = v.date()
         return v
-    if (pa.types.is_floating(tp) or pa.types.is_integer(tp)) and isinstance(v, float) and v != v:
-        return None
-    if (pa.types.is_list(tp) or pa.types.is_large_list(tp)) and isinstance(v, (list, tuple)):
-        return [_clean_cell(x, tp.value_type) for x in v]
-    if pa.types.is_struct(tp) and isinstance(v, dict):   # keys the type does not name are dropped
-        return {tp.field(i).name: _clean_cell(v.get(tp.field(i).name), tp.field(i).type) for i in range(tp.num_fields)}
+    if pa.types.is_floating(tp) or pa.types.is_integer(tp):
+        if isinstance(v, str):
+            v = float(v) if pa.types.is_floating(tp) or not v.strip().lstrip("+-").isdigit() else int(v)
+        if isinstance(v, float) and v != v:
+            return None
+        if pa.types.is_integer(tp) and not isinstance(v, (int, bool)):
+            return int(v)          # truncation, like a C cast
+        return v
+    if pa.types.is_boolean(tp):
+        if isinstance(v, str):
+            w = v.strip().lower()
+            if w not in _TRUE_WORDS + _FALSE_WORDS:
+                raise ValueError(f"{v!r} is not a boolean")
+            return w in _TRUE_WORDS
+        return bool(v)
+    if pa.types.is_string(tp) or pa.types.is_large_string(tp):
+        return v if isinstance(v, str) else (v.decode() if isinstance(v, bytes) else str(v))
+    if pa.types.is_list(tp) or pa.types.is_large_list(tp):
+        if isinstance(v, str):
+            import json
+
+            v = json.loads(v)
+        return [_clean_cell(x, tp.value_type) for x in v] if isinstance(v, (list, tuple)) else v
+    if pa.types.is_struct(tp):
+        if isinstance(v, str):
+            import json
+
+            v = json.loads(v)
+        if isinstance(v, dict):   # keys the type does not name are dropped
+            return {tp.field(i).name: _clean_cell(v.get(tp.field(i).name), tp.field(i).type)
+                    for i in range(tp.num_fields)}
     return v
 
 
@@ -254,6 +291,9 @@ def _cast_table(t: pa.Table, new: Schema) -> pa.Table:
             if whole.cast(c.type).equals(c):
                 c = whole
             c = pc.strftime(c, format="%Y-%m-%d %H:%M:%S").cast(tp)
+        elif c.type != tp and pa.types.is_floating(c.type) and (pa.types.is_string(tp) or pa.types.is_large_string(tp)):
+            # Python's float text ("1.0", "1.1"), what the reference's pandas / python casts write
+            c = pa.chunked_array([pa.array([None if x is None else str(x) for x in c.to_pylist()], type=tp)])
         elif c.type != tp:
             c = c.cast(tp, safe=False)
         cols.append(c)
@@ -290,8 +330,16 @@ class ArrowDataFrame(LocalDataFrame):
             self._native = t
         elif isinstance(df, DataFrame):
             t = df.as_arrow()
-            sch = Schema(schema) if schema is not None else df.schema
-            self._native = t if Schema(t.schema) == sch else t.cast(sch.pa_schema)
+            if isinstance(schema, (list, tuple)) and all(isinstance(x, str) and ":" not in x for x in schema):
+                sch = df.schema.extract(list(schema))        # a list of names: projection
+            else:
+                sch = Schema(schema) if schema is not None else df.schema
+            if Schema(t.schema) != sch:
+                missing = [n for n in sch.names if n not in t.schema.names]
+                if missing:
+                    raise FugueDataFrameOperationError(f"{missing} not in {Schema(t.schema)}")
+                t = _cast_table(t.select(sch.names), sch)
+            self._native = t
         elif isinstance(df, (list, tuple)) or hasattr(df, "__iter__"):
             if schema is None:
                 raise FugueDataFrameOperationError("schema is required to build a dataframe from rows")

@@ -208,3 +208,47 @@ def test_native_frames_keep_any_column_names():
     assert fa.get_column_names(fa.rename(pdf, {"0": "_0", "1": "_1", "2": "_2"})) == ["_0", "_1", "_2"]
     named = pd.DataFrame([[0, 1, 2]], columns=["a", "b", "c"])
     assert fa.get_column_names(fa.rename(named, {})) == ["a", "b", "c"]
+
+
+def test_row_values_are_converted_to_the_schema(mk):
+    """Rows are untyped Python data (tests/fugue/dataframe/test_array_dataframe.py:25-60, 86-140): text is parsed,
+    numbers become text, floats are truncated into integer columns, nested values may be JSON text."""
+    import json
+
+    data = [["a", 1], ["b", 2]]
+    assert mk(data, "a:str,b:str").as_array(type_safe=True) == [["a", "1"], ["b", "2"]]
+    assert mk(data, "a:str,b:double").as_array(type_safe=True) == [["a", 1.0], ["b", 2.0]]
+    mixed = mk([["a", 1], ["b", "2"]], "x:str,y:double")
+    assert mixed.count() == 2 and mixed.peek_array() == ["a", 1.0] and mixed.peek_dict() == dict(x="a", y=1.0)
+    (row,) = mk([[1.0, 1.1]], "a:double,b:int").as_array(type_safe=True)
+    assert row == [1.0, 1] and type(row[1]) is int
+    assert mk([[1.0, 1.1]], "a:double,b:int").as_array(["b", "a"], type_safe=True) == [[1, 1.0]]
+    assert mk([["2020-01-01", 1.1]], "a:datetime,b:int").as_array(type_safe=True) == [[datetime(2020, 1, 1), 1]]
+    assert mk([["TRUE", "no"], [1, 0]], "p:bool,q:bool").as_array() == [[True, False], [True, False]]
+    with pytest.raises(Exception):
+        mk([["maybe"]], "p:bool")
+    with pytest.raises(Exception):
+        mk([["x1"]], "p:int")
+    nested = [[dict(a=1, b=[3, 4], d=1.0)], [json.dumps(dict(b=[30, "40"]))]]
+    assert mk(nested, "a:{a:str,b:[int]}").as_array(type_safe=True) == \
+        [[dict(a="1", b=[3, 4])], [dict(a=None, b=[30, 40])]]
+    assert mk([[[json.dumps(dict(b=[30, "40"]))]]], "a:[{a:str,b:[int]}]").as_array(type_safe=True) == \
+        [[[dict(a=None, b=[30, 40])]]]
+
+
+def test_frames_built_from_frames(mk):
+    """A frame as the data argument: same schema, a cast, a reorder, or a projection by a list of names
+    (tests/fugue/dataframe/test_array_dataframe.py:36-58).  One divergence: the reference's ArrayDataFrame keeps
+    the rows as given, so its int 1 under ``b:double`` later prints as "1"; this frame is typed, 1.0 -> "1.0"."""
+    src = mk([["a", 1], ["b", 2]], "a:str,b:double")
+    assert mk(src, None).as_array(type_safe=True) == [["a", 1.0], ["b", 2.0]]
+    assert mk(src, "a:str,b:float64").schema == "a:str,b:double"
+    assert mk(src, "b:str,a:str").as_array(type_safe=True) == [["1.0", "a"], ["2.0", "b"]]
+    only_b = mk(src, ["b"])
+    assert only_b.schema == "b:double" and only_b.as_array(type_safe=True) == [[1.0], [2.0]]
+    assert mk(src, ["b:str"]).as_array(type_safe=True) == [["1.0"], ["2.0"]]
+    with pytest.raises(Exception):
+        mk(src, ["nope"])
+    with pytest.raises(Exception):
+        mk(123, None)
+    assert mk([], "x:str,y:double").empty and mk(None, "x:str,y:double").empty
