@@ -316,7 +316,9 @@ class ArrowDataFrame(LocalDataFrame):
             else:
                 sch = Schema(df.schema)
             self._native = df
-        elif isinstance(df, pd.DataFrame):
+        elif isinstance(df, (pd.DataFrame, pd.Series)):
+            if isinstance(df, pd.Series):
+                df = df.to_frame()
             if schema is None:
                 t = pa.Table.from_pandas(df, preserve_index=False)
                 if any(pa.types.is_large_string(f.type) for f in t.schema):
@@ -326,7 +328,11 @@ class ArrowDataFrame(LocalDataFrame):
                 sch = Schema(t.schema)
             else:
                 sch = Schema(schema)
-                t = pa.Table.from_pandas(df[sch.names], schema=sch.pa_schema, preserve_index=False, safe=False)
+                try:   # one pass when pandas' dtypes already fit the schema
+                    t = pa.Table.from_pandas(df[sch.names], schema=sch.pa_schema, preserve_index=False, safe=False)
+                except (pa.ArrowInvalid, pa.ArrowTypeError):
+                    # otherwise: the natural Arrow types first, then the casts of alter_columns (int -> "1")
+                    t = _cast_table(pa.Table.from_pandas(df[sch.names], preserve_index=False), sch)
             self._native = t
         elif isinstance(df, DataFrame):
             t = df.as_arrow()

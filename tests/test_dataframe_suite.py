@@ -252,3 +252,22 @@ def test_frames_built_from_frames(mk):
     with pytest.raises(Exception):
         mk(123, None)
     assert mk([], "x:str,y:double").empty and mk(None, "x:str,y:double").empty
+
+
+def test_pandas_input_with_a_schema():
+    """tests/fugue/dataframe/test_pandas_dataframe.py:45-93 (what the reference says about object identity of
+    the wrapped pandas frame does not apply: this frame is Arrow-backed)."""
+    pdf = pd.DataFrame([["a", 1], ["b", 2]], columns=["a", "b"])
+    assert PandasDataFrame(schema="a:str,b:int").count() == 0
+    assert PandasDataFrame(pdf, "a:str,b:str").as_array() == [["a", "1"], ["b", "2"]]
+    assert PandasDataFrame(pdf, "a:str,b:int").as_array() == [["a", 1], ["b", 2]]
+    assert PandasDataFrame(pdf, "a:str,b:double").as_array() == [["a", 1.0], ["b", 2.0]]
+    assert PandasDataFrame(pdf["b"], "b:str").as_array() == [["1"], ["2"]]          # a Series is a one-column frame
+    assert PandasDataFrame(pdf["b"], "b:double").as_array() == [[1.0], [2.0]]
+    xy = pd.DataFrame([["a", 1], ["b", 2]], columns=["x", "y"])
+    assert PandasDataFrame(xy).schema == "x:str,y:long"
+    reordered = PandasDataFrame(xy, "y:str,x:str")
+    assert reordered.as_array() == [["1", "a"], ["2", "b"]] and PandasDataFrame(reordered).as_array() == reordered.as_array()
+    assert PandasDataFrame([["a", "1"], ["b", "2"]], "x:str,y:double").peek_array() == ["a", 1.0]
+    with pytest.raises(Exception):
+        PandasDataFrame(123)
