@@ -34,13 +34,16 @@ class FugueInvalidOperation(Exception):
 
 
 def register_global_conf(conf: Dict[str, Any], on_dup: str = "overwrite") -> None:
-    """Base configs for engines created from now on (fugue/constants.py:56-70)."""
+    """Base configs for engines created from now on (fugue/constants.py:56-70).  ``on_dup``: "overwrite",
+    "ignore" (keep the old value) or "throw" - a ValueError when a key exists with a DIFFERENT value, and then
+    nothing of ``conf`` is registered (tests/fugue/execution/test_execution_engine.py:64-85)."""
+    if on_dup == "throw":
+        clash = {k: v for k, v in conf.items() if k in FUGUE_GLOBAL_CONF and FUGUE_GLOBAL_CONF[k] != v}
+        if clash:
+            raise ValueError(f"global conf already set with different values: {sorted(clash)}")
     for k, v in conf.items():
-        if k in FUGUE_GLOBAL_CONF:
-            if on_dup == "ignore":
-                continue
-            if on_dup == "throw":
-                raise KeyError(f"{k} is already a global conf")
+        if k in FUGUE_GLOBAL_CONF and on_dup == "ignore":
+            continue
         FUGUE_GLOBAL_CONF[k] = v
 
 

@@ -99,12 +99,47 @@ class StructuredRawSQL:
 
 
 class B200SQLEngine:
+    """The SQL facet (``SQLEngine``, fugue/execution/execution_engine.py:183-274)."""
+
     def __init__(self, execution_engine: Any):
+        import uuid
+
         self._engine = execution_engine
+        self._uid = "_" + uuid.uuid4().hex[:5] + "_"
 
     @property
     def execution_engine(self) -> Any:
         return self._engine
+
+    @property
+    def log(self) -> Any:
+        return self._engine.log
+
+    @property
+    def conf(self) -> Any:
+        return self._engine.conf
+
+    def to_df(self, df: Any, schema: Any = None) -> Any:
+        return self._engine.to_df(df, schema)
+
+    def encode_name(self, name: str) -> str:
+        """A table name no other statement of this process uses (:197-198)."""
+        return self._uid + name
+
+    def encode(self, dfs: Dict[str, Any], statement: "StructuredRawSQL") -> Tuple[Dict[str, Any], str]:
+        """Tables and statement text with the table references renamed consistently (:200-207)."""
+        return ({self.encode_name(k): v for k, v in dfs.items()},
+                statement.construct(self.encode_name, dialect=self.dialect))
+
+    def table_exists(self, table: str) -> bool:
+        raise NotImplementedError("the b200 SQL engine has no table catalogue")
+
+    def load_table(self, table: str, **kwargs: Any) -> Any:
+        raise NotImplementedError("the b200 SQL engine has no table catalogue")
+
+    def save_table(self, df: Any, table: str, mode: str = "overwrite", partition_spec: Any = None,
+                   **kwargs: Any) -> None:
+        raise NotImplementedError("the b200 SQL engine has no table catalogue")
 
     @property
     def dialect(self) -> Any:

@@ -155,3 +155,33 @@ def test_context_engine_is_per_thread():
         t.join()
         assert L.try_get_context_engine() is e
     assert seen["inside"] is None
+
+
+def test_global_conf_is_the_base_of_every_engine_conf():
+    """tests/fugue/execution/test_execution_engine.py:64-85."""
+    fa.register_global_conf({"ftest.a": 1})
+    assert StandIn().conf["ftest.a"] == 1 and StandIn({"ftest.a": 2}).conf["ftest.a"] == 2
+    fa.register_global_conf({"ftest.a": 1, "ftest.b": 2}, on_dup="throw")     # same value: not a clash
+    assert StandIn().conf["ftest.b"] == 2
+    with pytest.raises(ValueError):
+        fa.register_global_conf({"ftest.a": 2, "ftest.c": 3}, on_dup="throw")
+    assert "ftest.c" not in L.FUGUE_GLOBAL_CONF and L.FUGUE_GLOBAL_CONF["ftest.a"] == 1   # all or nothing
+    fa.register_global_conf({"ftest.a": 5, "ftest.d": 6}, on_dup="ignore")
+    assert (L.FUGUE_GLOBAL_CONF["ftest.a"], L.FUGUE_GLOBAL_CONF["ftest.d"]) == (1, 6)
+
+
+def test_sql_facet_encodes_table_names():
+    from fugue_b200.sql import B200SQLEngine, StructuredRawSQL
+
+    eng = StandIn()
+    eng.log = "the-log"
+    f1, f2 = B200SQLEngine(eng), B200SQLEngine(eng)
+    assert f1.execution_engine is eng and f1.conf is eng.conf and f1.log == "the-log" and f1.dialect is None
+    assert f1.encode_name("t") != f2.encode_name("t") and f1.encode_name("t").endswith("t")
+    dfs, text = f1.encode({"a": 1, "b": 2}, StructuredRawSQL([(False, "SELECT * FROM"), (True, "a"), (False, "JOIN"),
+                                                              (True, "b")]))
+    assert set(dfs) == {f1.encode_name("a"), f1.encode_name("b")}
+    assert text == f"SELECT * FROM {f1.encode_name('a')} JOIN {f1.encode_name('b')}"
+    for call in (lambda: f1.table_exists("x"), lambda: f1.load_table("x"), lambda: f1.save_table(None, "x")):
+        with pytest.raises(NotImplementedError):
+            call()
