@@ -96,7 +96,7 @@ def evaluate(e: Any, df: pd.DataFrame, aggs: Optional[Dict[str, pd.Series]] = No
         elif e.op == "-":
             res = -v
         elif e.op == "~":
-            res = ~(v.astype("boolean") if isinstance(v, pd.Series) else v)
+            res = ~v.astype("boolean") if isinstance(v, pd.Series) else (pd.NA if v is pd.NA else not bool(v))
         else:
             raise NotImplementedError(e.op)
     elif e.kind == Kind.BINARY:
