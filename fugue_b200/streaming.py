@@ -32,8 +32,8 @@ from .table import B200Table, _from_readonly, _np_storage, _storage_dtype
 
 
 def _eligible(table: pa.Table, schema: Schema, spec: PartitionSpec) -> bool:
-    if len(spec.partition_by) == 0 or spec.algo == "coarse" or len(spec.presort) > 0:
-        return False
+    if len(spec.partition_by) == 0 or spec.algo in ("coarse", "even", "rand") or len(spec.presort) > 0:
+        return False  # even / rand number the distinct keys first (device sorts): not a one-pass hash partition
     if table.num_rows == 0:
         return False
     for name, tp in zip(schema.names, schema.types):
