@@ -584,6 +584,7 @@ def show(df: Any, n: int = 10, with_count: bool = False, title: Optional[str] = 
 
 
 def get_native_as_df(df: Any) -> Any:
+    assert_or_throw(is_df(df), lambda: NotImplementedError(f"{type(df)} is not a dataframe"))
     return df.native_as_df() if isinstance(df, DataFrame) else df
 
 

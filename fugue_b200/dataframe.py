@@ -188,6 +188,21 @@ class DataFrame:
             lines.append(f"Metadata: {self.metadata}")
         print("\n".join(lines))
 
+    def get_info_str(self) -> str:
+        """One JSON line: schema, type, metadata (fugue/dataframe/dataframe.py ``get_info_str``)."""
+        import json
+
+        return json.dumps({"schema": str(self.schema), "type": f"{type(self).__module__}.{type(self).__name__}",
+                           "metadata": self.metadata if self.has_metadata else {}})
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}({self.schema})"
+
+    def _repr_html_(self) -> str:
+        import html
+
+        return html.escape(repr(self))
+
     def __copy__(self) -> "DataFrame":
         return self
 
@@ -484,7 +499,7 @@ def as_fugue_df(df: Any, schema: Any = None) -> DataFrame:
         return ArrowDataFrame(df, schema)
     if isinstance(df, (list, tuple)) or hasattr(df, "__iter__"):
         return ArrayDataFrame(df, schema)
-    raise ValueError(f"{type(df)} can't be converted to a Fugue DataFrame")
+    raise NotImplementedError(f"no conversion of {type(df)} to a Fugue DataFrame")  # fugue/dataframe/api.py
 
 
 def df_eq(df: Any, data: Any, schema: Any = None, digits: int = 8, check_order: bool = False,

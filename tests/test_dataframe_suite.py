@@ -271,3 +271,18 @@ def test_pandas_input_with_a_schema():
     assert PandasDataFrame([["a", "1"], ["b", "2"]], "x:str,y:double").peek_array() == ["a", 1.0]
     with pytest.raises(Exception):
         PandasDataFrame(123)
+
+
+def test_misc_frame_protocol(mk):
+    """tests/fugue/dataframe/test_dataframe.py:12-73."""
+    import copy
+    import json
+
+    for f in (fa.as_fugue_df, fa.get_native_as_df):
+        with pytest.raises(NotImplementedError):
+            f(10)
+    df = mk([["a", 1], ["b", 2]], "a:str,b:str")
+    assert copy.copy(df) is df and copy.deepcopy(df) is df
+    info = json.loads(df.get_info_str())
+    assert info["schema"] == "a:str,b:str" and info["metadata"] == {} and info["type"].endswith(type(df).__name__)
+    assert repr(df) == df._repr_html_() and "a:str,b:str" in repr(df)
