@@ -16,21 +16,24 @@ NUM = 16
 ROWS = [5000, 3777]
 
 
-def _shard(rank: int):
+def _shard(rank: int, rows=None, key_range: int = 500):
     rng = np.random.default_rng(100 + rank)
-    n = ROWS[rank]
-    return [rng.integers(0, 500, n).astype("int64"), rng.standard_normal(n),
+    n = (rows or ROWS)[rank]
+    return [rng.integers(0, key_range, n).astype("int64"), rng.standard_normal(n),
             (np.arange(n) + rank * 1_000_000).astype("int64")]
 
 
-def _worker(rank: int, world: int, port: int, ret):
+def _worker(rank: int, world: int, port: int, ret, num: int = NUM, rows=None, key_range: int = 500):
+    global NUM, ROWS
+    NUM, ROWS = num, list(rows or ROWS)
+    _shard_ = lambda r: _shard(r, ROWS, key_range)  # noqa: E731
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from fugue_b200.dist import ExchangePlan, exchange_column, gather_counts, owner_range, rearrange_cpu
 
-        cols = _shard(rank)
+        cols = _shard_(rank)
         part, off = hp.partition_table(cols, [0], NUM)          # what K1-K3 do on each GPU
         counts = gather_counts(torch.from_numpy(np.diff(off)))
         assert counts.shape == (world, NUM)
@@ -63,12 +66,18 @@ def _free_port() -> int:
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_exchange_matches_global_oracle():
-    world = 2
+@pytest.mark.parametrize("world,num,rows,key_range", [
+    (2, 16, [5000, 3777], 500),
+    (3, 7, [0, 2500, 1], 500),          # an empty shard, a one-row shard, partitions not divisible by the ranks
+    (3, 3, [40, 40, 40], 1),            # one key: every row lands in one partition of one rank
+    (2, 256, [300, 200], 100000),       # more partitions than distinct keys per rank: many empty segments
+], ids=["2x16", "3x7-empty-shard", "3x3-one-key", "2x256-sparse"])
+def test_exchange_matches_global_oracle(world, num, rows, key_range):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    shards = [_shard(r) for r in range(world)]
+    mp.spawn(_worker, args=(world, _free_port(), ret, num, rows, key_range), nprocs=world, join=True)
+    NUM, ROWS = num, rows
+    shards = [_shard(r, rows, key_range) for r in range(world)]
     glob = [np.concatenate([s[c] for s in shards]) for c in range(3)]
     exp_cols, exp_off = hp.partition_table(glob, [0], NUM)
     covered = 0
