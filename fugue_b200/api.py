@@ -272,14 +272,20 @@ class _FuncAsTransformer:
             out = [[r.get(n) for n in schema.names] for r in out]
         return ArrayDataFrame(out, schema)
 
-    def make_runner(self, output_schema: Schema, ignore_errors: List[type]
+    def make_runner(self, output_schema: Schema, ignore_errors: List[type], discard_output: bool = False
                     ) -> Callable[[PartitionCursor, DataFrame], DataFrame]:
         def run(cursor: PartitionCursor, df: DataFrame) -> DataFrame:
             kw = dict(self._params)
             for n in self._wants_cursor:
                 kw[n] = cursor
             try:
-                return self._to_output(self._func(self._to_input(df), **kw), output_schema)
+                out = self._func(self._to_input(df), **kw)
+                if discard_output:           # output transformer: only the side effects count
+                    if inspect.isgenerator(out):
+                        for _ in out:
+                            pass
+                    return ArrowDataFrame(None, output_schema)
+                return self._to_output(out, output_schema)
             except tuple(ignore_errors) if ignore_errors else ():  # processors.py:330-338
                 return ArrowDataFrame(None, output_schema)
 
@@ -362,6 +368,27 @@ def transform(
     if as_fugue or isinstance(df, DataFrame):
         return res
     return res.as_pandas() if res.is_local else res.native
+
+
+OUTPUT_TRANSFORMER_DUMMY_SCHEMA = "__output_no_data__:int"   # fugue/extensions/transformer/constants.py:1
+
+
+def out_transform(df: Any, using: Any, params: Any = None, partition: Any = None, callback: Any = None,
+                  ignore_errors: Optional[List[Any]] = None, engine: Any = None, engine_conf: Any = None) -> None:
+    """``fa.out_transform`` (fugue/workflow/api.py:187-250): run ``using`` on every partition for its side effects,
+    eagerly, returning nothing.  As in the reference (``_FuncAsOutputTransformer``, convert.py:386-403) the
+    function's result is dropped and every call hands an empty frame of a dummy schema back to the map engine."""
+    assert_or_throw(callback is None, NotImplementedError("callback (RPC) is out of scope"))
+    assert_or_throw(not isinstance(df, str) or df.lower().endswith(".parquet"),
+                    lambda: ValueError(f"fugue transform can only load parquet file paths (df={df})"))
+    e = make_execution_engine(engine, engine_conf, infer_by=[df])
+    if isinstance(df, str):
+        df = e.load_df(df, format_hint="parquet")
+    tf = _FuncAsTransformer(using, OUTPUT_TRANSFORMER_DUMMY_SCHEMA, params)
+    out_schema = Schema(OUTPUT_TRANSFORMER_DUMMY_SCHEMA)
+    inner = tf.make_runner(out_schema, list(ignore_errors or []), discard_output=True)
+    e.map_engine.map_dataframe(e.to_df(df), inner, out_schema, PartitionSpec(partition),
+                               map_func_format_hint=tf.get_format_hint())
 
 
 def _finish(e: Any, df: Any, res: DataFrame, as_fugue: bool, as_local: bool) -> Any:

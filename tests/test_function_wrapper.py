@@ -15,6 +15,7 @@ import pyarrow as pa
 import pytest
 
 from fugue_b200.api import _FuncAsTransformer
+from fugue_b200.lifecycle import EngineLifecycle
 from fugue_b200.dataframe import ArrayDataFrame, ArrowDataFrame
 from fugue_b200.partition import PartitionCursor, PartitionSpec
 from fugue_b200.schema import Schema
@@ -174,3 +175,66 @@ def test_format_hints():
     assert [hint(f) for f in (arrow_in, pandas_in, frames_in, tables_in, frames_out, table_out, rows)] == \
         ["pyarrow", "pandas", "pandas", "pyarrow", "pandas", "pyarrow", None]
     assert hint(device_in) == "b200" and hint(device_out) == "pandas" and hint(device_out_rows) is None
+
+
+class _HostEngine(EngineLifecycle):
+    """A stand-in engine for ``fa.out_transform`` on CPU: its map engine calls the runner once per key group of
+    a pandas frame - the part of ``map_dataframe`` that is host logic in every engine."""
+
+    def __init__(self):
+        self.conf: Dict[str, Any] = {}
+        self.calls: List[Any] = []
+
+    @property
+    def map_engine(self):
+        return self
+
+    def to_df(self, df, schema=None):
+        from fugue_b200.dataframe import as_fugue_df
+
+        return as_fugue_df(df, schema)
+
+    def map_dataframe(self, df, map_func, output_schema, partition_spec, on_init=None, map_func_format_hint=None):
+        pdf = df.as_pandas()
+        groups = [pdf] if not partition_spec.partition_by else \
+            [g for _, g in pdf.groupby(partition_spec.partition_by, sort=True)]
+        for no, g in enumerate(groups):
+            part = ArrowDataFrame(g.reset_index(drop=True), df.schema)
+            cursor = partition_spec.get_cursor(df.schema, 0)
+            cursor.set(lambda: part.peek_array(), no, 0)
+            out = map_func(cursor, part)
+            assert out.schema == output_schema and out.count() == 0
+            self.calls.append(map_func_format_hint)
+        return ArrowDataFrame(None, output_schema)
+
+
+def test_out_transform_runs_for_side_effects_only():
+    from fugue_b200 import api as fa
+
+    seen = []
+
+    def collect(df: pd.DataFrame, tag: str) -> None:
+        seen.append((tag, df.k.iloc[0], len(df)))
+
+    def lazy(df: List[List[Any]]) -> Iterable[List[Any]]:     # a generator has to be drained to have its effects
+        for r in df:
+            seen.append(("row", r[0], r[1]))
+            yield r
+
+    def boom(df: pd.DataFrame) -> None:
+        raise KeyError("x")
+
+    eng = _HostEngine()
+    pdf = pd.DataFrame(ROWS, columns=["k", "v"])
+    assert fa.out_transform(pdf, collect, params=dict(tag="t"), partition=dict(by=["k"]), engine=eng) is None
+    assert seen == [("t", 0, 2), ("t", 1, 1)] and eng.calls == ["pandas", "pandas"]
+    seen.clear()
+    fa.out_transform(pdf, lazy, engine=eng)
+    assert seen == [("row", 0, 1.5), ("row", 0, 2.5), ("row", 1, 4.0)]
+    fa.out_transform(pdf, boom, ignore_errors=[KeyError], engine=eng)      # swallowed per partition
+    with pytest.raises(KeyError):
+        fa.out_transform(pdf, boom, engine=eng)
+    with pytest.raises(ValueError):
+        fa.out_transform("x.csv", collect, engine=eng)
+    with pytest.raises(NotImplementedError):
+        fa.out_transform(pdf, collect, callback=print, engine=eng)
