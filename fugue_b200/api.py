@@ -324,8 +324,8 @@ def transform(
         assert_or_throw(pth is None or (isinstance(pth, str) and pth.lower().endswith(".parquet")),
                         lambda: ValueError(f"fugue transform can only load / save parquet file paths ({what}={pth})"))
     e = make_execution_engine(engine, engine_conf, infer_by=[df])
-    path_input = isinstance(df, str)
-    if path_input:
+    fugue_in = isinstance(df, DataFrame)      # decides the return type: a path or a native object in -> native out
+    if isinstance(df, str):
         df = e.load_df(df, format_hint="parquet")
     tf = _FuncAsTransformer(using, schema, params)
     spec = PartitionSpec(partition)
@@ -365,7 +365,7 @@ def transform(
             return save_path
         res = e.load_df(target, format_hint="parquet")
     res = e.convert_yield_dataframe(res, as_local)
-    if as_fugue or isinstance(df, DataFrame):
+    if as_fugue or fugue_in:
         return res
     return res.as_pandas() if res.is_local else res.native
 

@@ -185,9 +185,28 @@ class _HostEngine(EngineLifecycle):
         self.conf: Dict[str, Any] = {}
         self.calls: List[Any] = []
 
+    is_distributed = False
+
     @property
     def map_engine(self):
         return self
+
+    def persist(self, df, lazy=False, **kwargs):
+        self.calls.append("persist")
+        return df
+
+    def convert_yield_dataframe(self, df, as_local):
+        return df.as_local() if as_local else df
+
+    def save_df(self, df, path, format_hint=None, mode="overwrite", **kwargs):
+        from fugue_b200 import io as IO
+
+        IO.save_df(self.to_df(df), path, format_hint, mode, **kwargs)
+
+    def load_df(self, path, format_hint=None, columns=None, **kwargs):
+        from fugue_b200 import io as IO
+
+        return IO.load_df(path, format_hint, columns, **kwargs)
 
     def to_df(self, df, schema=None):
         from fugue_b200.dataframe import as_fugue_df
@@ -198,14 +217,16 @@ class _HostEngine(EngineLifecycle):
         pdf = df.as_pandas()
         groups = [pdf] if not partition_spec.partition_by else \
             [g for _, g in pdf.groupby(partition_spec.partition_by, sort=True)]
+        outs: List[Any] = []
         for no, g in enumerate(groups):
             part = ArrowDataFrame(g.reset_index(drop=True), df.schema)
             cursor = partition_spec.get_cursor(df.schema, 0)
             cursor.set(lambda: part.peek_array(), no, 0)
             out = map_func(cursor, part)
-            assert out.schema == output_schema and out.count() == 0
+            assert out.schema == output_schema
+            outs.append(out.as_pandas())
             self.calls.append(map_func_format_hint)
-        return ArrowDataFrame(None, output_schema)
+        return ArrowDataFrame(pd.concat(outs, ignore_index=True) if outs else None, output_schema)
 
 
 def test_out_transform_runs_for_side_effects_only():
@@ -238,3 +259,50 @@ def test_out_transform_runs_for_side_effects_only():
         fa.out_transform("x.csv", collect, engine=eng)
     with pytest.raises(NotImplementedError):
         fa.out_transform(pdf, collect, callback=print, engine=eng)
+
+
+def test_transform_control_flow_on_a_host_engine(tmp_path):
+    """``fa.transform`` around the map engine (fugue/workflow/api.py:34-184): schema resolution, params, the
+    return-type rule, persist, save_path / checkpoint, a parquet path as input - with the host stand-in engine."""
+    from fugue_b200 import api as fa
+    from fugue_b200.dataframe import DataFrame
+
+    def add(df: pd.DataFrame, n: float = 1.0) -> pd.DataFrame:
+        return df.assign(w=df.v + n)
+
+    eng = _HostEngine()
+    pdf = pd.DataFrame(ROWS, columns=["k", "v"])
+    want = [[0, 1.5, 3.5], [0, 2.5, 4.5], [1, 4.0, 6.0]]
+    out = fa.transform(pdf, add, schema="*,w:double", params=dict(n=2.0), partition=dict(by=["k"]), engine=eng)
+    assert isinstance(out, pd.DataFrame) and out.values.tolist() == want         # native in -> native out
+    fdf = fa.transform(ArrowDataFrame(pdf), add, schema="*,w:double", params=dict(n=2.0), engine=eng)
+    assert isinstance(fdf, DataFrame) and fdf.as_array() == want                  # Fugue frame in -> Fugue frame out
+    assert isinstance(fa.transform(pdf, add, schema="*,w:double", engine=eng, as_fugue=True), DataFrame)
+    eng.calls.clear()
+    fa.transform(pdf, add, schema="*,w:double", engine=eng, persist=True)
+    assert "persist" in eng.calls
+    # the declared schema is enforced on what the function returns (PandasDataFrame(output, schema) in the
+    # reference's adapter, function_wrapper.py:442-460): a double column declared long is cast
+    assert fa.transform(pdf, add, schema="*,w:long", engine=eng).values.tolist() == [[0, 1.5, 2], [0, 2.5, 3], [1, 4.0, 5]]
+    with pytest.raises(Exception):
+        fa.transform(pdf, add, schema="*,missing:long", engine=eng)               # a declared column is not produced
+
+    p1 = str(tmp_path / "out" / "a.parquet")
+    assert fa.transform(pdf, add, schema="*,w:double", engine=eng, save_path=p1) == p1
+    assert pd.read_parquet(p1).values.tolist() == [[0, 1.5, 2.5], [0, 2.5, 3.5], [1, 4.0, 5.0]]
+    def twice(df: pd.DataFrame) -> pd.DataFrame:
+        return df.assign(ww=df.w * 2)
+
+    again = fa.transform(p1, twice, schema="*,ww:double", engine=eng)              # a parquet path as input
+    assert list(again.columns) == ["k", "v", "w", "ww"] and len(again) == 3
+    ck = fa.transform(pdf, add, schema="*,w:double", engine=eng, save_path=str(tmp_path / "b.parquet"),
+                      checkpoint=True)
+    assert ck.values.tolist() == [[0, 1.5, 2.5], [0, 2.5, 3.5], [1, 4.0, 5.0]]      # continued from the file
+    for bad in (dict(save_path=str(tmp_path / "x.csv")), dict(checkpoint=True)):   # csv path; no checkpoint dir
+        with pytest.raises(ValueError):
+            fa.transform(pdf, add, schema="*,w:double", engine=eng, **bad)
+    eng.conf["fugue.workflow.checkpoint.path"] = str(tmp_path / "ckpt")
+    assert len(fa.transform(pdf, add, schema="*,w:double", engine=eng, checkpoint=True)) == 3
+    assert len(list((tmp_path / "ckpt").iterdir())) == 1
+    with pytest.raises(ValueError):
+        fa.transform("in.csv", add, schema="*,w:double", engine=eng)
