@@ -306,3 +306,39 @@ def test_transform_control_flow_on_a_host_engine(tmp_path):
     assert len(list((tmp_path / "ckpt").iterdir())) == 1
     with pytest.raises(ValueError):
         fa.transform("in.csv", add, schema="*,w:double", engine=eng)
+
+
+def test_chunked_frames_are_matched_by_column_name():
+    """fugue_test/builtin_suite.py:426-488 (the mapInPandas shape): chunks may come back with their columns in any
+    order, or not at all; a narrower Arrow type is widened to the declared one."""
+    from fugue_b200 import api as fa
+
+    # schema: *,c:int
+    def mt_pandas(dfs: Iterable[pd.DataFrame], empty: bool = False) -> Iterator[pd.DataFrame]:
+        for df in dfs:
+            if not empty:
+                df = df.assign(c=2)
+                yield df[list(reversed(list(df.columns)))]
+
+    # schema: *
+    def mt_arrow(dfs: Iterable[pa.Table], empty: bool = False) -> Iterator[pa.Table]:
+        for df in dfs:
+            if not empty:
+                yield df.select(list(reversed(df.schema.names)))
+
+    # schema: a:long
+    def mt_arrow_2(dfs: Iterable[pa.Table]) -> Iterator[pa.Table]:
+        for df in dfs:
+            yield df.drop(["b"])
+
+    eng = _HostEngine()
+    a = ArrowDataFrame([[1, 2], [3, 4]], "a:int,b:int")
+    got = fa.transform(a, mt_pandas, engine=eng)
+    assert got.schema == "a:int,b:int,c:int" and got.as_array() == [[1, 2, 2], [3, 4, 2]]
+    assert fa.transform(a, mt_arrow, engine=eng).as_array() == [[1, 2], [3, 4]]
+    narrow = fa.transform(a, mt_arrow_2, engine=eng)
+    assert narrow.schema == "a:long" and narrow.as_array() == [[1], [3]]
+    for f, schema in ((mt_pandas, "a:int,b:int,c:int"), (mt_arrow, "a:int,b:int")):
+        for part in (None, dict(by=["a"])):
+            out = fa.transform(a, f, params=dict(empty=True), partition=part, engine=eng)
+            assert out.schema == schema and out.count() == 0
