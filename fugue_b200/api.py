@@ -261,6 +261,8 @@ class _FuncAsTransformer:
             return ArrowDataFrame(out, schema)
         if out is None:
             return ArrowDataFrame(None, schema)
+        if isinstance(out, dict):   # Dict[str, Any]: ONE output row (function_wrapper.py:254-262)
+            out = [out]
         out = list(out)
         if out and all(isinstance(x, pd.DataFrame) for x in out):   # Iterable[pd.DataFrame]: chunks of the result
             frames = [x for x in out if x.shape[0] > 0]

@@ -146,6 +146,14 @@ def test_params_cursor_and_ignored_errors():
         _run(boom)
 
 
+def test_one_row_as_a_dict():
+    def first(rows: list[dict[str, Any]]) -> dict[str, Any]:      # built-in generics; one row out
+        return dict(v=rows[0]["v"], k=rows[0]["k"])
+
+    tf, out = _run(first)
+    assert out == [[0, 1.5]] and tf.get_format_hint() is None
+
+
 def test_none_and_empty_outputs():
     def none(df: pd.DataFrame) -> None:
         return None
