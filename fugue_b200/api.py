@@ -142,6 +142,14 @@ def repartition(df: Any, partition: Any, engine: Any = None, engine_conf: Any = 
 
 
 # ----------------------------------------------------------------------------------------
+class FugueWorkflowCompileValidationError(Exception):
+    """fugue/exceptions.py: a validation rule that does not need data was violated."""
+
+
+class FugueWorkflowRuntimeValidationError(Exception):
+    """fugue/exceptions.py: a validation rule on the input data (its schema) was violated."""
+
+
 # function wrapper: decides how the user function sees a partition
 # ----------------------------------------------------------------------------------------
 class _FuncAsTransformer:
@@ -168,26 +176,89 @@ class _FuncAsTransformer:
             "pa.Table, List[List[Any]], Iterable[List[Any]], List[Dict[str, Any]] or a Fugue DataFrame"))
         self._wants_cursor = [n for n in names[1:] if hints.get(n, None) is PartitionCursor]
         self._schema_expr = schema if schema is not None else self._schema_from_comment(func)
+        self._rules = self._rules_from_comment(func)
         assert_or_throw(self._schema_expr is not None, lambda: ValueError(
             "schema is required (argument or a '# schema:' comment above the function)"))
 
     @staticmethod
-    def _schema_from_comment(func: Callable) -> Optional[str]:
-        """The ``# schema: ...`` hint in the comment block directly above the function
-        (fugue/_utils/interfaceless.py:9-66): the LOWEST matching line wins, anything after a second
-        ``#`` on that line is a remark, an empty hint is a SyntaxError."""
+    def _comment_hint(func: Callable, key: str) -> Optional[str]:
+        """The ``# <key>: ...`` line of the comment block directly above the function
+        (fugue/_utils/interfaceless.py:9-40): the LOWEST matching line wins, anything after a second ``#`` on
+        that line is a remark.  None when there is no such line, "" when it is empty."""
         try:
             block = inspect.getcomments(func) or ""
         except Exception:
             return None
-        hint = re.compile(r"^\s*#\s*schema\s*:([^#]*)")
+        hint = re.compile(r"^\s*#\s*" + re.escape(key) + r"\s*:([^#]*)")
         for line in reversed(block.splitlines()):
             m = hint.match(line)
             if m is not None:
-                text = m.group(1).strip()
-                assert_or_throw(text != "", SyntaxError("incorrect schema annotation"))
-                return text
+                return m.group(1).strip()
         return None
+
+    @staticmethod
+    def _schema_from_comment(func: Callable) -> Optional[str]:
+        text = _FuncAsTransformer._comment_hint(func, "schema")
+        assert_or_throw(text != "", SyntaxError("incorrect schema annotation"))   # interfaceless.py:43-66
+        return text
+
+    @staticmethod
+    def _rules_from_comment(func: Callable) -> Dict[str, Any]:
+        """Validation rules written as comment hints above the function (fugue/extensions/_utils.py:36-81):
+        ``partitionby_has / partitionby_is`` (key names), ``presort_has / presort_is`` (presort expressions),
+        ``input_has`` (column names, optionally ``name:type``), ``input_is`` (a schema)."""
+        from .partition import parse_presort_exp
+
+        rules: Dict[str, Any] = {}
+        for key in ("partitionby_has", "partitionby_is", "presort_has", "presort_is", "input_has", "input_is"):
+            text = _FuncAsTransformer._comment_hint(func, key)
+            if text is None:
+                continue
+            assert_or_throw(text != "", lambda: SyntaxError(f"{key} can't be empty"))
+            if key.startswith("partitionby"):
+                rules[key] = PartitionSpec(by=[x.strip() for x in text.split(",")]).partition_by
+            elif key.startswith("presort"):
+                rules[key] = list(parse_presort_exp(text).items())
+            elif key == "input_has":
+                rules[key] = text.replace(" ", "").split(",")
+            else:
+                rules[key] = str(Schema(text))
+        return rules
+
+    def validate_on_compile(self, spec: PartitionSpec) -> None:
+        """What can be checked before any data is seen: the partitioning the call asks for against the
+        function's ``partitionby_* / presort_*`` rules (fugue/extensions/_utils.py:84-129)."""
+        def fail(msg: str) -> Any:
+            return lambda: FugueWorkflowCompileValidationError(msg)
+
+        for key, want in self._rules.items():
+            if key.startswith("partitionby"):
+                for k in want:
+                    assert_or_throw(k in spec.partition_by, fail(f"required partition key {k} is not in {spec}"))
+                if key == "partitionby_is":
+                    assert_or_throw(len(want) == len(spec.partition_by), fail(f"{want} does not match {spec}"))
+            elif key.startswith("presort"):
+                have = spec.presort
+                for k, asc in want:
+                    assert_or_throw(k in have, fail(f"required presort key {k} is not in presort of {spec}"))
+                    assert_or_throw(have[k] == asc, fail(f"order of {k} doesn't match presort of {spec}"))
+                if key == "presort_is":
+                    assert_or_throw(want == list(have.items()), fail(f"{want} does not match presort of {spec}"))
+
+    @property
+    def has_input_rules(self) -> bool:
+        return any(k.startswith("input_") for k in self._rules)
+
+    def validate_on_runtime(self, schema: Schema) -> None:
+        """``input_has / input_is`` against the schema of the actual input (fugue/extensions/_utils.py:132-150)."""
+        for key, want in self._rules.items():
+            if key == "input_has":
+                for c in want:
+                    assert_or_throw(c in schema, lambda: FugueWorkflowRuntimeValidationError(
+                        f"required column {c} is not in {schema}"))
+            elif key == "input_is":
+                assert_or_throw(schema == want, lambda: FugueWorkflowRuntimeValidationError(
+                    f"{want} does not match {schema}"))
 
     @staticmethod
     def _kind(tp: Any) -> Optional[str]:
@@ -331,6 +402,9 @@ def transform(
         df = e.load_df(df, format_hint="parquet")
     tf = _FuncAsTransformer(using, schema, params)
     spec = PartitionSpec(partition)
+    tf.validate_on_compile(spec)
+    if tf.has_input_rules:     # needs the input schema: only then is a native input looked at here
+        tf.validate_on_runtime(get_schema(df))
     res: Optional[DataFrame] = None
     if as_local and tf.get_format_hint() == "b200" and not isinstance(df, (B200DataFrame, B200Table)):
         # host input, host output, device function: overlap H2D / partition (/ exchange) / D2H column by column
@@ -387,6 +461,9 @@ def out_transform(df: Any, using: Any, params: Any = None, partition: Any = None
     if isinstance(df, str):
         df = e.load_df(df, format_hint="parquet")
     tf = _FuncAsTransformer(using, OUTPUT_TRANSFORMER_DUMMY_SCHEMA, params)
+    tf.validate_on_compile(PartitionSpec(partition))
+    if tf.has_input_rules:
+        tf.validate_on_runtime(get_schema(df))
     out_schema = Schema(OUTPUT_TRANSFORMER_DUMMY_SCHEMA)
     inner = tf.make_runner(out_schema, list(ignore_errors or []), discard_output=True)
     e.map_engine.map_dataframe(e.to_df(df), inner, out_schema, PartitionSpec(partition),

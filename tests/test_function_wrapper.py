@@ -350,3 +350,52 @@ def test_chunked_frames_are_matched_by_column_name():
         for part in (None, dict(by=["a"])):
             out = fa.transform(a, f, params=dict(empty=True), partition=part, engine=eng)
             assert out.schema == schema and out.count() == 0
+
+
+def test_validation_rules_from_comment_hints():
+    """fugue/extensions/_utils.py:36-150 and the uses in fugue_test/builtin_suite.py:638-730, 1403-1460: rules next
+    to the schema hint are checked before the function runs - partitioning rules without data, input rules
+    against the input's schema."""
+    from fugue_b200 import api as fa
+
+    # schema: *
+    # partitionby_has: k
+    # presort_is: v desc
+    # input_has: k, v:double
+    def strict(df: pd.DataFrame) -> pd.DataFrame:
+        return df
+
+    # partitionby_is: a, b
+    # presort_has: c
+    # input_is: k:long,v:double
+    def other(df: pd.DataFrame) -> None:
+        pass
+
+    # partitionby_has:
+    def empty_rule(df: pd.DataFrame) -> None:
+        pass
+
+    tf = _FuncAsTransformer(strict, None, None)
+    assert tf._rules == dict(partitionby_has=["k"], presort_is=[("v", False)], input_has=["k", "v:double"])
+    assert _FuncAsTransformer(other, "*", None)._rules == dict(
+        partitionby_is=["a", "b"], presort_has=[("c", True)], input_is="k:long,v:double")
+    with pytest.raises(SyntaxError):
+        _FuncAsTransformer(empty_rule, "*", None)
+
+    eng = _HostEngine()
+    pdf = pd.DataFrame(ROWS, columns=["k", "v"])
+    good = dict(by=["k"], presort="v desc")
+    assert len(fa.transform(pdf, strict, partition=good, engine=eng)) == 3
+    for bad in (None, dict(by=["v"]), dict(by=["k"]), dict(by=["k"], presort="v"), dict(by=["k"], presort="v desc, x")):
+        with pytest.raises(fa.FugueWorkflowCompileValidationError):
+            fa.transform(pdf, strict, partition=bad, engine=eng)
+    for frame in (pdf.rename(columns={"v": "w"}), pdf.assign(v=[1, 2, 3])):      # v missing; v is not a double
+        with pytest.raises(fa.FugueWorkflowRuntimeValidationError):
+            fa.transform(frame, strict, partition=good, engine=eng)
+
+    ok = dict(by=["a", "b"], presort="c")
+    wide = pd.DataFrame({"k": [1], "v": [1.0]})
+    with pytest.raises(fa.FugueWorkflowCompileValidationError):
+        fa.out_transform(wide, other, partition=dict(by=["a"], presort="c"), engine=eng)   # partitionby_is: exact set
+    with pytest.raises(fa.FugueWorkflowRuntimeValidationError):
+        fa.out_transform(wide.assign(extra=1), other, partition=ok, engine=eng)             # input_is: exact schema
